@@ -1,0 +1,251 @@
+"""TEST INFRASTRUCTURE -- generate tests/golden/*.npz from the LIVE, unmodified
+reference (/root/reference, imported through oracle/ref_shim.py).
+
+Run in the build container only:   python oracle/gen_golden.py
+The fixtures travel to the GPU box; /root/reference does not.
+
+Fixtures
+  native_c1.npz      config 1 (default box, 100 Gaussian PlaceCells, dt=10 ms), global
+                     NumPy RNG, jitter on: RNG state after construction + full history.
+  native_walls.npz   2x1 box with two internal walls, fast agent (bounces), line_of_sight
+                     PlaceCells + GridCells + BVCs, global RNG, jitter on.
+  modeA_motion.npz   teacher-forced single steps, zero jitter, injected normals
+                     (SURVEY.md section 8c mode A): inputs, outputs, collision masks.
+  modeA_rates.npz    get_state(evaluate_at=None, pos=P) for every cell type/variant,
+                     zero jitter.
+"""
+import contextlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+BOX_WALLS = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+
+
+def maze_walls(n=8, length=0.6):
+    """walls at x=k/9 alternately from floor / ceiling."""
+    out = []
+    for k in range(1, n + 1):
+        x = k / (n + 1)
+        out.append([[x, 0.0], [x, length]] if k % 2 else [[x, 1.0], [x, 1.0 - length]])
+    return out
+
+
+@contextlib.contextmanager
+def mode_a(tape):
+    """Zero the geometry jitter and feed ``scale == dt`` normals from ``tape``
+    (a list that is popped from the front)."""
+    orig = np.random.normal
+
+    def patched(loc=0.0, scale=1.0, size=None):
+        if scale in (1e-9, 1e-6):
+            return np.zeros(size)
+        n = int(np.prod(size)) if size not in (None, ()) else 1
+        vals = np.array([tape.pop(0) if tape else 0.0 for _ in range(n)], dtype=float)
+        out = loc + scale * vals
+        return out.reshape(size) if size not in (None, ()) else float(out[0])
+
+    np.random.normal = patched
+    try:
+        yield
+    finally:
+        np.random.normal = orig
+
+
+def main():
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox.Environment import Environment
+    from ratinabox.Agent import Agent
+    from ratinabox.Neurons import PlaceCells, GridCells, BoundaryVectorCells
+    os.makedirs(GOLD, exist_ok=True)
+
+    # ------------------------------------------------------------ native_c1
+    np.random.seed(0)
+    Env = Environment()
+    Ag = Agent(Env, {"dt": 0.01})
+    PCs = PlaceCells(Ag, {"n": 100})
+    init = dict(pos0=Ag.pos.copy(), vel0=Ag.velocity.copy(), centres=PCs.place_cell_centres.copy(),
+                widths=PCs.place_cell_widths.copy())
+    st = np.random.get_state()
+    for _ in range(600):
+        Ag.update()
+        PCs.update()
+    np.savez_compressed(
+        os.path.join(GOLD, "native_c1.npz"), rng_keys=st[1], rng_pos=st[2], rng_has_gauss=st[3],
+        rng_cached=st[4], **init, pos=np.array(Ag.history["pos"]), vel=np.array(Ag.history["vel"]),
+        rot_vel=np.array(Ag.history["rot_vel"]), head_direction=np.array(Ag.history["head_direction"]),
+        distance_travelled=np.array(Ag.history["distance_travelled"]), t=np.array(Ag.history["t"]),
+        firingrate=np.array(PCs.history["firingrate"]), spikes=np.packbits(np.array(PCs.history["spikes"])),
+        wall_geometry=np.array(PCs.wall_geometry))
+
+    # --------------------------------------------------------- native_walls
+    np.random.seed(1)
+    Env = Environment({"aspect": 2, "scale": 1})
+    Env.add_wall([[1, 0], [1, 0.35]])
+    Env.add_wall([[1, 0.65], [1, 1]])
+    Ag = Agent(Env, {"dt": 0.05, "speed_mean": 0.4})
+    Ag.pos = np.array([0.5, 0.5])
+    PCs = PlaceCells(Ag, {"n": 20, "description": "gaussian_threshold", "widths": 0.40,
+                          "wall_geometry": "line_of_sight", "max_fr": 10, "min_fr": 0.1})
+    PCs.place_cell_centres[-1] = np.array([1.1, 0.5])
+    GCs = GridCells(Ag, {"n": 12})
+    BVCs = BoundaryVectorCells(Ag, {"n": 10})
+    init = dict(pos0=Ag.pos.copy(), vel0=Ag.velocity.copy(), walls=Env.walls.copy(),
+                centres=PCs.place_cell_centres.copy(), widths=PCs.place_cell_widths.copy(),
+                gridscales=GCs.gridscales.copy(), phase_offsets=GCs.phase_offsets.copy(), gc_w=GCs.w.copy(),
+                bvc_mu_d=BVCs.tuning_distances.copy(), bvc_mu_t=BVCs.tuning_angles.copy(),
+                bvc_sg_d=BVCs.sigma_distances.copy(), bvc_sg_t=BVCs.sigma_angles.copy(),
+                bvc_norm=BVCs.cell_fr_norm.copy(), bvc_test_angles=BVCs.test_angles.copy(),
+                bvc_test_dirs=BVCs.test_directions.copy())
+    st = np.random.get_state()
+    ncoll = 0
+    orig_check = Env.check_wall_collisions
+
+    def counting_check(step):
+        nonlocal ncoll
+        r = orig_check(step)
+        ncoll += int(True in r[1])
+        return r
+
+    Env.check_wall_collisions = counting_check
+    for _ in range(1500):
+        Ag.update()
+        PCs.update()
+        GCs.update()
+        BVCs.update()
+    print("native_walls: wall bounces =", ncoll)
+    np.savez_compressed(
+        os.path.join(GOLD, "native_walls.npz"), rng_keys=st[1], rng_pos=st[2], rng_has_gauss=st[3],
+        rng_cached=st[4], **init, n_bounces=ncoll, pos=np.array(Ag.history["pos"]),
+        vel=np.array(Ag.history["vel"]), rot_vel=np.array(Ag.history["rot_vel"]),
+        head_direction=np.array(Ag.history["head_direction"]),
+        distance_travelled=np.array(Ag.history["distance_travelled"]),
+        pc_fr=np.array(PCs.history["firingrate"]), gc_fr=np.array(GCs.history["firingrate"]),
+        bvc_fr=np.array(BVCs.history["firingrate"]))
+
+    # --------------------------------------------------------- modeA_motion
+    rs = np.random.RandomState(1234)
+    for name, walls in (("box2", BOX_WALLS), ("maze8", maze_walls())):
+        Env = Environment()
+        for w in walls:
+            Env.add_wall(w)
+        Ag = Agent(Env, {"dt": 0.01})
+        A = 768
+        pos0 = rs.uniform(0.002, 0.998, size=(A, 2))
+        # a third of the agents hug a wall so that repulsion / bounces are exercised
+        near = rs.choice(A, A // 3, replace=False)
+        wl = Env.walls[rs.randint(0, len(Env.walls), size=len(near))]
+        lam = rs.uniform(0, 1, size=(len(near), 1))
+        pos0[near] = np.clip(wl[:, 0] + lam * (wl[:, 1] - wl[:, 0]) + rs.normal(scale=2e-3, size=(len(near), 2)),
+                             0.0005, 0.9995)
+        speed = rs.rayleigh(0.08, size=A) * rs.choice([1.0, 1.0, 6.0], size=A)
+        ang = rs.uniform(0, 2 * np.pi, size=A)
+        vel0 = speed[:, None] * np.stack((np.cos(ang), np.sin(ang)), axis=1)
+        rot0 = rs.normal(scale=2.0, size=A)
+        mv0 = vel0 + rs.normal(scale=0.01, size=(A, 2))
+        hd0 = mv0 / np.linalg.norm(mv0, axis=1, keepdims=True)
+        dist0 = rs.uniform(0, 5, size=A)
+        xi = rs.normal(size=(A, 2))
+        drift = rs.normal(scale=0.1, size=(A, 2))
+        use_drift = rs.uniform(size=A) < 0.25
+        out = {k: [] for k in ("pos", "vel", "rot", "mv", "mrot", "hd", "dist", "dclose", "n_iter", "first_hit")}
+        masks = np.zeros((A, 4, len(Env.walls)), dtype=bool)     # up to 4 loop iterations recorded
+        recorded = []
+        orig_check = Env.check_wall_collisions
+
+        def rec_check(step, _o=orig_check):
+            r = _o(step)
+            recorded.append(np.array(r[1]).copy())
+            return r
+
+        Env.check_wall_collisions = rec_check
+        for a in range(A):
+            Ag.pos, Ag.velocity = pos0[a].copy(), vel0[a].copy()
+            Ag.rotational_velocity = float(rot0[a])
+            Ag.measured_velocity = mv0[a].copy()
+            Ag.head_direction = hd0[a].copy()
+            Ag.distance_travelled = float(dist0[a])
+            Ag.t = 0.0
+            recorded.clear()
+            tape = list(xi[a])
+            with mode_a(tape):
+                if use_drift[a]:
+                    Ag.update(drift_velocity=drift[a].copy(), drift_to_random_strength_ratio=2.0)
+                else:
+                    Ag.update()
+            out["pos"].append(Ag.pos.copy()); out["vel"].append(Ag.velocity.copy())
+            out["rot"].append(Ag.rotational_velocity); out["mv"].append(Ag.measured_velocity.copy())
+            out["mrot"].append(Ag.measured_rotational_velocity); out["hd"].append(Ag.head_direction.copy())
+            out["dist"].append(Ag.distance_travelled); out["dclose"].append(Ag.distance_to_closest_wall)
+            out["n_iter"].append(len(recorded))
+            fh = [int(np.argwhere(m)[0][0]) for m in recorded if m.any()]
+            out["first_hit"].append((fh + [-1, -1, -1, -1])[:4])
+            for i, m in enumerate(recorded[:4]):
+                masks[a, i] = m
+        print(f"modeA_motion[{name}]: agents with a bounce = {int((np.array(out['n_iter']) > 1).sum())} / {A}")
+        np.savez_compressed(
+            os.path.join(GOLD, f"modeA_motion_{name}.npz"), walls=Env.walls, dt=0.01, pos0=pos0, vel0=vel0,
+            rot0=rot0, mv0=mv0, hd0=hd0, dist0=dist0, xi=xi, drift=drift, use_drift=use_drift,
+            drift_ratio=2.0, masks=np.packbits(masks), masks_shape=np.array(masks.shape),
+            **{"out_" + k: np.array(v) for k, v in out.items()})
+
+    # ---------------------------------------------------------- modeA_rates
+    rs = np.random.RandomState(4321)
+    P = rs.uniform(0.001, 0.999, size=(384, 2))
+    res = {"P": P}
+    with mode_a([]):
+        Env = Environment()
+        for w in BOX_WALLS:
+            Env.add_wall(w)
+        Ag = Agent(Env, {"dt": 0.01})
+        np.random.seed(7)
+        for desc in ("gaussian", "gaussian_threshold", "diff_of_gaussians", "top_hat", "one_hot"):
+            for geom in ("euclidean", "line_of_sight"):
+                pc = PlaceCells(Ag, {"n": 96, "description": desc, "wall_geometry": geom, "widths": 0.2,
+                                     "min_fr": 0.05, "max_fr": 3.0})
+                res[f"pc_{desc}_{geom}"] = pc.get_state(evaluate_at=None, pos=P)
+                res[f"pc_{desc}_{geom}_centres"] = pc.place_cell_centres.copy()
+        # geodesic needs exactly one internal wall
+        Env1 = Environment()
+        Env1.add_wall([[0.5, 0.0], [0.5, 0.6]])
+        Ag1 = Agent(Env1, {"dt": 0.01})
+        pc = PlaceCells(Ag1, {"n": 64, "wall_geometry": "geodesic", "widths": 0.15})
+        res["pc_gaussian_geodesic"] = pc.get_state(evaluate_at=None, pos=P)
+        res["pc_gaussian_geodesic_centres"] = pc.place_cell_centres.copy()
+        res["geodesic_walls"] = Env1.walls.copy()
+        for desc in ("rectified_cosines", "shifted_cosines"):
+            gs = np.random.uniform(0.2, 1.0, size=80)
+            th = np.random.uniform(0, np.pi / 3, size=80)
+            ph = np.random.uniform(0, 2 * np.pi, size=(80, 2))
+            gc = GridCells(Ag, {"gridscale": gs, "orientation": th, "phase_offset": ph, "description": desc,
+                                "min_fr": 0.1, "max_fr": 2.0})
+            res[f"gc_{desc}"] = gc.get_state(evaluate_at=None, pos=P)
+            res[f"gc_{desc}_gridscales"], res[f"gc_{desc}_orient"], res[f"gc_{desc}_phase"] = gs, th, ph
+            res[f"gc_{desc}_w"] = gc.w.copy()
+        for name, walls in (("box2", BOX_WALLS), ("maze8", maze_walls())):
+            E = Environment()
+            for w in walls:
+                E.add_wall(w)
+            AgE = Agent(E, {"dt": 0.01})
+            bvc = BoundaryVectorCells(AgE, {"n": 48, "min_fr": 0.0, "max_fr": 5.0})
+            res[f"bvc_{name}"] = bvc.get_state(evaluate_at=None, pos=P)
+            res[f"bvc_{name}_walls"] = E.walls.copy()
+            for k in ("tuning_distances", "tuning_angles", "sigma_distances", "sigma_angles", "cell_fr_norm",
+                      "test_angles", "test_directions"):
+                res[f"bvc_{name}_{k}"] = np.array(getattr(bvc, k)).copy()
+    res["box2_walls"] = Env.walls.copy()
+    np.savez_compressed(os.path.join(GOLD, "modeA_rates.npz"), **res)
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

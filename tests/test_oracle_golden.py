@@ -1,0 +1,132 @@
+"""Pin the CPU oracle (oracle/riab_oracle.py) against fixtures produced by the
+LIVE unmodified reference (oracle/gen_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import riab_oracle as O
+
+
+def _restore_rng(g):
+    np.random.set_state(("MT19937", g["rng_keys"], int(g["rng_pos"]), int(g["rng_has_gauss"]),
+                         float(g["rng_cached"])))
+
+
+def test_native_c1_bit_exact(golden):
+    """Config 1, global RNG, jitter ON: the oracle consumes the RNG in the
+    reference's order and must reproduce its history bit for bit."""
+    g = golden("native_c1.npz")
+    env = O.OracleEnvironment()
+    ag = O.OracleAgent(env, g["pos0"], g["vel0"], {"dt": 0.01})
+    centres, widths = g["centres"], g["widths"]
+    rng = O.GlobalRNG()
+    pcs = O.OracleNeurons(ag, len(widths), lambda pos, r: O.place_cells_get_state(
+        env, centres, widths, pos, r, "gaussian", "euclidean"))
+    assert str(g["wall_geometry"]) == "geodesic"      # W == 4 -> plain euclidean distances
+    _restore_rng(g)
+    for _ in range(600):
+        ag.update(rng)
+        pcs.update(rng)
+    for key, hk in (("pos", "pos"), ("vel", "vel"), ("rot_vel", "rot_vel"), ("head_direction", "head_direction"),
+                    ("distance_travelled", "distance_travelled"), ("t", "t")):
+        assert np.array_equal(np.array(ag.history[hk]), g[key]), key
+    assert np.array_equal(np.array(pcs.history["firingrate"]), g["firingrate"])
+    spikes = np.unpackbits(g["spikes"])[: 600 * 100].reshape(600, 100).astype(bool)
+    assert np.array_equal(np.array(pcs.history["spikes"]), spikes)
+
+
+def test_native_walls_bit_exact(golden):
+    """2x1 box, two internal walls, fast agent that bounces; line_of_sight
+    gaussian_threshold PlaceCells + GridCells + BVCs; global RNG, jitter ON."""
+    g = golden("native_walls.npz")
+    env = O.OracleEnvironment(scale=1, aspect=2, walls=[[[1, 0], [1, 0.35]], [[1, 0.65], [1, 1]]])
+    assert np.array_equal(env.walls, g["walls"])
+    ag = O.OracleAgent(env, g["pos0"], g["vel0"], {"dt": 0.05, "speed_mean": 0.4})
+    rng = O.GlobalRNG()
+    pcs = O.OracleNeurons(ag, 20, lambda pos, r: O.place_cells_get_state(
+        env, g["centres"], g["widths"], pos, r, "gaussian_threshold", "line_of_sight", 0.1, 10))
+    gcs = O.OracleNeurons(ag, 12, lambda pos, r: O.grid_cells_get_state(
+        g["gridscales"], g["phase_offsets"], g["gc_w"], pos))
+    bvcs = O.OracleNeurons(ag, 10, lambda pos, r: O.bvc_get_state(
+        env, g["bvc_mu_d"], g["bvc_mu_t"], g["bvc_sg_d"], g["bvc_sg_t"], pos, r))
+    dirs, angs = O.bvc_test_angles(2)
+    assert np.array_equal(dirs, g["bvc_test_dirs"]) and np.array_equal(angs, g["bvc_test_angles"])
+    assert np.array_equal(O.bvc_cell_fr_norm(angs, g["bvc_sg_t"]), g["bvc_norm"])
+    _restore_rng(g)
+    nb = 0
+    for _ in range(1500):
+        info = ag.update(rng)
+        nb += len(info["first_hit"]) > 0
+        pcs.update(rng)
+        gcs.update(rng)
+        bvcs.update(rng)
+    assert nb == int(g["n_bounces"]) and nb > 0
+    assert np.array_equal(np.array(ag.history["pos"]), g["pos"])
+    assert np.array_equal(np.array(ag.history["vel"]), g["vel"])
+    assert np.array_equal(np.array(ag.history["rot_vel"]), g["rot_vel"])
+    assert np.array_equal(np.array(ag.history["head_direction"]), g["head_direction"])
+    assert np.array_equal(np.array(ag.history["distance_travelled"]), g["distance_travelled"])
+    assert np.array_equal(np.array(pcs.history["firingrate"]), g["pc_fr"])
+    assert np.array_equal(np.array(gcs.history["firingrate"]), g["gc_fr"])
+    assert np.array_equal(np.array(bvcs.history["firingrate"]), g["bvc_fr"])
+
+
+@pytest.mark.parametrize("name", ["box2", "maze8"])
+def test_modeA_motion(golden, name):
+    """Teacher-forced single steps, zero jitter, injected normals."""
+    g = golden(f"modeA_motion_{name}.npz")
+    env = O.OracleEnvironment(walls=g["walls"][4:])
+    assert np.array_equal(env.walls, g["walls"])
+    A = len(g["pos0"])
+    shp = tuple(g["masks_shape"])
+    masks = np.unpackbits(g["masks"])[: int(np.prod(shp))].reshape(shp).astype(bool)
+    for a in range(A):
+        ag = O.OracleAgent(env, g["pos0"][a], g["vel0"][a], {"dt": 0.01})
+        ag.rotational_velocity = float(g["rot0"][a])
+        ag.measured_velocity = g["mv0"][a].copy()
+        ag.head_direction = g["hd0"][a].copy()
+        ag.distance_travelled = float(g["dist0"][a])
+        rng = O.TapeRNG(agent_xi=g["xi"][a])
+        if g["use_drift"][a]:
+            info = ag.update(rng, drift_velocity=g["drift"][a], drift_to_random_strength_ratio=float(g["drift_ratio"]))
+        else:
+            info = ag.update(rng)
+        assert np.array_equal(ag.pos, g["out_pos"][a]), a
+        assert np.array_equal(ag.velocity, g["out_vel"][a]), a
+        assert ag.rotational_velocity == g["out_rot"][a]
+        assert np.array_equal(ag.measured_velocity, g["out_mv"][a])
+        assert ag.measured_rotational_velocity == g["out_mrot"][a]
+        assert np.array_equal(ag.head_direction, g["out_hd"][a])
+        assert ag.distance_travelled == g["out_dist"][a]
+        assert ag.distance_to_closest_wall == g["out_dclose"][a]
+        assert len(info["collisions"]) == g["out_n_iter"][a]
+        for i, m in enumerate(info["collisions"][:4]):
+            assert np.array_equal(m, masks[a, i])
+        assert (info["first_hit"] + [-1] * 4)[:4] == list(g["out_first_hit"][a])
+
+
+def test_modeA_rates(golden):
+    g = golden("modeA_rates.npz")
+    P = g["P"]
+    rng = O.TapeRNG()
+    env = O.OracleEnvironment(walls=g["box2_walls"][4:])
+    for desc in ("gaussian", "gaussian_threshold", "diff_of_gaussians", "top_hat", "one_hot"):
+        for geom in ("euclidean", "line_of_sight"):
+            c = g[f"pc_{desc}_{geom}_centres"]
+            fr = O.place_cells_get_state(env, c, 0.2 * np.ones(len(c)), P, rng, desc, geom, 0.05, 3.0, scalar_width=0.2)
+            assert np.array_equal(fr, g[f"pc_{desc}_{geom}"]), (desc, geom)
+    env1 = O.OracleEnvironment(walls=g["geodesic_walls"][4:])
+    c = g["pc_gaussian_geodesic_centres"]
+    fr = O.place_cells_get_state(env1, c, 0.15 * np.ones(len(c)), P, rng, "gaussian", "geodesic")
+    assert np.array_equal(fr, g["pc_gaussian_geodesic"])
+    for desc in ("rectified_cosines", "shifted_cosines"):
+        w = O.grid_cells_w(g[f"gc_{desc}_orient"])
+        assert np.array_equal(w, g[f"gc_{desc}_w"])
+        fr = O.grid_cells_get_state(g[f"gc_{desc}_gridscales"], g[f"gc_{desc}_phase"], w, P, desc,
+                                    min_fr=0.1, max_fr=2.0)
+        assert np.array_equal(fr, g[f"gc_{desc}"]), desc
+    for name in ("box2", "maze8"):
+        e = O.OracleEnvironment(walls=g[f"bvc_{name}_walls"][4:])
+        fr = O.bvc_get_state(e, g[f"bvc_{name}_tuning_distances"], g[f"bvc_{name}_tuning_angles"],
+                             g[f"bvc_{name}_sigma_distances"], g[f"bvc_{name}_sigma_angles"], P, rng,
+                             min_fr=0.0, max_fr=5.0)
+        assert np.array_equal(fr, g[f"bvc_{name}"]), name
