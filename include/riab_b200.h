@@ -1,0 +1,231 @@
+/* riab_b200.h -- C ABI of the B200-native batched step engine for RatInABox's
+ * per-step hot path (Agent.update + Neurons.update for PlaceCells, GridCells,
+ * BoundaryVectorCells).
+ *
+ * The reference (RatInABox v1.15.3) is pure Python: it has no FFI.  Its
+ * extension boundary is two overridable methods,
+ *     Agent.update(dt, drift_velocity, drift_to_random_strength_ratio, **kw)   ratinabox/Agent.py:160
+ *     Neurons.update(**kw) -> get_state(evaluate_at, **kw)                     ratinabox/Neurons.py:145,173
+ * and that is what this library sits behind.  Each entry point below names the
+ * reference function it replaces.  The Python host mirror (ratinabox_b200/)
+ * binds these symbols with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no torch / C++ types.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (the Python
+ *     host allocates them with torch); "host" pointers are ordinary memory.
+ *   - every launch goes to the CUDA stream passed as `stream` (a cudaStream_t
+ *     cast to void*; NULL = legacy default stream).  No host sync inside.
+ *   - return value: 0 on success, negative riab_status otherwise;
+ *     riab_last_error() gives the message (thread local).
+ *   - agent state is float64 (the reference's dtype, Agent.py:197-198); firing
+ *     rates / history rows are float32.
+ */
+#ifndef RIAB_B200_H
+#define RIAB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIAB_ABI_VERSION 1
+
+typedef enum {
+  RIAB_OK = 0,
+  RIAB_ERR_INVALID = -1,   /* bad argument (the reference would assert / raise ValueError) */
+  RIAB_ERR_CUDA = -2,      /* CUDA runtime error */
+  RIAB_ERR_UNSUPPORTED = -3 /* outside the supported path (see DESIGN.md "out of scope") */
+} riab_status;
+
+int riab_abi_version(void);
+const char* riab_last_error(void);
+
+/* ---------------------------------------------------------------- Environment
+ * walls: (n_walls,2,2) float64, boundary walls first (Environment.py:137-144),
+ * then user walls (add_wall, :330-342).  Solid rectangular 2D box only. */
+typedef struct {
+  const double* walls_dev;     /* device, n_walls*4 doubles */
+  int32_t n_walls;
+  int32_t n_boundary_walls;    /* 4: Environment.py:715-717 `walls[4:]` */
+  double extent[4];            /* left,right,bottom,top  (Environment.py:171-173) */
+} riab_env;
+
+/* ---------------------------------------------------------------------- Agent
+ * Structure-of-arrays batched state; every pointer is a device array with
+ * n_agents rows.  Mirrors the attributes Agent.update mutates (Agent.py:193-201,
+ * SURVEY 8(b)). */
+typedef struct {
+  int64_t n_agents;
+  int64_t id_offset;             /* global id of row 0 (multi-GPU shards; keys the Philox stream) */
+  double* pos;                   /* (A,2)  Agent.pos */
+  double* velocity;              /* (A,2)  Agent.velocity */
+  double* rotational_velocity;   /* (A)    Agent.rotational_velocity */
+  double* measured_velocity;     /* (A,2)  Agent.measured_velocity */
+  double* measured_rotational_velocity; /* (A) */
+  double* head_direction;        /* (A,2) */
+  double* distance_travelled;    /* (A) */
+  double* distance_to_closest_wall; /* (A) */
+} riab_agents;
+
+/* Scalar parameters of one Agent.update call.  `*_kw` are the values after the
+ * per-call kwargs override (Agent.py:280-285, :353-355); the others are the
+ * attributes the reference reads directly. */
+typedef struct {
+  double dt;
+  double speed_coherence_time_kw;               /* Agent.py:283 */
+  double speed_mean_kw;                         /* Agent.py:284: Rayleigh sigma of the speed process */
+  double speed_mean;                            /* attribute: wall repulsion (:370) and bounce speed (:439) */
+  double speed_std;                             /* attribute: ==0 -> constant speed (:310) */
+  double speed_coherence_time;                  /* attribute: drift update (:340) */
+  double rotational_velocity_coherence_time_kw; /* :281 */
+  double rotational_velocity_std_kw;            /* :280 */
+  double rotational_velocity_drift_kw;          /* :282 */
+  double head_direction_smoothing_timescale;    /* attribute (:489) */
+  double thigmotaxis_kw;                        /* :355 */
+  double wall_repel_distance_kw;                /* :354 */
+  double wall_repel_strength_kw;                /* :353 */
+  double drift_to_random_strength_ratio;        /* Agent.update arg */
+} riab_motion_params;
+
+/* Optional per-step inputs / parity taps (device pointers, may be NULL). */
+typedef struct {
+  const double* drift_velocity;   /* (A,2) Agent.update(drift_velocity=...), Agent.py:324-341 */
+  const double* xi;               /* (A,2) injected standard normals for the two OU draws
+                                     (oracle mode A); NULL -> Philox4x32-10(seed, step, agent id) */
+  uint64_t seed;
+  uint64_t step;                  /* step counter (Philox counter word) */
+  uint8_t* collision_mask;        /* (A, RIAB_MAX_REC_ITERS, n_walls) per-iteration wall_collisions
+                                     of Environment.check_wall_collisions (Environment.py:820-841) */
+  int32_t* first_hit;             /* (A, RIAB_MAX_REC_ITERS) lowest colliding wall index or -1 (Agent.py:437) */
+  int32_t* n_iters;               /* (A) number of collision-loop iterations executed */
+  float* history_row;             /* (A,8) float32: pos.xy, vel.xy (measured), head_direction.xy,
+                                     rot_vel, distance_travelled -- Agent.save_to_history, Agent.py:509-521 */
+} riab_step_io;
+
+#define RIAB_MAX_REC_ITERS 4
+#define RIAB_MAX_BOUNCE_ITERS 32
+
+/* Agent.update (Agent.py:160-242, random-motion branch) for n_agents agents. */
+int riab_agent_update(const riab_agents* agents, const riab_env* env,
+                      const riab_motion_params* prm, const riab_step_io* io, void* stream);
+
+/* ----------------------------------------------------------------- PlaceCells */
+typedef enum { RIAB_PC_GAUSSIAN = 0, RIAB_PC_GAUSSIAN_THRESHOLD = 1, RIAB_PC_DIFF_OF_GAUSSIANS = 2,
+               RIAB_PC_TOP_HAT = 3, RIAB_PC_ONE_HOT = 4 } riab_pc_description;   /* Neurons.py:959-976 */
+typedef enum { RIAB_GEOM_EUCLIDEAN = 0, RIAB_GEOM_LINE_OF_SIGHT = 1, RIAB_GEOM_GEODESIC = 2 } riab_wall_geometry; /* Environment.py:707-774 */
+
+typedef struct {
+  int32_t n_cells;
+  int32_t description;     /* riab_pc_description */
+  int32_t wall_geometry;   /* riab_wall_geometry */
+  int32_t n_inner_walls;   /* walls[4:] used by line_of_sight / geodesic */
+  float min_fr, max_fr;    /* Neurons.py:978-980 */
+  double top_hat_width;    /* the scalar `widths` param (Neurons.py:975-976) */
+  const float* packed_dev; /* device block written by riab_place_pack (size riab_place_pack_floats) */
+  const double* centres_dev; /* (N,2) float64 centres, used by the exact fall-back of the wall predicates */
+  /* filled by riab_place_pack: */
+  float eps[8];            /* relative uncertainty band of the float32 line-of-sight predicate, per inner wall */
+  int32_t ep_valid;        /* geodesic: bit k set iff end k of walls[4] lies strictly inside the box (Environment.py:748) */
+  int32_t n_pad;           /* n_cells rounded up to a multiple of 4 */
+} riab_place_cells;
+
+/* Host-side packing of PlaceCells parameters (place_cell_centres (N,2) f64,
+ * place_cell_widths (N) f64, walls (W,2,2) f64) into the float32 block the
+ * kernels read.  Returns number of floats written / needed. */
+int64_t riab_place_pack_floats(int32_t n_cells, int32_t n_inner_walls);
+int riab_place_pack(const double* centres_host, const double* widths_host, int32_t n_cells,
+                    const double* walls_host, int32_t n_walls, int32_t n_boundary_walls,
+                    const double* extent, int32_t wall_geometry, riab_place_cells* meta_out, float* out_host);
+
+/* PlaceCells.get_state(evaluate_at=None, pos=P) (Neurons.py:936-981):
+ * pos_dev (n_pos,2) f64 -> out_dev (n_pos, ld_out) f32, row = position, col = cell
+ * (the transposed, coalesced view of the reference's (n_cells,n_pos)). */
+int riab_place_rates(const double* pos_dev, int64_t n_pos, const riab_env* env,
+                     const riab_place_cells* pc, float* out_dev, int64_t ld_out, void* stream);
+
+/* ------------------------------------------------------------------ GridCells */
+typedef enum { RIAB_GC_RECTIFIED_COSINES = 0, RIAB_GC_SHIFTED_COSINES = 1 } riab_gc_description; /* Neurons.py:1203-1218 */
+typedef struct {
+  int32_t n_cells;
+  int32_t description;
+  double width_ratio;      /* Neurons.py:1064 */
+  float min_fr, max_fr;
+  const float* packed_dev; /* riab_grid_pack output */
+  int32_t n_pad;           /* filled by riab_grid_pack */
+} riab_grid_cells;
+int64_t riab_grid_pack_floats(int32_t n_cells);
+int riab_grid_pack(const double* gridscales_host, const double* phase_offsets_host /* (N,2) */,
+                   const double* w_host /* (N,3,2) */, int32_t n_cells, const double* extent,
+                   riab_grid_cells* meta_out, float* out_host);
+/* GridCells.get_state (2D), Neurons.py:1172-1236 */
+int riab_grid_rates(const double* pos_dev, int64_t n_pos, const riab_env* env,
+                    const riab_grid_cells* gc, float* out_dev, int64_t ld_out, void* stream);
+
+/* -------------------------------------------------------- BoundaryVectorCells */
+typedef struct {
+  int32_t n_cells;
+  int32_t n_test_angles;   /* T = int(360/dtheta), Neurons.py:1588 */
+  float min_fr, max_fr;
+  const float* packed_dev;       /* riab_bvc_pack output (per-cell tuning + von Mises table tiles) */
+  const double* test_dirs_dev;   /* (T,2) f64 test_directions (Neurons.py:1584-1596, duplicated-0 quirk kept) */
+  int32_t n_pad;                 /* filled by riab_bvc_pack: n_cells rounded up to the cell tile (64) */
+} riab_bvc_cells;
+int64_t riab_bvc_pack_floats(int32_t n_cells, int32_t n_test_angles);
+int riab_bvc_pack(const double* tuning_distances, const double* tuning_angles, const double* sigma_distances,
+                  const double* sigma_angles, int32_t n_cells, const double* test_angles, int32_t n_test_angles,
+                  riab_bvc_cells* meta_out, float* out_host);
+/* BoundaryVectorCells.get_state (allocentric), Neurons.py:1617-1778.
+ * scratch_dev: riab_bvc_scratch_floats(n_pos, T) float32 workspace holding dist_to_first_wall in
+ * [agent tile of 32][T][32] order; first_wall_dev optional (n_pos,T) int32 (argmax wall id, Neurons.py:1677-1679). */
+int64_t riab_bvc_scratch_floats(int64_t n_pos, int32_t n_test_angles);
+int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_bvc_cells* bvc,
+                   float* scratch_dev, int32_t* first_wall_dev, float* out_dev, int64_t ld_out, void* stream);
+
+/* ------------------------------------------------------- Neurons.update extras
+ * OU noise (Neurons.py:153-160) and spikes (Neurons.py:681-684) for a block of
+ * rates already written to rates_dev.  noise_dev (A,N) f32 state (NULL when
+ * noise_std == 0); spikes (A, 4*ceil(N/32)) bytes, bit-packed little-endian (bit c of the row = cell c), NULL to skip. */
+typedef struct {
+  float noise_std, noise_coherence_time, dt;
+  uint64_t seed, step;
+  int64_t id_offset;
+  int32_t population_id;    /* distinguishes the Philox streams of populations of one Agent */
+} riab_neuron_noise;
+
+/* --------------------------------------------------------------- fused step
+ * One launch = Agent.update for every agent + Neurons.update of ONE population
+ * (motion -> rates [-> noise] [-> spikes] -> history row).  `cells_kind` selects
+ * which of pc / gc / bvc is read. */
+typedef enum { RIAB_CELLS_PLACE = 0, RIAB_CELLS_GRID = 1, RIAB_CELLS_BVC = 2 } riab_cells_kind;
+typedef struct {
+  float* rates_row;        /* (A, ld) f32: firing rates of this step (doubles as the history row) */
+  int64_t ld;
+  uint32_t* spikes_row;    /* (A, ceil(N/32)) uint32 words, bit c%32 of word c/32 = cell c; or NULL */
+  float* noise_state;      /* (A, ld) f32 OU noise state or NULL (noise_std == 0) */
+  float* bvc_scratch;      /* (A, T) f32, BVC only */
+} riab_rates_out;
+
+int riab_step_fused(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                    const riab_step_io* io, int32_t cells_kind, const void* cells /* riab_place_cells* etc. */,
+                    const riab_neuron_noise* noise, const riab_rates_out* out, void* stream);
+
+/* Number of kernels launched by the library since load (bench.py "gpu_launches"). */
+int64_t riab_launch_count(void);
+
+/* -------------------------------------------------- host-buffer (e2e) entry
+ * The reference-facing call with HOST buffers: copies drift (may be NULL) to the
+ * device, runs riab_step_fused, copies pos (A,2 f64) back.  Buffers should be
+ * pinned for the copies to be asynchronous.  staging_* are device scratch. */
+int riab_step_fused_host(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                         riab_step_io* io, int32_t cells_kind, const void* cells,
+                         const riab_neuron_noise* noise, const riab_rates_out* out,
+                         const double* drift_host, double* drift_staging_dev,
+                         double* pos_out_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIAB_B200_H */

@@ -1,0 +1,372 @@
+"""Host mirror of ``ratinabox.Agent`` -- batched over ``n_agents`` -- whose
+``update()`` runs on the GPU through libriab_b200 (C ABI: include/riab_b200.h).
+
+API parity with the reference (ratinabox/Agent.py):
+  * ``Agent(Environment, params)``; same ``default_params`` keys (Agent.py:68-84) plus
+    ``n_agents`` (batch size, default 1), ``seed``, ``id_offset`` (multi-GPU shard
+    offset), ``history_bytes_limit``.
+  * ``update(dt=None, drift_velocity=None, drift_to_random_strength_ratio=1, **kwargs)``
+    with the reference's per-call kwargs (Agent.py:280-285, :353-355).
+  * state attributes ``pos, velocity, rotational_velocity, measured_velocity,
+    measured_rotational_velocity, head_direction, distance_travelled,
+    distance_to_closest_wall, t, dt`` are readable AND writable between steps (the
+    reference's tests poke them: tests/test_advanced.py:47-48).  With ``n_agents == 1``
+    they have the reference's shapes ((2,) / scalar); otherwise a leading agent axis.
+  * ``history`` / ``get_history_arrays()`` (Agent.py:111-120, :1093-1102), backed by a
+    device ring buffer that is only materialised on access.
+
+The launch is lazy: ``update()`` queues the motion step, and the first
+``Neurons.update()`` that follows runs it fused with its firing rates in one
+kernel (riab_step_fused).  Reading any state attribute, or a second ``update()``,
+flushes a queued step through the stand-alone kernel (riab_agent_update), so the
+observable behaviour is that of the reference's eager calls.
+
+There is no CPU fallback: without a CUDA device or the built library this raises.
+"""
+import copy
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+_STATE = ("pos", "velocity", "rotational_velocity", "measured_velocity", "measured_rotational_velocity",
+          "head_direction", "distance_travelled", "distance_to_closest_wall")
+_VEC = {"pos", "velocity", "measured_velocity", "head_direction"}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("ratinabox_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+class _HistoryView:
+    """dict-like view with the reference's keys; values are materialised lazily."""
+
+    def __init__(self, owner):
+        self._o = owner
+
+    def keys(self):
+        return self._o._history_keys()
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __contains__(self, k):
+        return k in self.keys()
+
+    def __getitem__(self, k):
+        return self._o.get_history_arrays()[k]
+
+    def items(self):
+        a = self._o.get_history_arrays()
+        return [(k, a[k]) for k in self.keys()]
+
+
+class Agent:
+    default_params = {                                              # ratinabox/Agent.py:68-84
+        "name": None,
+        "dt": 0.05,
+        "speed_coherence_time": 0.7,
+        "speed_mean": 0.08,
+        "speed_std": 0.08,
+        "rotational_velocity_coherence_time": 0.08,
+        "rotational_velocity_std": (120 * (np.pi / 180)),
+        "head_direction_smoothing_timescale": 0.15,
+        "thigmotaxis": 0.5,
+        "wall_repel_distance": 0.1,
+        "wall_repel_strength": 1.0,
+        "save_history": True,
+        # ---- batch-engine additions
+        "n_agents": 1,
+        "seed": 0,
+        "id_offset": 0,
+        "history_bytes_limit": 2 << 30,
+    }
+
+    def __init__(self, Environment, params={}):
+        torch = _torch()
+        self._lib = _lib.load()
+        self.params = copy.deepcopy(__class__.default_params)
+        self.params.update(params)
+        unexpected = [k for k in params if k not in __class__.default_params]
+        if unexpected:
+            warnings.warn(f"Found {len(unexpected)} unexpected params key(s) while initializing Agent: {unexpected}")
+        for k, v in self.params.items():
+            setattr(self, k, v)
+        self.Environment = Environment
+        self.agent_idx = len(Environment.Agents)
+        if self.name is None:
+            self.name = f"agent_{self.agent_idx}"
+        Environment.add_agent(agent=self)
+        self.Neurons = []
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_agents = int(self.n_agents)
+        A = self.n_agents
+
+        self.prev_t = 0
+        self.t = 0
+        self.average_measured_speed = max(self.speed_mean, self.speed_std)
+        self.use_imported_trajectory = False
+        self._step = 0
+        self._t_hist = []
+        self._shadow = {}
+        self._pending = None
+        self._tape = None
+        self._rec = None
+
+        # ---- initial state (Agent.py:523-535, :136-141), sampled on the host like the reference
+        pos = Environment.sample_positions(n=A, method="random")
+        direction = np.random.uniform(0, 2 * np.pi, size=A)
+        vel = self.speed_mean * np.stack((np.cos(direction), np.sin(direction)), axis=1)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._s = {
+            "pos": torch.as_tensor(pos, **f64).contiguous(),
+            "velocity": torch.as_tensor(vel, **f64).contiguous(),
+            "rotational_velocity": torch.zeros(A, **f64),
+            "measured_velocity": torch.as_tensor(vel, **f64).contiguous().clone(),
+            "measured_rotational_velocity": torch.zeros(A, **f64),
+            "head_direction": torch.as_tensor(vel / np.linalg.norm(vel, axis=1, keepdims=True), **f64).contiguous(),
+            "distance_travelled": torch.zeros(A, **f64),
+            "distance_to_closest_wall": torch.full((A,), float("inf"), **f64),
+        }
+        self._agents_c = _lib.Agents()
+        self._refresh_agents_struct()
+        self._mp = _lib.MotionParams()
+        self._io = _lib.StepIO()
+        self._env_c = _lib.Env()
+        self._drift_dev = None
+        # ---- history ring (device)
+        self._hist = None
+        self._hist_cap = 0
+        self._hist_rows = 0        # rows written since reset
+        self._history_view = _HistoryView(self)
+        self._last_history_array_cache_time = None
+        self._history_arrays = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _refresh_agents_struct(self):
+        a = self._agents_c
+        a.n_agents = self.n_agents
+        a.id_offset = int(self.id_offset)
+        for k in _STATE:
+            setattr(a, {"velocity": "velocity"}.get(k, k), self._s[k].data_ptr())
+
+    def _env_struct(self):
+        env = self.Environment
+        walls = env.walls_device(self.device)
+        e = self._env_c
+        e.walls_dev = walls.data_ptr()
+        e.n_walls = int(walls.shape[0])
+        e.n_boundary_walls = int(env.n_boundary_walls)
+        for i in range(4):
+            e.extent[i] = float(env.extent[i])
+        self._walls_keepalive = walls
+        return e
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _squeeze(self, name, arr):
+        if self.n_agents != 1:
+            return arr
+        return arr[0].copy() if name in _VEC else arr[0].item()
+
+    def _get_state(self, name):
+        self._flush_pending()
+        if name in self._shadow:
+            return self._shadow[name][0]
+        host = self._s[name].cpu().numpy()
+        val = self._squeeze(name, host)
+        if isinstance(val, np.ndarray):
+            self._shadow[name] = (val, val.copy())
+        return val
+
+    def _set_state(self, name, value):
+        import torch
+        self._flush_pending()
+        self._shadow.pop(name, None)
+        arr = np.asarray(value, dtype=np.float64)
+        if name in _VEC:
+            arr = np.broadcast_to(arr.reshape(-1, 2) if arr.size == 2 * self.n_agents else arr, (self.n_agents, 2))
+        else:
+            arr = np.broadcast_to(arr.reshape(-1) if arr.size == self.n_agents else arr, (self.n_agents,))
+        self._s[name].copy_(torch.as_tensor(np.array(arr, dtype=np.float64, order="C", copy=True)))
+
+    def _sync_user_writes(self):
+        """Upload state arrays the user mutated in place since they were read."""
+        for name, (host, snap) in list(self._shadow.items()):
+            if not np.array_equal(host, snap, equal_nan=True):
+                self._shadow.pop(name)
+                self._set_state(name, host)
+        self._shadow.clear()
+
+    # state attributes (properties are generated below the class body)
+
+    # -------------------------------------------------------------------- update
+    def update(self, dt=None, drift_velocity=None, drift_to_random_strength_ratio=1, **kwargs):
+        """Agent.update (ratinabox/Agent.py:160-242), random-motion branch, for every agent."""
+        import torch
+        self._flush_pending()
+        if kwargs.get("forced_next_position", None) is not None or self.use_imported_trajectory:
+            raise NotImplementedError("imported / forced trajectories are outside the CUDA hot path (SURVEY.md section 2 row 8)")
+        dt = (dt or self.dt)
+        self.dt = dt
+        self.prev_t = self.t
+        self.t += dt
+        self._sync_user_writes()
+
+        mp = self._mp
+        mp.dt = float(dt)
+        mp.speed_coherence_time_kw = float(kwargs.get("speed_coherence_time", self.speed_coherence_time))
+        mp.speed_mean_kw = float(kwargs.get("speed_mean", self.speed_mean))
+        mp.speed_mean = float(self.speed_mean)
+        mp.speed_std = float(self.speed_std)
+        mp.speed_coherence_time = float(self.speed_coherence_time)
+        mp.rotational_velocity_coherence_time_kw = float(
+            kwargs.get("rotational_velocity_coherence_time", self.rotational_velocity_coherence_time))
+        mp.rotational_velocity_std_kw = float(kwargs.get("rotational_velocity_std", self.rotational_velocity_std))
+        mp.rotational_velocity_drift_kw = float(kwargs.get("rotational_velocity_drift", 0))
+        mp.head_direction_smoothing_timescale = float(self.head_direction_smoothing_timescale)
+        mp.thigmotaxis_kw = float(kwargs.get("thigmotaxis", self.thigmotaxis))
+        mp.wall_repel_distance_kw = float(kwargs.get("wall_repel_distance", self.wall_repel_distance))
+        mp.wall_repel_strength_kw = float(kwargs.get("wall_repel_strength", self.wall_repel_strength))
+        mp.drift_to_random_strength_ratio = float(drift_to_random_strength_ratio)
+
+        io = self._io
+        io.drift_velocity = None
+        if drift_velocity is not None:
+            if isinstance(drift_velocity, torch.Tensor):
+                d = drift_velocity.to(device=self.device, dtype=torch.float64)
+            else:
+                assert isinstance(drift_velocity, np.ndarray), "drift_velocity must be an np.array"   # Agent.py:333
+                d = torch.as_tensor(np.ascontiguousarray(drift_velocity, dtype=np.float64), device=self.device)
+            assert d.shape in ((2,), (self.n_agents, 2)), "drift_velocity must have shape (Env.D,) or (n_agents, Env.D)"
+            self._drift_dev = d.expand(self.n_agents, 2).contiguous()
+            io.drift_velocity = self._drift_dev.data_ptr()
+        io.xi = None
+        self._tape = None
+        xi = kwargs.get("_xi", None)          # parity tap: injected standard normals (oracle mode A)
+        if xi is not None:
+            self._tape = torch.as_tensor(np.ascontiguousarray(xi, dtype=np.float64).reshape(self.n_agents, 2),
+                                         device=self.device)
+            io.xi = self._tape.data_ptr()
+        io.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
+        io.step = self._step
+        io.collision_mask = io.first_hit = io.n_iters = None
+        self._rec = None
+        if kwargs.get("_record_collisions", False):
+            W = int(self.Environment.walls.shape[0])
+            self._rec = dict(
+                mask=torch.zeros((self.n_agents, _lib.MAX_REC_ITERS, W), dtype=torch.uint8, device=self.device),
+                first_hit=torch.full((self.n_agents, _lib.MAX_REC_ITERS), -1, dtype=torch.int32, device=self.device),
+                n_iters=torch.zeros(self.n_agents, dtype=torch.int32, device=self.device))
+            io.collision_mask = self._rec["mask"].data_ptr()
+            io.first_hit = self._rec["first_hit"].data_ptr()
+            io.n_iters = self._rec["n_iters"].data_ptr()
+        io.history_row = None
+        if self.save_history:
+            io.history_row = self._history_row_ptr()
+            self._t_hist.append(self.t)
+        self._pending = True
+        self._step += 1
+
+    def _flush_pending(self):
+        """Run a queued motion step that no Neurons.update() fused with."""
+        if self._pending:
+            self._pending = None
+            _lib.check(self._lib.riab_agent_update(C.byref(self._agents_c), C.byref(self._env_struct()),
+                                                   C.byref(self._mp), C.byref(self._io), self._stream()))
+
+    def _take_pending(self):
+        """Called by Neurons.update(): hands over the queued step for fusion."""
+        if self._pending:
+            self._pending = None
+            return True
+        return False
+
+    def last_collision_info(self):
+        """Parity tap (needs update(_record_collisions=True)): per loop iteration
+        ``wall_collisions`` masks (Environment.check_wall_collisions), first-hit wall
+        indices (Agent.py:437) and the number of loop iterations."""
+        self._flush_pending()
+        if self._rec is None:
+            raise RuntimeError("call update(_record_collisions=True) first")
+        return {k: v.cpu().numpy() for k, v in self._rec.items()}
+
+    # ------------------------------------------------------------------- history
+    def _history_keys(self):
+        return ["t", "pos", "distance_travelled", "vel", "rot_vel", "head_direction"]
+
+    def _history_row_ptr(self):
+        import torch
+        A = self.n_agents
+        row_bytes = A * 8 * 4
+        if self._hist is None:
+            cap = int(max(1, min(1024, self.history_bytes_limit // row_bytes)))
+            self._hist = torch.empty((cap, A, 8), dtype=torch.float32, device=self.device)
+            self._hist_cap = cap
+        elif self._hist_rows == self._hist_cap and 2 * self._hist_cap * row_bytes <= self.history_bytes_limit:
+            new = torch.empty((2 * self._hist_cap, A, 8), dtype=torch.float32, device=self.device)
+            new[: self._hist_cap].copy_(self._hist)
+            self._hist, self._hist_cap = new, 2 * self._hist_cap
+        slot = self._hist_rows % self._hist_cap
+        self._hist_rows += 1
+        return self._hist.data_ptr() + slot * row_bytes
+
+    @property
+    def history(self):
+        return self._history_view
+
+    def get_history_arrays(self):
+        """dict of arrays (Agent.py:1093-1102).  With n_agents > 1 the arrays carry an
+        agent axis after the time axis.  If the ring wrapped, the most recent
+        ``capacity`` steps are returned (``history_dropped`` counts the rest)."""
+        self._flush_pending()
+        if self._last_history_array_cache_time != (self.t, self._hist_rows):
+            self._last_history_array_cache_time = (self.t, self._hist_rows)
+            n = min(self._hist_rows, self._hist_cap)
+            if n == 0:
+                rows = np.zeros((0, self.n_agents, 8), dtype=np.float32)
+            else:
+                h = self._hist[: self._hist_cap]
+                start = self._hist_rows % self._hist_cap if self._hist_rows > self._hist_cap else 0
+                import torch
+                idx = (torch.arange(n, device=self.device) + start) % self._hist_cap
+                rows = h[idx].cpu().numpy()
+            sq = (lambda x: x[:, 0]) if self.n_agents == 1 else (lambda x: x)
+            self.history_dropped = self._hist_rows - n
+            self._history_arrays = {
+                "t": np.array(self._t_hist[len(self._t_hist) - n:]),
+                "pos": sq(rows[:, :, 0:2]).astype(np.float64),
+                "vel": sq(rows[:, :, 2:4]).astype(np.float64),
+                "head_direction": sq(rows[:, :, 4:6]).astype(np.float64),
+                "rot_vel": sq(rows[:, :, 6]).astype(np.float64),
+                "distance_travelled": sq(rows[:, :, 7]).astype(np.float64),
+            }
+        return self._history_arrays
+
+    def reset_history(self):                                        # Agent.py:537-541
+        self._flush_pending()
+        self._hist_rows = 0
+        self._t_hist = []
+        self._last_history_array_cache_time = None
+
+    def initialise_position_and_velocity(self):                     # Agent.py:523-535
+        A = self.n_agents
+        self.pos = self.Environment.sample_positions(n=A, method="random")
+        direction = np.random.uniform(0, 2 * np.pi, size=A)
+        self.velocity = self.speed_mean * np.stack((np.cos(direction), np.sin(direction)), axis=1)
+        self.rotational_velocity = np.zeros(A)
+
+
+def _make_prop(name):
+    return property(lambda self: self._get_state(name), lambda self, v: self._set_state(name, v))
+
+
+for _n in _STATE:
+    setattr(Agent, _n, _make_prop(_n))

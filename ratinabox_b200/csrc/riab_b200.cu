@@ -1,0 +1,780 @@
+// libriab_b200.so -- kernels + C ABI (include/riab_b200.h).  sm_100a only.
+//
+// Kernel inventory
+//   k_agent_update      Agent.update, one agent per thread (float64)
+//   k_tile<P,FUSED>     (agents x cells) tile kernel for PlaceCells / GridCells:
+//                       [FUSED: warp 0 runs Agent.update for the tile's 32 agents]
+//                       -> per-agent float32 records in shared memory -> every thread
+//                       streams its 4 cells (registers) over the tile's agents and
+//                       writes float4 rate rows (+ OU noise, + bit-packed spikes)
+//   k_bvc_rays<FUSED>   BVC phase A (float64 rays) [+ Agent.update]
+//   k_bvc_integrate     BVC phase B (float32 angular integral, TMA-staged tables)
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "riab_bvc.cuh"
+#include "riab_grid.cuh"
+#include "riab_motion.cuh"
+#include "riab_place.cuh"
+
+using namespace riab;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define RIAB_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) return fail(RIAB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int TA = 32;      // agents per tile (one warp runs their motion)
+constexpr int NT = 256;     // threads per CTA in the tile kernels
+constexpr int MAXW = 64;    // walls staged in shared memory
+constexpr int CELL_PAD = 128;  // packed per-cell arrays are padded to 4 cells x 32 lanes
+
+struct EnvK {
+  const double* walls;
+  int W, nb, aligned;
+  double ext[4];
+  double cxm, cym;
+};
+
+struct OutK {
+  float* rates;
+  long long ld;
+  uint32_t* spikes;
+  long long spike_ld;       // words per row
+  float* noise;
+  float dt, noise_decay, noise_sig;   // n <- n + (-n*dt/tau) + sig*xi ; decay = dt/tau
+  unsigned long long seed, step;
+  long long id_offset;
+  int pop, vec_ok;
+};
+
+// ---------------------------------------------------------------------------
+// walls -> shared memory through a 1-D TMA bulk copy when 16-byte aligned.
+__device__ __forceinline__ void stage_walls(double* s_walls, uint64_t* bar, const EnvK& env) {
+  const uint32_t bytes = (uint32_t)env.W * 32u;
+  if (env.aligned) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(bar, bytes);
+      tma_bulk_g2s(s_walls, env.walls, bytes, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+  } else {
+    for (int i = threadIdx.x; i < env.W * 4; i += blockDim.x) s_walls[i] = env.walls[i];
+    __syncthreads();
+  }
+}
+
+// One agent's Agent.update inside a kernel (loads/stores its state).
+template <bool REC>
+__device__ __forceinline__ void agent_update_one(const riab_agents& ag, const riab_motion_params& mp,
+                                                 const riab_step_io& io, const EnvK& env,
+                                                 const double* s_walls, long long i, AgentState& s) {
+  load_agent(ag, i, s);
+  double n1, n2;
+  const unsigned long long gid = (unsigned long long)(ag.id_offset + i);
+  if (io.xi != nullptr) { n1 = io.xi[2 * i]; n2 = io.xi[2 * i + 1]; }
+  else agent_normals(io.seed, io.step, gid, n1, n2);
+  const bool has_drift = io.drift_velocity != nullptr;
+  double drx = 0.0, dry = 0.0;
+  if (has_drift) { drx = io.drift_velocity[2 * i]; dry = io.drift_velocity[2 * i + 1]; }
+  // fall-back normals for an exactly-zero displacement (Agent.py:460-461): separate Philox stream
+  uint32_t c[4];
+  philox_ctr(c, gid, 0u, io.step, RIAB_STREAM_MEASURE, 0u);
+  philox4x32_10(c, (uint32_t)io.seed, (uint32_t)(io.seed >> 32));
+  const double f1 = 2.0 * u01_53(c[0], c[1]) - 1.0, f2 = 2.0 * u01_53(c[2], c[3]) - 1.0;
+  uint8_t* mask = (REC && io.collision_mask) ? io.collision_mask + (size_t)i * RIAB_MAX_REC_ITERS * env.W : nullptr;
+  int32_t* fh = (REC && io.first_hit) ? io.first_hit + (size_t)i * RIAB_MAX_REC_ITERS : nullptr;
+  int32_t* ni = (REC && io.n_iters) ? io.n_iters + i : nullptr;
+  motion_step<REC>(s, s_walls, env.W, mp, env.ext, n1, n2, has_drift, drx, dry, f1, f2, mask, fh, ni);
+  store_agent(ag, i, s);
+  if (io.history_row != nullptr) store_history_row(io.history_row + 8 * (size_t)i, s);
+}
+
+template <bool REC>
+__global__ void __launch_bounds__(128) k_agent_update(const riab_agents ag, const riab_motion_params mp,
+                                                      const riab_step_io io, const EnvK env) {
+  __shared__ __align__(16) double s_walls[MAXW * 4];
+  __shared__ uint64_t s_bar;
+  stage_walls(s_walls, &s_bar, env);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ag.n_agents) return;
+  AgentState s;
+  agent_update_one<REC>(ag, mp, io, env, s_walls, i, s);
+}
+
+// ---------------------------------------------------------------------------
+// Neurons.update tail for 4 consecutive cells of one agent: OU noise
+// (Neurons.py:153-160,168), rate store, spikes (Neurons.py:681-684).
+__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long long row, int cell0, int n_cells) {
+  const unsigned long long gid = (unsigned long long)(out.id_offset + row);
+  if (out.noise != nullptr) {
+    uint32_t c[4];
+    philox_ctr(c, gid, (uint32_t)(cell0 >> 2), out.step, RIAB_STREAM_CELL_NOISE, (uint32_t)out.pop);
+    philox4x32_10(c, (uint32_t)out.seed, (uint32_t)(out.seed >> 32));
+    float z[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float u1 = u01_24(c[2 * h]), u2 = u01_24(c[2 * h + 1]);
+      const float r = sqrtf(-2.0f * __logf(u1));
+      float sn, cs;
+      __sincosf(6.2831853071795865f * u2, &sn, &cs);
+      z[2 * h] = r * cs; z[2 * h + 1] = r * sn;
+    }
+    float* np_ = out.noise + row * out.ld + cell0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (cell0 + i < n_cells) {
+        float n = np_[i];
+        n = n + (-n * out.noise_decay) + out.noise_sig * z[i];
+        np_[i] = n;
+        o[i] += n;
+      }
+    }
+  }
+  float* dst = out.rates + row * out.ld + cell0;
+  if (out.vec_ok && cell0 + 3 < n_cells) {
+    st_cs_f4(dst, o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (cell0 + i < n_cells) st_cs_f1(dst + i, o[i]);
+  }
+  if (out.spikes != nullptr) {
+    uint32_t c[4];
+    philox_ctr(c, gid, (uint32_t)(cell0 >> 2), out.step, RIAB_STREAM_SPIKES, (uint32_t)out.pop);
+    uint32_t k0 = (uint32_t)out.seed, k1 = (uint32_t)(out.seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }   // Philox4x32-7
+    uint32_t nib = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      nib |= ((cell0 + i < n_cells) && (u01_24(c[i]) < out.dt * o[i])) ? (1u << i) : 0u;
+    uint32_t v = nib | (__shfl_down_sync(0xffffffffu, nib, 1) << 4);
+    v |= __shfl_down_sync(0xffffffffu, v, 2) << 8;
+    v |= __shfl_down_sync(0xffffffffu, v, 4) << 16;
+    if ((threadIdx.x & 7) == 0 && cell0 < n_cells) out.spikes[row * out.spike_ld + (cell0 >> 5)] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Cell-type policies for the tile kernel.
+template <int WI>
+struct PlacePolicy {
+  using Const = PlaceConst;
+  using Regs = PlaceCellRegs<WI>;
+  static constexpr int REC = PLACE_REC;
+  static __device__ __forceinline__ void record(float* rec, double px, double py, const double* s_walls,
+                                                const Const& c, const EnvK& env) {
+    place_agent_record(rec, px, py, s_walls + 4 * env.nb, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym);
+  }
+  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI>(r, c, cell0); }
+  static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int cell0,
+                                                const float* rec, const double* pos64, const double* s_walls,
+                                                const EnvK& env) {
+    place_rates4<WI>(o, r, c, cell0, rec, pos64, s_walls + 4 * env.nb);
+  }
+};
+
+struct GridPolicy {
+  using Const = GridConst;
+  using Regs = GridCellRegs;
+  static constexpr int REC = 2;
+  static __device__ __forceinline__ void record(float* rec, double px, double py, const double*, const Const&,
+                                                const EnvK& env) {
+    rec[0] = (float)(px - env.cxm);
+    rec[1] = (float)(py - env.cym);
+  }
+  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { grid_load_cells(r, c, cell0); }
+  static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int, const float* rec,
+                                                const double*, const double*, const EnvK&) {
+    grid_rates4(o, r, c, rec);
+  }
+};
+
+template <class P, bool FUSED, bool REC>
+__global__ void __launch_bounds__(NT) k_tile(const EnvK env, const riab_agents ag, const riab_motion_params mp,
+                                             const riab_step_io io, const typename P::Const pc, const OutK out,
+                                             const double* __restrict__ pos_in, const long long n_rows) {
+  __shared__ __align__(16) double s_walls[MAXW * 4];
+  __shared__ __align__(16) float s_rec[TA][P::REC];
+  __shared__ __align__(16) double s_pos[TA][2];
+  __shared__ uint64_t s_bar;
+  stage_walls(s_walls, &s_bar, env);
+
+  const long long a0 = (long long)blockIdx.x * TA;
+  const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
+  if (threadIdx.x < TA && (int)threadIdx.x < na) {
+    const long long i = a0 + threadIdx.x;
+    double px, py;
+    if (FUSED) {
+      AgentState s;
+      agent_update_one<REC>(ag, mp, io, env, s_walls, i, s);
+      px = s.px; py = s.py;
+    } else {
+      px = pos_in[2 * i]; py = pos_in[2 * i + 1];
+    }
+    s_pos[threadIdx.x][0] = px;
+    s_pos[threadIdx.x][1] = py;
+    P::record(s_rec[threadIdx.x], px, py, s_walls, pc, env);
+  }
+  __syncthreads();
+
+  // NaN position -> zero rates (Neurons.py:163-164) is handled by the host mirror.
+  for (int cell0 = 4 * (int)threadIdx.x; cell0 < pc.n_pad; cell0 += 4 * NT) {
+    typename P::Regs r;
+    P::load(r, pc, cell0);
+    for (int a = 0; a < na; ++a) {
+      float o[4];
+      P::rates4(o, r, pc, cell0, s_rec[a], s_pos[a], s_walls, env);
+      finish4(o, out, a0 + a, cell0, pc.n_cells);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BVC phase A (+ optional fused Agent.update): one CTA per tile of 32 agents.
+template <bool FUSED, bool REC>
+__global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agents ag, const riab_motion_params mp,
+                                                 const riab_step_io io, const BvcConst bc,
+                                                 const double* __restrict__ pos_in, const long long n_rows,
+                                                 float* __restrict__ scratch, int32_t* __restrict__ first_wall) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  double* s_dirs = reinterpret_cast<double*>(dyn);                 // T*2
+  __shared__ __align__(16) double s_walls[MAXW * 4];
+  __shared__ __align__(16) double s_pos[TA][2];
+  __shared__ uint64_t s_bar;
+  stage_walls(s_walls, &s_bar, env);
+  for (int i = threadIdx.x; i < 2 * bc.T; i += blockDim.x) s_dirs[i] = bc.test_dirs[i];
+
+  const long long a0 = (long long)blockIdx.x * TA;
+  const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
+  if (threadIdx.x < TA) {
+    double px = 0.5 * (env.ext[0] + env.ext[1]), py = 0.5 * (env.ext[2] + env.ext[3]);   // padding rows: box centre
+    if ((int)threadIdx.x < na) {
+      const long long i = a0 + threadIdx.x;
+      if (FUSED) {
+        AgentState s;
+        agent_update_one<REC>(ag, mp, io, env, s_walls, i, s);
+        px = s.px; py = s.py;
+      } else {
+        px = pos_in[2 * i]; py = pos_in[2 * i + 1];
+      }
+    }
+    s_pos[threadIdx.x][0] = px;
+    s_pos[threadIdx.x][1] = py;
+  }
+  __syncthreads();
+  float* tile = scratch + (size_t)blockIdx.x * bc.T * BVC_AT;
+  for (int idx = threadIdx.x; idx < bc.T * BVC_AT; idx += blockDim.x) {
+    const int th = idx >> 5, a = idx & 31;
+    double d;
+    int wid;
+    bvc_first_wall(s_pos[a][0], s_pos[a][1], s_dirs[2 * th], s_dirs[2 * th + 1], s_walls, env.W, d, wid);
+    tile[idx] = (float)d;
+    if (first_wall != nullptr && a < na) first_wall[(a0 + a) * bc.T + th] = wid;
+  }
+}
+
+// BVC phase B: grid.x = cell tiles, grid.y = agent-tile lanes; 256 threads:
+// cell = tid & 63, agent group g = tid >> 6 handles agents 8g..8g+7 of the tile.
+__global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const float* __restrict__ scratch,
+                                                      const long long n_rows, const long long n_tiles,
+                                                      const OutK out) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  const int T = bc.T;
+  float* s_vm = reinterpret_cast<float*>(dyn);                     // [T][64]
+  float* s_d0 = s_vm + (size_t)T * BVC_CT;                         // [T][32] x 2 buffers
+  float* s_d1 = s_d0 + (size_t)T * BVC_AT;
+  __shared__ uint64_t bar_vm, bar_d[2];
+  const int ct = blockIdx.x;
+  const int tid = threadIdx.x, cl = tid & 63, g = tid >> 6;
+  const int cell = ct * BVC_CT + cl;
+  const uint32_t vm_bytes = (uint32_t)T * BVC_CT * 4u, d_bytes = (uint32_t)T * BVC_AT * 4u;
+  const float* vm_src = bc.packed + 3 * (size_t)bc.n_pad + (size_t)ct * T * BVC_CT;
+  if (tid == 0) {
+    mbar_init(&bar_vm, 1); mbar_init(&bar_d[0], 1); mbar_init(&bar_d[1], 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar_vm, vm_bytes);
+    tma_bulk_g2s(s_vm, vm_src, vm_bytes, &bar_vm);
+    long long t0 = blockIdx.y;
+    if (t0 < n_tiles) { mbar_expect_tx(&bar_d[0], d_bytes); tma_bulk_g2s(s_d0, scratch + (size_t)t0 * T * BVC_AT, d_bytes, &bar_d[0]); }
+  }
+  __syncthreads();
+  const float sc = bc.packed[cell], mc = bc.packed[bc.n_pad + cell], scale = bc.packed[2 * bc.n_pad + cell];
+  mbar_wait(&bar_vm, 0);
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  for (long long t = blockIdx.y; t < n_tiles; t += gridDim.y, buf ^= 1) {
+    const long long tn = t + gridDim.y;
+    if (tid == 0 && tn < n_tiles) {          // prefetch the next agent tile into the other buffer
+      mbar_expect_tx(&bar_d[buf ^ 1], d_bytes);
+      tma_bulk_g2s(buf ? s_d0 : s_d1, scratch + (size_t)tn * T * BVC_AT, d_bytes, &bar_d[buf ^ 1]);
+    }
+    mbar_wait(&bar_d[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    const float* sd = (buf ? s_d1 : s_d0) + 8 * g;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int th = 0; th < T; ++th) {
+      const float vm = s_vm[th * BVC_CT + cl];
+      const float4 da = *reinterpret_cast<const float4*>(sd + th * BVC_AT);
+      const float4 db = *reinterpret_cast<const float4*>(sd + th * BVC_AT + 4);
+      const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(dv[i], sc, -mc);                    // (d - mu_d) * s
+        acc[i] = fmaf(ex2f(-u * u), vm, acc[i]);                 // gaussian * von Mises
+      }
+    }
+    if (cell < bc.n_cells) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long row = t * BVC_AT + 8 * g + i;
+        if (row < n_rows) st_cs_f1(out.rates + row * out.ld + cell, fmaf(acc[i] * scale, bc.span, bc.min_fr));
+      }
+    }
+    __syncthreads();   // everyone done with this buffer before it is refilled two iterations later
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host helpers
+int make_env(const riab_env* env, EnvK& k) {
+  if (env == nullptr || env->walls_dev == nullptr) return fail(RIAB_ERR_INVALID, "env / walls_dev is NULL");
+  if (env->n_walls < 0 || env->n_walls > MAXW) return fail(RIAB_ERR_UNSUPPORTED, "n_walls=%d exceeds %d", env->n_walls, MAXW);
+  if (env->n_boundary_walls < 0 || env->n_boundary_walls > env->n_walls)
+    return fail(RIAB_ERR_INVALID, "n_boundary_walls=%d out of range", env->n_boundary_walls);
+  k.walls = env->walls_dev; k.W = env->n_walls; k.nb = env->n_boundary_walls;
+  k.aligned = (((uintptr_t)env->walls_dev) % 16 == 0) && env->n_walls > 0;
+  for (int i = 0; i < 4; ++i) k.ext[i] = env->extent[i];
+  k.cxm = 0.5 * (env->extent[0] + env->extent[1]);
+  k.cym = 0.5 * (env->extent[2] + env->extent[3]);
+  return 0;
+}
+
+int check_agents(const riab_agents* a) {
+  if (a == nullptr) return fail(RIAB_ERR_INVALID, "agents is NULL");
+  if (a->n_agents < 0) return fail(RIAB_ERR_INVALID, "n_agents < 0");
+  if (a->n_agents > 0 && (!a->pos || !a->velocity || !a->rotational_velocity || !a->measured_velocity ||
+                          !a->measured_rotational_velocity || !a->head_direction || !a->distance_travelled ||
+                          !a->distance_to_closest_wall))
+    return fail(RIAB_ERR_INVALID, "agents: NULL state array");
+  return 0;
+}
+
+int check_motion(const riab_motion_params* p) {
+  if (p == nullptr) return fail(RIAB_ERR_INVALID, "motion params NULL");
+  if (!(p->dt > 0.0)) return fail(RIAB_ERR_INVALID, "dt must be > 0");
+  return 0;
+}
+
+int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, double dt, long long id_offset, OutK& k) {
+  if (o == nullptr || o->rates_row == nullptr) return fail(RIAB_ERR_INVALID, "rates_row is NULL");
+  if (o->ld < n_cells) return fail(RIAB_ERR_INVALID, "ld (%lld) < n_cells (%d)", (long long)o->ld, n_cells);
+  memset(&k, 0, sizeof(k));
+  k.rates = o->rates_row; k.ld = o->ld;
+  k.spikes = o->spikes_row; k.spike_ld = (n_cells + 31) / 32;
+  k.noise = nullptr;
+  k.dt = (float)dt;
+  k.id_offset = id_offset;
+  if (nz != nullptr) {
+    k.seed = nz->seed; k.step = nz->step; k.pop = nz->population_id;
+    if (nz->noise_std != 0.f) {
+      if (o->noise_state == nullptr) return fail(RIAB_ERR_INVALID, "noise_std != 0 needs noise_state");
+      k.noise = o->noise_state;
+      const double tau = nz->noise_coherence_time;
+      k.noise_decay = (float)(dt / tau);
+      k.noise_sig = (float)(sqrt(2.0 * (double)nz->noise_std * nz->noise_std / (tau * dt)) * dt);
+    }
+  } else if (o->spikes_row != nullptr) {
+    return fail(RIAB_ERR_INVALID, "spikes need a riab_neuron_noise (seed/step)");
+  }
+  k.vec_ok = (o->ld % 4 == 0) && (((uintptr_t)o->rates_row) % 16 == 0);
+  return 0;
+}
+
+int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
+  if (pc == nullptr || pc->packed_dev == nullptr) return fail(RIAB_ERR_INVALID, "place cells / packed_dev NULL");
+  if (pc->description == RIAB_PC_ONE_HOT) return fail(RIAB_ERR_UNSUPPORTED, "one_hot place cells are not on the CUDA path yet");
+  if (pc->description < 0 || pc->description > RIAB_PC_ONE_HOT) return fail(RIAB_ERR_INVALID, "bad description %d", pc->description);
+  if (pc->wall_geometry < 0 || pc->wall_geometry > RIAB_GEOM_GEODESIC) return fail(RIAB_ERR_INVALID, "bad wall_geometry");
+  const int n_inner = env.W - env.nb;
+  if (pc->wall_geometry != RIAB_GEOM_EUCLIDEAN) {
+    if (pc->n_inner_walls != n_inner) return fail(RIAB_ERR_INVALID, "packed for %d inner walls, env has %d (re-pack after add_wall)", pc->n_inner_walls, n_inner);
+    if (n_inner > PLACE_MAX_WI) return fail(RIAB_ERR_UNSUPPORTED, "line_of_sight supports at most %d inner walls (got %d)", PLACE_MAX_WI, n_inner);
+    if (pc->centres_dev == nullptr) return fail(RIAB_ERR_INVALID, "centres_dev NULL");
+    if (pc->wall_geometry == RIAB_GEOM_GEODESIC && n_inner > 1)
+      return fail(RIAB_ERR_INVALID, "geodesic geometry is only defined with one additional wall (Environment.py:736-739)");
+  }
+  if (pc->description == RIAB_PC_TOP_HAT && pc->centres_dev == nullptr) return fail(RIAB_ERR_INVALID, "centres_dev NULL");
+  c.desc = pc->description; c.geometry = pc->wall_geometry; c.n_cells = pc->n_cells; c.n_pad = pc->n_pad;
+  c.n_inner = (pc->wall_geometry == RIAB_GEOM_EUCLIDEAN) ? 0 : n_inner;
+  c.ep_valid = pc->ep_valid;
+  c.min_fr = pc->min_fr; c.span = pc->max_fr - pc->min_fr;
+  c.top_hat_w = pc->top_hat_width; c.top_hat_w2 = (float)(pc->top_hat_width * pc->top_hat_width);
+  for (int j = 0; j < PLACE_MAX_WI; ++j) c.eps[j] = pc->eps[j];
+  c.packed = pc->packed_dev; c.centres64 = pc->centres_dev;
+  c.cxm = env.cxm; c.cym = env.cym;
+  return 0;
+}
+
+int make_grid(const riab_grid_cells* gc, const EnvK& env, GridConst& c) {
+  if (gc == nullptr || gc->packed_dev == nullptr) return fail(RIAB_ERR_INVALID, "grid cells / packed_dev NULL");
+  c.n_cells = gc->n_cells; c.n_pad = gc->n_pad;
+  if (gc->description == RIAB_GC_RECTIFIED_COSINES) {
+    if (!(gc->width_ratio > 0.0 && gc->width_ratio <= 1.0)) return fail(RIAB_ERR_INVALID, "width_ratio must be between 0 and 1");
+    const double full = (1.0 / 3.0) * (2.0 * cos(sqrt(3.0) * M_PI * gc->width_ratio / 2.0) + 1.0);   // Neurons.py:1211
+    c.A = (float)((1.0 / 3.0) / (1.0 - full));
+    c.B = (float)(-full / (1.0 - full));
+    c.rectify = 1;
+  } else if (gc->description == RIAB_GC_SHIFTED_COSINES) {
+    c.A = (float)(2.0 / 9.0); c.B = (float)(1.0 / 3.0); c.rectify = 0;                                 // Neurons.py:1216-1218
+  } else return fail(RIAB_ERR_INVALID, "bad grid description %d", gc->description);
+  c.min_fr = gc->min_fr; c.span = gc->max_fr - gc->min_fr;
+  c.packed = gc->packed_dev; c.cxm = env.cxm; c.cym = env.cym;
+  return 0;
+}
+
+template <class P, bool FUSED>
+int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
+                const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+  if (n_rows == 0) return 0;
+  const unsigned grid = (unsigned)((n_rows + TA - 1) / TA);
+  const bool rec = FUSED && (io.collision_mask || io.first_hit || io.n_iters);
+  if (rec) k_tile<P, FUSED, FUSED><<<grid, NT, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
+  else k_tile<P, FUSED, false><<<grid, NT, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
+  g_launches++;
+  RIAB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <bool FUSED>
+int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
+                 const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+  const int wi = pc.n_inner;
+  if (wi == 0) return launch_tile<PlacePolicy<0>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 1) return launch_tile<PlacePolicy<1>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 2) return launch_tile<PlacePolicy<2>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi <= 4) return launch_tile<PlacePolicy<4>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  return launch_tile<PlacePolicy<8>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+}
+
+template <bool FUSED>
+int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
+               const riab_bvc_cells* bvc, const OutK& out, const double* pos_in, long long n_rows, float* scratch,
+               int32_t* first_wall, cudaStream_t s) {
+  if (bvc == nullptr || bvc->packed_dev == nullptr || bvc->test_dirs_dev == nullptr)
+    return fail(RIAB_ERR_INVALID, "bvc cells / packed_dev / test_dirs_dev NULL");
+  if (scratch == nullptr) return fail(RIAB_ERR_INVALID, "bvc scratch NULL");
+  if (n_rows == 0) return 0;
+  BvcConst bc;
+  bc.n_cells = bvc->n_cells; bc.n_pad = bvc->n_pad; bc.T = bvc->n_test_angles;
+  bc.min_fr = bvc->min_fr; bc.span = bvc->max_fr - bvc->min_fr;
+  bc.packed = bvc->packed_dev; bc.test_dirs = bvc->test_dirs_dev;
+  const long long n_tiles = (n_rows + BVC_AT - 1) / BVC_AT;
+  const size_t smemA = (size_t)bc.T * 2 * sizeof(double);
+  const size_t smemB = (size_t)bc.T * (BVC_CT + 2 * BVC_AT) * sizeof(float);
+  if (smemB > 220 * 1024) return fail(RIAB_ERR_UNSUPPORTED, "n_test_angles=%d too large for shared memory", bc.T);
+  if ((bc.T * BVC_AT * 4) % 16 != 0 || ((uintptr_t)scratch) % 16 != 0 || ((uintptr_t)bvc->packed_dev) % 16 != 0)
+    return fail(RIAB_ERR_INVALID, "bvc buffers must be 16-byte aligned");
+  const bool rec = FUSED && (io.collision_mask || io.first_hit || io.n_iters);
+  if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, io, bc, pos_in, n_rows, scratch, first_wall);
+  else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, io, bc, pos_in, n_rows, scratch, first_wall);
+  g_launches++;
+  RIAB_CUDA_OK(cudaGetLastError());
+  static bool attr_set = false;
+  if (!attr_set) {
+    RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const unsigned cts = (unsigned)(bc.n_pad / BVC_CT);
+  unsigned gy = (unsigned)((2 * 148 + cts - 1) / cts);           // ~2 CTAs per SM in total
+  if (gy > n_tiles) gy = (unsigned)n_tiles;
+  if (gy < 1) gy = 1;
+  k_bvc_integrate<<<dim3(cts, gy), NT, smemB, s>>>(bc, scratch, n_rows, n_tiles, out);
+  g_launches++;
+  RIAB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int riab_abi_version(void) { return RIAB_ABI_VERSION; }
+const char* riab_last_error(void) { return g_err; }
+int64_t riab_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int riab_agent_update(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                      const riab_step_io* io, void* stream) {
+  EnvK ek;
+  int rc;
+  if ((rc = check_agents(agents)) || (rc = make_env(env, ek)) || (rc = check_motion(prm))) return rc;
+  if (io == nullptr) return fail(RIAB_ERR_INVALID, "io is NULL");
+  if (agents->n_agents == 0) return 0;
+  const unsigned grid = (unsigned)((agents->n_agents + 127) / 128);
+  const bool rec = io->collision_mask || io->first_hit || io->n_iters;
+  if (rec) k_agent_update<true><<<grid, 128, 0, (cudaStream_t)stream>>>(*agents, *prm, *io, ek);
+  else k_agent_update<false><<<grid, 128, 0, (cudaStream_t)stream>>>(*agents, *prm, *io, ek);
+  g_launches++;
+  RIAB_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ----------------------------------------------------------------- PlaceCells
+static int place_n_pad(int n) { return (n + CELL_PAD - 1) / CELL_PAD * CELL_PAD; }
+
+int64_t riab_place_pack_floats(int32_t n_cells, int32_t n_inner_walls) {
+  return (int64_t)place_n_pad(n_cells) * (4 + 2 * (n_inner_walls > 0 ? n_inner_walls : 0) + 2);
+}
+
+int riab_place_pack(const double* centres, const double* widths, int32_t n, const double* walls, int32_t n_walls,
+                    int32_t n_boundary, const double* extent, int32_t geometry, riab_place_cells* meta, float* out) {
+  if (!centres || !widths || !extent || !meta || !out || n <= 0) return fail(RIAB_ERR_INVALID, "riab_place_pack: bad argument");
+  const int np = place_n_pad(n);
+  const int n_inner = (geometry == RIAB_GEOM_EUCLIDEAN) ? 0 : (n_walls - n_boundary);
+  if (n_inner < 0) return fail(RIAB_ERR_INVALID, "n_walls < n_boundary_walls");
+  if (n_inner > 0 && !walls) return fail(RIAB_ERR_INVALID, "walls NULL");
+  const double cxm = 0.5 * (extent[0] + extent[1]), cym = 0.5 * (extent[2] + extent[3]);
+  const int64_t total = riab_place_pack_floats(n, n_inner);
+  for (int64_t i = 0; i < total; ++i) out[i] = 0.f;
+  float *cx = out, *cy = out + np, *kk = out + 2 * np;
+  for (int i = 0; i < np; ++i) {
+    if (i < n) {
+      cx[i] = (float)(centres[2 * i] - cxm);
+      cy[i] = (float)(centres[2 * i + 1] - cym);
+      kk[i] = (float)(1.4426950408889634 / (2.0 * widths[i] * widths[i]));   // log2(e) / (2 w^2)
+    } else { cx[i] = 1.0e3f; cy[i] = 1.0e3f; kk[i] = 0.f; }
+  }
+  meta->n_pad = np;
+  meta->n_inner_walls = n_inner;
+  meta->ep_valid = 0;
+  for (int j = 0; j < 8; ++j) meta->eps[j] = 0.f;
+  for (int j = 0; j < n_inner; ++j) {
+    const double* w = walls + 4 * (n_boundary + j);
+    float* fc = out + (size_t)(4 + 2 * j) * np;
+    float* tc = out + (size_t)(5 + 2 * j) * np;
+    double tmax = 1.0;
+    for (int i = 0; i < np; ++i) {
+      if (i < n) {
+        double f, t;
+        wall_coords(centres[2 * i], centres[2 * i + 1], w[0], w[1], w[2], w[3], f, t);
+        fc[i] = (float)f; tc[i] = (float)t;
+        if (fabs(t) + 1.0 > tmax) tmax = fabs(t) + 1.0;
+      } else { fc[i] = 1.f; tc[i] = 0.f; }
+    }
+    for (int cxi = 0; cxi < 2; ++cxi)
+      for (int cyi = 0; cyi < 2; ++cyi) {            // agents live inside the box: bound |t| over its corners
+        double f, t;
+        wall_coords(extent[cxi], extent[2 + cyi], w[0], w[1], w[2], w[3], f, t);
+        if (fabs(t) + 1.0 > tmax) tmax = fabs(t) + 1.0;
+      }
+    if (j < 8) meta->eps[j] = (float)(2.0e-6 * tmax);
+  }
+  if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
+    const double* w = walls + 4 * n_boundary;
+    float* ce0 = out + (size_t)(4 + 2 * n_inner) * np;
+    float* ce1 = out + (size_t)(5 + 2 * n_inner) * np;
+    for (int e = 0; e < 2; ++e) {
+      const double ex = w[2 * e], ey = w[2 * e + 1];
+      if (ex > extent[0] && ex < extent[1] && ey > extent[2] && ey < extent[3]) meta->ep_valid |= (1 << e);
+    }
+    for (int i = 0; i < n; ++i) {
+      const double a = centres[2 * i] - w[0], b = centres[2 * i + 1] - w[1];
+      const double c = centres[2 * i] - w[2], d = centres[2 * i + 1] - w[3];
+      ce0[i] = (float)sqrt(a * a + b * b);
+      ce1[i] = (float)sqrt(c * c + d * d);
+    }
+  }
+  return 0;
+}
+
+int riab_place_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_place_cells* pc,
+                     float* out_dev, int64_t ld_out, void* stream) {
+  EnvK ek;
+  PlaceConst c;
+  OutK ok;
+  int rc;
+  if ((rc = make_env(env, ek)) || (rc = make_place(pc, ek, c))) return rc;
+  if (n_pos > 0 && pos_dev == nullptr) return fail(RIAB_ERR_INVALID, "pos_dev NULL");
+  riab_rates_out ro;
+  memset(&ro, 0, sizeof(ro));
+  ro.rates_row = out_dev; ro.ld = ld_out;
+  if ((rc = make_out(&ro, nullptr, pc->n_cells, 1.0, 0, ok))) return rc;
+  riab_agents ag; memset(&ag, 0, sizeof(ag));
+  riab_motion_params mp; memset(&mp, 0, sizeof(mp));
+  riab_step_io io; memset(&io, 0, sizeof(io));
+  return launch_place<false>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ GridCells
+int64_t riab_grid_pack_floats(int32_t n_cells) { return (int64_t)place_n_pad(n_cells) * 9; }
+
+int riab_grid_pack(const double* gridscales, const double* phase_offsets, const double* w, int32_t n,
+                   const double* extent, riab_grid_cells* meta, float* out) {
+  if (!gridscales || !phase_offsets || !w || !extent || !meta || !out || n <= 0)
+    return fail(RIAB_ERR_INVALID, "riab_grid_pack: bad argument");
+  const int np = place_n_pad(n);
+  const double cxm = 0.5 * (extent[0] + extent[1]), cym = 0.5 * (extent[2] + extent[3]);
+  for (int64_t i = 0; i < (int64_t)np * 9; ++i) out[i] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const double kappa = (2.0 * M_PI) / gridscales[i];
+    // origin = gridscale * phase_offset / (2 pi)   (Neurons.py:1191)
+    const double ox = gridscales[i] * phase_offsets[2 * i] / (2.0 * M_PI) - cxm;
+    const double oy = gridscales[i] * phase_offsets[2 * i + 1] / (2.0 * M_PI) - cym;
+    for (int k = 0; k < 3; ++k) {
+      const double wx = w[6 * i + 2 * k], wy = w[6 * i + 2 * k + 1];
+      double ph = kappa * (ox * wx + oy * wy);
+      ph = remainder(ph, 2.0 * M_PI);
+      out[(size_t)(3 * k + 0) * np + i] = (float)(kappa * wx);
+      out[(size_t)(3 * k + 1) * np + i] = (float)(kappa * wy);
+      out[(size_t)(3 * k + 2) * np + i] = (float)ph;
+    }
+  }
+  meta->n_pad = np;
+  return 0;
+}
+
+int riab_grid_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_grid_cells* gc,
+                    float* out_dev, int64_t ld_out, void* stream) {
+  EnvK ek;
+  GridConst c;
+  OutK ok;
+  int rc;
+  if ((rc = make_env(env, ek)) || (rc = make_grid(gc, ek, c))) return rc;
+  if (n_pos > 0 && pos_dev == nullptr) return fail(RIAB_ERR_INVALID, "pos_dev NULL");
+  riab_rates_out ro;
+  memset(&ro, 0, sizeof(ro));
+  ro.rates_row = out_dev; ro.ld = ld_out;
+  if ((rc = make_out(&ro, nullptr, gc->n_cells, 1.0, 0, ok))) return rc;
+  riab_agents ag; memset(&ag, 0, sizeof(ag));
+  riab_motion_params mp; memset(&mp, 0, sizeof(mp));
+  riab_step_io io; memset(&io, 0, sizeof(io));
+  return launch_tile<GridPolicy, false>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------ BVC
+static int bvc_n_pad(int n) { return (n + BVC_CT - 1) / BVC_CT * BVC_CT; }
+
+int64_t riab_bvc_pack_floats(int32_t n_cells, int32_t T) {
+  const int64_t np = bvc_n_pad(n_cells);
+  return 3 * np + np * (int64_t)T;
+}
+int64_t riab_bvc_scratch_floats(int64_t n_pos, int32_t T) {
+  return ((n_pos + BVC_AT - 1) / BVC_AT) * (int64_t)T * BVC_AT;
+}
+
+int riab_bvc_pack(const double* mu_d, const double* mu_t, const double* sg_d, const double* sg_t, int32_t n,
+                  const double* test_angles, int32_t T, riab_bvc_cells* meta, float* out) {
+  if (!mu_d || !mu_t || !sg_d || !sg_t || !test_angles || !meta || !out || n <= 0 || T <= 0)
+    return fail(RIAB_ERR_INVALID, "riab_bvc_pack: bad argument");
+  const int np = bvc_n_pad(n);
+  const int64_t total = riab_bvc_pack_floats(n, T);
+  for (int64_t i = 0; i < total; ++i) out[i] = 0.f;
+  float* s = out; float* m = out + np; float* sc = out + 2 * np; float* vm = out + 3 * (size_t)np;
+  for (int i = 0; i < n; ++i) {
+    const double sv = sqrt(1.4426950408889634 / 2.0) / sg_d[i];       // exp(-(d-mu)^2/(2 sg^2)) = 2^-((d-mu) s)^2
+    s[i] = (float)sv; m[i] = (float)(mu_d[i] * sv);
+    const double kappa = 1.0 / (sg_t[i] * sg_t[i]);                   // utils.von_mises (utils.py:441-457), norm=1
+    double norm = 0.0;
+    for (int t = 0; t < T; ++t) norm += exp(kappa * cos(test_angles[t] - 0.0)) * (1.0 / exp(kappa));   // Neurons.py:1599-1604
+    sc[i] = (float)(1.0 / norm);
+    const int tile = i / BVC_CT, cl = i % BVC_CT;
+    for (int t = 0; t < T; ++t)
+      vm[((size_t)tile * T + t) * BVC_CT + cl] = (float)(exp(kappa * cos(test_angles[t] - mu_t[i])) * (1.0 / exp(kappa)));
+  }
+  meta->n_pad = np;
+  return 0;
+}
+
+int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_bvc_cells* bvc,
+                   float* scratch_dev, int32_t* first_wall_dev, float* out_dev, int64_t ld_out, void* stream) {
+  EnvK ek;
+  OutK ok;
+  int rc;
+  if ((rc = make_env(env, ek))) return rc;
+  if (bvc == nullptr) return fail(RIAB_ERR_INVALID, "bvc NULL");
+  if (n_pos > 0 && pos_dev == nullptr) return fail(RIAB_ERR_INVALID, "pos_dev NULL");
+  riab_rates_out ro;
+  memset(&ro, 0, sizeof(ro));
+  ro.rates_row = out_dev; ro.ld = ld_out;
+  if ((rc = make_out(&ro, nullptr, bvc->n_cells, 1.0, 0, ok))) return rc;
+  riab_agents ag; memset(&ag, 0, sizeof(ag));
+  riab_motion_params mp; memset(&mp, 0, sizeof(mp));
+  riab_step_io io; memset(&io, 0, sizeof(io));
+  return launch_bvc<false>(ek, ag, mp, io, bvc, ok, pos_dev, n_pos, scratch_dev, first_wall_dev, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------- fused step
+int riab_step_fused(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                    const riab_step_io* io, int32_t cells_kind, const void* cells, const riab_neuron_noise* noise,
+                    const riab_rates_out* out, void* stream) {
+  EnvK ek;
+  OutK ok;
+  int rc;
+  if ((rc = check_agents(agents)) || (rc = make_env(env, ek)) || (rc = check_motion(prm))) return rc;
+  if (io == nullptr || cells == nullptr) return fail(RIAB_ERR_INVALID, "io / cells NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cells_kind == RIAB_CELLS_PLACE) {
+    const riab_place_cells* pc = (const riab_place_cells*)cells;
+    PlaceConst c;
+    if ((rc = make_place(pc, ek, c)) || (rc = make_out(out, noise, pc->n_cells, prm->dt, agents->id_offset, ok))) return rc;
+    return launch_place<true>(ek, *agents, *prm, *io, c, ok, nullptr, agents->n_agents, s);
+  }
+  if (cells_kind == RIAB_CELLS_GRID) {
+    const riab_grid_cells* gc = (const riab_grid_cells*)cells;
+    GridConst c;
+    if ((rc = make_grid(gc, ek, c)) || (rc = make_out(out, noise, gc->n_cells, prm->dt, agents->id_offset, ok))) return rc;
+    return launch_tile<GridPolicy, true>(ek, *agents, *prm, *io, c, ok, nullptr, agents->n_agents, s);
+  }
+  if (cells_kind == RIAB_CELLS_BVC) {
+    const riab_bvc_cells* bvc = (const riab_bvc_cells*)cells;
+    if ((rc = make_out(out, noise, bvc->n_cells, prm->dt, agents->id_offset, ok))) return rc;
+    if (ok.noise != nullptr || ok.spikes != nullptr)
+      return fail(RIAB_ERR_UNSUPPORTED, "noise / spikes for BVCs go through riab_neurons_finish");
+    return launch_bvc<true>(ek, *agents, *prm, *io, bvc, ok, nullptr, agents->n_agents, out->bvc_scratch, nullptr, s);
+  }
+  return fail(RIAB_ERR_INVALID, "bad cells_kind %d", cells_kind);
+}
+
+int riab_step_fused_host(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                         riab_step_io* io, int32_t cells_kind, const void* cells, const riab_neuron_noise* noise,
+                         const riab_rates_out* out, const double* drift_host, double* drift_staging_dev,
+                         double* pos_out_host, void* stream) {
+  if (agents == nullptr || io == nullptr) return fail(RIAB_ERR_INVALID, "agents / io NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)agents->n_agents * 2 * sizeof(double);
+  if (drift_host != nullptr) {
+    if (drift_staging_dev == nullptr) return fail(RIAB_ERR_INVALID, "drift_staging_dev NULL");
+    RIAB_CUDA_OK(cudaMemcpyAsync(drift_staging_dev, drift_host, bytes, cudaMemcpyHostToDevice, s));
+    io->drift_velocity = drift_staging_dev;
+  }
+  const int rc = riab_step_fused(agents, env, prm, io, cells_kind, cells, noise, out, stream);
+  if (rc) return rc;
+  if (pos_out_host != nullptr) RIAB_CUDA_OK(cudaMemcpyAsync(pos_out_host, agents->pos, bytes, cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+}  // extern "C"

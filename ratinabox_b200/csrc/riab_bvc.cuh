@@ -1,0 +1,87 @@
+// BoundaryVectorCells.get_state, allocentric (ratinabox/Neurons.py:1617-1778).
+//
+// Phase A (float64, per agent x test angle): the reference casts T rays
+// pos -> pos + test_direction, intersects each with every wall
+// (utils.vector_intercepts, utils.py:30-118), scores the walls with
+// boundary_vector_preference_function (Neurons.py:1746-1778) and keeps
+// l_a of the arg-max wall = distance to the first wall along the ray.  We
+// evaluate exactly those float64 expressions (D = non-contracting double) so
+// the chosen wall and distance equal the oracle's; the only short-cut is that
+// the `l_b < 0` / `l_b > 1` rejections are decided from the signs / magnitudes of
+// numerator and denominator (exact for IEEE division) so l_a's division is only
+// done for walls that survive.
+//
+// Phase B (float32, per agent x cell): fr = sum_theta gauss(d_theta; mu_d, sigma_d) *
+// vonmises(theta; mu_theta, sigma_theta) / cell_fr_norm.  The von Mises factor does
+// not depend on the agent, so it is a precomputed (cell tile x T) table staged into
+// shared memory by TMA bulk copies; the Gaussian is one FFMA + FMUL + MUFU.EX2.
+//
+// Packed block (float32, riab_bvc_pack), Np = n_cells rounded up to BVC_CT (64):
+//   s[Np] | m[Np] | scale[Np] | VM tiles: [Np/64][T][64]
+//   s = sqrt(log2(e)/2)/sigma_d, m = mu_d*s, scale = 1/cell_fr_norm
+// Scratch (phase A -> B): dist_to_first_wall as [agent tile of 32][T][32] float32.
+#pragma once
+#include "riab_common.cuh"
+
+namespace riab {
+
+constexpr int BVC_CT = 64;   // cells per tile
+constexpr int BVC_AT = 32;   // agents per tile
+
+// One ray against all walls -> (distance to first wall, wall id).  Neurons.py:1655-1684.
+RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const double* __restrict__ walls, int W,
+                             double& dist, int& wall_id) {
+  const D a0x(px), a0y(py);
+  const D a1x = a0x + D(ux), a1y = a0y + D(uy);      // pos_line_segments[:, :, 1, :] += test_directions
+  const D sax = a1x - a0x, say = a1y - a0y;
+  const D sapx = -say, sapy = sax;
+  double best = -INFINITY;                           // running max of pref (np.argmax keeps the first max)
+  int besti = 0;
+  double best_la = 0.0;
+  for (int w = 0; w < W; ++w) {
+    const D bx0(walls[4 * w]), by0(walls[4 * w + 1]), bx1(walls[4 * w + 2]), by1(walls[4 * w + 3]);
+    const D d0x = bx0 - a0x, d0y = by0 - a0y;
+    const D sbx = bx1 - bx0, sby = by1 - by0;
+    const D sbpx = -sby, sbpy = sbx;
+    const D numB = (-d0x) * sapx + (-d0y) * sapy;
+    const D denB = sbx * sapx + sby * sapy;
+    // l_b = numB/denB : decide (l_b < 0) || (l_b > 1) without dividing
+    bool rej;
+    if (denB.v != 0.0 && numB.v == numB.v && fabs(denB.v) != INFINITY && fabs(numB.v) != INFINITY) {
+      const bool same = (numB.v > 0.0) == (denB.v > 0.0);
+      rej = (numB.v != 0.0) && (!same || fabs(numB.v) > fabs(denB.v));
+    } else {
+      const double lb = (numB / denB).v;
+      rej = (lb < 0.0) || (lb > 1.0);
+    }
+    double pref, la = 0.0;
+    if (rej) {
+      pref = -1.0;
+    } else {
+      const D numA = d0x * sbpx + d0y * sbpy;
+      const D denA = sax * sbpx + say * sbpy;
+      la = (numA / denA).v;
+      pref = (la > 0.0) ? __ddiv_rn(1.0, la) : ((la < 0.0) ? -1.0 : 0.0);
+    }
+    if (pref > best) { best = pref; besti = w; best_la = la; }
+  }
+  // if the arg-max wall was rejected (every pref == -1 -> wall 0) its l_a was not computed above
+  if (best == -1.0) {
+    const D bx0(walls[4 * besti]), by0(walls[4 * besti + 1]), bx1(walls[4 * besti + 2]), by1(walls[4 * besti + 3]);
+    const D d0x = bx0 - a0x, d0y = by0 - a0y;
+    const D sbx = bx1 - bx0, sby = by1 - by0;
+    const D sbpx = -sby, sbpy = sbx;
+    best_la = ((d0x * sbpx + d0y * sbpy) / (sax * sbpx + say * sbpy)).v;
+  }
+  dist = best_la;
+  wall_id = besti;
+}
+
+struct BvcConst {
+  int n_cells, n_pad, T;
+  float min_fr, span;
+  const float* packed;
+  const double* test_dirs;   // device (T,2)
+};
+
+}  // namespace riab

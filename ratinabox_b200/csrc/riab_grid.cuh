@@ -1,0 +1,55 @@
+// GridCells.get_state, 2D (ratinabox/Neurons.py:1172-1236): rectified / shifted sum
+// of three cosines, float32.
+//
+// Packed block (float32, riab_grid_pack), Np = n_cells rounded up to 4:
+//   for k = 0..2:  kx_k[Np] | ky_k[Np] | ph_k[Np]
+// with (kx,ky) = (2 pi / gridscale) * w_k  and  ph_k = (2 pi / gridscale) * ((origin - box centre) . w_k)
+// reduced to [-pi, pi] in float64, so that   phi_k = ph_k - (p' . k_k),  p' = pos - box centre
+// (Neurons.py:1191-1201: vecs = origin - pos, phi = (2 pi / gridscale) (vecs . w)).
+#pragma once
+#include "riab_common.cuh"
+
+namespace riab {
+
+struct GridConst {
+  int n_cells, n_pad, rectify;
+  float A, B;          // f = A * (cos1+cos2+cos3) + B   (then max(0,.) when rectify)
+  float min_fr, span;
+  const float* packed;
+  double cxm, cym;
+};
+
+struct GridCellRegs {
+  float kx[3][4], ky[3][4], ph[3][4];
+};
+
+RIAB_DEV void grid_load_cells(GridCellRegs& r, const GridConst& c, int cell0) {
+  const int np = c.n_pad;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(c.packed + (3 * k + 0) * np + cell0);
+    const float4 b = *reinterpret_cast<const float4*>(c.packed + (3 * k + 1) * np + cell0);
+    const float4 d = *reinterpret_cast<const float4*>(c.packed + (3 * k + 2) * np + cell0);
+    r.kx[k][0] = a.x; r.kx[k][1] = a.y; r.kx[k][2] = a.z; r.kx[k][3] = a.w;
+    r.ky[k][0] = b.x; r.ky[k][1] = b.y; r.ky[k][2] = b.z; r.ky[k][3] = b.w;
+    r.ph[k][0] = d.x; r.ph[k][1] = d.y; r.ph[k][2] = d.z; r.ph[k][3] = d.w;
+  }
+}
+
+RIAB_DEV void grid_rates4(float (&out)[4], const GridCellRegs& r, const GridConst& c, const float* __restrict__ rec) {
+  const float2 p = *reinterpret_cast<const float2*>(rec);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float phi = fmaf(-p.y, r.ky[k][i], fmaf(-p.x, r.kx[k][i], r.ph[k][i]));
+      s += __cosf(phi);
+    }
+    float v = fmaf(s, c.A, c.B);
+    if (c.rectify) v = fmaxf(v, 0.f);                 // Neurons.py:1214
+    out[i] = fmaf(v, c.span, c.min_fr);               // Neurons.py:1232-1234
+  }
+}
+
+}  // namespace riab

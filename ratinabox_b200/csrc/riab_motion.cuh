@@ -1,0 +1,215 @@
+// Agent.update (ratinabox/Agent.py:160-242, random-motion branch, 2D solid
+// rectangular box) for ONE agent per thread, in float64.  Expressions follow the
+// order NumPy evaluates them in the reference (D = non-contracting double) so
+// that the wall-collision decisions are bit-identical to the oracle's.
+#pragma once
+#include "riab_common.cuh"
+
+namespace riab {
+
+struct AgentState {
+  double px, py, vx, vy, rot, mvx, mvy, mrot, hdx, hdy, dist, dclose;
+};
+
+RIAB_DEV void load_agent(const riab_agents& ag, int64_t i, AgentState& s) {
+  const double2 p = reinterpret_cast<const double2*>(ag.pos)[i];
+  const double2 v = reinterpret_cast<const double2*>(ag.velocity)[i];
+  const double2 mv = reinterpret_cast<const double2*>(ag.measured_velocity)[i];
+  const double2 hd = reinterpret_cast<const double2*>(ag.head_direction)[i];
+  s.px = p.x; s.py = p.y; s.vx = v.x; s.vy = v.y; s.mvx = mv.x; s.mvy = mv.y; s.hdx = hd.x; s.hdy = hd.y;
+  s.rot = ag.rotational_velocity[i];
+  s.mrot = ag.measured_rotational_velocity[i];
+  s.dist = ag.distance_travelled[i];
+  s.dclose = ag.distance_to_closest_wall[i];
+}
+
+RIAB_DEV void store_agent(const riab_agents& ag, int64_t i, const AgentState& s) {
+  reinterpret_cast<double2*>(ag.pos)[i] = make_double2(s.px, s.py);
+  reinterpret_cast<double2*>(ag.velocity)[i] = make_double2(s.vx, s.vy);
+  reinterpret_cast<double2*>(ag.measured_velocity)[i] = make_double2(s.mvx, s.mvy);
+  reinterpret_cast<double2*>(ag.head_direction)[i] = make_double2(s.hdx, s.hdy);
+  ag.rotational_velocity[i] = s.rot;
+  ag.measured_rotational_velocity[i] = s.mrot;
+  ag.distance_travelled[i] = s.dist;
+  ag.distance_to_closest_wall[i] = s.dclose;
+}
+
+// utils.ornstein_uhlenbeck (utils.py:347-368): returns dx; `n` is the standard
+// normal, np.random.normal(scale=dt) == dt*n.
+RIAB_DEV D ou_dx(D dt, D x, D drift, D noise_scale, D tau, D n) {
+  const D sigma = dsqrt((D(2.0) * (noise_scale * noise_scale)) / (tau * dt));
+  const D theta = D(1.0) / tau;
+  return theta * (drift - x) * dt + sigma * (dt * n);
+}
+
+// utils.get_angle for a 2-vector (utils.py:231-273): atan2(y, x+1e-6) mod 2pi
+RIAB_DEV double get_angle(double x, double y) {
+  return np_mod(atan2(y, __dadd_rn(x, 1e-6)), 2.0 * M_PI);
+}
+
+// walls: shared/global array of W*(ax,ay,bx,by) doubles.
+// REC: write the per-iteration collision masks (parity taps).
+template <bool REC>
+RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W, const riab_motion_params& p,
+                          const double* __restrict__ ext, double xi1, double xi2, bool has_drift, double drx,
+                          double dry, double fallback_n1, double fallback_n2, uint8_t* __restrict__ mask,
+                          int32_t* __restrict__ first_hit, int32_t* __restrict__ n_iters_out) {
+  const D dt(p.dt);
+  const D ppx(s.px), ppy(s.py);          // prev_pos           Agent.py:199
+  const double pmvx = s.mvx, pmvy = s.mvy;  // prev_measured_velocity :201
+
+  // ---- A1: rotational velocity OU + rotation (Agent.py:289-296, utils.py:293-301)
+  D rot(s.rot);
+  rot = rot + ou_dx(dt, rot, D(p.rotational_velocity_drift_kw), D(p.rotational_velocity_std_kw),
+                    D(p.rotational_velocity_coherence_time_kw), D(xi1));
+  double sn, cs;
+  sincos((rot * dt).v, &sn, &cs);
+  D vx = D(cs) * D(s.vx) + D(-sn) * D(s.vy);
+  D vy = D(sn) * D(s.vx) + D(cs) * D(s.vy);
+
+  // ---- A2: speed, Rayleigh <-> normal OU (Agent.py:298-312, utils.py:409-421)
+  D speed = dsqrt(vx * vx + vy * vy);
+  if (speed.v == 0.0) { vx = D(1e-8); vy = D(0.0); speed = D(1e-8); }
+  {
+    const D sm(p.speed_mean_kw);
+    double u = (D(1.0) - D(exp((-(speed * speed) / (D(2.0) * (sm * sm))).v))).v;
+    u = fmin(fmax(1e-6, u), 1.0 - 1e-6);
+    D z(normcdfinv(u));
+    z = z + ou_dx(dt, z, D(0.0), D(1.0), D(p.speed_coherence_time_kw), D(xi2));
+    const D cdf(normcdf(z.v));
+    D speed_new = sm * dsqrt(D(-2.0) * D(log((D(1.0) - cdf).v)));
+    if (p.speed_std == 0.0) speed_new = sm;
+    const D f = speed_new / speed;
+    vx = f * vx; vy = f * vy;
+  }
+
+  // ---- A3: drift towards drift_velocity (Agent.py:324-341; noise_scale = 0)
+  if (has_drift) {
+    const D tau = D(p.speed_coherence_time) / D(p.drift_to_random_strength_ratio);
+    const D theta = D(1.0) / tau;
+    vx = vx + (theta * (D(drx) - vx) * dt + D(0.0));
+    vy = vy + (theta * (D(dry) - vy) * dt + D(0.0));
+  }
+
+  // ---- A4: wall repulsion (Agent.py:343-421, utils.py:121-184; zero jitter)
+  D px(s.px), py(s.py);
+  if (p.wall_repel_strength_kw != 0.0 && W > 0) {
+    const D d(p.wall_repel_distance_kw);
+    const D v0 = D(p.wall_repel_strength_kw) * D(p.speed_mean);
+    const D k = (v0 * v0) / (d * d);
+    D accx(0.0), accy(0.0), spx(0.0), spy(0.0);
+    double dmin = INFINITY;
+    for (int w = 0; w < W; ++w) {
+      const D ax(walls[4 * w]), ay(walls[4 * w + 1]), bx(walls[4 * w + 2]), by(walls[4 * w + 3]);
+      const D ddx = px - ax, ddy = py - ay, sx = bx - ax, sy = by - ay;
+      D l = (ddx * sx + ddy * sy) / (sx * sx + sy * sy);
+      if (l.v > 1.0) l = D(1.0);
+      if (l.v < 0.0) l = D(0.0);
+      const D qx = px - (ax + l * sx), qy = py - (ay + l * sy);
+      const D x = dsqrt(qx * qx + qy * qy);
+      const D ux = qx / x, uy = qy / x;
+      dmin = (x.v < dmin || x.v != x.v) ? x.v : dmin;
+      D acc(0.0), spd(0.0);
+      if (x <= d) {
+        acc = k * (d - x);
+        const D dx2 = (d - x) * (d - x);
+        spd = v0 * (D(1.0) - dsqrt(D(1.0) - dx2 / (d * d)));
+      }
+      if (w == 0) { accx = acc * ux; accy = acc * uy; spx = spd * ux; spy = spd * uy; }
+      else { accx = accx + acc * ux; accy = accy + acc * uy; spx = spx + spd * ux; spy = spy + spd * uy; }
+    }
+    s.dclose = dmin;
+    const D th(p.thigmotaxis_kw);
+    const D cv = D(3.0) * ((D(1.0) - th) * (D(1.0) - th));
+    vx = vx + cv * (accx * dt);
+    vy = vy + cv * (accy * dt);
+    const D cp = D(6.0) * (th * th);
+    px = px + cp * (spx * dt);
+    py = py + cp * (spy * dt);
+  }
+
+  // ---- A5: integrate (Agent.py:216)
+  px = px + vx * dt;
+  py = py + vy * dt;
+
+  // ---- A6: collision loop (Agent.py:423-441, Environment.py:820-841, utils.py:30-118)
+  int iters = 0;
+  for (; iters < RIAB_MAX_BOUNCE_ITERS; ++iters) {
+    const D sbx = px - ppx, sby = py - ppy;         // step segment (b list): prev_pos -> pos
+    const D sbpx = -sby, sbpy = sbx;
+    int first = -1;
+    for (int w = 0; w < W; ++w) {
+      const D ax(walls[4 * w]), ay(walls[4 * w + 1]), bx(walls[4 * w + 2]), by(walls[4 * w + 3]);
+      const D d0x = ppx - ax, d0y = ppy - ay;       // b0 - a0
+      const D sax = bx - ax, say = by - ay;
+      const D sapx = -say, sapy = sax;
+      const D la = (d0x * sbpx + d0y * sbpy) / (sax * sbpx + say * sbpy);
+      const D lb = ((-d0x) * sapx + (-d0y) * sapy) / (sbx * sapx + sby * sapy);
+      const bool hit = (la.v > 0.0) && (la.v < 1.0) && (lb.v > 0.0) && (lb.v < 1.0);
+      if (REC && mask != nullptr && iters < RIAB_MAX_REC_ITERS) mask[iters * W + w] = hit ? 1 : 0;
+      if (hit && first < 0) first = w;
+    }
+    if (REC && first_hit != nullptr && iters < RIAB_MAX_REC_ITERS) first_hit[iters] = first;
+    if (first < 0) { ++iters; break; }
+    // utils.wall_bounce (utils.py:304-328) + rescale to 0.5*speed_mean (Agent.py:439)
+    const double* wl = walls + 4 * first;
+    D parx = D(wl[2]) - D(wl[0]), pary = D(wl[3]) - D(wl[1]);
+    D perx = -pary, pery = parx;
+    if ((perx * vx + pery * vy).v <= 0.0) { perx = -perx; pery = -pery; }
+    if ((parx * vx + pary * vy).v <= 0.0) { parx = -parx; pary = -pary; }
+    const D npar = dsqrt(parx * parx + pary * pary), nper = dsqrt(perx * perx + pery * pery);
+    parx = parx / npar; pary = pary / npar; perx = perx / nper; pery = pery / nper;
+    const D dpar = vx * parx + vy * pary, dper = vx * perx + vy * pery;
+    D nvx = parx * dpar - perx * dper, nvy = pary * dpar - pery * dper;
+    const D f = (D(0.5) * D(p.speed_mean)) / dsqrt(nvx * nvx + nvy * nvy);
+    vx = f * nvx; vy = f * nvy;
+    px = ppx + vx * dt; py = ppy + vy * dt;
+  }
+  if (REC && n_iters_out != nullptr) *n_iters_out = iters;
+
+  // ---- A7: still inside? else clamp (Environment.py:781-818, :880-889)
+  if (!((px.v > ext[0]) && (px.v < ext[1]) && (py.v > ext[2]) && (py.v < ext[3]))) {
+    px = D(fmin(fmax(px.v, ext[0] + 0.01), ext[1] - 0.01));
+    py = D(fmin(fmax(py.v, ext[2] + 0.01), ext[3] - 0.01));
+  }
+
+  // ---- A8: measured velocity / rotational velocity (Agent.py:444-472)
+  D mvx = (px - ppx) / dt, mvy = (py - ppy) / dt;
+  if (dsqrt(mvx * mvx + mvy * mvy).v == 0.0) { mvx = D(1e-8 * fallback_n1); mvy = D(1e-8 * fallback_n2); }
+  {
+    const double now = get_angle(mvx.v, mvy.v), before = get_angle(pmvx, pmvy);
+    double x = np_mod(__dsub_rn(now, before), 2.0 * M_PI);      // utils.pi_domain (utils.py:331-341)
+    if (x > M_PI) x = __dadd_rn(-2.0 * M_PI, x);
+    s.mrot = __ddiv_rn(x, dt.v);
+  }
+
+  // ---- A9: head direction low-pass (Agent.py:474-500)
+  {
+    const D nmv = dsqrt(mvx * mvx + mvy * mvy);
+    const D ix = mvx / nmv, iy = mvy / nmv;
+    const D tau(p.head_direction_smoothing_timescale);
+    if (tau.v <= dt.v) { s.hdx = ix.v; s.hdy = iy.v; }
+    else {
+      const D a = D(1.0) - dt / tau, b = dt / tau;
+      const D hx = D(s.hdx) * a + b * ix, hy = D(s.hdy) * a + b * iy;
+      const D nh = dsqrt(hx * hx + hy * hy);
+      s.hdx = (hx / nh).v; s.hdy = (hy / nh).v;
+    }
+  }
+
+  // ---- A10: distance travelled (Agent.py:502-507)
+  {
+    const D ex = px - ppx, ey = py - ppy;
+    s.dist = (D(s.dist) + dsqrt(ex * ex + ey * ey)).v;
+  }
+  s.px = px.v; s.py = py.v; s.vx = vx.v; s.vy = vy.v; s.rot = rot.v; s.mvx = mvx.v; s.mvy = mvy.v;
+}
+
+// Agent.save_to_history row (Agent.py:509-521) as 8 float32
+RIAB_DEV void store_history_row(float* __restrict__ row, const AgentState& s) {
+  float4* r = reinterpret_cast<float4*>(row);
+  r[0] = make_float4((float)s.px, (float)s.py, (float)s.mvx, (float)s.mvy);
+  r[1] = make_float4((float)s.hdx, (float)s.hdy, (float)s.mrot, (float)s.dist);
+}
+
+}  // namespace riab

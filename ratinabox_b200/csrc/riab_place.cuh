@@ -1,0 +1,205 @@
+// PlaceCells.get_state (ratinabox/Neurons.py:936-981) over an (agents x cells)
+// tile, float32, with Environment.get_distances_between___accounting_for_environment
+// (ratinabox/Environment.py:677-779) for euclidean / line_of_sight / geodesic.
+//
+// Layout of the packed per-population block (float32, written by riab_place_pack):
+//   cx[Np] | cy[Np] | k[Np] | (spare)[Np] | per inner wall j: fc_j[Np], tc_j[Np] | ce0[Np] | ce1[Np]
+//   Np = n_cells rounded up to a multiple of 4 (padding cells sit far away, k = 0).
+//   Coordinates are relative to the box centre (halves the float32 rounding error).
+//   fc_j = signed distance of the centre to wall j's line, tc_j = its parameter
+//   along the wall; ce_k = distance centre -> wall end k (geodesic only).
+//
+// Line-of-sight predicate.  The reference tests segment(centre->pos) against
+// each inner wall with utils.vector_intercepts (utils.py:30-118): blocked iff
+// 0<l_a<1 and 0<l_b<1.  With f = signed distance to the wall's line and t = the
+// parameter along the wall, l_a = f_c/(f_c-f_p) and l_b = (f_c t_p - f_p t_c)/(f_c-f_p),
+// so per (agent, cell, wall) the float32 fast path is ~11 instructions on
+// per-cell registers and per-agent shared-memory broadcasts.  Results within a
+// relative band eps of 0 or 1 are re-evaluated in float64 with the reference's
+// exact expression (los_blocked_exact), so the decision equals the oracle's.
+#pragma once
+#include "riab_common.cuh"
+
+namespace riab {
+
+constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
+constexpr int PLACE_REC = 2 + 2 * PLACE_MAX_WI + 2;  // floats per agent record (px,py,(fp,tp)xWI,ep0,ep1)
+
+RIAB_HD void wall_coords(double qx, double qy, double ax, double ay, double bx, double by, double& f, double& t) {
+  const double sx = bx - ax, sy = by - ay;
+  const double n2 = sx * sx + sy * sy;
+  f = (sx * (qy - ay) - sy * (qx - ax)) / sqrt(n2);
+  t = ((qx - ax) * sx + (qy - ay) * sy) / n2;
+}
+
+// The reference's exact float64 test for one (centre, pos, wall) triple:
+// a-list = segment centre->pos, b-list = wall  (Environment.py:718-721, utils.py:74-106)
+RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, const double* __restrict__ w) {
+  const D ax(cx), ay(cy), bx(px), by(py);
+  const D wx0(w[0]), wy0(w[1]), wx1(w[2]), wy1(w[3]);
+  const D d0x = wx0 - ax, d0y = wy0 - ay;
+  const D sax = bx - ax, say = by - ay;
+  const D sbx = wx1 - wx0, sby = wy1 - wy0;
+  const D sapx = -say, sapy = sax, sbpx = -sby, sbpy = sbx;
+  const D la = (d0x * sbpx + d0y * sbpy) / (sax * sbpx + say * sbpy);
+  const D lb = ((-d0x) * sapx + (-d0y) * sapy) / (sbx * sapx + sby * sapy);
+  return (la.v > 0.0) && (la.v < 1.0) && (lb.v > 0.0) && (lb.v < 1.0);
+}
+
+// Per-agent record for the rate phase, from the float64 position.
+// inner = walls + 4*n_boundary (float64 endpoints), cxm/cym = box centre.
+RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, const double* __restrict__ inner,
+                                 int n_inner, int geometry, double cxm, double cym) {
+  rec[0] = (float)(px - cxm);
+  rec[1] = (float)(py - cym);
+  for (int j = 0; j < n_inner && j < PLACE_MAX_WI; ++j) {
+    double f, t;
+    wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
+    rec[2 + 2 * j] = (float)f;
+    rec[3 + 2 * j] = (float)t;
+  }
+  for (int j = n_inner; j < PLACE_MAX_WI; ++j) { rec[2 + 2 * j] = 1.f; rec[3 + 2 * j] = 0.f; }  // dummy walls never block
+  if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
+    // utils.get_distances_between(wall_edge, pos2)  (Environment.py:749-751)
+    const double e0x = inner[0] - px, e0y = inner[1] - py, e1x = inner[2] - px, e1y = inner[3] - py;
+    rec[2 + 2 * PLACE_MAX_WI] = (float)sqrt(e0x * e0x + e0y * e0y);
+    rec[3 + 2 * PLACE_MAX_WI] = (float)sqrt(e1x * e1x + e1y * e1y);
+  }
+}
+
+struct PlaceConst {                  // uniform per launch
+  int desc, geometry, n_cells, n_pad, n_inner, ep_valid;
+  float min_fr, span, top_hat_w2;
+  double top_hat_w;
+  float eps[PLACE_MAX_WI];
+  const float* packed;               // device
+  const double* centres64;           // device (N,2)
+  double cxm, cym;
+};
+
+// Per-thread cell registers: 4 consecutive cells.
+template <int WI>
+struct PlaceCellRegs {
+  float cx[4], cy[4], k[4];
+  float fc[WI > 0 ? WI : 1][4], tc[WI > 0 ? WI : 1][4];
+  float ce0[4], ce1[4];
+};
+
+template <int WI>
+RIAB_DEV void place_load_cells(PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0) {
+  const float* base = c.packed;
+  const int np = c.n_pad;
+  const float4 x = *reinterpret_cast<const float4*>(base + cell0);
+  const float4 y = *reinterpret_cast<const float4*>(base + np + cell0);
+  const float4 k = *reinterpret_cast<const float4*>(base + 2 * np + cell0);
+  r.cx[0] = x.x; r.cx[1] = x.y; r.cx[2] = x.z; r.cx[3] = x.w;
+  r.cy[0] = y.x; r.cy[1] = y.y; r.cy[2] = y.z; r.cy[3] = y.w;
+  r.k[0] = k.x; r.k[1] = k.y; r.k[2] = k.z; r.k[3] = k.w;
+#pragma unroll
+  for (int j = 0; j < WI; ++j) {
+    float4 f = make_float4(1.f, 1.f, 1.f, 1.f), t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < c.n_inner) {
+      f = *reinterpret_cast<const float4*>(base + (4 + 2 * j) * np + cell0);
+      t = *reinterpret_cast<const float4*>(base + (5 + 2 * j) * np + cell0);
+    }
+    r.fc[j][0] = f.x; r.fc[j][1] = f.y; r.fc[j][2] = f.z; r.fc[j][3] = f.w;
+    r.tc[j][0] = t.x; r.tc[j][1] = t.y; r.tc[j][2] = t.z; r.tc[j][3] = t.w;
+  }
+  if (WI > 0 && c.geometry == RIAB_GEOM_GEODESIC) {
+    const float4 a = *reinterpret_cast<const float4*>(base + (4 + 2 * c.n_inner) * np + cell0);
+    const float4 b = *reinterpret_cast<const float4*>(base + (5 + 2 * c.n_inner) * np + cell0);
+    r.ce0[0] = a.x; r.ce0[1] = a.y; r.ce0[2] = a.z; r.ce0[3] = a.w;
+    r.ce1[0] = b.x; r.ce1[1] = b.y; r.ce1[2] = b.z; r.ce1[3] = b.w;
+  }
+}
+
+// Neurons.py:959-976 epilogue on the squared distance (float32)
+RIAB_DEV float place_profile(float d2, float k, int desc) {
+  const float g = ex2f(-d2 * k);
+  if (desc == RIAB_PC_GAUSSIAN) return g;
+  if (desc == RIAB_PC_GAUSSIAN_THRESHOLD)
+    return fmaxf(g - 0.60653065971263342f, 0.f) * 2.5414940825367984f;   // exp(-1/2), 1/(1-exp(-1/2))
+  // diff_of_gaussians, ratio = 1.5: (g - g2/ratio^2) * ratio^2/(ratio^2-1)
+  const float g2 = ex2f(-d2 * k * (1.0f / 2.25f));
+  return (g - (1.0f / 2.25f) * g2) * 1.8f;
+}
+
+// Rates of one agent for this thread's 4 cells.
+//   rec    : the agent's float32 record in shared memory (broadcast reads)
+//   pos64  : the agent's float64 position (exact fall-back only)
+//   inner64: float64 inner walls in shared memory (exact fall-back only)
+template <int WI>
+RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0,
+                           const float* __restrict__ rec, const double* __restrict__ pos64,
+                           const double* __restrict__ inner64) {
+  const float2 p = *reinterpret_cast<const float2*>(rec);
+  float d2[4];
+  bool blocked[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float dx = p.x - r.cx[i], dy = p.y - r.cy[i];
+    d2[i] = fmaf(dy, dy, dx * dx);
+    blocked[i] = false;
+  }
+  if (WI > 0) {
+#pragma unroll
+    for (int j = 0; j < WI; ++j) {
+      const float2 pw = *reinterpret_cast<const float2*>(rec + 2 + 2 * j);   // (f_p, t_p)
+      const float eps = c.eps[j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float fc = r.fc[j][i], tcv = r.tc[j][i];
+        const float Dd = fc - pw.x;                       // f_c - f_p (no cancellation when signs differ)
+        const float M = fmaf(-pw.x, tcv, fc * pw.y);      // f_c t_p - f_p t_c
+        const float DM = Dd - M;
+        const float band = eps * fabsf(Dd);
+        const bool opp = (fc * pw.x) < 0.f;               // 0 < l_a < 1
+        bool hit = opp && ((M * DM) > 0.f);               // 0 < l_b < 1
+        const bool unsure = opp && ((fabsf(M) < band) || (fabsf(DM) < band));
+        if (unsure) {
+          const int cell = cell0 + i;
+          if (cell < c.n_cells)
+            hit = los_blocked_exact(c.centres64[2 * cell], c.centres64[2 * cell + 1], pos64[0], pos64[1],
+                                    inner64 + 4 * j);
+        }
+        blocked[i] = blocked[i] || hit;
+      }
+    }
+  }
+  const bool geodesic = (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
+  float2 ep = make_float2(0.f, 0.f);
+  if (geodesic) ep = *reinterpret_cast<const float2*>(rec + 2 + 2 * PLACE_MAX_WI);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float dd = d2[i];
+    if (WI > 0) {
+      if (geodesic) {
+        // Environment.py:745-773: min over the wall ends that lie inside the box
+        float via = INFINITY;
+        if (c.ep_valid & 1) via = r.ce0[i] + ep.x;
+        if (c.ep_valid & 2) via = fminf(via, r.ce1[i] + ep.y);
+        dd = blocked[i] ? via * via : dd;
+      } else {
+        dd = blocked[i] ? 1.0e6f : dd;                    // distance 1000 (Environment.py:730)
+      }
+    }
+    float v;
+    if (c.desc == RIAB_PC_TOP_HAT) {
+      // Neurons.py:975-976: 1*(dist < widths) with the scalar `widths`
+      bool in = dd < c.top_hat_w2;
+      if (fabsf(dd - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !(WI > 0 && blocked[i])) {
+        const int cell = cell0 + i;
+        if (cell < c.n_cells) {
+          const D ex = D(c.centres64[2 * cell]) - D(pos64[0]), ey = D(c.centres64[2 * cell + 1]) - D(pos64[1]);
+          in = dsqrt(ex * ex + ey * ey).v < c.top_hat_w;
+        }
+      }
+      v = in ? 1.f : 0.f;
+    } else {
+      v = place_profile(dd, r.k[i], c.desc);
+    }
+    out[i] = fmaf(v, c.span, c.min_fr);                   // Neurons.py:978-980
+  }
+}
+
+}  // namespace riab

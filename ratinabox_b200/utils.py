@@ -1,0 +1,71 @@
+"""Host-side set-up helpers (one-off parameter sampling; not on the per-step path).
+
+These follow the semantics of the reference's helpers so that populations built
+with the same params and NumPy seed get the same parameters:
+``utils.rotate`` (ratinabox/utils.py:293-301), ``utils.distribution_sampler``
+(:460-538) and ``utils.create_random_assembly`` (:1115-1219).
+"""
+import numpy as np
+
+
+def rotate(vector, theta):
+    c, s = np.cos(theta), np.sin(theta)
+    return np.matmul(np.array([[c, -s], [s, c]]), vector)
+
+
+def distribution_sampler(distribution_name="uniform", distribution_parameters=(1,), shape=(10,)):
+    prm = distribution_parameters
+    prm = tuple(prm) if isinstance(prm, (list, tuple)) else (prm,)
+    if distribution_name == "uniform":
+        low, high = (0.5 * prm[0], 1.5 * prm[0]) if len(prm) == 1 else (prm[0], prm[1])
+        return np.random.uniform(low, high, size=shape)
+    if distribution_name == "rayleigh":
+        return np.random.rayleigh(scale=prm[0], size=shape)
+    if distribution_name == "normal":
+        return np.random.normal(loc=prm[0], scale=prm[1], size=shape)
+    if distribution_name == "logarithmic":
+        assert len(shape) == 1, "Logarithmic distribution only works for 1D arrays"
+        return np.logspace(np.log10(prm[0]), np.log10(prm[1]), num=shape[0], base=10)
+    if distribution_name == "delta":
+        return prm[0] * np.ones(shape)
+    if distribution_name == "modules":
+        assert len(shape) == 1, "Modules distribution only works for 1D arrays"
+        per = shape[0] // len(prm)
+        out = prm[-1] * np.ones(shape)          # remainder goes to the last module
+        for i, val in enumerate(prm):
+            out[i * per:(i + 1) * per] = val
+        return out
+    if distribution_name == "truncnorm":
+        import scipy.stats
+        lower, upper, mu, sigma = prm[:4]
+        return scipy.stats.truncnorm.rvs((lower - mu) / sigma, (upper - mu) / sigma, scale=sigma, loc=mu, size=shape)
+    raise ValueError("This distribution is not recognised")
+
+
+def create_random_assembly(tuning_distance_distribution="uniform", tuning_distance=(0.02, 0.3),
+                           tuning_angle_distribution="uniform", tuning_angle=(0.0, 360.0),
+                           sigma_angle_distribution="uniform", sigma_angle=(10, 30),
+                           sigma_distance_distribution="diverging", sigma_distance=(0.08, 12), n=10, **kwargs):
+    """Random vector-cell tuning: (tuning_distance, tuning_angle [rad], sigma_distance, sigma_angle [rad]).
+    Draw order (distance, [sigma_d], angle, sigma_angle) matches the reference so seeds line up."""
+    given = [p for p in (tuning_distance, tuning_angle, sigma_distance, sigma_angle) if type(p) in (list, np.ndarray)]
+    if given:
+        lengths = {len(p) for p in given}
+        assert len(lengths) == 1, "If more than one parameter is passed as a list, they must all have the same length"
+        n = lengths.pop()
+
+    def draw(value, dist):
+        if type(value) in (list, np.ndarray):
+            return np.array(value, dtype=float)
+        return distribution_sampler(dist, value, (n,))
+
+    mu_d = np.abs(draw(tuning_distance, tuning_distance_distribution))
+    if type(sigma_distance) in (list, np.ndarray):
+        sg_d = np.array(sigma_distance, dtype=float)
+    elif sigma_distance_distribution == "diverging":
+        sg_d = sigma_distance[0] + mu_d / sigma_distance[1]        # Hartley: xi + mu/beta
+    else:
+        sg_d = distribution_sampler(sigma_distance_distribution, sigma_distance, (n,))
+    mu_t = draw(tuning_angle, tuning_angle_distribution) * (np.pi / 180)
+    sg_t = draw(sigma_angle, sigma_angle_distribution) * (np.pi / 180)
+    return mu_d, mu_t, sg_d, sg_t

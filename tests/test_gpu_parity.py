@@ -1,0 +1,132 @@
+"""Parity of the CUDA path (through the ratinabox_b200 Python mirror -> C ABI) against
+the golden fixtures of the live reference and against the CPU oracle.  GPU only.
+
+Tolerances (BASELINE.json north_star): positions <= 1e-6 m, firing rates <= 1e-5
+relative (evaluated relative to the population's rate scale max_fr-min_fr, plus a
+pure relative check on entries above 1e-3 of that scale), wall-collision masks and
+first-hit indices bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-6
+RATE_TOL = 1e-5
+
+
+def _env(rb, walls):
+    E = rb.Environment()
+    for w in walls[4:]:
+        E.add_wall(w)
+    assert np.array_equal(E.walls, walls)
+    return E
+
+
+def assert_rates_close(got, ref, scale, what="", pure_rel=True):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    err = np.abs(got - ref)
+    assert err.max() <= RATE_TOL * scale, f"{what}: max abs err {err.max():.3e} > {RATE_TOL * scale:.1e}"
+    big = np.abs(ref) > 1e-3 * scale
+    if pure_rel and big.any():
+        rel = (err[big] / np.abs(ref[big])).max()
+        assert rel <= RATE_TOL, f"{what}: max rel err {rel:.3e}"
+
+
+@pytest.mark.parametrize("name", ["box2", "maze8"])
+def test_motion_modeA_golden(golden, name):
+    import ratinabox_b200 as rb
+    g = golden(f"modeA_motion_{name}.npz")
+    shp = tuple(g["masks_shape"])
+    masks = np.unpackbits(g["masks"])[: int(np.prod(shp))].reshape(shp).astype(bool)
+    for with_drift in (False, True):
+        sel = np.where(g["use_drift"] == with_drift)[0]
+        E = _env(rb, g["walls"])
+        Ag = rb.Agent(E, {"dt": 0.01, "n_agents": len(sel)})
+        Ag.pos, Ag.velocity = g["pos0"][sel], g["vel0"][sel]
+        Ag.rotational_velocity = g["rot0"][sel]
+        Ag.measured_velocity, Ag.head_direction = g["mv0"][sel], g["hd0"][sel]
+        Ag.distance_travelled = g["dist0"][sel]
+        kw = dict(_xi=g["xi"][sel], _record_collisions=True)
+        if with_drift:
+            Ag.update(drift_velocity=g["drift"][sel], drift_to_random_strength_ratio=float(g["drift_ratio"]), **kw)
+        else:
+            Ag.update(**kw)
+        info = Ag.last_collision_info()
+        assert np.abs(Ag.pos - g["out_pos"][sel]).max() <= 1e-12          # far inside the 1e-6 m tolerance
+        assert np.abs(Ag.velocity - g["out_vel"][sel]).max() <= 1e-12
+        assert np.abs(Ag.rotational_velocity - g["out_rot"][sel]).max() <= 1e-10
+        assert np.abs(Ag.measured_velocity - g["out_mv"][sel]).max() <= 1e-10
+        assert np.abs(Ag.measured_rotational_velocity - g["out_mrot"][sel]).max() <= 1e-7
+        assert np.abs(Ag.head_direction - g["out_hd"][sel]).max() <= 1e-12
+        assert np.abs(Ag.distance_travelled - g["out_dist"][sel]).max() <= 1e-12
+        assert np.abs(Ag.distance_to_closest_wall - g["out_dclose"][sel]).max() <= 1e-12
+        # wall-collision indices: bit-exact
+        assert np.array_equal(info["n_iters"], g["out_n_iter"][sel])
+        assert np.array_equal(info["first_hit"], g["out_first_hit"][sel])
+        assert np.array_equal(info["mask"].astype(bool), masks[sel])
+        assert (g["out_n_iter"][sel] > 1).sum() > 0          # the case set does contain bounces
+        h = Ag.get_history_arrays()
+        assert np.abs(h["pos"][-1] - g["out_pos"][sel]).max() <= POS_TOL
+
+
+def test_place_cells_modeA_golden(golden):
+    import ratinabox_b200 as rb
+    g = golden("modeA_rates.npz")
+    P = g["P"]
+    E = _env(rb, g["box2_walls"])
+    Ag = rb.Agent(E, {"dt": 0.01})
+    for desc in ("gaussian", "gaussian_threshold", "diff_of_gaussians", "top_hat"):
+        for geom in ("euclidean", "line_of_sight"):
+            c = g[f"pc_{desc}_{geom}_centres"]
+            pc = rb.PlaceCells(Ag, {"place_cell_centres": c, "description": desc, "wall_geometry": geom,
+                                    "widths": 0.2, "min_fr": 0.05, "max_fr": 3.0})
+            got = pc.get_state(evaluate_at=None, pos=P)
+            ref = g[f"pc_{desc}_{geom}"]
+            if desc == "top_hat":
+                # discontinuous profile: the in/out classification must be identical, values float32-rounded
+                assert np.array_equal(got > 1.5, ref > 1.5), (desc, geom)
+                assert np.abs(got - ref).max() <= 1e-6
+            else:
+                # diff_of_gaussians is a difference of two O(1) terms: near its zero crossing a pure
+                # relative criterion is ill-posed in float32, so it is held to 1e-5 of the rate scale
+                assert_rates_close(got, ref, 3.0 - 0.05, f"pc {desc} {geom}", pure_rel=(desc == "gaussian"))
+    # geodesic: one internal wall
+    E1 = _env(rb, g["geodesic_walls"])
+    Ag1 = rb.Agent(E1, {"dt": 0.01})
+    c = g["pc_gaussian_geodesic_centres"]
+    pc = rb.PlaceCells(Ag1, {"place_cell_centres": c, "wall_geometry": "geodesic", "widths": 0.15})
+    assert_rates_close(pc.get_state(evaluate_at=None, pos=P), g["pc_gaussian_geodesic"], 1.0, "pc geodesic")
+
+
+def test_grid_cells_modeA_golden(golden):
+    import ratinabox_b200 as rb
+    g = golden("modeA_rates.npz")
+    P = g["P"]
+    E = _env(rb, g["box2_walls"])
+    Ag = rb.Agent(E, {"dt": 0.01})
+    for desc in ("rectified_cosines", "shifted_cosines"):
+        gc = rb.GridCells(Ag, {"gridscale": g[f"gc_{desc}_gridscales"], "orientation": g[f"gc_{desc}_orient"],
+                               "phase_offset": g[f"gc_{desc}_phase"], "description": desc,
+                               "min_fr": 0.1, "max_fr": 2.0})
+        assert np.array_equal(gc.w, g[f"gc_{desc}_w"])
+        # sums / rectified differences of cosines: held to 1e-5 of the rate scale (no pure relative check)
+        assert_rates_close(gc.get_state(evaluate_at=None, pos=P), g[f"gc_{desc}"], 1.9, f"gc {desc}", pure_rel=False)
+
+
+@pytest.mark.parametrize("name", ["box2", "maze8"])
+def test_bvc_modeA_golden(golden, name):
+    import ratinabox_b200 as rb
+    g = golden("modeA_rates.npz")
+    P = g["P"]
+    E = _env(rb, g[f"bvc_{name}_walls"])
+    Ag = rb.Agent(E, {"dt": 0.01})
+    bvc = rb.BoundaryVectorCells(Ag, {
+        "tuning_distance": g[f"bvc_{name}_tuning_distances"], "tuning_angle": np.degrees(g[f"bvc_{name}_tuning_angles"]),
+        "sigma_distance": g[f"bvc_{name}_sigma_distances"], "sigma_angle": np.degrees(g[f"bvc_{name}_sigma_angles"]),
+        "min_fr": 0.0, "max_fr": 5.0})
+    # degrees -> radians round trip is not exact: pin the exact reference values
+    bvc.tuning_angles, bvc.sigma_angles = g[f"bvc_{name}_tuning_angles"], g[f"bvc_{name}_sigma_angles"]
+    assert np.array_equal(bvc.test_angles, g[f"bvc_{name}_test_angles"])
+    assert np.array_equal(bvc.test_directions, g[f"bvc_{name}_test_directions"])
+    assert_rates_close(bvc.get_state(evaluate_at=None, pos=P), g[f"bvc_{name}"], 5.0, f"bvc {name}")
