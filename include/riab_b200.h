@@ -212,6 +212,38 @@ int riab_step_fused(const riab_agents* agents, const riab_env* env, const riab_m
                     const riab_step_io* io, int32_t cells_kind, const void* cells /* riab_place_cells* etc. */,
                     const riab_neuron_noise* noise, const riab_rates_out* out, void* stream);
 
+/* Neurons.update (Neurons.py:145-171) alone, for the agents' CURRENT positions
+ * (agents->pos): rates [-> noise] [-> spikes].  Used for the 2nd, 3rd ... population
+ * of an Agent after riab_step_fused / riab_agent_update moved it. */
+int riab_neurons_update(const riab_agents* agents, const riab_env* env, int32_t cells_kind, const void* cells,
+                        const riab_neuron_noise* noise, const riab_rates_out* out, void* stream);
+
+/* ------------------------------------------------------------- multi-step run
+ * `for _ in range(n_steps): Ag.update(); [Ns.update() for Ns in Ag.Neurons]`
+ * (tests/test_advanced.py:21-23) without returning to the host between steps.
+ * Population 0 is fused with the motion kernel, the others use riab_neurons_update.
+ * History rows go to device rings: row (next + s) % rows for step s. */
+typedef struct {
+  int32_t kind;                 /* riab_cells_kind */
+  const void* cells;            /* riab_place_cells* / riab_grid_cells* / riab_bvc_cells* */
+  riab_neuron_noise noise;      /* seed/step base; step is advanced per step */
+  riab_rates_out out;           /* ld, noise_state, bvc_scratch; rates_row/spikes_row are set from the rings */
+  float* rates_ring;            /* (rows, A, ld) f32 */
+  uint32_t* spikes_ring;        /* (rows, A, ceil(N/32)) or NULL */
+  int32_t ring_rows;
+  int32_t ring_next;            /* in: first row to write */
+} riab_population;
+
+typedef struct {
+  float* ring;                  /* (rows, A, 8) f32 agent history rows, or NULL */
+  int32_t ring_rows;
+  int32_t ring_next;
+} riab_agent_history;
+
+int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm, const riab_step_io* io,
+             const riab_population* pops, int32_t n_pops, const riab_agent_history* hist, int64_t n_steps,
+             void* stream);
+
 /* Number of kernels launched by the library since load (bench.py "gpu_launches"). */
 int64_t riab_launch_count(void);
 

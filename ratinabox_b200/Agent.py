@@ -289,6 +289,79 @@ class Agent:
             return True
         return False
 
+    def run(self, n_steps, **kwargs):
+        """``for _ in range(n_steps): self.update(**kwargs); [Ns.update() for Ns in self.Neurons]``
+        (the reference's user loop, tests/test_advanced.py:21-23) executed by libriab_b200's
+        riab_run without returning to Python between steps.  History rows land in the
+        device rings exactly as the per-step calls would put them."""
+        import torch
+        n_steps = int(n_steps)
+        if n_steps <= 0:
+            return
+        if "drift_velocity" in kwargs and kwargs["drift_velocity"] is not None:
+            raise NotImplementedError("run() is the free-exploration loop; step with update(drift_velocity=...) for control")
+        # stage everything exactly like one update() would, then hand the loop to C
+        self.update(**kwargs)
+        self._pending = None
+        dt = self.dt
+        first_step = self._step - 1
+        A = self.n_agents
+        # rings: make room for n_steps rows (the single update() above already reserved one)
+        if self.save_history:
+            self._hist_rows -= 1
+            self._t_hist.pop()
+            self._reserve_history(n_steps)
+            hist = _lib.AgentHistory(self._hist.data_ptr(), self._hist_cap, self._hist_rows % self._hist_cap)
+        else:
+            hist = _lib.AgentHistory(None, 0, 0)
+        pops = (_lib.Population * max(1, len(self.Neurons)))()
+        for i, ns in enumerate(self.Neurons):
+            cells = ns._cells()
+            ns._reserve_history(n_steps)
+            out, nz = ns._fill_out_structs(None, None)
+            nz.step = first_step
+            p = pops[i]
+            p.kind, p.cells = ns._cells_kind, C.cast(C.pointer(cells), C.c_void_p)
+            p.noise, p.out = nz, out
+            p.rates_ring = ns._hist.data_ptr()
+            p.spikes_ring = ns._spk.data_ptr() if (ns.save_history and ns.save_spikes) else None
+            p.ring_rows, p.ring_next = ns._hist_cap, ns._hist_rows % ns._hist_cap
+        self._io.step = first_step
+        _lib.check(self._lib.riab_run(C.byref(self._agents_c), C.byref(self._env_struct()), C.byref(self._mp),
+                                      C.byref(self._io), pops, len(self.Neurons), C.byref(hist), n_steps,
+                                      self._stream()))
+        # host-side bookkeeping of the n_steps that just ran
+        t0 = self.t - dt
+        ts = [t0 + dt * (k + 1) for k in range(n_steps)]
+        self.prev_t, self.t = ts[-2] if n_steps > 1 else t0, ts[-1]
+        self._step = first_step + n_steps
+        if self.save_history:
+            self._hist_rows += n_steps
+            self._t_hist.extend(ts)
+        for ns in self.Neurons:
+            last = (ns._hist_rows + n_steps - 1) % ns._hist_cap
+            ns._hist_rows += n_steps
+            ns._last_row = ns._hist[last]
+            if ns.save_history:
+                ns._t_hist.extend(ts)
+
+    def _reserve_history(self, n_more):
+        """Grow the ring (within history_bytes_limit) so that n_more further rows fit without wrapping."""
+        import torch
+        A = self.n_agents
+        row_bytes = A * 8 * 4
+        need = self._hist_rows + n_more
+        if self._hist is None:
+            cap = int(max(1, min(max(1024, need), self.history_bytes_limit // row_bytes)))
+            self._hist = torch.empty((cap, A, 8), dtype=torch.float32, device=self.device)
+            self._hist_cap = cap
+        elif need > self._hist_cap and self._hist_rows <= self._hist_cap:
+            cap = int(min(max(need, 2 * self._hist_cap), self.history_bytes_limit // row_bytes))
+            if cap > self._hist_cap:
+                new = torch.empty((cap, A, 8), dtype=torch.float32, device=self.device)
+                new[: self._hist_cap].copy_(self._hist)
+                self._hist, self._hist_cap = new, cap
+
     def last_collision_info(self):
         """Parity tap (needs update(_record_collisions=True)): per loop iteration
         ``wall_collisions`` masks (Environment.check_wall_collisions), first-hit wall

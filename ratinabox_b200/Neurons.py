@@ -129,18 +129,36 @@ class Neurons:
         self._hist_rows += 1
         return self._hist[slot], self._spk[slot]
 
+    def _reserve_history(self, n_more):
+        """Grow the ring (within history_bytes_limit) so n_more further rows fit without wrapping if possible."""
+        torch = self._torch
+        A, ld = self.Agent.n_agents, self._ld()
+        words = (self.n + 31) // 32
+        row_bytes = A * ld * 4
+        limit_rows = max(1, self.history_bytes_limit // row_bytes)
+        need = self._hist_rows + n_more if self.save_history else 1
+        if self._hist is None:
+            cap = int(max(1, min(max(256, need), limit_rows))) if self.save_history else 1
+            self._hist = torch.empty((cap, A, ld), dtype=torch.float32, device=self.device)
+            self._spk = torch.zeros((cap, A, words), dtype=torch.int32, device=self.device)
+            self._hist_cap = cap
+        elif need > self._hist_cap and self._hist_rows <= self._hist_cap:
+            cap = int(min(max(need, 2 * self._hist_cap), limit_rows))
+            if cap > self._hist_cap:
+                new = torch.empty((cap, A, ld), dtype=torch.float32, device=self.device)
+                new[: self._hist_cap].copy_(self._hist)
+                spk = torch.zeros((cap, A, words), dtype=torch.int32, device=self.device)
+                spk[: self._hist_cap].copy_(self._spk)
+                self._hist, self._spk, self._hist_cap = new, spk, cap
+
     # -------------------------------------------------------------------- update
-    def update(self, **kwargs):
-        """Neurons.update (ratinabox/Neurons.py:145-171)."""
+    def _fill_out_structs(self, row, spk):
         ag = self.Agent
-        cells = self._cells()
-        row, spk = self._row_buffers()
-        self._last_row = row
         out, nz = self._out, self._nz
-        out.rates_row = row.data_ptr()
+        out.rates_row = row.data_ptr() if row is not None else None
         out.ld = self._ld()
         want_spikes = bool(self.save_history and self.save_spikes)
-        out.spikes_row = spk.data_ptr() if want_spikes else None
+        out.spikes_row = spk.data_ptr() if (want_spikes and spk is not None) else None
         out.noise_state = None
         if self.noise_std != 0:
             if self._noise is None:
@@ -154,7 +172,16 @@ class Neurons:
         nz.step = max(ag._step - 1, 0)
         nz.id_offset = int(ag.id_offset)
         nz.population_id = self._population_id
-        if ag._take_pending() and self._can_fuse():
+        return out, nz
+
+    def update(self, **kwargs):
+        """Neurons.update (ratinabox/Neurons.py:145-171)."""
+        ag = self.Agent
+        cells = self._cells()
+        row, spk = self._row_buffers()
+        self._last_row = row
+        out, nz = self._fill_out_structs(row, spk)
+        if ag._take_pending():
             _lib.check(self._lib.riab_step_fused(C.byref(ag._agents_c), C.byref(ag._env_struct()), C.byref(ag._mp),
                                                  C.byref(ag._io), self._cells_kind, C.byref(cells), C.byref(nz),
                                                  C.byref(out), ag._stream()))
@@ -164,15 +191,11 @@ class Neurons:
         if self.save_history:
             self._t_hist.append(ag.t)
 
-    def _can_fuse(self):
-        return True
-
     def _update_unfused(self, cells, out, nz):
         """Rates for the agents' current positions (no queued motion step to fuse with)."""
         ag = self.Agent
-        self._rates_from_positions(ag._s["pos"], ag.n_agents, self._last_row)
-        if out.noise_state or out.spikes_row:
-            raise NotImplementedError("noise / spikes need the fused step: call Agent.update() before Neurons.update()")
+        _lib.check(self._lib.riab_neurons_update(C.byref(ag._agents_c), C.byref(ag._env_struct()), self._cells_kind,
+                                                 C.byref(cells), C.byref(nz), C.byref(out), ag._stream()))
 
     def _scratch_ptr(self, n):
         return None
@@ -494,15 +517,6 @@ class BoundaryVectorCells(Neurons):
 
     def _scratch_ptr(self, n):
         return self._scratch_for(n).data_ptr()
-
-    def _can_fuse(self):
-        return self.noise_std == 0 and not (self.save_history and self.save_spikes)
-
-    def update(self, **kwargs):
-        if self.save_history and self.save_spikes:
-            # spikes for BVCs are not on the CUDA path yet: keep rates, skip spikes
-            self.save_spikes = False
-        return super().update(**kwargs)
 
     def _rates_from_positions(self, pos_dev, n_pos, out, first_wall=None):
         ag = self.Agent

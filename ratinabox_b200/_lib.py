@@ -69,6 +69,16 @@ class RatesOut(C.Structure):
                 ("noise_state", C.c_void_p), ("bvc_scratch", C.c_void_p)]
 
 
+class Population(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("cells", C.c_void_p), ("noise", NeuronNoise), ("out", RatesOut),
+                ("rates_ring", C.c_void_p), ("spikes_ring", C.c_void_p), ("ring_rows", C.c_int32),
+                ("ring_next", C.c_int32)]
+
+
+class AgentHistory(C.Structure):
+    _fields_ = [("ring", C.c_void_p), ("ring_rows", C.c_int32), ("ring_next", C.c_int32)]
+
+
 PC_DESCRIPTIONS = {"gaussian": 0, "gaussian_threshold": 1, "diff_of_gaussians": 2, "top_hat": 3, "one_hot": 4}
 WALL_GEOMETRIES = {"euclidean": 0, "line_of_sight": 1, "geodesic": 2}
 GC_DESCRIPTIONS = {"rectified_cosines": 0, "shifted_cosines": 1}
@@ -96,6 +106,10 @@ SYMBOLS = {
                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "riab_step_fused": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
                                   C.c_int32, C.c_void_p, C.POINTER(NeuronNoise), C.POINTER(RatesOut), C.c_void_p]),
+    "riab_neurons_update": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.c_int32, C.c_void_p, C.POINTER(NeuronNoise),
+                                      C.POINTER(RatesOut), C.c_void_p]),
+    "riab_run": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
+                           C.POINTER(Population), C.c_int32, C.POINTER(AgentHistory), C.c_int64, C.c_void_p]),
     "riab_step_fused_host": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
                                        C.c_int32, C.c_void_p, C.POINTER(NeuronNoise), C.POINTER(RatesOut),
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -250,6 +250,18 @@ __global__ void __launch_bounds__(NT) k_tile(const EnvK env, const riab_agents a
   }
 }
 
+// Noise + spikes post-pass over rate rows that a kernel without finish4 produced (BVC).
+__global__ void __launch_bounds__(NT) k_finish_rows(const OutK out, const int n_cells, const int n_pad128,
+                                                    const long long n_rows) {
+  const long long row = blockIdx.y;
+  const int cell0 = (blockIdx.x * NT + threadIdx.x) * 4;
+  if (row >= n_rows || cell0 >= n_pad128) return;          // warp-uniform: a warp covers 128 consecutive cells
+  float o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = (cell0 + i < n_cells) ? out.rates[row * out.ld + cell0 + i] : 0.f;
+  finish4(o, out, row, cell0, n_cells);
+}
+
 // ---------------------------------------------------------------------------
 // BVC phase A (+ optional fused Agent.update): one CTA per tile of 32 agents.
 template <bool FUSED, bool REC>
@@ -515,6 +527,12 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   k_bvc_integrate<<<dim3(cts, gy), NT, smemB, s>>>(bc, scratch, n_rows, n_tiles, out);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
+  if (out.noise != nullptr || out.spikes != nullptr) {
+    const int np128 = (bc.n_cells + CELL_PAD - 1) / CELL_PAD * CELL_PAD;
+    k_finish_rows<<<dim3((unsigned)((np128 / 4 + NT - 1) / NT), (unsigned)n_rows), NT, 0, s>>>(out, bc.n_cells, np128, n_rows);
+    g_launches++;
+    RIAB_CUDA_OK(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -728,35 +746,93 @@ int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, co
 }
 
 // ----------------------------------------------------------------- fused step
-int riab_step_fused(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
-                    const riab_step_io* io, int32_t cells_kind, const void* cells, const riab_neuron_noise* noise,
-                    const riab_rates_out* out, void* stream) {
+// FUSED: motion + rates of one population; !FUSED: rates for agents->pos as it is.
+}  // extern "C"
+template <bool FUSED>
+static int neurons_update_impl(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                               const riab_step_io* io, int32_t cells_kind, const void* cells,
+                               const riab_neuron_noise* noise, const riab_rates_out* out, void* stream) {
   EnvK ek;
   OutK ok;
   int rc;
-  if ((rc = check_agents(agents)) || (rc = make_env(env, ek)) || (rc = check_motion(prm))) return rc;
-  if (io == nullptr || cells == nullptr) return fail(RIAB_ERR_INVALID, "io / cells NULL");
+  if ((rc = check_agents(agents)) || (rc = make_env(env, ek))) return rc;
+  if (FUSED && (rc = check_motion(prm))) return rc;
+  if (cells == nullptr || (FUSED && io == nullptr)) return fail(RIAB_ERR_INVALID, "io / cells NULL");
+  riab_motion_params mp0; memset(&mp0, 0, sizeof(mp0));
+  riab_step_io io0; memset(&io0, 0, sizeof(io0));
+  const riab_motion_params& mp = FUSED ? *prm : mp0;
+  const riab_step_io& sio = FUSED ? *io : io0;
+  const double dt = FUSED ? prm->dt : (noise ? (double)noise->dt : 1.0);
+  const double* pos_in = FUSED ? nullptr : agents->pos;
   cudaStream_t s = (cudaStream_t)stream;
   if (cells_kind == RIAB_CELLS_PLACE) {
     const riab_place_cells* pc = (const riab_place_cells*)cells;
     PlaceConst c;
-    if ((rc = make_place(pc, ek, c)) || (rc = make_out(out, noise, pc->n_cells, prm->dt, agents->id_offset, ok))) return rc;
-    return launch_place<true>(ek, *agents, *prm, *io, c, ok, nullptr, agents->n_agents, s);
+    if ((rc = make_place(pc, ek, c)) || (rc = make_out(out, noise, pc->n_cells, dt, agents->id_offset, ok))) return rc;
+    return launch_place<FUSED>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_GRID) {
     const riab_grid_cells* gc = (const riab_grid_cells*)cells;
     GridConst c;
-    if ((rc = make_grid(gc, ek, c)) || (rc = make_out(out, noise, gc->n_cells, prm->dt, agents->id_offset, ok))) return rc;
-    return launch_tile<GridPolicy, true>(ek, *agents, *prm, *io, c, ok, nullptr, agents->n_agents, s);
+    if ((rc = make_grid(gc, ek, c)) || (rc = make_out(out, noise, gc->n_cells, dt, agents->id_offset, ok))) return rc;
+    return launch_tile<GridPolicy, FUSED>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_BVC) {
     const riab_bvc_cells* bvc = (const riab_bvc_cells*)cells;
-    if ((rc = make_out(out, noise, bvc->n_cells, prm->dt, agents->id_offset, ok))) return rc;
-    if (ok.noise != nullptr || ok.spikes != nullptr)
-      return fail(RIAB_ERR_UNSUPPORTED, "noise / spikes for BVCs go through riab_neurons_finish");
-    return launch_bvc<true>(ek, *agents, *prm, *io, bvc, ok, nullptr, agents->n_agents, out->bvc_scratch, nullptr, s);
+    if ((rc = make_out(out, noise, bvc->n_cells, dt, agents->id_offset, ok))) return rc;
+    return launch_bvc<FUSED>(ek, *agents, mp, sio, bvc, ok, pos_in, agents->n_agents, out->bvc_scratch, nullptr, s);
   }
   return fail(RIAB_ERR_INVALID, "bad cells_kind %d", cells_kind);
+}
+extern "C" {
+
+int riab_step_fused(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                    const riab_step_io* io, int32_t cells_kind, const void* cells, const riab_neuron_noise* noise,
+                    const riab_rates_out* out, void* stream) {
+  return neurons_update_impl<true>(agents, env, prm, io, cells_kind, cells, noise, out, stream);
+}
+
+int riab_neurons_update(const riab_agents* agents, const riab_env* env, int32_t cells_kind, const void* cells,
+                        const riab_neuron_noise* noise, const riab_rates_out* out, void* stream) {
+  return neurons_update_impl<false>(agents, env, nullptr, nullptr, cells_kind, cells, noise, out, stream);
+}
+
+int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm, const riab_step_io* io,
+             const riab_population* pops, int32_t n_pops, const riab_agent_history* hist, int64_t n_steps,
+             void* stream) {
+  if (agents == nullptr || io == nullptr || n_pops < 0 || (n_pops > 0 && pops == nullptr))
+    return fail(RIAB_ERR_INVALID, "riab_run: bad argument");
+  const int64_t A = agents->n_agents;
+  for (int64_t st = 0; st < n_steps; ++st) {
+    riab_step_io sio = *io;
+    sio.step = io->step + (uint64_t)st;
+    sio.history_row = nullptr;
+    if (hist != nullptr && hist->ring != nullptr && hist->ring_rows > 0)
+      sio.history_row = hist->ring + (size_t)((hist->ring_next + st) % hist->ring_rows) * A * 8;
+    if (n_pops == 0) {
+      const int rc = riab_agent_update(agents, env, prm, &sio, stream);
+      if (rc) return rc;
+    }
+    for (int p = 0; p < n_pops; ++p) {
+      const riab_population& pp = pops[p];
+      if (pp.rates_ring == nullptr || pp.ring_rows <= 0) return fail(RIAB_ERR_INVALID, "population %d: no rates ring", p);
+      const size_t slot = (size_t)((pp.ring_next + st) % pp.ring_rows);
+      riab_rates_out ro = pp.out;
+      ro.rates_row = pp.rates_ring + slot * A * pp.out.ld;
+      int n_cells = 0;
+      if (pp.kind == RIAB_CELLS_PLACE) n_cells = ((const riab_place_cells*)pp.cells)->n_cells;
+      else if (pp.kind == RIAB_CELLS_GRID) n_cells = ((const riab_grid_cells*)pp.cells)->n_cells;
+      else if (pp.kind == RIAB_CELLS_BVC) n_cells = ((const riab_bvc_cells*)pp.cells)->n_cells;
+      ro.spikes_row = pp.spikes_ring ? pp.spikes_ring + slot * A * (size_t)((n_cells + 31) / 32) : nullptr;
+      riab_neuron_noise nz = pp.noise;
+      nz.step = pp.noise.step + (uint64_t)st;
+      nz.dt = (float)prm->dt;
+      const int rc = (p == 0) ? riab_step_fused(agents, env, prm, &sio, pp.kind, pp.cells, &nz, &ro, stream)
+                              : riab_neurons_update(agents, env, pp.kind, pp.cells, &nz, &ro, stream);
+      if (rc) return rc;
+    }
+  }
+  return 0;
 }
 
 int riab_step_fused_host(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,

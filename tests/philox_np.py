@@ -1,0 +1,57 @@
+"""NumPy Philox4x32 (Salmon et al. SC'11) mirroring ratinabox_b200/csrc/riab_common.cuh:
+counter layout, key schedule, uniform / normal conversions.  Test infrastructure."""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = 0x9E3779B9, 0xBB67AE85
+STREAM_AGENT_OU, STREAM_CELL_NOISE, STREAM_SPIKES, STREAM_MEASURE = 0, 1, 2, 3
+
+
+def philox4x32(ctr, key, rounds=10):
+    """ctr: (...,4) uint32, key: (2,) ints -> (...,4) uint32."""
+    c = [np.asarray(ctr[..., i], dtype=np.uint64) for i in range(4)]
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(rounds):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return np.stack([x.astype(np.uint32) for x in c], axis=-1)
+
+
+def counter(agent, sub, step, stream, pop=0):
+    agent = np.asarray(agent, dtype=np.uint64)
+    sub = np.asarray(sub, dtype=np.uint64)
+    c = np.zeros(np.broadcast(agent, sub).shape + (4,), dtype=np.uint32)
+    c[..., 0] = (agent & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    c[..., 1] = ((sub ^ ((agent >> np.uint64(32)) << np.uint64(24))) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    c[..., 2] = np.uint32(step & 0xFFFFFFFF)
+    c[..., 3] = np.uint32(((step >> 32) & 0xFFFF) | ((pop & 0xFF) << 16) | (stream << 24))
+    return c
+
+
+def u01_53(hi, lo):
+    x = ((hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)) >> np.uint64(11)
+    return (x.astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
+
+
+def u01_24(x):
+    return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+
+
+def agent_normals(seed, step, agents):
+    """The two standard normals of Agent.update's OU draws (Box-Muller on 2x53-bit uniforms)."""
+    r = philox4x32(counter(agents, 0, step, STREAM_AGENT_OU), (seed & 0xFFFFFFFF, seed >> 32))
+    u1, u2 = u01_53(r[..., 0], r[..., 1]), u01_53(r[..., 2], r[..., 3])
+    rad = np.sqrt(-2.0 * np.log(u1))
+    return np.stack((rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)), axis=-1)
+
+
+def spike_uniforms(seed, step, agents, n_cells, pop=0):
+    """(A, n_cells) float32 uniforms of the spike draw (Philox4x32-7, one call per 4 cells)."""
+    groups = (n_cells + 3) // 4
+    a = np.asarray(agents, dtype=np.uint64)[:, None]
+    g = np.arange(groups, dtype=np.uint64)[None, :]
+    r = philox4x32(counter(a, g, step, STREAM_SPIKES, pop), (seed & 0xFFFFFFFF, seed >> 32), rounds=7)
+    return u01_24(r).reshape(len(agents), groups * 4)[:, :n_cells]

@@ -1,0 +1,211 @@
+"""End-to-end behaviour of the engine through the reference-shaped Python API
+(fused step, riab_run, Philox streams, spikes, history, attribute mutability) checked
+against the CPU oracle.  GPU only."""
+import numpy as np
+import pytest
+
+import riab_oracle as O
+from philox_np import agent_normals, spike_uniforms
+
+pytestmark = pytest.mark.gpu
+
+BOX_WALLS = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+
+
+def make(rb, A, walls=BOX_WALLS, seed=3, **agent_params):
+    np.random.seed(seed)
+    E = rb.Environment()
+    for w in walls:
+        E.add_wall(w)
+    Ag = rb.Agent(E, dict({"dt": 0.01, "n_agents": A, "seed": 11}, **agent_params))
+    return E, Ag
+
+
+def oracle_step(env, pos, vel, xi, dt=0.01, **state):
+    oa = O.OracleAgent(env, pos, vel, {"dt": dt})
+    for k, v in state.items():
+        setattr(oa, k, v)
+    info = oa.update(O.TapeRNG(agent_xi=xi))
+    return oa, info
+
+
+def test_fused_step_all_cell_types():
+    """Ag.update(); Ns.update() -> one fused kernel per (motion, cell type); every population
+    of the same Agent sees the same new positions."""
+    import ratinabox_b200 as rb
+    A = 200
+    E, Ag = make(rb, A)
+    pos0, vel0 = Ag.pos.copy(), Ag.velocity.copy()
+    PCs = rb.PlaceCells(Ag, {"n": 150, "wall_geometry": "line_of_sight"})
+    GCs = rb.GridCells(Ag, {"n": 60})
+    BVCs = rb.BoundaryVectorCells(Ag, {"n": 40})
+    xi = np.random.RandomState(5).normal(size=(A, 2))
+    Ag.update(_xi=xi)
+    PCs.update(); GCs.update(); BVCs.update()
+    pos1 = Ag.pos
+    env = O.OracleEnvironment(walls=BOX_WALLS)
+    ref_pos = np.zeros((A, 2))
+    for a in range(A):
+        oa, _ = oracle_step(env, pos0[a], vel0[a], xi[a])
+        ref_pos[a] = oa.pos
+    assert np.abs(pos1 - ref_pos).max() <= 1e-12
+    rng = O.TapeRNG()
+    ref_pc = O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, ref_pos, rng, "gaussian", "line_of_sight")
+    ref_gc = O.grid_cells_get_state(GCs.gridscales, GCs.phase_offsets, GCs.w, ref_pos)
+    ref_bvc = O.bvc_get_state(env, BVCs.tuning_distances, BVCs.tuning_angles, BVCs.sigma_distances, BVCs.sigma_angles, ref_pos, rng)
+    assert np.abs(PCs.firingrate - ref_pc.T).max() <= 1e-5
+    assert np.abs(GCs.firingrate - ref_gc.T).max() <= 1e-5
+    assert np.abs(BVCs.firingrate - ref_bvc.T).max() <= 1e-5
+    assert PCs.firingrate.shape == (A, 150)
+
+
+def test_philox_stream_and_run_equals_stepping():
+    """Production RNG: Philox4x32-10 keyed on (seed, step, global agent id).  The GPU draws
+    equal the NumPy mirror's, so the oracle fed with them tracks the GPU; riab_run (C loop)
+    equals per-step Python calls bit for bit; results do not depend on how agents are sharded."""
+    import ratinabox_b200 as rb
+    A, steps = 96, 25
+    E, Ag = make(rb, A)
+    pos0, vel0 = Ag.pos.copy(), Ag.velocity.copy()
+    PCs = rb.PlaceCells(Ag, {"n": 64})
+    Ag.run(steps)
+    pos_run, fr_run = Ag.pos, PCs.firingrate
+    hist_run = Ag.get_history_arrays()["pos"]
+
+    E2, Ag2 = make(rb, A)
+    Ag2.pos, Ag2.velocity, Ag2.measured_velocity = pos0, vel0, vel0
+    PCs2 = rb.PlaceCells(Ag2, {"place_cell_centres": PCs.place_cell_centres})
+    for _ in range(steps):
+        Ag2.update(); PCs2.update()
+    assert np.array_equal(Ag2.pos, pos_run)
+    assert np.array_equal(PCs2.firingrate, fr_run)
+    assert np.array_equal(Ag2.get_history_arrays()["pos"], hist_run)
+    assert np.array_equal(PCs2.get_history_arrays()["spikes"], PCs.get_history_arrays()["spikes"])
+
+    # sharding invariance: the second half of the agents as its own shard (id_offset = A/2)
+    E3, Ag3 = make(rb, A // 2, id_offset=A // 2)
+    Ag3.pos, Ag3.velocity, Ag3.measured_velocity = pos0[A // 2:], vel0[A // 2:], vel0[A // 2:]
+    Ag3.run(steps)
+    assert np.array_equal(Ag3.pos, pos_run[A // 2:])
+
+    # oracle driven by the NumPy mirror of the Philox stream
+    env = O.OracleEnvironment(walls=BOX_WALLS)
+    worst = 0.0
+    for a in range(0, A, 7):
+        oa = O.OracleAgent(env, pos0[a], vel0[a], {"dt": 0.01})
+        for s in range(steps):
+            oa.update(O.TapeRNG(agent_xi=agent_normals(11, s, np.array([a]))[0]))
+        worst = max(worst, np.abs(oa.pos - pos_run[a]).max())
+    assert worst <= 1e-9, worst
+
+
+def test_spikes_match_numpy_philox():
+    """Neurons.save_to_history spikes: uniform < dt*firingrate (Neurons.py:682-684) with the
+    Philox4x32-7 spike stream; bit-packed on the device, unpacked by get_history_arrays."""
+    import ratinabox_b200 as rb
+    A, N = 40, 100
+    E, Ag = make(rb, A, dt=0.05)
+    PCs = rb.PlaceCells(Ag, {"n": N, "max_fr": 15.0, "widths": 0.3})
+    for _ in range(3):
+        Ag.update(); PCs.update()
+    h = PCs.get_history_arrays()
+    assert h["firingrate"].shape == (3, A, N) and h["spikes"].shape == (3, A, N) and h["spikes"].dtype == bool
+    for s in range(3):
+        u = spike_uniforms(11, s, np.arange(A), N, pop=0)
+        want = u < (np.float32(0.05) * h["firingrate"][s].astype(np.float32))
+        assert np.array_equal(h["spikes"][s], want), s
+    assert 0.02 < h["spikes"].mean() < 0.6
+
+
+def test_multistep_tracking_config1():
+    """Config 1 (1 agent, default box, 100 Gaussian PlaceCells, dt = 10 ms), 3000 steps with the
+    same injected normals: the float64 GPU trajectory tracks the oracle to <= 1e-6 m throughout."""
+    import ratinabox_b200 as rb
+    np.random.seed(0)
+    E = rb.Environment()
+    Ag = rb.Agent(E, {"dt": 0.01})
+    PCs = rb.PlaceCells(Ag, {"n": 100})
+    assert PCs.wall_geometry == "geodesic"
+    pos0, vel0 = Ag.pos.copy(), Ag.velocity.copy()
+    assert pos0.shape == (2,)
+    steps = 3000
+    xi = np.random.RandomState(9).normal(size=(steps, 2))
+    for s in range(steps):
+        Ag.update(_xi=xi[s])
+        PCs.update()
+    h = Ag.get_history_arrays()
+    assert h["pos"].shape == (steps, 2) and h["t"].shape == (steps,)
+    env = O.OracleEnvironment()
+    oa = O.OracleAgent(env, pos0, vel0, {"dt": 0.01})
+    on = O.OracleNeurons(oa, 100, lambda p, r: O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, p, r))
+    for s in range(steps):
+        oa.update(O.TapeRNG(agent_xi=xi[s]))
+        on.update(O.TapeRNG())
+    ref = np.array(oa.history["pos"])
+    assert np.abs(Ag.pos - oa.pos).max() <= 1e-9
+    assert np.abs(h["pos"] - ref).max() <= 1e-6            # history rows are float32
+    assert np.abs(h["rot_vel"] - np.array(oa.history["rot_vel"])).max() <= 2e-4 * np.abs(oa.history["rot_vel"]).max()
+    assert np.abs(h["head_direction"] - np.array(oa.history["head_direction"])).max() <= 1e-6
+    assert np.abs(h["distance_travelled"] - np.array(oa.history["distance_travelled"])).max() <= 1e-5
+    assert np.allclose(h["t"], np.array(oa.history["t"]))
+    fr = PCs.get_history_arrays()["firingrate"]
+    assert fr.shape == (steps, 100)
+    assert np.abs(fr - np.array(on.history["firingrate"])).max() <= 1e-5
+
+
+def test_attribute_mutation_and_post_init_writes():
+    """tests/test_advanced.py:35-72 pokes Ag.pos, Ag.speed_mean and PCs.place_cell_centres[-1]
+    after construction, and calls update(dt=...): all must take effect."""
+    import ratinabox_b200 as rb
+    np.random.seed(2)
+    Env = rb.Environment(params={"aspect": 2, "scale": 1})
+    Env.add_wall([[1, 0], [1, 0.35]])
+    Env.add_wall([[1, 0.65], [1, 1]])
+    Ag = rb.Agent(Env)
+    Ag.pos = np.array([0.5, 0.5])
+    Ag.speed_mean = 0.2
+    PCs = rb.PlaceCells(Ag, params={"n": 20, "description": "gaussian_threshold", "widths": 0.40,
+                                    "wall_geometry": "line_of_sight", "max_fr": 10, "min_fr": 0.1, "color": "C1"})
+    PCs.place_cell_centres[-1] = np.array([1.1, 0.5])
+    BVCs = rb.BoundaryVectorCells(Ag, params={"n": 10, "color": "C2"})
+    for i in range(200):
+        Ag.update(dt=50e-3)
+        PCs.update()
+        BVCs.update()
+    assert Ag.dt == 50e-3 and abs(Ag.t - 200 * 50e-3) < 1e-9
+    p = Ag.pos
+    assert p.shape == (2,) and 0 < p[0] < 2 and 0 < p[1] < 1
+    env = O.OracleEnvironment(scale=1, aspect=2, walls=[[[1, 0], [1, 0.35]], [[1, 0.65], [1, 1]]])
+    ref = O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, p, O.TapeRNG(),
+                                  "gaussian_threshold", "line_of_sight", 0.1, 10)[:, 0]
+    assert np.abs(PCs.firingrate - ref).max() <= 1e-4          # scale 9.9 -> 1e-5 relative
+    assert PCs.get_history_arrays()["firingrate"].shape == (200, 20)
+    # in-place mutation of a state array that was read
+    q = Ag.pos
+    q[0] = 0.25
+    Ag.update(dt=50e-3)
+    assert abs(Ag.get_history_arrays()["pos"][-1][0] - 0.25) < 0.05
+    # unknown parameters warn like the reference (utils.check_params)
+    with pytest.warns(UserWarning):
+        rb.PlaceCells(Ag, {"n": 4, "not_a_param": 1})
+
+
+def test_get_state_all_and_errors():
+    import ratinabox_b200 as rb
+    from ratinabox_b200._lib import RiabError
+    E, Ag = make(rb, 1)
+    PCs = rb.PlaceCells(Ag, {"n": 30, "wall_geometry": "line_of_sight"})
+    m = PCs.get_state(evaluate_at="all")
+    assert m.shape == (30, E.flattened_discrete_coords.shape[0]) and m.dtype == np.float64
+    env = O.OracleEnvironment(walls=BOX_WALLS)
+    ref = O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, E.flattened_discrete_coords,
+                                  O.TapeRNG(), "gaussian", "line_of_sight")
+    assert np.abs(m - ref).max() <= 1e-5
+    # empty and ragged inputs
+    assert PCs.get_state(evaluate_at=None, pos=np.zeros((0, 2))).shape == (30, 0)
+    assert PCs.get_state(evaluate_at=None, pos=np.array([0.4, 0.6])).shape == (30, 1)
+    one_hot = rb.PlaceCells(Ag, {"n": 8, "description": "one_hot"})
+    with pytest.raises(RiabError):
+        one_hot.get_state(evaluate_at="all")
+    with pytest.raises(NotImplementedError):
+        rb.Environment({"boundary_conditions": "periodic"})
