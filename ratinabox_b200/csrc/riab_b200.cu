@@ -124,9 +124,15 @@ __global__ void __launch_bounds__(128) k_agent_update(const riab_agents ag, cons
 // ---------------------------------------------------------------------------
 // Neurons.update tail for 4 consecutive cells of one agent: OU noise
 // (Neurons.py:153-160,168), rate store, spikes (Neurons.py:681-684).
-__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long long row, int cell0, int n_cells) {
+// `full4`: all 4 cells exist and the row is 16-byte aligned (vector store).
+template <bool SPIKES, bool NOISE>
+__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long long row, int cell0, int n_cells,
+                                        bool full4) {
   const unsigned long long gid = (unsigned long long)(out.id_offset + row);
-  if (out.noise != nullptr) {
+  const unsigned vmask = full4 ? 0xFu : ((cell0 < n_cells ? 1u : 0u) | (cell0 + 1 < n_cells ? 2u : 0u) |
+                                         (cell0 + 2 < n_cells ? 4u : 0u) | (cell0 + 3 < n_cells ? 8u : 0u));
+  const long long off = row * (long long)(int)out.ld + cell0;     // ld < 2^31
+  if (NOISE && out.noise != nullptr) {
     uint32_t c[4];
     philox_ctr(c, gid, (uint32_t)(cell0 >> 2), out.step, RIAB_STREAM_CELL_NOISE, (uint32_t)out.pop);
     philox4x32_10(c, (uint32_t)out.seed, (uint32_t)(out.seed >> 32));
@@ -139,10 +145,10 @@ __device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long lon
       __sincosf(6.2831853071795865f * u2, &sn, &cs);
       z[2 * h] = r * cs; z[2 * h + 1] = r * sn;
     }
-    float* np_ = out.noise + row * out.ld + cell0;
+    float* np_ = out.noise + off;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if (cell0 + i < n_cells) {
+      if ((vmask >> i) & 1u) {
         float n = np_[i];
         n = n + (-n * out.noise_decay) + out.noise_sig * z[i];
         np_[i] = n;
@@ -150,34 +156,38 @@ __device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long lon
       }
     }
   }
-  float* dst = out.rates + row * out.ld + cell0;
-  if (out.vec_ok && cell0 + 3 < n_cells) {
+  float* dst = out.rates + off;
+  if (full4) {
     st_cs_f4(dst, o[0], o[1], o[2], o[3]);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (cell0 + i < n_cells) st_cs_f1(dst + i, o[i]);
+      if ((vmask >> i) & 1u) st_cs_f1(dst + i, o[i]);
   }
-  if (out.spikes != nullptr) {
+  if (SPIKES && (!NOISE || out.spikes != nullptr)) {
     uint32_t c[4];
     philox_ctr(c, gid, (uint32_t)(cell0 >> 2), out.step, RIAB_STREAM_SPIKES, (uint32_t)out.pop);
     uint32_t k0 = (uint32_t)out.seed, k1 = (uint32_t)(out.seed >> 32);
 #pragma unroll
     for (int i = 0; i < 7; ++i) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }   // Philox4x32-7
-    uint32_t nib = 0;
+    // spike <=> uniform < dt * rate  (Neurons.py:682-684); uniform = (x>>8 + 0.5) * 2^-24
+    unsigned nib = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      nib |= ((cell0 + i < n_cells) && (u01_24(c[i]) < out.dt * o[i])) ? (1u << i) : 0u;
-    uint32_t v = nib | (__shfl_down_sync(0xffffffffu, nib, 1) << 4);
+    for (int i = 0; i < 4; ++i) {
+      const float u = fmaf((float)(c[i] >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+      nib |= (u < out.dt * o[i]) ? (1u << i) : 0u;
+    }
+    nib &= vmask;
+    unsigned v = nib | (__shfl_down_sync(0xffffffffu, nib, 1) << 4);
     v |= __shfl_down_sync(0xffffffffu, v, 2) << 8;
     v |= __shfl_down_sync(0xffffffffu, v, 4) << 16;
-    if ((threadIdx.x & 7) == 0 && cell0 < n_cells) out.spikes[row * out.spike_ld + (cell0 >> 5)] = v;
+    if ((threadIdx.x & 7) == 0 && cell0 < n_cells) out.spikes[row * (long long)(int)out.spike_ld + (cell0 >> 5)] = v;
   }
 }
 
 // ---------------------------------------------------------------------------
-// Cell-type policies for the tile kernel.
-template <int WI>
+// Cell-type policies for the step kernel.
+template <int WI, int DESC>
 struct PlacePolicy {
   using Const = PlaceConst;
   using Regs = PlaceCellRegs<WI>;
@@ -190,14 +200,14 @@ struct PlacePolicy {
   static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int cell0,
                                                 const float* rec, const double* pos64, const double* s_walls,
                                                 const EnvK& env) {
-    place_rates4<WI>(o, r, c, cell0, rec, pos64, s_walls + 4 * env.nb);
+    place_rates4<WI, DESC>(o, r, c, cell0, rec, pos64, s_walls + 4 * env.nb);
   }
 };
 
 struct GridPolicy {
   using Const = GridConst;
   using Regs = GridCellRegs;
-  static constexpr int REC = 2;
+  static constexpr int REC = 4;
   static __device__ __forceinline__ void record(float* rec, double px, double py, const double*, const Const&,
                                                 const EnvK& env) {
     rec[0] = (float)(px - env.cxm);
@@ -210,42 +220,121 @@ struct GridPolicy {
   }
 };
 
-template <class P, bool FUSED, bool REC>
-__global__ void __launch_bounds__(NT) k_tile(const EnvK env, const riab_agents ag, const riab_motion_params mp,
-                                             const riab_step_io io, const typename P::Const pc, const OutK out,
-                                             const double* __restrict__ pos_in, const long long n_rows) {
+// ---------------------------------------------------------------------------
+// k_step: persistent, warp-specialised step kernel (one CTA per SM).
+//   warps [0, MW)        producers: each takes a tile of 32 agents, runs Agent.update for its
+//                        lane's agent in float64 (MOTION) or just reads the position, writes the
+//                        agent state back, and publishes a float32 "rate record" per agent into a
+//                        shared-memory ring slot (mbarrier full[slot]).
+//   warps [MW, MW+RW)    consumers: every thread keeps 4 consecutive cells in registers, waits for
+//                        a slot, streams the slot's agents through the rate evaluator and writes
+//                        float4 rate rows (+ noise + bit-packed spikes), then frees the slot
+//                        (mbarrier empty[slot]).
+// The float64 motion latency (a ~2.5k-instruction dependent chain) is thereby hidden behind the
+// HBM-bound rate writes of earlier tiles instead of idling the CTA.
+constexpr int MW = 4;     // producer warps
+constexpr int RW = 16;    // consumer warps
+constexpr int NS = 8;     // ring slots (multiple of MW)
+constexpr int STEP_THREADS = (MW + RW) * 32;
+
+template <int REC>
+struct __align__(16) StepSlot {
+  float rec[TA][REC];
+  double pos[TA][2];
+  int na;
+  int pad[3];
+};
+
+template <class P, bool MOTION, bool SPIKES, bool NOISE>
+__global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const riab_agents ag,
+                                                          const riab_motion_params mp, const riab_step_io io,
+                                                          const typename P::Const pc, const OutK out,
+                                                          const double* __restrict__ pos_in, const long long n_rows) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
-  __shared__ __align__(16) float s_rec[TA][P::REC];
-  __shared__ __align__(16) double s_pos[TA][2];
-  __shared__ uint64_t s_bar;
-  stage_walls(s_walls, &s_bar, env);
-
-  const long long a0 = (long long)blockIdx.x * TA;
-  const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
-  if (threadIdx.x < TA && (int)threadIdx.x < na) {
-    const long long i = a0 + threadIdx.x;
-    double px, py;
-    if (FUSED) {
-      AgentState s;
-      agent_update_one<REC>(ag, mp, io, env, s_walls, i, s);
-      px = s.px; py = s.py;
-    } else {
-      px = pos_in[2 * i]; py = pos_in[2 * i + 1];
-    }
-    s_pos[threadIdx.x][0] = px;
-    s_pos[threadIdx.x][1] = py;
-    P::record(s_rec[threadIdx.x], px, py, s_walls, pc, env);
+  __shared__ StepSlot<P::REC> s_slot[NS];
+  __shared__ uint64_t s_bar, s_full[NS], s_empty[NS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RW); }
+    mbar_fence_init();
   }
-  __syncthreads();
+  stage_walls(s_walls, &s_bar, env);     // includes __syncthreads()
 
-  // NaN position -> zero rates (Neurons.py:163-164) is handled by the host mirror.
-  for (int cell0 = 4 * (int)threadIdx.x; cell0 < pc.n_pad; cell0 += 4 * NT) {
-    typename P::Regs r;
-    P::load(r, pc, cell0);
-    for (int a = 0; a < na; ++a) {
-      float o[4];
-      P::rates4(o, r, pc, cell0, s_rec[a], s_pos[a], s_walls, env);
-      finish4(o, out, a0 + a, cell0, pc.n_cells);
+  const long long n_tiles = (n_rows + TA - 1) / TA;
+  const long long nq = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp < MW) {
+    // ------------------------------------------------------------- producers
+    for (long long q = warp; q < nq; q += MW) {
+      const int s = (int)(q % NS);
+      const uint32_t k = (uint32_t)(q / NS);
+      mbar_wait(&s_empty[s], (k & 1u) ^ 1u);
+      const long long tile = (long long)blockIdx.x + q * gridDim.x;
+      const long long a0 = tile * TA;
+      const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
+      if (lane < na) {
+        const long long i = a0 + lane;
+        double px, py;
+        if (MOTION) {
+          AgentState st;
+          agent_update_one<false>(ag, mp, io, env, s_walls, i, st);
+          px = st.px; py = st.py;
+        } else {
+          px = pos_in[2 * i]; py = pos_in[2 * i + 1];
+        }
+        s_slot[s].pos[lane][0] = px;
+        s_slot[s].pos[lane][1] = py;
+        P::record(s_slot[s].rec[lane], px, py, s_walls, pc, env);
+      }
+      if (lane == 0) s_slot[s].na = na;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_full[s]);
+    }
+  } else {
+    // ------------------------------------------------------------- consumers
+    const int ctid = threadIdx.x - MW * 32;
+    constexpr int NC = RW * 32;
+    const int CT = pc.n_pad >> 2;                       // cell-threads needed (multiple of 32)
+    const int chunks = (CT + NC - 1) / NC;
+    const int G = (chunks == 1) ? (NC / CT) : 1;        // agent groups when the cells need fewer threads
+    const int grp = (chunks == 1) ? (ctid / CT) : 0;
+    const bool idle = (chunks == 1) && (grp >= G);
+    typename P::Regs regs;
+    int cell0 = (chunks == 1) ? (ctid % CT) * 4 : 0;
+    bool full4 = false;
+    if (chunks == 1 && !idle) {
+      P::load(regs, pc, cell0);
+      full4 = out.vec_ok && (cell0 + 3 < pc.n_cells);
+    }
+    for (long long q = 0; q < nq; ++q) {
+      const int s = (int)(q % NS);
+      mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
+      const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * TA;
+      const int na = s_slot[s].na;
+      if (chunks == 1) {
+        if (!idle) {
+          for (int a = grp; a < na; a += G) {
+            float o[4];
+            P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], s_slot[s].pos[a], s_walls, env);
+            finish4<SPIKES, NOISE>(o, out, a0 + a, cell0, pc.n_cells, full4);
+          }
+        }
+      } else {
+        for (int ch = 0; ch < chunks; ++ch) {
+          cell0 = (ch * NC + ctid) * 4;
+          if (cell0 < pc.n_pad) {                       // warp-uniform (n_pad is a multiple of 128)
+            P::load(regs, pc, cell0);
+            full4 = out.vec_ok && (cell0 + 3 < pc.n_cells);
+            for (int a = 0; a < na; ++a) {
+              float o[4];
+              P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], s_slot[s].pos[a], s_walls, env);
+              finish4<SPIKES, NOISE>(o, out, a0 + a, cell0, pc.n_cells, full4);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
     }
   }
 }
@@ -259,7 +348,7 @@ __global__ void __launch_bounds__(NT) k_finish_rows(const OutK out, const int n_
   float o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) o[i] = (cell0 + i < n_cells) ? out.rates[row * out.ld + cell0 + i] : 0.f;
-  finish4(o, out, row, cell0, n_cells);
+  finish4<true, true>(o, out, row, cell0, n_cells, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -468,28 +557,46 @@ int make_grid(const riab_grid_cells* gc, const EnvK& env, GridConst& c) {
   return 0;
 }
 
+int g_num_sms = 0;
+
 template <class P, bool FUSED>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                 const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   if (n_rows == 0) return 0;
-  const unsigned grid = (unsigned)((n_rows + TA - 1) / TA);
-  const bool rec = FUSED && (io.collision_mask || io.first_hit || io.n_iters);
-  if (rec) k_tile<P, FUSED, FUSED><<<grid, NT, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
-  else k_tile<P, FUSED, false><<<grid, NT, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    RIAB_CUDA_OK(cudaGetDevice(&dev));
+    RIAB_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long long n_tiles = (n_rows + TA - 1) / TA;
+  const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
+  const bool spikes = out.spikes != nullptr, noise = out.noise != nullptr;
+  if (noise) k_step<P, FUSED, true, true><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
+  else if (spikes) k_step<P, FUSED, true, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
+  else k_step<P, FUSED, false, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
+template <bool FUSED, int DESC>
+int launch_place_d(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
+                   const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+  const int wi = pc.n_inner;
+  if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi <= 4) return launch_tile<PlacePolicy<4, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  return launch_tile<PlacePolicy<8, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+}
+
 template <bool FUSED>
 int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                  const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
-  const int wi = pc.n_inner;
-  if (wi == 0) return launch_tile<PlacePolicy<0>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi == 1) return launch_tile<PlacePolicy<1>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi == 2) return launch_tile<PlacePolicy<2>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi <= 4) return launch_tile<PlacePolicy<4>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  return launch_tile<PlacePolicy<8>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  // the common Gaussian profile without geodesic detours gets a compile-time specialisation
+  if (pc.desc == RIAB_PC_GAUSSIAN && pc.geometry != RIAB_GEOM_GEODESIC)
+    return launch_place_d<FUSED, RIAB_PC_GAUSSIAN>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  return launch_place_d<FUSED, -1>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
 }
 
 template <bool FUSED>
@@ -594,22 +701,32 @@ int riab_place_pack(const double* centres, const double* widths, int32_t n, cons
     const double* w = walls + 4 * (n_boundary + j);
     float* fc = out + (size_t)(4 + 2 * j) * np;
     float* tc = out + (size_t)(5 + 2 * j) * np;
-    double tmax = 1.0;
+    double tmax = 1.0, dmax = 0.0;
+    for (int cxi = 0; cxi < 2; ++cxi)
+      for (int cyi = 0; cyi < 2; ++cyi) {            // agents live inside the box: bound |f|, |t| over its corners
+        double f, t;
+        wall_coords(extent[cxi], extent[2 + cyi], w[0], w[1], w[2], w[3], f, t);
+        if (fabs(t) + 1.0 > tmax) tmax = fabs(t) + 1.0;
+        if (fabs(f) > dmax) dmax = fabs(f);
+      }
+    double fcmax = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double f, t;
+      wall_coords(centres[2 * i], centres[2 * i + 1], w[0], w[1], w[2], w[3], f, t);
+      if (fabs(t) + 1.0 > tmax) tmax = fabs(t) + 1.0;
+      if (fabs(f) > fcmax) fcmax = fabs(f);
+    }
+    const double band = 2.0e-6 * (dmax + fcmax) * tmax;   // ~10x the float32 rounding error of M' and |D|
     for (int i = 0; i < np; ++i) {
       if (i < n) {
         double f, t;
         wall_coords(centres[2 * i], centres[2 * i + 1], w[0], w[1], w[2], w[3], f, t);
         fc[i] = (float)f; tc[i] = (float)t;
-        if (fabs(t) + 1.0 > tmax) tmax = fabs(t) + 1.0;
+        // a centre (numerically) on the wall's line: force the exact float64 path (NaN poisons the fast test)
+        if (fabs(f) < 1.0e-6 * (dmax + fcmax)) tc[i] = nanf("");
       } else { fc[i] = 1.f; tc[i] = 0.f; }
     }
-    for (int cxi = 0; cxi < 2; ++cxi)
-      for (int cyi = 0; cyi < 2; ++cyi) {            // agents live inside the box: bound |t| over its corners
-        double f, t;
-        wall_coords(extent[cxi], extent[2 + cyi], w[0], w[1], w[2], w[3], f, t);
-        if (fabs(t) + 1.0 > tmax) tmax = fabs(t) + 1.0;
-      }
-    if (j < 8) meta->eps[j] = (float)(2.0e-6 * tmax);
+    if (j < 8) meta->eps[j] = (float)band;
   }
   if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
     const double* w = walls + 4 * n_boundary;
@@ -631,6 +748,7 @@ int riab_place_pack(const double* centres, const double* widths, int32_t n, cons
 
 int riab_place_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_place_cells* pc,
                      float* out_dev, int64_t ld_out, void* stream) {
+  if (n_pos == 0) return 0;
   EnvK ek;
   PlaceConst c;
   OutK ok;
@@ -677,6 +795,7 @@ int riab_grid_pack(const double* gridscales, const double* phase_offsets, const 
 
 int riab_grid_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_grid_cells* gc,
                     float* out_dev, int64_t ld_out, void* stream) {
+  if (n_pos == 0) return 0;
   EnvK ek;
   GridConst c;
   OutK ok;
@@ -729,6 +848,7 @@ int riab_bvc_pack(const double* mu_d, const double* mu_t, const double* sg_d, co
 
 int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_bvc_cells* bvc,
                    float* scratch_dev, int32_t* first_wall_dev, float* out_dev, int64_t ld_out, void* stream) {
+  if (n_pos == 0) return 0;
   EnvK ek;
   OutK ok;
   int rc;
@@ -760,9 +880,14 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
   if (cells == nullptr || (FUSED && io == nullptr)) return fail(RIAB_ERR_INVALID, "io / cells NULL");
   riab_motion_params mp0; memset(&mp0, 0, sizeof(mp0));
   riab_step_io io0; memset(&io0, 0, sizeof(io0));
+  if (FUSED && (io->collision_mask || io->first_hit || io->n_iters) && cells_kind != RIAB_CELLS_BVC) {
+    // parity taps are only implemented in the stand-alone motion kernel
+    if ((rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
+    return neurons_update_impl<false>(agents, env, prm, io, cells_kind, cells, noise, out, stream);
+  }
   const riab_motion_params& mp = FUSED ? *prm : mp0;
   const riab_step_io& sio = FUSED ? *io : io0;
-  const double dt = FUSED ? prm->dt : (noise ? (double)noise->dt : 1.0);
+  const double dt = (prm != nullptr) ? prm->dt : (noise ? (double)noise->dt : 1.0);
   const double* pos_in = FUSED ? nullptr : agents->pos;
   cudaStream_t s = (cudaStream_t)stream;
   if (cells_kind == RIAB_CELLS_PLACE) {

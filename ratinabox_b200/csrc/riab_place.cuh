@@ -56,7 +56,7 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
     double f, t;
     wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
     rec[2 + 2 * j] = (float)f;
-    rec[3 + 2 * j] = (float)t;
+    rec[3 + 2 * j] = (fabs(f) < 1e-9) ? nanf("") : (float)t;   // agent on the wall's line: exact path
   }
   for (int j = n_inner; j < PLACE_MAX_WI; ++j) { rec[2 + 2 * j] = 1.f; rec[3 + 2 * j] = 0.f; }  // dummy walls never block
   if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
@@ -113,8 +113,11 @@ RIAB_DEV void place_load_cells(PlaceCellRegs<WI>& r, const PlaceConst& c, int ce
   }
 }
 
-// Neurons.py:959-976 epilogue on the squared distance (float32)
-RIAB_DEV float place_profile(float d2, float k, int desc) {
+// Neurons.py:959-976 epilogue on the squared distance (float32).  DESC is a
+// compile-time description, or -1 for a run-time switch on c.desc.
+template <int DESC>
+RIAB_DEV float place_profile(float d2, float k, int desc_rt) {
+  const int desc = (DESC >= 0) ? DESC : desc_rt;
   const float g = ex2f(-d2 * k);
   if (desc == RIAB_PC_GAUSSIAN) return g;
   if (desc == RIAB_PC_GAUSSIAN_THRESHOLD)
@@ -124,49 +127,86 @@ RIAB_DEV float place_profile(float d2, float k, int desc) {
   return (g - (1.0f / 2.25f) * g2) * 1.8f;
 }
 
-// Rates of one agent for this thread's 4 cells.
+// Exact (float64) line-of-sight flags for this thread's 4 cells: the rare path taken when
+// any float32 predicate of the group fell inside its uncertainty band.
+template <int WI>
+__device__ __noinline__ unsigned place_blocked_exact4(const PlaceConst& c, int cell0, const double* __restrict__ pos64,
+                                                      const double* __restrict__ inner64) {
+  unsigned m = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int cell = cell0 + i;
+    if (cell >= c.n_cells) continue;
+    const double cx = c.centres64[2 * cell], cy = c.centres64[2 * cell + 1];
+    bool b = false;
+    for (int j = 0; j < WI && j < c.n_inner; ++j) b = b || los_blocked_exact(cx, cy, pos64[0], pos64[1], inner64 + 4 * j);
+    m |= b ? (1u << i) : 0u;
+  }
+  return m;
+}
+
+// Rates of one agent for this thread's 4 cells (branch-free fast path; one rare branch).
 //   rec    : the agent's float32 record in shared memory (broadcast reads)
 //   pos64  : the agent's float64 position (exact fall-back only)
 //   inner64: float64 inner walls in shared memory (exact fall-back only)
-template <int WI>
+template <int WI, int DESC>
 RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0,
                            const float* __restrict__ rec, const double* __restrict__ pos64,
                            const double* __restrict__ inner64) {
-  const float2 p = *reinterpret_cast<const float2*>(rec);
+  const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, f_p0, t_p0
   float d2[4];
-  bool blocked[4];
+  bool unsure = false;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float dx = p.x - r.cx[i], dy = p.y - r.cy[i];
+    const float dx = r0.x - r.cx[i], dy = r0.y - r.cy[i];
     d2[i] = fmaf(dy, dy, dx * dx);
-    blocked[i] = false;
   }
+  bool blocked[4] = {false, false, false, false};
   if (WI > 0) {
+    // With s = sign(f_c) and the agent on the other side of the wall's line (opp):
+    //   |D| = |f_c| + |f_p|,  M' = s*M = |f_c| t_p + |f_p| t_c  (a convex combination of t_p, t_c),
+    //   blocked  <=>  opp and 0 < M' < |D|  <=>  opp and min(M', |D| - M') > 0.
+    // |min(..)| below the band => re-evaluate in float64 (conservatively, regardless of opp).
+    float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
 #pragma unroll
     for (int j = 0; j < WI; ++j) {
-      const float2 pw = *reinterpret_cast<const float2*>(rec + 2 + 2 * j);   // (f_p, t_p)
-      const float eps = c.eps[j];
+      float fp, tp;
+      if (j == 0) { fp = r0.z; tp = r0.w; }
+      else {
+        const float2 pw = *reinterpret_cast<const float2*>(rec + 2 + 2 * j);
+        fp = pw.x; tp = pw.y;
+      }
+      const float afp = fabsf(fp);
+      const float band = c.eps[j];                       // absolute band (eps * max |D| over the box)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float fc = r.fc[j][i], tcv = r.tc[j][i];
-        const float Dd = fc - pw.x;                       // f_c - f_p (no cancellation when signs differ)
-        const float M = fmaf(-pw.x, tcv, fc * pw.y);      // f_c t_p - f_p t_c
-        const float DM = Dd - M;
-        const float band = eps * fabsf(Dd);
-        const bool opp = (fc * pw.x) < 0.f;               // 0 < l_a < 1
-        bool hit = opp && ((M * DM) > 0.f);               // 0 < l_b < 1
-        const bool unsure = opp && ((fabsf(M) < band) || (fabsf(DM) < band));
-        if (unsure) {
-          const int cell = cell0 + i;
-          if (cell < c.n_cells)
-            hit = los_blocked_exact(c.centres64[2 * cell], c.centres64[2 * cell + 1], pos64[0], pos64[1],
-                                    inner64 + 4 * j);
-        }
-        blocked[i] = blocked[i] || hit;
+        const float fc = r.fc[j][i];
+        const float Mp = fmaf(afp, r.tc[j][i], fabsf(fc) * tp);
+        const float Da = fabsf(fc) + afp;
+        const float mn = fminf(Mp, Da - Mp);
+        const bool opp = (__float_as_int(fc) ^ __float_as_int(fp)) < 0;   // strictly opposite sides (or a zero)
+        const bool hit = opp & (mn > 0.f);
+        dd[i] = hit ? 1.0e6f : dd[i];                    // distance 1000 (Environment.py:730)
+        unsure = unsure | !(fabsf(mn) >= band);          // also true for NaN (degenerate centre / agent)
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) blocked[i] = dd[i] != d2[i];
+    if (unsure) {                                        // rare: redo the group's flags with the reference's float64 test
+      const unsigned m = place_blocked_exact4<WI>(c, cell0, pos64, inner64);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) blocked[i] = (m >> i) & 1u;
     }
   }
   const bool geodesic = (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
+  const int desc = (DESC >= 0) ? DESC : c.desc;
+  if (desc != RIAB_PC_TOP_HAT && !geodesic) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dd = (WI > 0 && blocked[i]) ? 1.0e6f : d2[i];       // distance 1000 (Environment.py:730)
+      out[i] = fmaf(place_profile<DESC>(dd, r.k[i], c.desc), c.span, c.min_fr);   // Neurons.py:978-980
+    }
+    return;
+  }
   float2 ep = make_float2(0.f, 0.f);
   if (geodesic) ep = *reinterpret_cast<const float2*>(rec + 2 + 2 * PLACE_MAX_WI);
 #pragma unroll
@@ -180,11 +220,11 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
         if (c.ep_valid & 2) via = fminf(via, r.ce1[i] + ep.y);
         dd = blocked[i] ? via * via : dd;
       } else {
-        dd = blocked[i] ? 1.0e6f : dd;                    // distance 1000 (Environment.py:730)
+        dd = blocked[i] ? 1.0e6f : dd;
       }
     }
     float v;
-    if (c.desc == RIAB_PC_TOP_HAT) {
+    if (desc == RIAB_PC_TOP_HAT) {
       // Neurons.py:975-976: 1*(dist < widths) with the scalar `widths`
       bool in = dd < c.top_hat_w2;
       if (fabsf(dd - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !(WI > 0 && blocked[i])) {
@@ -196,9 +236,9 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       }
       v = in ? 1.f : 0.f;
     } else {
-      v = place_profile(dd, r.k[i], c.desc);
+      v = place_profile<DESC>(dd, r.k[i], c.desc);
     }
-    out[i] = fmaf(v, c.span, c.min_fr);                   // Neurons.py:978-980
+    out[i] = fmaf(v, c.span, c.min_fr);
   }
 }
 

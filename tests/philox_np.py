@@ -37,7 +37,9 @@ def u01_53(hi, lo):
 
 
 def u01_24(x):
-    return ((x >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    # fma(x>>8, 2^-24, 2^-25): exact in float32 ((x>>8)+0.5 has 25 significant bits only when x>>8 >= 2^23,
+    # where the fused result rounds once) -- mirror with float64 arithmetic rounded once to float32
+    return ((x >> np.uint32(8)).astype(np.float64) * 2.0 ** -24 + 2.0 ** -25).astype(np.float32)
 
 
 def agent_normals(seed, step, agents):
