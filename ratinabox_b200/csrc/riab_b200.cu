@@ -62,6 +62,7 @@ struct OutK {
   unsigned long long seed, step;
   long long id_offset;
   int pop, vec_ok;
+  uint32_t rk7[14];         // Philox4x32-7 round keys of the spike stream (host-computed, constant bank)
 };
 
 // ---------------------------------------------------------------------------
@@ -86,7 +87,7 @@ __device__ __forceinline__ void stage_walls(double* s_walls, uint64_t* bar, cons
 // One agent's Agent.update inside a kernel (loads/stores its state).
 template <bool REC>
 __device__ __forceinline__ void agent_update_one(const riab_agents& ag, const riab_motion_params& mp,
-                                                 const riab_step_io& io, const EnvK& env,
+                                                 const MotionDerived& md, const riab_step_io& io, const EnvK& env,
                                                  const double* s_walls, long long i, AgentState& s) {
   load_agent(ag, i, s);
   double n1, n2;
@@ -96,45 +97,80 @@ __device__ __forceinline__ void agent_update_one(const riab_agents& ag, const ri
   const bool has_drift = io.drift_velocity != nullptr;
   double drx = 0.0, dry = 0.0;
   if (has_drift) { drx = io.drift_velocity[2 * i]; dry = io.drift_velocity[2 * i + 1]; }
-  // fall-back normals for an exactly-zero displacement (Agent.py:460-461): separate Philox stream
-  uint32_t c[4];
-  philox_ctr(c, gid, 0u, io.step, RIAB_STREAM_MEASURE, 0u);
-  philox4x32_10(c, (uint32_t)io.seed, (uint32_t)(io.seed >> 32));
-  const double f1 = 2.0 * u01_53(c[0], c[1]) - 1.0, f2 = 2.0 * u01_53(c[2], c[3]) - 1.0;
+  // exactly-zero displacement (Agent.py:460-461) draws from a separate Philox stream, lazily
+  const double f1 = __longlong_as_double((long long)io.seed), f2 = __longlong_as_double((long long)(io.step ^ (gid << 20)));
   uint8_t* mask = (REC && io.collision_mask) ? io.collision_mask + (size_t)i * RIAB_MAX_REC_ITERS * env.W : nullptr;
   int32_t* fh = (REC && io.first_hit) ? io.first_hit + (size_t)i * RIAB_MAX_REC_ITERS : nullptr;
   int32_t* ni = (REC && io.n_iters) ? io.n_iters + i : nullptr;
-  motion_step<REC>(s, s_walls, env.W, mp, env.ext, n1, n2, has_drift, drx, dry, f1, f2, mask, fh, ni);
+  motion_step<REC>(s, s_walls, env.W, mp, md, env.ext, n1, n2, has_drift, drx, dry, f1, f2, mask, fh, ni);
   store_agent(ag, i, s);
   if (io.history_row != nullptr) store_history_row(io.history_row + 8 * (size_t)i, s);
 }
 
 template <bool REC>
 __global__ void __launch_bounds__(128) k_agent_update(const riab_agents ag, const riab_motion_params mp,
-                                                      const riab_step_io io, const EnvK env) {
+                                                      const MotionDerived md, const riab_step_io io, const EnvK env) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
   __shared__ uint64_t s_bar;
   stage_walls(s_walls, &s_bar, env);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ag.n_agents) return;
   AgentState s;
-  agent_update_one<REC>(ag, mp, io, env, s_walls, i, s);
+  agent_update_one<REC>(ag, mp, md, io, env, s_walls, i, s);
 }
 
 // ---------------------------------------------------------------------------
 // Neurons.update tail for 4 consecutive cells of one agent: OU noise
 // (Neurons.py:153-160,168), rate store, spikes (Neurons.py:681-684).
 // `full4`: all 4 cells exist and the row is 16-byte aligned (vector store).
+// Per-thread constants of the rate tail (4 consecutive cells).
+struct TailCtx {
+  int cell0, n_cells;
+  unsigned vmask;          // which of the 4 cells exist
+  bool full4;              // all 4 exist and rows are 16-byte aligned -> one vector store
+  uint32_t sub;            // Philox counter word 1: cell group index
+  uint32_t c2, c3_spk;     // Philox counter words 2,3 (step, stream | population)
+};
+
+// Row cursor of one thread: pointers into the current agent's rows, advanced per agent.
+struct RowCursor {
+  float* dst;              // rates row + cell0
+  float* nz;               // noise-state row + cell0 (or NULL)
+  uint8_t* spk;            // spikes row (bytes) + cell0/8
+  unsigned long long gid;  // global agent id
+};
+
+__device__ __forceinline__ void tail_init(TailCtx& t, const OutK& out, int cell0, int n_cells) {
+  t.cell0 = cell0; t.n_cells = n_cells;
+  t.vmask = (cell0 < n_cells ? 1u : 0u) | (cell0 + 1 < n_cells ? 2u : 0u) | (cell0 + 2 < n_cells ? 4u : 0u) |
+            (cell0 + 3 < n_cells ? 8u : 0u);
+  t.full4 = out.vec_ok && (t.vmask == 0xFu);
+  t.sub = (uint32_t)(cell0 >> 2);
+  t.c2 = (uint32_t)out.step;
+  const uint32_t hi = ((uint32_t)(out.step >> 32) & 0xffffu) | (((uint32_t)out.pop & 0xffu) << 16);
+  t.c3_spk = hi | (RIAB_STREAM_SPIKES << 24);
+}
+
+__device__ __forceinline__ void cursor_init(RowCursor& rc, const OutK& out, const TailCtx& t, long long row) {
+  rc.dst = out.rates + row * out.ld + t.cell0;
+  rc.nz = out.noise ? out.noise + row * out.ld + t.cell0 : nullptr;
+  rc.spk = out.spikes ? reinterpret_cast<uint8_t*>(out.spikes + row * out.spike_ld) + (t.cell0 >> 3) : nullptr;
+  rc.gid = (unsigned long long)(out.id_offset + row);
+}
+__device__ __forceinline__ void cursor_advance(RowCursor& rc, const OutK& out, int rows) {
+  rc.dst += (long long)rows * out.ld;
+  if (rc.nz) rc.nz += (long long)rows * out.ld;
+  if (rc.spk) rc.spk += (long long)rows * out.spike_ld * 4;
+  rc.gid += (unsigned long long)rows;
+}
+
+// Neurons.update tail for 4 consecutive cells of one agent: OU noise (Neurons.py:153-160,168),
+// rate store, spikes (Neurons.py:681-684; bit c of the row's byte string = cell c).
 template <bool SPIKES, bool NOISE>
-__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long long row, int cell0, int n_cells,
-                                        bool full4) {
-  const unsigned long long gid = (unsigned long long)(out.id_offset + row);
-  const unsigned vmask = full4 ? 0xFu : ((cell0 < n_cells ? 1u : 0u) | (cell0 + 1 < n_cells ? 2u : 0u) |
-                                         (cell0 + 2 < n_cells ? 4u : 0u) | (cell0 + 3 < n_cells ? 8u : 0u));
-  const long long off = row * (long long)(int)out.ld + cell0;     // ld < 2^31
-  if (NOISE && out.noise != nullptr) {
+__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc) {
+  if (NOISE && rc.nz != nullptr) {
     uint32_t c[4];
-    philox_ctr(c, gid, (uint32_t)(cell0 >> 2), out.step, RIAB_STREAM_CELL_NOISE, (uint32_t)out.pop);
+    philox_ctr(c, rc.gid, t.sub, out.step, RIAB_STREAM_CELL_NOISE, (uint32_t)out.pop);
     philox4x32_10(c, (uint32_t)out.seed, (uint32_t)(out.seed >> 32));
     float z[4];
 #pragma unroll
@@ -145,43 +181,37 @@ __device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, long lon
       __sincosf(6.2831853071795865f * u2, &sn, &cs);
       z[2 * h] = r * cs; z[2 * h + 1] = r * sn;
     }
-    float* np_ = out.noise + off;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      if ((vmask >> i) & 1u) {
-        float n = np_[i];
+      if ((t.vmask >> i) & 1u) {
+        float n = rc.nz[i];
         n = n + (-n * out.noise_decay) + out.noise_sig * z[i];
-        np_[i] = n;
+        rc.nz[i] = n;
         o[i] += n;
       }
     }
   }
-  float* dst = out.rates + off;
-  if (full4) {
-    st_cs_f4(dst, o[0], o[1], o[2], o[3]);
+  if (t.full4) {
+    st_cs_f4(rc.dst, o[0], o[1], o[2], o[3]);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if ((vmask >> i) & 1u) st_cs_f1(dst + i, o[i]);
+      if ((t.vmask >> i) & 1u) st_cs_f1(rc.dst + i, o[i]);
   }
-  if (SPIKES && (!NOISE || out.spikes != nullptr)) {
-    uint32_t c[4];
-    philox_ctr(c, gid, (uint32_t)(cell0 >> 2), out.step, RIAB_STREAM_SPIKES, (uint32_t)out.pop);
-    uint32_t k0 = (uint32_t)out.seed, k1 = (uint32_t)(out.seed >> 32);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }   // Philox4x32-7
-    // spike <=> uniform < dt * rate  (Neurons.py:682-684); uniform = (x>>8 + 0.5) * 2^-24
+  if (SPIKES && (!NOISE || rc.spk != nullptr)) {
+    // counter = (agent id, cell group, step, stream|population); see philox_ctr
+    uint32_t c[4] = {(uint32_t)rc.gid, t.sub ^ ((uint32_t)(rc.gid >> 32) << 24), t.c2, t.c3_spk};
+    philox_keyed<7>(c, out.rk7);
+    // spike <=> uniform < dt * rate (Neurons.py:682-684); uniform = fma(float(x), 2^-32, 2^-33)
     unsigned nib = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float u = fmaf((float)(c[i] >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+      const float u = fmaf(__uint2float_rn(c[i]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
       nib |= (u < out.dt * o[i]) ? (1u << i) : 0u;
     }
-    nib &= vmask;
-    unsigned v = nib | (__shfl_down_sync(0xffffffffu, nib, 1) << 4);
-    v |= __shfl_down_sync(0xffffffffu, v, 2) << 8;
-    v |= __shfl_down_sync(0xffffffffu, v, 4) << 16;
-    if ((threadIdx.x & 7) == 0 && cell0 < n_cells) out.spikes[row * (long long)(int)out.spike_ld + (cell0 >> 5)] = v;
+    nib &= t.vmask;
+    const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);      // odd lane's nibble = cells 4..7 of the byte
+    if ((threadIdx.x & 1) == 0 && t.vmask != 0u) *rc.spk = (uint8_t)(nib | (hi << 4));
   }
 }
 
@@ -247,8 +277,8 @@ struct __align__(16) StepSlot {
 
 template <class P, bool MOTION, bool SPIKES, bool NOISE>
 __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const riab_agents ag,
-                                                          const riab_motion_params mp, const riab_step_io io,
-                                                          const typename P::Const pc, const OutK out,
+                                                          const riab_motion_params mp, const MotionDerived md,
+                                                          const riab_step_io io, const typename P::Const pc, const OutK out,
                                                           const double* __restrict__ pos_in, const long long n_rows) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
   __shared__ StepSlot<P::REC> s_slot[NS];
@@ -277,7 +307,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
         double px, py;
         if (MOTION) {
           AgentState st;
-          agent_update_one<false>(ag, mp, io, env, s_walls, i, st);
+          agent_update_one<false>(ag, mp, md, io, env, s_walls, i, st);
           px = st.px; py = st.py;
         } else {
           px = pos_in[2 * i]; py = pos_in[2 * i + 1];
@@ -301,10 +331,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
     const bool idle = (chunks == 1) && (grp >= G);
     typename P::Regs regs;
     int cell0 = (chunks == 1) ? (ctid % CT) * 4 : 0;
-    bool full4 = false;
+    TailCtx tc;
     if (chunks == 1 && !idle) {
       P::load(regs, pc, cell0);
-      full4 = out.vec_ok && (cell0 + 3 < pc.n_cells);
+      tail_init(tc, out, cell0, pc.n_cells);
     }
     for (long long q = 0; q < nq; ++q) {
       const int s = (int)(q % NS);
@@ -313,10 +343,17 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
       const int na = s_slot[s].na;
       if (chunks == 1) {
         if (!idle) {
+          RowCursor rc;
+          cursor_init(rc, out, tc, a0 + grp);
+          const float* recp = s_slot[s].rec[grp];
+          const double* posp = s_slot[s].pos[grp];
           for (int a = grp; a < na; a += G) {
             float o[4];
-            P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], s_slot[s].pos[a], s_walls, env);
-            finish4<SPIKES, NOISE>(o, out, a0 + a, cell0, pc.n_cells, full4);
+            P::rates4(o, regs, pc, cell0, recp, posp, s_walls, env);
+            finish4<SPIKES, NOISE>(o, out, tc, rc);
+            cursor_advance(rc, out, G);
+            recp += G * P::REC;
+            posp += G * 2;
           }
         }
       } else {
@@ -324,11 +361,14 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
           cell0 = (ch * NC + ctid) * 4;
           if (cell0 < pc.n_pad) {                       // warp-uniform (n_pad is a multiple of 128)
             P::load(regs, pc, cell0);
-            full4 = out.vec_ok && (cell0 + 3 < pc.n_cells);
+            tail_init(tc, out, cell0, pc.n_cells);
+            RowCursor rc;
+            cursor_init(rc, out, tc, a0);
             for (int a = 0; a < na; ++a) {
               float o[4];
               P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], s_slot[s].pos[a], s_walls, env);
-              finish4<SPIKES, NOISE>(o, out, a0 + a, cell0, pc.n_cells, full4);
+              finish4<SPIKES, NOISE>(o, out, tc, rc);
+              cursor_advance(rc, out, 1);
             }
           }
         }
@@ -348,14 +388,19 @@ __global__ void __launch_bounds__(NT) k_finish_rows(const OutK out, const int n_
   float o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) o[i] = (cell0 + i < n_cells) ? out.rates[row * out.ld + cell0 + i] : 0.f;
-  finish4<true, true>(o, out, row, cell0, n_cells, false);
+  TailCtx tc;
+  tail_init(tc, out, cell0, n_cells);
+  tc.full4 = false;
+  RowCursor rc;
+  cursor_init(rc, out, tc, row);
+  finish4<true, true>(o, out, tc, rc);
 }
 
 // ---------------------------------------------------------------------------
 // BVC phase A (+ optional fused Agent.update): one CTA per tile of 32 agents.
 template <bool FUSED, bool REC>
 __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agents ag, const riab_motion_params mp,
-                                                 const riab_step_io io, const BvcConst bc,
+                                                 const MotionDerived md, const riab_step_io io, const BvcConst bc,
                                                  const double* __restrict__ pos_in, const long long n_rows,
                                                  float* __restrict__ scratch, int32_t* __restrict__ first_wall) {
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -374,7 +419,7 @@ __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agen
       const long long i = a0 + threadIdx.x;
       if (FUSED) {
         AgentState s;
-        agent_update_one<REC>(ag, mp, io, env, s_walls, i, s);
+        agent_update_one<REC>(ag, mp, md, io, env, s_walls, i, s);
         px = s.px; py = s.py;
       } else {
         px = pos_in[2 * i]; py = pos_in[2 * i + 1];
@@ -512,6 +557,10 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
     return fail(RIAB_ERR_INVALID, "spikes need a riab_neuron_noise (seed/step)");
   }
   k.vec_ok = (o->ld % 4 == 0) && (((uintptr_t)o->rates_row) % 16 == 0);
+  {
+    uint32_t k0 = (uint32_t)k.seed, k1 = (uint32_t)(k.seed >> 32);
+    for (int i = 0; i < 7; ++i) { k.rk7[2 * i] = k0; k.rk7[2 * i + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  }
   return 0;
 }
 
@@ -571,9 +620,12 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   const long long n_tiles = (n_rows + TA - 1) / TA;
   const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
   const bool spikes = out.spikes != nullptr, noise = out.noise != nullptr;
-  if (noise) k_step<P, FUSED, true, true><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
-  else if (spikes) k_step<P, FUSED, true, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
-  else k_step<P, FUSED, false, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, io, pc, out, pos_in, n_rows);
+  MotionDerived md;
+  memset(&md, 0, sizeof(md));
+  if (FUSED) derive_motion(mp, md);
+  if (noise) k_step<P, FUSED, true, true><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else if (spikes) k_step<P, FUSED, true, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else k_step<P, FUSED, false, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   return 0;
@@ -618,8 +670,11 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   if ((bc.T * BVC_AT * 4) % 16 != 0 || ((uintptr_t)scratch) % 16 != 0 || ((uintptr_t)bvc->packed_dev) % 16 != 0)
     return fail(RIAB_ERR_INVALID, "bvc buffers must be 16-byte aligned");
   const bool rec = FUSED && (io.collision_mask || io.first_hit || io.n_iters);
-  if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, io, bc, pos_in, n_rows, scratch, first_wall);
-  else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, io, bc, pos_in, n_rows, scratch, first_wall);
+  MotionDerived md;
+  memset(&md, 0, sizeof(md));
+  if (FUSED) derive_motion(mp, md);
+  if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall);
+  else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   static bool attr_set = false;
@@ -661,8 +716,10 @@ int riab_agent_update(const riab_agents* agents, const riab_env* env, const riab
   if (agents->n_agents == 0) return 0;
   const unsigned grid = (unsigned)((agents->n_agents + 127) / 128);
   const bool rec = io->collision_mask || io->first_hit || io->n_iters;
-  if (rec) k_agent_update<true><<<grid, 128, 0, (cudaStream_t)stream>>>(*agents, *prm, *io, ek);
-  else k_agent_update<false><<<grid, 128, 0, (cudaStream_t)stream>>>(*agents, *prm, *io, ek);
+  MotionDerived md;
+  derive_motion(*prm, md);
+  if (rec) k_agent_update<true><<<grid, 128, 0, (cudaStream_t)stream>>>(*agents, *prm, md, *io, ek);
+  else k_agent_update<false><<<grid, 128, 0, (cudaStream_t)stream>>>(*agents, *prm, md, *io, ek);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   return 0;

@@ -52,6 +52,26 @@ RIAB_HD void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   }
 }
 
+// Philox4x32-R with the round keys precomputed (warp-uniform): 2 wide multiplies + 2 three-input
+// XORs per round.
+template <int R>
+RIAB_DEV void philox_keyed(uint32_t (&c)[4], const uint32_t (&rk)[2 * R]) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    unsigned long long p0, p1;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(c[0]), "r"(0xD2511F53u));
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(c[2]), "r"(0xCD9E8D57u));
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ rk[2 * i], n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ rk[2 * i + 1];
+    c[1] = (uint32_t)p1; c[3] = (uint32_t)p0; c[0] = n0; c[2] = n2;
+  }
+}
+template <int R>
+RIAB_DEV void philox_round_keys(uint32_t (&rk)[2 * R], unsigned long long seed) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < R; ++i) { rk[2 * i] = k0; rk[2 * i + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
 // Stream ids (third counter word, top byte)
 enum : uint32_t { RIAB_STREAM_AGENT_OU = 0, RIAB_STREAM_CELL_NOISE = 1, RIAB_STREAM_SPIKES = 2, RIAB_STREAM_MEASURE = 3 };
 

@@ -34,12 +34,51 @@ RIAB_DEV void store_agent(const riab_agents& ag, int64_t i, const AgentState& s)
   ag.distance_to_closest_wall[i] = s.dclose;
 }
 
+// Per-call scalars that are the same for every agent, computed once on the host with
+// the reference's operation order (plain IEEE double arithmetic, no contraction).
+struct MotionDerived {
+  double w_theta, w_sigma;      // rotational OU: theta = 1/tau, sigma = sqrt(2 std^2 / (tau dt))   utils.py:364-366
+  double v_theta, v_sigma;      // speed OU (noise_scale = 1)
+  double two_sm2;               // 2 * speed_mean_kw^2                                          utils.py:418
+  double drift_theta;           // 1 / (speed_coherence_time / ratio)                           Agent.py:340
+  double v0, k, d, d2;          // wall_repel_strength * speed_mean, v0^2/d^2, d, d*d           Agent.py:367-389
+  double cv, cp;                // 3 (1-thig)^2, 6 thig^2                                       Agent.py:399,415
+  double hd_a, hd_b;            // 1 - dt/tau, dt/tau                                           Agent.py:498
+  double half_sm;               // 0.5 * speed_mean                                             Agent.py:439
+};
+
+inline void derive_motion(const riab_motion_params& p, MotionDerived& m) {
+  const double dt = p.dt;
+  m.w_theta = 1.0 / p.rotational_velocity_coherence_time_kw;
+  m.w_sigma = sqrt((2.0 * (p.rotational_velocity_std_kw * p.rotational_velocity_std_kw)) /
+                   (p.rotational_velocity_coherence_time_kw * dt));
+  m.v_theta = 1.0 / p.speed_coherence_time_kw;
+  m.v_sigma = sqrt((2.0 * (1.0 * 1.0)) / (p.speed_coherence_time_kw * dt));
+  m.two_sm2 = 2.0 * (p.speed_mean_kw * p.speed_mean_kw);
+  m.drift_theta = 1.0 / (p.speed_coherence_time / p.drift_to_random_strength_ratio);
+  m.d = p.wall_repel_distance_kw;
+  m.v0 = p.wall_repel_strength_kw * p.speed_mean;
+  m.d2 = m.d * m.d;
+  m.k = (m.v0 * m.v0) / m.d2;
+  m.cv = 3.0 * ((1.0 - p.thigmotaxis_kw) * (1.0 - p.thigmotaxis_kw));
+  m.cp = 6.0 * (p.thigmotaxis_kw * p.thigmotaxis_kw);
+  m.hd_b = dt / p.head_direction_smoothing_timescale;
+  m.hd_a = 1.0 - m.hd_b;
+  m.half_sm = 0.5 * p.speed_mean;
+}
+
 // utils.ornstein_uhlenbeck (utils.py:347-368): returns dx; `n` is the standard
 // normal, np.random.normal(scale=dt) == dt*n.
-RIAB_DEV D ou_dx(D dt, D x, D drift, D noise_scale, D tau, D n) {
-  const D sigma = dsqrt((D(2.0) * (noise_scale * noise_scale)) / (tau * dt));
-  const D theta = D(1.0) / tau;
+RIAB_DEV D ou_dx(D dt, D x, D drift, D theta, D sigma, D n) {
   return theta * (drift - x) * dt + sigma * (dt * n);
+}
+
+// 0 < num/den < 1 decided without the division.  Exactly the IEEE result: for finite
+// operands fl(num/den) > 0 <=> num, den share a sign (num != 0), and fl(num/den) < 1 <=>
+// |num| < |den|; NaN / zero denominators compare false like the reference's NaN / inf.
+RIAB_DEV bool unit_open(D num, D den) {
+  const bool same = (num.v > 0.0 && den.v > 0.0) || (num.v < 0.0 && den.v < 0.0);
+  return same && (fabs(num.v) < fabs(den.v));
 }
 
 // utils.get_angle for a 2-vector (utils.py:231-273): atan2(y, x+1e-6) mod 2pi
@@ -51,7 +90,7 @@ RIAB_DEV double get_angle(double x, double y) {
 // REC: write the per-iteration collision masks (parity taps).
 template <bool REC>
 RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W, const riab_motion_params& p,
-                          const double* __restrict__ ext, double xi1, double xi2, bool has_drift, double drx,
+                          const MotionDerived& m, const double* __restrict__ ext, double xi1, double xi2, bool has_drift, double drx,
                           double dry, double fallback_n1, double fallback_n2, uint8_t* __restrict__ mask,
                           int32_t* __restrict__ first_hit, int32_t* __restrict__ n_iters_out) {
   const D dt(p.dt);
@@ -60,8 +99,7 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
 
   // ---- A1: rotational velocity OU + rotation (Agent.py:289-296, utils.py:293-301)
   D rot(s.rot);
-  rot = rot + ou_dx(dt, rot, D(p.rotational_velocity_drift_kw), D(p.rotational_velocity_std_kw),
-                    D(p.rotational_velocity_coherence_time_kw), D(xi1));
+  rot = rot + ou_dx(dt, rot, D(p.rotational_velocity_drift_kw), D(m.w_theta), D(m.w_sigma), D(xi1));
   double sn, cs;
   sincos((rot * dt).v, &sn, &cs);
   D vx = D(cs) * D(s.vx) + D(-sn) * D(s.vy);
@@ -72,10 +110,10 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
   if (speed.v == 0.0) { vx = D(1e-8); vy = D(0.0); speed = D(1e-8); }
   {
     const D sm(p.speed_mean_kw);
-    double u = (D(1.0) - D(exp((-(speed * speed) / (D(2.0) * (sm * sm))).v))).v;
+    double u = (D(1.0) - D(exp((-(speed * speed) / D(m.two_sm2)).v))).v;
     u = fmin(fmax(1e-6, u), 1.0 - 1e-6);
     D z(normcdfinv(u));
-    z = z + ou_dx(dt, z, D(0.0), D(1.0), D(p.speed_coherence_time_kw), D(xi2));
+    z = z + ou_dx(dt, z, D(0.0), D(m.v_theta), D(m.v_sigma), D(xi2));
     const D cdf(normcdf(z.v));
     D speed_new = sm * dsqrt(D(-2.0) * D(log((D(1.0) - cdf).v)));
     if (p.speed_std == 0.0) speed_new = sm;
@@ -85,8 +123,7 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
 
   // ---- A3: drift towards drift_velocity (Agent.py:324-341; noise_scale = 0)
   if (has_drift) {
-    const D tau = D(p.speed_coherence_time) / D(p.drift_to_random_strength_ratio);
-    const D theta = D(1.0) / tau;
+    const D theta(m.drift_theta);
     vx = vx + (theta * (D(drx) - vx) * dt + D(0.0));
     vy = vy + (theta * (D(dry) - vy) * dt + D(0.0));
   }
@@ -94,11 +131,10 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
   // ---- A4: wall repulsion (Agent.py:343-421, utils.py:121-184; zero jitter)
   D px(s.px), py(s.py);
   if (p.wall_repel_strength_kw != 0.0 && W > 0) {
-    const D d(p.wall_repel_distance_kw);
-    const D v0 = D(p.wall_repel_strength_kw) * D(p.speed_mean);
-    const D k = (v0 * v0) / (d * d);
+    const D d(m.d), v0(m.v0), k(m.k), dd2(m.d2);
     D accx(0.0), accy(0.0), spx(0.0), spy(0.0);
-    double dmin = INFINITY;
+    double dmin2 = INFINITY;
+    const double near2 = m.d2 * (1.0 + 1e-9);          // conservative pre-filter for x <= d
     for (int w = 0; w < W; ++w) {
       const D ax(walls[4 * w]), ay(walls[4 * w + 1]), bx(walls[4 * w + 2]), by(walls[4 * w + 3]);
       const D ddx = px - ax, ddy = py - ay, sx = bx - ax, sy = by - ay;
@@ -106,24 +142,25 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
       if (l.v > 1.0) l = D(1.0);
       if (l.v < 0.0) l = D(0.0);
       const D qx = px - (ax + l * sx), qy = py - (ay + l * sy);
-      const D x = dsqrt(qx * qx + qy * qy);
-      const D ux = qx / x, uy = qy / x;
-      dmin = (x.v < dmin || x.v != x.v) ? x.v : dmin;
-      D acc(0.0), spd(0.0);
-      if (x <= d) {
-        acc = k * (d - x);
-        const D dx2 = (d - x) * (d - x);
-        spd = v0 * (D(1.0) - dsqrt(D(1.0) - dx2 / (d * d)));
+      const D x2 = qx * qx + qy * qy;
+      dmin2 = (x2.v < dmin2 || x2.v != x2.v) ? x2.v : dmin2;     // min of the distances == sqrt(min x^2)
+      if (x2.v <= near2 || x2.v != x2.v) {
+        // only walls within wall_repel_distance contribute (the others add exact zeros, Agent.py:390-393)
+        const D x = dsqrt(x2);
+        if (x <= d) {
+          const D ux = qx / x, uy = qy / x;
+          const D acc = k * (d - x);
+          const D dx2 = (d - x) * (d - x);
+          const D spd = v0 * (D(1.0) - dsqrt(D(1.0) - dx2 / dd2));
+          accx = accx + acc * ux; accy = accy + acc * uy;
+          spx = spx + spd * ux; spy = spy + spd * uy;
+        }
       }
-      if (w == 0) { accx = acc * ux; accy = acc * uy; spx = spd * ux; spy = spd * uy; }
-      else { accx = accx + acc * ux; accy = accy + acc * uy; spx = spx + spd * ux; spy = spy + spd * uy; }
     }
-    s.dclose = dmin;
-    const D th(p.thigmotaxis_kw);
-    const D cv = D(3.0) * ((D(1.0) - th) * (D(1.0) - th));
+    s.dclose = __dsqrt_rn(dmin2);
+    const D cv(m.cv), cp(m.cp);
     vx = vx + cv * (accx * dt);
     vy = vy + cv * (accy * dt);
-    const D cp = D(6.0) * (th * th);
     px = px + cp * (spx * dt);
     py = py + cp * (spy * dt);
   }
@@ -143,9 +180,9 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
       const D d0x = ppx - ax, d0y = ppy - ay;       // b0 - a0
       const D sax = bx - ax, say = by - ay;
       const D sapx = -say, sapy = sax;
-      const D la = (d0x * sbpx + d0y * sbpy) / (sax * sbpx + say * sbpy);
-      const D lb = ((-d0x) * sapx + (-d0y) * sapy) / (sbx * sapx + sby * sapy);
-      const bool hit = (la.v > 0.0) && (la.v < 1.0) && (lb.v > 0.0) && (lb.v < 1.0);
+      // 0 < l_a < 1 and 0 < l_b < 1 (utils.py:96-106) without the two divisions (unit_open is exact)
+      const bool hit = unit_open(d0x * sbpx + d0y * sbpy, sax * sbpx + say * sbpy) &&
+                       unit_open((-d0x) * sapx + (-d0y) * sapy, sbx * sapx + sby * sapy);
       if (REC && mask != nullptr && iters < RIAB_MAX_REC_ITERS) mask[iters * W + w] = hit ? 1 : 0;
       if (hit && first < 0) first = w;
     }
@@ -161,7 +198,7 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
     parx = parx / npar; pary = pary / npar; perx = perx / nper; pery = pery / nper;
     const D dpar = vx * parx + vy * pary, dper = vx * perx + vy * pery;
     D nvx = parx * dpar - perx * dper, nvy = pary * dpar - pery * dper;
-    const D f = (D(0.5) * D(p.speed_mean)) / dsqrt(nvx * nvx + nvy * nvy);
+    const D f = D(m.half_sm) / dsqrt(nvx * nvx + nvy * nvy);
     vx = f * nvx; vy = f * nvy;
     px = ppx + vx * dt; py = ppy + vy * dt;
   }
@@ -175,7 +212,14 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
 
   // ---- A8: measured velocity / rotational velocity (Agent.py:444-472)
   D mvx = (px - ppx) / dt, mvy = (py - ppy) / dt;
-  if (dsqrt(mvx * mvx + mvy * mvy).v == 0.0) { mvx = D(1e-8 * fallback_n1); mvy = D(1e-8 * fallback_n2); }
+  if (dsqrt(mvx * mvx + mvy * mvy).v == 0.0) {
+    // 1e-8 * randn(2) in the reference; here a Philox draw keyed by the (bit-cast) seed / step^agent words
+    uint32_t c[4] = {(uint32_t)__double_as_longlong(fallback_n2), (uint32_t)(__double_as_longlong(fallback_n2) >> 32),
+                     0x4d454153u, RIAB_STREAM_MEASURE << 24};
+    philox4x32_10(c, (uint32_t)__double_as_longlong(fallback_n1), (uint32_t)(__double_as_longlong(fallback_n1) >> 32));
+    mvx = D(1e-8 * (2.0 * u01_53(c[0], c[1]) - 1.0));
+    mvy = D(1e-8 * (2.0 * u01_53(c[2], c[3]) - 1.0));
+  }
   {
     const double now = get_angle(mvx.v, mvy.v), before = get_angle(pmvx, pmvy);
     double x = np_mod(__dsub_rn(now, before), 2.0 * M_PI);      // utils.pi_domain (utils.py:331-341)
@@ -190,7 +234,7 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
     const D tau(p.head_direction_smoothing_timescale);
     if (tau.v <= dt.v) { s.hdx = ix.v; s.hdy = iy.v; }
     else {
-      const D a = D(1.0) - dt / tau, b = dt / tau;
+      const D a(m.hd_a), b(m.hd_b);
       const D hx = D(s.hdx) * a + b * ix, hy = D(s.hdy) * a + b * iy;
       const D nh = dsqrt(hx * hx + hy * hy);
       s.hdx = (hx / nh).v; s.hdy = (hy / nh).v;

@@ -160,13 +160,13 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     const float dx = r0.x - r.cx[i], dy = r0.y - r.cy[i];
     d2[i] = fmaf(dy, dy, dx * dx);
   }
-  bool blocked[4] = {false, false, false, false};
+  // final squared distances (blocked pairs get distance 1000, Environment.py:730)
+  float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
   if (WI > 0) {
     // With s = sign(f_c) and the agent on the other side of the wall's line (opp):
     //   |D| = |f_c| + |f_p|,  M' = s*M = |f_c| t_p + |f_p| t_c  (a convex combination of t_p, t_c),
     //   blocked  <=>  opp and 0 < M' < |D|  <=>  opp and min(M', |D| - M') > 0.
     // |min(..)| below the band => re-evaluate in float64 (conservatively, regardless of opp).
-    float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
 #pragma unroll
     for (int j = 0; j < WI; ++j) {
       float fp, tp;
@@ -176,7 +176,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
         fp = pw.x; tp = pw.y;
       }
       const float afp = fabsf(fp);
-      const float band = c.eps[j];                       // absolute band (eps * max |D| over the box)
+      const float band = c.eps[j];                       // absolute band (eps * max |D| * max |t| over the box)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float fc = r.fc[j][i];
@@ -184,50 +184,42 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
         const float Da = fabsf(fc) + afp;
         const float mn = fminf(Mp, Da - Mp);
         const bool opp = (__float_as_int(fc) ^ __float_as_int(fp)) < 0;   // strictly opposite sides (or a zero)
-        const bool hit = opp & (mn > 0.f);
-        dd[i] = hit ? 1.0e6f : dd[i];                    // distance 1000 (Environment.py:730)
+        dd[i] = (opp & (mn > 0.f)) ? 1.0e6f : dd[i];
         unsure = unsure | !(fabsf(mn) >= band);          // also true for NaN (degenerate centre / agent)
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) blocked[i] = dd[i] != d2[i];
     if (unsure) {                                        // rare: redo the group's flags with the reference's float64 test
       const unsigned m = place_blocked_exact4<WI>(c, cell0, pos64, inner64);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) blocked[i] = (m >> i) & 1u;
+      for (int i = 0; i < 4; ++i) dd[i] = ((m >> i) & 1u) ? 1.0e6f : d2[i];
     }
   }
-  const bool geodesic = (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
+  const bool geodesic = (DESC < 0) && (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
   const int desc = (DESC >= 0) ? DESC : c.desc;
   if (desc != RIAB_PC_TOP_HAT && !geodesic) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float dd = (WI > 0 && blocked[i]) ? 1.0e6f : d2[i];       // distance 1000 (Environment.py:730)
-      out[i] = fmaf(place_profile<DESC>(dd, r.k[i], c.desc), c.span, c.min_fr);   // Neurons.py:978-980
-    }
+    for (int i = 0; i < 4; ++i)
+      out[i] = fmaf(place_profile<DESC>(dd[i], r.k[i], c.desc), c.span, c.min_fr);   // Neurons.py:978-980
     return;
   }
   float2 ep = make_float2(0.f, 0.f);
   if (geodesic) ep = *reinterpret_cast<const float2*>(rec + 2 + 2 * PLACE_MAX_WI);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float dd = d2[i];
-    if (WI > 0) {
-      if (geodesic) {
-        // Environment.py:745-773: min over the wall ends that lie inside the box
-        float via = INFINITY;
-        if (c.ep_valid & 1) via = r.ce0[i] + ep.x;
-        if (c.ep_valid & 2) via = fminf(via, r.ce1[i] + ep.y);
-        dd = blocked[i] ? via * via : dd;
-      } else {
-        dd = blocked[i] ? 1.0e6f : dd;
-      }
+    const bool blocked = (WI > 0) && (dd[i] != d2[i]);
+    float dv = dd[i];
+    if (geodesic && blocked) {
+      // Environment.py:745-773: min over the wall ends that lie inside the box
+      float via = INFINITY;
+      if (c.ep_valid & 1) via = r.ce0[i] + ep.x;
+      if (c.ep_valid & 2) via = fminf(via, r.ce1[i] + ep.y);
+      dv = via * via;
     }
     float v;
     if (desc == RIAB_PC_TOP_HAT) {
       // Neurons.py:975-976: 1*(dist < widths) with the scalar `widths`
-      bool in = dd < c.top_hat_w2;
-      if (fabsf(dd - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !(WI > 0 && blocked[i])) {
+      bool in = dv < c.top_hat_w2;
+      if (fabsf(dv - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !blocked) {
         const int cell = cell0 + i;
         if (cell < c.n_cells) {
           const D ex = D(c.centres64[2 * cell]) - D(pos64[0]), ey = D(c.centres64[2 * cell + 1]) - D(pos64[1]);
@@ -236,7 +228,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       }
       v = in ? 1.f : 0.f;
     } else {
-      v = place_profile<DESC>(dd, r.k[i], c.desc);
+      v = place_profile<DESC>(dv, r.k[i], c.desc);
     }
     out[i] = fmaf(v, c.span, c.min_fr);
   }

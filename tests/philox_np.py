@@ -56,4 +56,6 @@ def spike_uniforms(seed, step, agents, n_cells, pop=0):
     a = np.asarray(agents, dtype=np.uint64)[:, None]
     g = np.arange(groups, dtype=np.uint64)[None, :]
     r = philox4x32(counter(a, g, step, STREAM_SPIKES, pop), (seed & 0xFFFFFFFF, seed >> 32), rounds=7)
-    return u01_24(r).reshape(len(agents), groups * 4)[:, :n_cells]
+    # device: fma(float32(x), 2^-32, 2^-33) -- float32(x) rounds to nearest, the fma rounds once more
+    u = (r.astype(np.float32).astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
+    return u.reshape(len(agents), groups * 4)[:, :n_cells]
