@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libriab_b200.so")
+LIB = os.environ.get("RIAB_LIB", os.path.join(HERE, "libriab_b200.so"))
 SOURCES = ["riab_b200.cu"]
 HEADERS = ["riab_common.cuh", "riab_motion.cuh", "riab_place.cuh", "riab_grid.cuh", "riab_bvc.cuh",
            os.path.join("..", "..", "include", "riab_b200.h")]

@@ -2,11 +2,10 @@
 //
 // Kernel inventory
 //   k_agent_update      Agent.update, one agent per thread (float64)
-//   k_tile<P,FUSED>     (agents x cells) tile kernel for PlaceCells / GridCells:
-//                       [FUSED: warp 0 runs Agent.update for the tile's 32 agents]
-//                       -> per-agent float32 records in shared memory -> every thread
-//                       streams its 4 cells (registers) over the tile's agents and
-//                       writes float4 rate rows (+ OU noise, + bit-packed spikes)
+//   k_step<P,MODE,..>   persistent warp-specialised step kernel for PlaceCells / GridCells:
+//                       producer warps run Agent.update (float64) and publish per-agent float32
+//                       records through an mbarrier ring; consumer warps keep 4 cells per thread
+//                       in registers and stream float4 rate rows (+ OU noise, + bit-packed spikes)
 //   k_bvc_rays<FUSED>   BVC phase A (float64 rays) [+ Agent.update]
 //   k_bvc_integrate     BVC phase B (float32 angular integral, TMA-staged tables)
 #include <atomic>
@@ -262,9 +261,15 @@ struct GridPolicy {
 //                        (mbarrier empty[slot]).
 // The float64 motion latency (a ~2.5k-instruction dependent chain) is thereby hidden behind the
 // HBM-bound rate writes of earlier tiles instead of idling the CTA.
-constexpr int MW = 4;     // producer warps
-constexpr int RW = 16;    // consumer warps
-constexpr int NS = 8;     // ring slots (multiple of MW)
+#ifndef RIAB_MW
+#define RIAB_MW 4
+#endif
+#ifndef RIAB_RW
+#define RIAB_RW 16
+#endif
+constexpr int MW = RIAB_MW;   // producer warps
+constexpr int RW = RIAB_RW;   // consumer warps
+constexpr int NS = (MW >= 8) ? MW : 2 * MW;    // ring slots (multiple of MW; static smem <= 48 KB)
 constexpr int STEP_THREADS = (MW + RW) * 32;
 
 template <int REC>
@@ -275,7 +280,7 @@ struct __align__(16) StepSlot {
   int pad[3];
 };
 
-template <class P, bool MOTION, bool SPIKES, bool NOISE>
+template <class P, int MODE, bool SPIKES, bool NOISE>
 __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
                                                           const riab_step_io io, const typename P::Const pc, const OutK out,
@@ -302,11 +307,29 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
       const long long tile = (long long)blockIdx.x + q * gridDim.x;
       const long long a0 = tile * TA;
       const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
+      if (MODE == 2) {
+        // skewed: publish the records of the CURRENT positions first, then advance the agents
+        // (the next launch's rates) -- consumers never wait for the float64 motion chain.
+        if (lane < na) {
+          const long long i = a0 + lane;
+          const double px = ag.pos[2 * i], py = ag.pos[2 * i + 1];
+          s_slot[s].pos[lane][0] = px;
+          s_slot[s].pos[lane][1] = py;
+          P::record(s_slot[s].rec[lane], px, py, s_walls, pc, env);
+        }
+        if (lane == 0) s_slot[s].na = na;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[s]);
+        if (lane < na) {
+          AgentState st;
+          agent_update_one<false>(ag, mp, md, io, env, s_walls, a0 + lane, st);
+        }
+        continue;
+      }
       if (lane < na) {
         const long long i = a0 + lane;
         double px, py;
-        if (MOTION) {
-          AgentState st;
+        if (MODE == 1) {          AgentState st;
           agent_update_one<false>(ag, mp, md, io, env, s_walls, i, st);
           px = st.px; py = st.py;
         } else {
@@ -608,7 +631,9 @@ int make_grid(const riab_grid_cells* gc, const EnvK& env, GridConst& c) {
 
 int g_num_sms = 0;
 
-template <class P, bool FUSED>
+// MODE 0: rates for given positions; 1: motion -> rates (one step); 2: skewed (rates of the current
+// positions, then motion for the NEXT step -- used inside riab_run).
+template <class P, int MODE>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                 const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   if (n_rows == 0) return 0;
@@ -622,33 +647,33 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   const bool spikes = out.spikes != nullptr, noise = out.noise != nullptr;
   MotionDerived md;
   memset(&md, 0, sizeof(md));
-  if (FUSED) derive_motion(mp, md);
-  if (noise) k_step<P, FUSED, true, true><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else if (spikes) k_step<P, FUSED, true, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else k_step<P, FUSED, false, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  if (MODE != 0) derive_motion(mp, md);
+  if (noise) k_step<P, MODE, true, true><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else if (spikes) k_step<P, MODE, true, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else k_step<P, MODE, false, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-template <bool FUSED, int DESC>
+template <int MODE, int DESC>
 int launch_place_d(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                    const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   const int wi = pc.n_inner;
-  if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi <= 4) return launch_tile<PlacePolicy<4, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  return launch_tile<PlacePolicy<8, DESC>, FUSED>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi <= 4) return launch_tile<PlacePolicy<4, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  return launch_tile<PlacePolicy<8, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
 }
 
-template <bool FUSED>
+template <int MODE>
 int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                  const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   // the common Gaussian profile without geodesic detours gets a compile-time specialisation
   if (pc.desc == RIAB_PC_GAUSSIAN && pc.geometry != RIAB_GEOM_GEODESIC)
-    return launch_place_d<FUSED, RIAB_PC_GAUSSIAN>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  return launch_place_d<FUSED, -1>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+    return launch_place_d<MODE, RIAB_PC_GAUSSIAN>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  return launch_place_d<MODE, -1>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
 }
 
 template <bool FUSED>
@@ -819,7 +844,7 @@ int riab_place_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, 
   riab_agents ag; memset(&ag, 0, sizeof(ag));
   riab_motion_params mp; memset(&mp, 0, sizeof(mp));
   riab_step_io io; memset(&io, 0, sizeof(io));
-  return launch_place<false>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+  return launch_place<0>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ GridCells
@@ -866,7 +891,7 @@ int riab_grid_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, c
   riab_agents ag; memset(&ag, 0, sizeof(ag));
   riab_motion_params mp; memset(&mp, 0, sizeof(mp));
   riab_step_io io; memset(&io, 0, sizeof(io));
-  return launch_tile<GridPolicy, false>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+  return launch_tile<GridPolicy, 0>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------ BVC
@@ -923,9 +948,9 @@ int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, co
 }
 
 // ----------------------------------------------------------------- fused step
-// FUSED: motion + rates of one population; !FUSED: rates for agents->pos as it is.
+// MODE 1: motion + rates of one population; 0: rates for agents->pos as it is; 2: skewed (riab_run).
 }  // extern "C"
-template <bool FUSED>
+template <int MODE>
 static int neurons_update_impl(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
                                const riab_step_io* io, int32_t cells_kind, const void* cells,
                                const riab_neuron_noise* noise, const riab_rates_out* out, void* stream) {
@@ -933,36 +958,37 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
   OutK ok;
   int rc;
   if ((rc = check_agents(agents)) || (rc = make_env(env, ek))) return rc;
-  if (FUSED && (rc = check_motion(prm))) return rc;
-  if (cells == nullptr || (FUSED && io == nullptr)) return fail(RIAB_ERR_INVALID, "io / cells NULL");
-  riab_motion_params mp0; memset(&mp0, 0, sizeof(mp0));
-  riab_step_io io0; memset(&io0, 0, sizeof(io0));
-  if (FUSED && (io->collision_mask || io->first_hit || io->n_iters) && cells_kind != RIAB_CELLS_BVC) {
+  if (MODE != 0 && (rc = check_motion(prm))) return rc;
+  if (cells == nullptr || (MODE != 0 && io == nullptr)) return fail(RIAB_ERR_INVALID, "io / cells NULL");
+  if (MODE == 1 && (io->collision_mask || io->first_hit || io->n_iters) && cells_kind != RIAB_CELLS_BVC) {
     // parity taps are only implemented in the stand-alone motion kernel
     if ((rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
-    return neurons_update_impl<false>(agents, env, prm, io, cells_kind, cells, noise, out, stream);
+    return neurons_update_impl<0>(agents, env, prm, io, cells_kind, cells, noise, out, stream);
   }
-  const riab_motion_params& mp = FUSED ? *prm : mp0;
-  const riab_step_io& sio = FUSED ? *io : io0;
+  riab_motion_params mp0; memset(&mp0, 0, sizeof(mp0));
+  riab_step_io io0; memset(&io0, 0, sizeof(io0));
+  const riab_motion_params& mp = (MODE != 0) ? *prm : mp0;
+  const riab_step_io& sio = (MODE != 0) ? *io : io0;
   const double dt = (prm != nullptr) ? prm->dt : (noise ? (double)noise->dt : 1.0);
-  const double* pos_in = FUSED ? nullptr : agents->pos;
+  const double* pos_in = (MODE == 1) ? nullptr : agents->pos;
   cudaStream_t s = (cudaStream_t)stream;
   if (cells_kind == RIAB_CELLS_PLACE) {
     const riab_place_cells* pc = (const riab_place_cells*)cells;
     PlaceConst c;
     if ((rc = make_place(pc, ek, c)) || (rc = make_out(out, noise, pc->n_cells, dt, agents->id_offset, ok))) return rc;
-    return launch_place<FUSED>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
+    return launch_place<MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_GRID) {
     const riab_grid_cells* gc = (const riab_grid_cells*)cells;
     GridConst c;
     if ((rc = make_grid(gc, ek, c)) || (rc = make_out(out, noise, gc->n_cells, dt, agents->id_offset, ok))) return rc;
-    return launch_tile<GridPolicy, FUSED>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
+    return launch_tile<GridPolicy, MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_BVC) {
+    if (MODE == 2) return fail(RIAB_ERR_UNSUPPORTED, "BVC populations are stepped unskewed");
     const riab_bvc_cells* bvc = (const riab_bvc_cells*)cells;
     if ((rc = make_out(out, noise, bvc->n_cells, dt, agents->id_offset, ok))) return rc;
-    return launch_bvc<FUSED>(ek, *agents, mp, sio, bvc, ok, pos_in, agents->n_agents, out->bvc_scratch, nullptr, s);
+    return launch_bvc<(MODE == 1)>(ek, *agents, mp, sio, bvc, ok, pos_in, agents->n_agents, out->bvc_scratch, nullptr, s);
   }
   return fail(RIAB_ERR_INVALID, "bad cells_kind %d", cells_kind);
 }
@@ -971,12 +997,12 @@ extern "C" {
 int riab_step_fused(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
                     const riab_step_io* io, int32_t cells_kind, const void* cells, const riab_neuron_noise* noise,
                     const riab_rates_out* out, void* stream) {
-  return neurons_update_impl<true>(agents, env, prm, io, cells_kind, cells, noise, out, stream);
+  return neurons_update_impl<1>(agents, env, prm, io, cells_kind, cells, noise, out, stream);
 }
 
 int riab_neurons_update(const riab_agents* agents, const riab_env* env, int32_t cells_kind, const void* cells,
                         const riab_neuron_noise* noise, const riab_rates_out* out, void* stream) {
-  return neurons_update_impl<false>(agents, env, nullptr, nullptr, cells_kind, cells, noise, out, stream);
+  return neurons_update_impl<0>(agents, env, nullptr, nullptr, cells_kind, cells, noise, out, stream);
 }
 
 int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm, const riab_step_io* io,
@@ -985,17 +1011,34 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
   if (agents == nullptr || io == nullptr || n_pops < 0 || (n_pops > 0 && pops == nullptr))
     return fail(RIAB_ERR_INVALID, "riab_run: bad argument");
   const int64_t A = agents->n_agents;
-  for (int64_t st = 0; st < n_steps; ++st) {
+  // Skewed schedule (population 0 is a Place/Grid population): motion(0) alone, then per step one
+  // kernel that evaluates rates(s) of the current positions while its producer warps already run
+  // motion(s+1); the last step is rates only.  Same results as the plain sequence, but the
+  // float64 motion chain never gates the rate warps.
+  const bool skew = n_pops >= 1 && pops[0].kind != RIAB_CELLS_BVC && n_steps >= 1 && io->xi == nullptr &&
+                    !io->collision_mask && !io->first_hit && !io->n_iters;
+  auto step_io = [&](int64_t st) {
     riab_step_io sio = *io;
     sio.step = io->step + (uint64_t)st;
     sio.history_row = nullptr;
     if (hist != nullptr && hist->ring != nullptr && hist->ring_rows > 0)
       sio.history_row = hist->ring + (size_t)((hist->ring_next + st) % hist->ring_rows) * A * 8;
+    return sio;
+  };
+  int rc;
+  if (skew) {
+    const riab_step_io s0 = step_io(0);
+    if ((rc = riab_agent_update(agents, env, prm, &s0, stream))) return rc;
+  }
+  for (int64_t st = 0; st < n_steps; ++st) {
+    const riab_step_io sio = step_io(st);
     if (n_pops == 0) {
-      const int rc = riab_agent_update(agents, env, prm, &sio, stream);
-      if (rc) return rc;
+      if ((rc = riab_agent_update(agents, env, prm, &sio, stream))) return rc;
+      continue;
     }
-    for (int p = 0; p < n_pops; ++p) {
+    // populations 1.. first (they read the positions of step st), population 0 last (it may advance them)
+    for (int pi = 0; pi < n_pops; ++pi) {
+      const int p = skew ? ((pi + 1) % n_pops) : pi;
       const riab_population& pp = pops[p];
       if (pp.rates_ring == nullptr || pp.ring_rows <= 0) return fail(RIAB_ERR_INVALID, "population %d: no rates ring", p);
       const size_t slot = (size_t)((pp.ring_next + st) % pp.ring_rows);
@@ -1009,8 +1052,11 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
       riab_neuron_noise nz = pp.noise;
       nz.step = pp.noise.step + (uint64_t)st;
       nz.dt = (float)prm->dt;
-      const int rc = (p == 0) ? riab_step_fused(agents, env, prm, &sio, pp.kind, pp.cells, &nz, &ro, stream)
-                              : riab_neurons_update(agents, env, pp.kind, pp.cells, &nz, &ro, stream);
+      if (p == 0 && !skew) rc = riab_step_fused(agents, env, prm, &sio, pp.kind, pp.cells, &nz, &ro, stream);
+      else if (p == 0 && st + 1 < n_steps) {
+        const riab_step_io nxt = step_io(st + 1);          // the motion it runs belongs to step st+1
+        rc = neurons_update_impl<2>(agents, env, prm, &nxt, pp.kind, pp.cells, &nz, &ro, stream);
+      } else rc = riab_neurons_update(agents, env, pp.kind, pp.cells, &nz, &ro, stream);
       if (rc) return rc;
     }
   }

@@ -221,10 +221,13 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
     mvy = D(1e-8 * (2.0 * u01_53(c[2], c[3]) - 1.0));
   }
   {
-    const double now = get_angle(mvx.v, mvy.v), before = get_angle(pmvx, pmvy);
-    double x = np_mod(__dsub_rn(now, before), 2.0 * M_PI);      // utils.pi_domain (utils.py:331-341)
-    if (x > M_PI) x = __dadd_rn(-2.0 * M_PI, x);
-    s.mrot = __ddiv_rn(x, dt.v);
+    // utils.pi_domain(get_angle(now) - get_angle(before)) (utils.py:231-273, :331-341).  get_angle is
+    // atan2(y, x + 1e-6) mod 2pi; the wrapped difference of the two angles equals the signed angle
+    // between the eps-shifted vectors, atan2(cross, dot): one atan2 instead of two plus three fmods
+    // (identical up to rounding; pi_domain maps to (-pi, pi] like atan2).
+    const double x1 = __dadd_rn(pmvx, 1e-6), y1 = pmvy, x2 = __dadd_rn(mvx.v, 1e-6), y2 = mvy.v;
+    const double ang = atan2(x1 * y2 - y1 * x2, x1 * x2 + y1 * y2);
+    s.mrot = __ddiv_rn(ang, dt.v);
   }
 
   // ---- A9: head direction low-pass (Agent.py:474-500)
