@@ -221,6 +221,7 @@ struct PlacePolicy {
   using Const = PlaceConst;
   using Regs = PlaceCellRegs<WI>;
   static constexpr int REC = PLACE_REC;
+  static constexpr bool LIGHT = (WI == 0) && (DESC >= 0);   // few instructions per rate: HBM-bound consumers
   static __device__ __forceinline__ void record(float* rec, double px, double py, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
     place_agent_record(rec, px, py, s_walls + 4 * env.nb, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym);
@@ -237,6 +238,7 @@ struct GridPolicy {
   using Const = GridConst;
   using Regs = GridCellRegs;
   static constexpr int REC = 4;
+  static constexpr bool LIGHT = false;    // 36 cell registers per thread do not fit StepCfg<8>'s 56-register consumers
   static __device__ __forceinline__ void record(float* rec, double px, double py, const double*, const Const&,
                                                 const EnvK& env) {
     rec[0] = (float)(px - env.cxm);
@@ -261,16 +263,24 @@ struct GridPolicy {
 //                        (mbarrier empty[slot]).
 // The float64 motion latency (a ~2.5k-instruction dependent chain) is thereby hidden behind the
 // HBM-bound rate writes of earlier tiles instead of idling the CTA.
-#ifndef RIAB_MW
-#define RIAB_MW 4
-#endif
-#ifndef RIAB_RW
-#define RIAB_RW 16
-#endif
-constexpr int MW = RIAB_MW;   // producer warps
-constexpr int RW = RIAB_RW;   // consumer warps
-constexpr int NS = (MW >= 8) ? MW : 2 * MW;    // ring slots (multiple of MW; static smem <= 48 KB)
-constexpr int STEP_THREADS = (MW + RW) * 32;
+// Warp-role configuration.  The register file is re-balanced between the roles with setmaxnreg
+// (producers run ~130-register float64 code, consumers need 56..88):
+//   StepCfg<4>: 4 producer + 16 consumer warps (640 threads x 96 regs): heavy consumers
+//               (line-of-sight / spikes / noise) -- the consumers set the pace, 4 producers suffice.
+//   StepCfg<8>: 8 producer + 16 consumer warps (768 threads x 80 regs): light consumers (Euclidean
+//               Gaussian / grid cells without spikes) run at the HBM write rate, so the float64
+//               motion chain (~14 us per 32-agent tile) needs twice the producer warps to keep up.
+constexpr int RW = 16;    // consumer warps
+template <int MW_>
+struct StepCfg {
+  static constexpr int MW = MW_;
+  static constexpr int NS = (MW_ >= 8) ? MW_ : 2 * MW_;      // ring slots (multiple of MW; static smem <= 48 KB)
+  static constexpr int THREADS = (MW_ + RW) * 32;
+  static constexpr int REGS_PRODUCER = (MW_ >= 8) ? 128 : 128;
+  static constexpr int REGS_CONSUMER = (MW_ >= 8) ? 56 : 88;
+};
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <int REC>
 struct __align__(16) StepSlot {
@@ -280,12 +290,13 @@ struct __align__(16) StepSlot {
   int pad[3];
 };
 
-template <class P, int MODE, bool SPIKES, bool NOISE>
-__global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const riab_agents ag,
+template <class P, int MODE, bool SPIKES, bool NOISE, class C>
+__global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
                                                           const riab_step_io io, const typename P::Const pc, const OutK out,
                                                           const double* __restrict__ pos_in, const long long n_rows) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
+  constexpr int MW = C::MW, NS = C::NS;
   __shared__ StepSlot<P::REC> s_slot[NS];
   __shared__ uint64_t s_bar, s_full[NS], s_empty[NS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -300,6 +311,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
 
   if (warp < MW) {
     // ------------------------------------------------------------- producers
+    reg_inc<C::REGS_PRODUCER>();
     for (long long q = warp; q < nq; q += MW) {
       const int s = (int)(q % NS);
       const uint32_t k = (uint32_t)(q / NS);
@@ -345,6 +357,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 1) k_step(const EnvK env, const 
     }
   } else {
     // ------------------------------------------------------------- consumers
+    reg_dec<C::REGS_CONSUMER>();
     const int ctid = threadIdx.x - MW * 32;
     constexpr int NC = RW * 32;
     const int CT = pc.n_pad >> 2;                       // cell-threads needed (multiple of 32)
@@ -648,9 +661,10 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (MODE != 0) derive_motion(mp, md);
-  if (noise) k_step<P, MODE, true, true><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else if (spikes) k_step<P, MODE, true, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else k_step<P, MODE, false, false><<<grid, STEP_THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  if (noise) k_step<P, MODE, true, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else if (spikes) k_step<P, MODE, true, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else if (P::LIGHT && MODE != 0) k_step<P, MODE, false, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else k_step<P, MODE, false, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   return 0;

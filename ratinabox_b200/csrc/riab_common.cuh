@@ -90,16 +90,20 @@ RIAB_HD double u01_53(uint32_t hi, uint32_t lo) {
 }
 RIAB_HD float u01_24(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
-// Two standard normals for the agent OU draws (Box-Muller on 2x53-bit uniforms).
+// Two standard normals for the agent OU draws: Philox4x32-10 -> two 32-bit uniforms ->
+// Box-Muller in float32 (logf / sqrtf / sincospif are the accurate single-precision routines),
+// widened to double.  The draws are noise: their float32 resolution is irrelevant to the
+// dynamics, and float32 keeps ~150 dependent float64 operations off the motion chain.
 RIAB_DEV void agent_normals(uint64_t seed, uint64_t step, uint64_t agent, double& n1, double& n2) {
   uint32_t c[4];
   philox_ctr(c, agent, 0u, step, RIAB_STREAM_AGENT_OU, 0u);
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const double u1 = u01_53(c[0], c[1]), u2 = u01_53(c[2], c[3]);
-  const double r = sqrt(-2.0 * log(u1));
-  double s, co;
-  sincospi(2.0 * u2, &s, &co);
-  n1 = r * co; n2 = r * s;
+  const float u1 = fmaf(__uint2float_rn(c[0]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0,1]
+  const float u2 = __uint2float_rn(c[2]) * 2.3283064365386963e-10f;                                  // [0,1]
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, co;
+  sincospif(2.0f * u2, &s, &co);
+  n1 = (double)(r * co); n2 = (double)(r * s);
 }
 
 // ---------------------------------------------------------------------------

@@ -43,11 +43,17 @@ def u01_24(x):
 
 
 def agent_normals(seed, step, agents):
-    """The two standard normals of Agent.update's OU draws (Box-Muller on 2x53-bit uniforms)."""
+    """The two standard normals of Agent.update's OU draws: Box-Muller in float32 on two 32-bit
+    uniforms (mirrors riab_common.cuh: agent_normals; equal up to the last float32 ulps of
+    logf / sincospif)."""
     r = philox4x32(counter(agents, 0, step, STREAM_AGENT_OU), (seed & 0xFFFFFFFF, seed >> 32))
-    u1, u2 = u01_53(r[..., 0], r[..., 1]), u01_53(r[..., 2], r[..., 3])
-    rad = np.sqrt(-2.0 * np.log(u1))
-    return np.stack((rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)), axis=-1)
+    f32 = np.float32
+    u1 = (r[..., 0].astype(f32).astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(f32)
+    u2 = (r[..., 2].astype(f32) * f32(2.0 ** -32)).astype(f32)
+    rad = np.sqrt(f32(-2.0) * np.log(u1)).astype(f32)
+    ang = (f32(2.0) * u2).astype(np.float64) * np.pi
+    return np.stack(((rad * np.cos(ang).astype(f32)).astype(np.float64),
+                     (rad * np.sin(ang).astype(f32)).astype(np.float64)), axis=-1)
 
 
 def spike_uniforms(seed, step, agents, n_cells, pop=0):

