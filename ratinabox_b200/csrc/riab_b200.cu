@@ -266,7 +266,8 @@ struct GridPolicy {
 // Warp-role configuration.  The register file is re-balanced between the roles with setmaxnreg
 // (producers run ~130-register float64 code, consumers need 56..88):
 //   StepCfg<4>: 4 producer + 16 consumer warps (640 threads x 96 regs): heavy consumers
-//               (line-of-sight / spikes / noise) -- the consumers set the pace, 4 producers suffice.
+//               (line-of-sight / spikes / noise) set the pace, so they get 104 registers and the 4
+//               producers run (spilling) in 64 -- their latency stays hidden (measured: r104 > r96 > r88).
 //   StepCfg<8>: 8 producer + 16 consumer warps (768 threads x 80 regs): light consumers (Euclidean
 //               Gaussian / grid cells without spikes) run at the HBM write rate, so the float64
 //               motion chain (~14 us per 32-agent tile) needs twice the producer warps to keep up.
@@ -276,11 +277,21 @@ struct StepCfg {
   static constexpr int MW = MW_;
   static constexpr int NS = (MW_ >= 8) ? MW_ : 2 * MW_;      // ring slots (multiple of MW; static smem <= 48 KB)
   static constexpr int THREADS = (MW_ + RW) * 32;
-  static constexpr int REGS_PRODUCER = (MW_ >= 8) ? 128 : 128;
-  static constexpr int REGS_CONSUMER = (MW_ >= 8) ? 56 : 88;
+  static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;   // what __launch_bounds__(THREADS, 1) allocates
+#ifndef RIAB_RP4
+#define RIAB_RP4 64
+#endif
+#ifndef RIAB_RC4
+#define RIAB_RC4 104
+#endif
+  static constexpr int REGS_PRODUCER = (MW_ >= 8) ? 128 : RIAB_RP4;
+  static constexpr int REGS_CONSUMER = (MW_ >= 8) ? 56 : RIAB_RC4;
 };
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+// setmaxnreg towards N registers from the launch allocation L (inc when N > L, dec when N < L)
+template <int N, int L> __device__ __forceinline__ void reg_set() {
+  if (N > L) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+  else if (N < L) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
 
 template <int REC>
 struct __align__(16) StepSlot {
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
 
   if (warp < MW) {
     // ------------------------------------------------------------- producers
-    reg_inc<C::REGS_PRODUCER>();
+    reg_set<C::REGS_PRODUCER, C::REGS_LAUNCH>();
     for (long long q = warp; q < nq; q += MW) {
       const int s = (int)(q % NS);
       const uint32_t k = (uint32_t)(q / NS);
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
     }
   } else {
     // ------------------------------------------------------------- consumers
-    reg_dec<C::REGS_CONSUMER>();
+    reg_set<C::REGS_CONSUMER, C::REGS_LAUNCH>();
     const int ctid = threadIdx.x - MW * 32;
     constexpr int NC = RW * 32;
     const int CT = pc.n_pad >> 2;                       // cell-threads needed (multiple of 32)
