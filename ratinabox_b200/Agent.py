@@ -114,6 +114,7 @@ class Agent:
         self._step = 0
         self._t_hist = []
         self._shadow = {}
+        self._pinned = {}
         self._pending = None
         self._tape = None
         self._rec = None
@@ -176,11 +177,27 @@ class Agent:
             return arr
         return arr[0].copy() if name in _VEC else arr[0].item()
 
+    _SHADOW_MAX = 4096      # above this many agents state reads are read-only views (no write tracking)
+
     def _get_state(self, name):
         self._flush_pending()
         if name in self._shadow:
             return self._shadow[name][0]
-        host = self._s[name].cpu().numpy()
+        import torch
+        t = self._s[name]
+        if self.n_agents > self._SHADOW_MAX:
+            # large batches: one pinned staging buffer per state array, asynchronous D2H on the current
+            # stream + one stream sync; the returned array is a read-only view (assign to write:
+            # ``Ag.pos = new_positions``)
+            buf = self._pinned.get(name)
+            if buf is None:
+                buf = self._pinned[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            buf.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            arr = buf.numpy()
+            arr.flags.writeable = False
+            return arr
+        host = t.cpu().numpy()
         val = self._squeeze(name, host)
         if isinstance(val, np.ndarray):
             self._shadow[name] = (val, val.copy())
@@ -240,13 +257,18 @@ class Agent:
         io = self._io
         io.drift_velocity = None
         if drift_velocity is not None:
+            if self._drift_dev is None:
+                self._drift_dev = torch.empty((self.n_agents, 2), dtype=torch.float64, device=self.device)
             if isinstance(drift_velocity, torch.Tensor):
-                d = drift_velocity.to(device=self.device, dtype=torch.float64)
+                d = drift_velocity
             else:
                 assert isinstance(drift_velocity, np.ndarray), "drift_velocity must be an np.array"   # Agent.py:333
-                d = torch.as_tensor(np.ascontiguousarray(drift_velocity, dtype=np.float64), device=self.device)
-            assert d.shape in ((2,), (self.n_agents, 2)), "drift_velocity must have shape (Env.D,) or (n_agents, Env.D)"
-            self._drift_dev = d.expand(self.n_agents, 2).contiguous()
+                d = torch.as_tensor(drift_velocity)        # zero-copy view of the host array
+            assert tuple(d.shape) in ((2,), (self.n_agents, 2)), "drift_velocity must have shape (Env.D,) or (n_agents, Env.D)"
+            if d.dtype != torch.float64:
+                d = d.to(torch.float64)
+            # host -> device on the current stream (asynchronous when the host buffer is pinned)
+            self._drift_dev.copy_(d.expand(self.n_agents, 2), non_blocking=True)
             io.drift_velocity = self._drift_dev.data_ptr()
         io.xi = None
         self._tape = None
