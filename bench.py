@@ -79,35 +79,49 @@ def synthetic_agents(n, walls, seed):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions: one streaming
+    `nvidia-smi -lms 50` process (per-call start-up would miss short regions)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.rows, self._p, self._t = index, [], None, None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+    def _pump(self):
+        try:
+            for line in self._p.stdout:
+                parts = [x.strip() for x in line.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+        except Exception:
+            pass
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                        "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._pump, daemon=True)
+            self._t.start()
+            time.sleep(0.3)            # let the first samples arrive before the timed region starts
+            self.rows.clear()
+        except Exception:
+            self._p = None
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        if self._p is not None:
+            time.sleep(0.06)
+            self._p.terminate()
+            try:
+                self._p.wait(timeout=5)
+            except Exception:
+                self._p.kill()
+            if self._t:
+                self._t.join(timeout=2)
+        num = lambda x: x.replace(".", "", 1).isdigit()
+        sm = [float(r[0]) for r in self.rows if num(r[0])]
+        mx = [float(r[1]) for r in self.rows if num(r[1])]
         reasons = set()
         for r in self.rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):

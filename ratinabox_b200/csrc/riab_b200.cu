@@ -156,11 +156,17 @@ __device__ __forceinline__ void cursor_init(RowCursor& rc, const OutK& out, cons
   rc.spk = out.spikes ? reinterpret_cast<uint8_t*>(out.spikes + row * out.spike_ld) + (t.cell0 >> 3) : nullptr;
   rc.gid = (unsigned long long)(out.id_offset + row);
 }
-__device__ __forceinline__ void cursor_advance(RowCursor& rc, const OutK& out, int rows) {
-  rc.dst += (long long)rows * out.ld;
-  if (rc.nz) rc.nz += (long long)rows * out.ld;
-  if (rc.spk) rc.spk += (long long)rows * out.spike_ld * 4;
-  rc.gid += (unsigned long long)rows;
+struct RowStride { long long rate, spk; int rows; };      // element strides for `rows` agents (warp-uniform)
+__device__ __forceinline__ RowStride make_stride(const OutK& out, int rows) {
+  RowStride st;
+  st.rate = (long long)rows * out.ld; st.spk = (long long)rows * out.spike_ld * 4; st.rows = rows;
+  return st;
+}
+__device__ __forceinline__ void cursor_advance(RowCursor& rc, const RowStride& st) {
+  rc.dst += st.rate;
+  if (rc.nz) rc.nz += st.rate;
+  if (rc.spk) rc.spk += st.spk;
+  rc.gid += (unsigned long long)st.rows;
 }
 
 // Neurons.update tail for 4 consecutive cells of one agent: OU noise (Neurons.py:153-160,168),
@@ -392,13 +398,14 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
         if (!idle) {
           RowCursor rc;
           cursor_init(rc, out, tc, a0 + grp);
+          const RowStride stride = make_stride(out, G);
           const float* recp = s_slot[s].rec[grp];
           const double* posp = s_slot[s].pos[grp];
           for (int a = grp; a < na; a += G) {
             float o[4];
             P::rates4(o, regs, pc, cell0, recp, posp, s_walls, env);
             finish4<SPIKES, NOISE>(o, out, tc, rc);
-            cursor_advance(rc, out, G);
+            cursor_advance(rc, stride);
             recp += G * P::REC;
             posp += G * 2;
           }
@@ -411,11 +418,12 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
             tail_init(tc, out, cell0, pc.n_cells);
             RowCursor rc;
             cursor_init(rc, out, tc, a0);
+            const RowStride stride = make_stride(out, 1);
             for (int a = 0; a < na; ++a) {
               float o[4];
               P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], s_slot[s].pos[a], s_walls, env);
               finish4<SPIKES, NOISE>(o, out, tc, rc);
-              cursor_advance(rc, out, 1);
+              cursor_advance(rc, stride);
             }
           }
         }

@@ -183,7 +183,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
         const float Mp = fmaf(afp, r.tc[j][i], fabsf(fc) * tp);
         const float Da = fabsf(fc) + afp;
         const float mn = fminf(Mp, Da - Mp);
-        const bool opp = (__float_as_int(fc) ^ __float_as_int(fp)) < 0;   // strictly opposite sides (or a zero)
+        const bool opp = (fc * fp) < 0.f;                // strictly opposite sides of the wall's line (FMA pipe)
         dd[i] = (opp & (mn > 0.f)) ? 1.0e6f : dd[i];
         unsure = unsure | !(fabsf(mn) >= band);          // also true for NaN (degenerate centre / agent)
       }
