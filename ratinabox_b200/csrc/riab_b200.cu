@@ -169,13 +169,14 @@ __device__ __forceinline__ void cursor_advance(RowCursor& rc, const RowStride& s
   rc.gid += (unsigned long long)st.rows;
 }
 
-// Neurons.update tail for 4 consecutive cells of one agent: OU noise (Neurons.py:153-160,168),
-// rate store, spikes (Neurons.py:681-684; bit c of the row's byte string = cell c).
-template <bool SPIKES, bool NOISE>
-__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc) {
+// Neurons.update tail for 4 consecutive cells of one agent, part 1: OU noise
+// (Neurons.py:153-160,168) and the rate store.
+template <bool NOISE>
+__device__ __forceinline__ void store4(float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc,
+                                       long long row_off /* extra rows, in elements of ld */) {
   if (NOISE && rc.nz != nullptr) {
     uint32_t c[4];
-    philox_ctr(c, rc.gid, t.sub, out.step, RIAB_STREAM_CELL_NOISE, (uint32_t)out.pop);
+    philox_ctr(c, rc.gid + (row_off != 0 ? 1ull : 0ull), t.sub, out.step, RIAB_STREAM_CELL_NOISE, (uint32_t)out.pop);
     philox4x32_10(c, (uint32_t)out.seed, (uint32_t)(out.seed >> 32));
     float z[4];
 #pragma unroll
@@ -186,38 +187,78 @@ __device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, const Ta
       __sincosf(6.2831853071795865f * u2, &sn, &cs);
       z[2 * h] = r * cs; z[2 * h + 1] = r * sn;
     }
+    float* nzp = rc.nz + row_off;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if ((t.vmask >> i) & 1u) {
-        float n = rc.nz[i];
+        float n = nzp[i];
         n = n + (-n * out.noise_decay) + out.noise_sig * z[i];
-        rc.nz[i] = n;
+        nzp[i] = n;
         o[i] += n;
       }
     }
   }
+  float* dst = rc.dst + row_off;
   if (t.full4) {
-    st_cs_f4(rc.dst, o[0], o[1], o[2], o[3]);
+    st_cs_f4(dst, o[0], o[1], o[2], o[3]);
   } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if ((t.vmask >> i) & 1u) st_cs_f1(rc.dst + i, o[i]);
+      if ((t.vmask >> i) & 1u) st_cs_f1(dst + i, o[i]);
   }
-  if (SPIKES && (!NOISE || rc.spk != nullptr)) {
-    // counter = (agent id, cell group, step, stream|population); see philox_ctr
-    uint32_t c[4] = {(uint32_t)rc.gid, t.sub ^ ((uint32_t)(rc.gid >> 32) << 24), t.c2, t.c3_spk};
-    philox_keyed<7>(c, out.rk7);
-    // spike <=> uniform < dt * rate (Neurons.py:682-684); uniform = fma(float(x), 2^-32, 2^-33)
-    unsigned nib = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float u = fmaf(__uint2float_rn(c[i]), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-      nib |= (u < out.dt * o[i]) ? (1u << i) : 0u;
-    }
-    nib &= t.vmask;
-    const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);      // odd lane's nibble = cells 4..7 of the byte
-    if ((threadIdx.x & 1) == 0 && t.vmask != 0u) *rc.spk = (uint8_t)(nib | (hi << 4));
-  }
+}
+
+// Part 2: spikes (Neurons.py:681-684), spike <=> uniform < dt * rate.
+// One Philox4x32-7 call serves the 4 cells of TWO agents (global ids 2k, 2k+1):
+//   r = Philox7(ctr = (gid >> 1, cell group, step, stream|population), key = seed)
+//   agent half h = gid & 1 takes words r[2h], r[2h+1]: four 16-bit integers m_i (cell i = half-word i);
+//   all eight share the dither v = ((r0^r1^r2^r3) >> 8) * 2^-24; uniform_i = (m_i + v) * 2^-16.
+// (m_i + v) is uniform on [0, 65536) with 40 random bits; sharing v only correlates the sub-2^-16
+// fractions of the eight uniforms (covariance < 6e-11).
+__device__ __forceinline__ void spike_words(uint32_t (&c)[4], const OutK& out, const TailCtx& t, unsigned long long gid) {
+  const unsigned long long pair = gid >> 1;
+  c[0] = (uint32_t)pair; c[1] = t.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = t.c2; c[3] = t.c3_spk;
+  philox_keyed<7>(c, out.rk7);
+}
+__device__ __forceinline__ unsigned spike_nibble(uint32_t w0, uint32_t w1, float v, const float (&o)[4], float q) {
+  // q = dt * 65536
+  unsigned nib = 0;
+  nib |= (((float)(w0 & 0xffffu) + v) < q * o[0]) ? 1u : 0u;
+  nib |= (((float)(w0 >> 16) + v) < q * o[1]) ? 2u : 0u;
+  nib |= (((float)(w1 & 0xffffu) + v) < q * o[2]) ? 4u : 0u;
+  nib |= (((float)(w1 >> 16) + v) < q * o[3]) ? 8u : 0u;
+  return nib;
+}
+__device__ __forceinline__ float spike_dither(const uint32_t (&c)[4]) {
+  return (float)((c[0] ^ c[1] ^ c[2] ^ c[3]) >> 8) * 5.9604644775390625e-08f;
+}
+__device__ __forceinline__ void spike_store(unsigned nib, const TailCtx& t, uint8_t* spk) {
+  nib &= t.vmask;
+  const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);        // odd lane's nibble = cells 4..7 of the byte
+  if ((threadIdx.x & 1) == 0 && t.vmask != 0u) *spk = (uint8_t)(nib | (hi << 4));
+}
+// one agent
+__device__ __forceinline__ void spikes1(const float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc) {
+  uint32_t c[4];
+  spike_words(c, out, t, rc.gid);
+  const float v = spike_dither(c);
+  const unsigned h = (unsigned)(rc.gid & 1ull);
+  spike_store(spike_nibble(h ? c[2] : c[0], h ? c[3] : c[1], v, o, out.dt * 65536.0f), t, rc.spk);
+}
+// two agents with consecutive global ids, the first one even (rows rc and rc + 1)
+__device__ __forceinline__ void spikes2(const float (&oa)[4], const float (&ob)[4], const OutK& out, const TailCtx& t,
+                                        const RowCursor& rc) {
+  uint32_t c[4];
+  spike_words(c, out, t, rc.gid);
+  const float v = spike_dither(c), q = out.dt * 65536.0f;
+  spike_store(spike_nibble(c[0], c[1], v, oa, q), t, rc.spk);
+  spike_store(spike_nibble(c[2], c[3], v, ob, q), t, rc.spk + out.spike_ld * 4);
+}
+
+template <bool SPIKES, bool NOISE>
+__device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc) {
+  store4<NOISE>(o, out, t, rc, 0);
+  if (SPIKES && (!NOISE || rc.spk != nullptr)) spikes1(o, out, t, rc);
 }
 
 // ---------------------------------------------------------------------------
@@ -396,18 +437,36 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       const int na = s_slot[s].na;
       if (chunks == 1) {
         if (!idle) {
+          // agents are taken in pairs (2p, 2p+1) so that one Philox call feeds the spikes of both
           RowCursor rc;
-          cursor_init(rc, out, tc, a0 + grp);
-          const RowStride stride = make_stride(out, G);
-          const float* recp = s_slot[s].rec[grp];
-          const double* posp = s_slot[s].pos[grp];
-          for (int a = grp; a < na; a += G) {
-            float o[4];
-            P::rates4(o, regs, pc, cell0, recp, posp, s_walls, env);
-            finish4<SPIKES, NOISE>(o, out, tc, rc);
+          cursor_init(rc, out, tc, a0 + 2 * grp);
+          const RowStride stride = make_stride(out, 2 * G);
+          const float* recp = s_slot[s].rec[2 * grp];
+          const double* posp = s_slot[s].pos[2 * grp];
+          const bool even = ((rc.gid & 1ull) == 0ull);      // uniform: a0 and 2*grp are even
+          for (int a = 2 * grp; a < na; a += 2 * G) {
+            float oa[4], ob[4];
+            const bool has_b = (a + 1 < na);
+            P::rates4(oa, regs, pc, cell0, recp, posp, s_walls, env);
+            store4<NOISE>(oa, out, tc, rc, 0);
+            if (has_b) {
+              P::rates4(ob, regs, pc, cell0, recp + P::REC, posp + 2, s_walls, env);
+              store4<NOISE>(ob, out, tc, rc, out.ld);
+            }
+            if (SPIKES && (!NOISE || rc.spk != nullptr)) {
+              if (has_b && even) spikes2(oa, ob, out, tc, rc);
+              else {
+                spikes1(oa, out, tc, rc);
+                if (has_b) {
+                  RowCursor rb = rc;
+                  rb.gid += 1; rb.spk += out.spike_ld * 4;
+                  spikes1(ob, out, tc, rb);
+                }
+              }
+            }
             cursor_advance(rc, stride);
-            recp += G * P::REC;
-            posp += G * 2;
+            recp += 2 * G * P::REC;
+            posp += 2 * G * 2;
           }
         }
       } else {
@@ -432,6 +491,101 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       if (lane == 0) mbar_arrive(&s_empty[s]);
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// PlaceCells description "one_hot" (Neurons.py:972-974): rate = 1 for the cell with the smallest
+// distance (np.argmin: first index of the minimum), 0 elsewhere.  One warp per position.  Pass 1 finds the
+// minimum float32 squared distance (line-of-sight flags from the same float32 predicate as the rate
+// kernels; pairs inside the predicate's uncertainty band count with their unblocked distance); pass 2
+// re-evaluates every cell within a relative 1e-5 of that minimum in float64 exactly like the reference
+// (np.linalg.norm, utils.vector_intercepts) and keeps the smallest (distance, index).
+__device__ __forceinline__ double onehot_exact_dist(const PlaceConst& c, int cell, double px, double py,
+                                                    const double* __restrict__ inner64) {
+  const double cx = c.centres64[2 * cell], cy = c.centres64[2 * cell + 1];
+  bool blocked = false;
+  for (int j = 0; j < c.n_inner; ++j) blocked = blocked || los_blocked_exact(cx, cy, px, py, inner64 + 4 * j);
+  const D ex = D(cx) - D(px), ey = D(cy) - D(py);
+  const double d = dsqrt(ex * ex + ey * ey).v;
+  if (!blocked) return d;
+  if (c.geometry == RIAB_GEOM_GEODESIC) {
+    double via = INFINITY;
+    for (int e = 0; e < 2; ++e) {
+      if (!((c.ep_valid >> e) & 1)) continue;
+      const D wx(inner64[2 * e]), wy(inner64[2 * e + 1]);
+      const D ax = D(cx) - wx, ay = D(cy) - wy, bx = wx - D(px), by = wy - D(py);
+      const double v = (dsqrt(ax * ax + ay * ay) + dsqrt(bx * bx + by * by)).v;
+      via = fmin(via, v);
+    }
+    return via;
+  }
+  return 1000.0;
+}
+
+__global__ void __launch_bounds__(NT) k_place_onehot(const EnvK env, const PlaceConst pc, const double* __restrict__ pos,
+                                                     const long long n_rows, const OutK out) {
+  __shared__ __align__(16) double s_walls[MAXW * 4];
+  __shared__ uint64_t s_bar;
+  stage_walls(s_walls, &s_bar, env);
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const double px = pos[2 * row], py = pos[2 * row + 1];
+  const double* inner = s_walls + 4 * env.nb;
+  const float pxf = (float)(px - env.cxm), pyf = (float)(py - env.cym);
+  float fp[PLACE_MAX_WI], tp[PLACE_MAX_WI];
+  for (int j = 0; j < PLACE_MAX_WI; ++j) {
+    fp[j] = 1.f; tp[j] = 0.f;
+    if (j < pc.n_inner) {
+      double f, t;
+      wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
+      fp[j] = (float)f; tp[j] = (fabs(f) < 1e-9) ? nanf("") : (float)t;
+    }
+  }
+  const int np = pc.n_pad;
+  auto d2_of = [&](int cell, bool& unsure) -> float {          // optimistic float32 squared distance of one cell
+    const float dx = pxf - pc.packed[cell], dy = pyf - pc.packed[np + cell];
+    float d2 = fmaf(dy, dy, dx * dx);
+    bool hit = false;
+    for (int j = 0; j < pc.n_inner; ++j) {
+      const float fc = pc.packed[(size_t)(4 + 2 * j) * np + cell], tcv = pc.packed[(size_t)(5 + 2 * j) * np + cell];
+      const float afp = fabsf(fp[j]);
+      const float Mp = fmaf(afp, tcv, fabsf(fc) * tp[j]);
+      const float mn = fminf(Mp, (fabsf(fc) + afp) - Mp);
+      const bool u = !(fabsf(mn) >= pc.eps[j]);
+      unsure = unsure || u;
+      hit = hit || (((fc * fp[j]) < 0.f) && (mn > 0.f) && !u);
+    }
+    return hit ? 1.0e6f : d2;
+  };
+  float best = INFINITY;
+  for (int cell = lane; cell < pc.n_cells; cell += 32) {
+    bool u = false;
+    best = fminf(best, d2_of(cell, u));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  // geodesic detours are shorter than 1000: every blocked cell is a candidate there
+  const float thr = (pc.geometry == RIAB_GEOM_GEODESIC && pc.n_inner > 0) ? INFINITY : best * (1.0f + 1e-5f) + 1e-12f;
+  double bd = INFINITY;
+  int bi = 0x7fffffff;
+  for (int cell = lane; cell < pc.n_cells; cell += 32) {
+    bool u = false;
+    const float d2 = d2_of(cell, u);
+    if (d2 <= thr || u) {
+      const double d = onehot_exact_dist(pc, cell, px, py, inner);
+      if (d < bd || (d == bd && cell < bi)) { bd = d; bi = cell; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+  }
+  const float lo = pc.min_fr, hi = pc.min_fr + pc.span;
+  float* dst = out.rates + row * out.ld;
+  for (int cell = lane; cell < pc.n_cells; cell += 32) st_cs_f1(dst + cell, cell == bi ? hi : lo);
 }
 
 // Noise + spikes post-pass over rate rows that a kernel without finish4 produced (BVC).
@@ -461,10 +615,14 @@ __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agen
   extern __shared__ __align__(128) unsigned char dyn[];
   double* s_dirs = reinterpret_cast<double*>(dyn);                 // T*2
   __shared__ __align__(16) double s_walls[MAXW * 4];
+  __shared__ __align__(16) float4 s_wf[MAXW];
   __shared__ __align__(16) double s_pos[TA][2];
   __shared__ uint64_t s_bar;
   stage_walls(s_walls, &s_bar, env);
   for (int i = threadIdx.x; i < 2 * bc.T; i += blockDim.x) s_dirs[i] = bc.test_dirs[i];
+  for (int w = threadIdx.x; w < env.W; w += blockDim.x)
+    s_wf[w] = make_float4((float)s_walls[4 * w], (float)s_walls[4 * w + 1], (float)(s_walls[4 * w + 2] - s_walls[4 * w]),
+                          (float)(s_walls[4 * w + 3] - s_walls[4 * w + 1]));
 
   const long long a0 = (long long)blockIdx.x * TA;
   const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
@@ -489,7 +647,7 @@ __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agen
     const int th = idx >> 5, a = idx & 31;
     double d;
     int wid;
-    bvc_first_wall(s_pos[a][0], s_pos[a][1], s_dirs[2 * th], s_dirs[2 * th + 1], s_walls, env.W, d, wid);
+    bvc_first_wall(s_pos[a][0], s_pos[a][1], s_dirs[2 * th], s_dirs[2 * th + 1], s_walls, s_wf, env.W, d, wid);
     tile[idx] = (float)d;
     if (first_wall != nullptr && a < na) first_wall[(a0 + a) * bc.T + th] = wid;
   }
@@ -621,7 +779,6 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
 
 int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
   if (pc == nullptr || pc->packed_dev == nullptr) return fail(RIAB_ERR_INVALID, "place cells / packed_dev NULL");
-  if (pc->description == RIAB_PC_ONE_HOT) return fail(RIAB_ERR_UNSUPPORTED, "one_hot place cells are not on the CUDA path yet");
   if (pc->description < 0 || pc->description > RIAB_PC_ONE_HOT) return fail(RIAB_ERR_INVALID, "bad description %d", pc->description);
   if (pc->wall_geometry < 0 || pc->wall_geometry > RIAB_GEOM_GEODESIC) return fail(RIAB_ERR_INVALID, "bad wall_geometry");
   const int n_inner = env.W - env.nb;
@@ -632,7 +789,8 @@ int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
     if (pc->wall_geometry == RIAB_GEOM_GEODESIC && n_inner > 1)
       return fail(RIAB_ERR_INVALID, "geodesic geometry is only defined with one additional wall (Environment.py:736-739)");
   }
-  if (pc->description == RIAB_PC_TOP_HAT && pc->centres_dev == nullptr) return fail(RIAB_ERR_INVALID, "centres_dev NULL");
+  if ((pc->description == RIAB_PC_TOP_HAT || pc->description == RIAB_PC_ONE_HOT) && pc->centres_dev == nullptr)
+    return fail(RIAB_ERR_INVALID, "centres_dev NULL");
   c.desc = pc->description; c.geometry = pc->wall_geometry; c.n_cells = pc->n_cells; c.n_pad = pc->n_pad;
   c.n_inner = (pc->wall_geometry == RIAB_GEOM_EUCLIDEAN) ? 0 : n_inner;
   c.ep_valid = pc->ep_valid;
@@ -700,9 +858,28 @@ int launch_place_d(const EnvK& env, const riab_agents& ag, const riab_motion_par
   return launch_tile<PlacePolicy<8, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
 }
 
+int launch_onehot(const EnvK& env, const PlaceConst& pc, const OutK& out, const double* pos, long long n_rows,
+                  cudaStream_t s) {
+  if (n_rows == 0) return 0;
+  k_place_onehot<<<(unsigned)((n_rows + NT / 32 - 1) / (NT / 32)), NT, 0, s>>>(env, pc, pos, n_rows, out);
+  g_launches++;
+  RIAB_CUDA_OK(cudaGetLastError());
+  if (out.noise != nullptr || out.spikes != nullptr) {
+    const int np128 = (pc.n_cells + CELL_PAD - 1) / CELL_PAD * CELL_PAD;
+    k_finish_rows<<<dim3((unsigned)((np128 / 4 + NT - 1) / NT), (unsigned)n_rows), NT, 0, s>>>(out, pc.n_cells, np128, n_rows);
+    g_launches++;
+    RIAB_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
 template <int MODE>
 int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                  const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+  if (pc.desc == RIAB_PC_ONE_HOT) {
+    if (MODE != 0) return fail(RIAB_ERR_INVALID, "one_hot is launched unfused");
+    return launch_onehot(env, pc, out, pos_in, n_rows, s);
+  }
   // the common Gaussian profile without geodesic detours gets a compile-time specialisation
   if (pc.desc == RIAB_PC_GAUSSIAN && pc.geometry != RIAB_GEOM_GEODESIC)
     return launch_place_d<MODE, RIAB_PC_GAUSSIAN>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
@@ -1009,6 +1186,11 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
     const riab_place_cells* pc = (const riab_place_cells*)cells;
     PlaceConst c;
     if ((rc = make_place(pc, ek, c)) || (rc = make_out(out, noise, pc->n_cells, dt, agents->id_offset, ok))) return rc;
+    if (c.desc == RIAB_PC_ONE_HOT) {             // arg-min across cells: its own kernel after the motion kernel
+      if (MODE == 2) return fail(RIAB_ERR_UNSUPPORTED, "one_hot populations are stepped unskewed");
+      if (MODE == 1 && (rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
+      return launch_place<0>(ek, *agents, mp0, io0, c, ok, agents->pos, agents->n_agents, s);
+    }
     return launch_place<MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_GRID) {
@@ -1021,7 +1203,11 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
     if (MODE == 2) return fail(RIAB_ERR_UNSUPPORTED, "BVC populations are stepped unskewed");
     const riab_bvc_cells* bvc = (const riab_bvc_cells*)cells;
     if ((rc = make_out(out, noise, bvc->n_cells, dt, agents->id_offset, ok))) return rc;
-    return launch_bvc<(MODE == 1)>(ek, *agents, mp, sio, bvc, ok, pos_in, agents->n_agents, out->bvc_scratch, nullptr, s);
+    // The ray kernel wants all its CTAs resident in ONE wave (the float64 ray chains are latency-bound);
+    // fusing the 128-register motion code into it halves its occupancy and adds a tail wave, so the
+    // motion runs as its own (14 us) kernel first.
+    if (MODE == 1 && (rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
+    return launch_bvc<false>(ek, *agents, mp0, io0, bvc, ok, agents->pos, agents->n_agents, out->bvc_scratch, nullptr, s);
   }
   return fail(RIAB_ERR_INVALID, "bad cells_kind %d", cells_kind);
 }
@@ -1048,7 +1234,9 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
   // kernel that evaluates rates(s) of the current positions while its producer warps already run
   // motion(s+1); the last step is rates only.  Same results as the plain sequence, but the
   // float64 motion chain never gates the rate warps.
-  const bool skew = n_pops >= 1 && pops[0].kind != RIAB_CELLS_BVC && n_steps >= 1 && io->xi == nullptr &&
+  const bool onehot0 = n_pops >= 1 && pops[0].kind == RIAB_CELLS_PLACE && pops[0].cells != nullptr &&
+                       ((const riab_place_cells*)pops[0].cells)->description == RIAB_PC_ONE_HOT;
+  const bool skew = n_pops >= 1 && pops[0].kind != RIAB_CELLS_BVC && !onehot0 && n_steps >= 1 && io->xi == nullptr &&
                     !io->collision_mask && !io->first_hit && !io->n_iters;
   auto step_io = [&](int64_t st) {
     riab_step_io sio = *io;

@@ -29,8 +29,9 @@ constexpr int BVC_CT = 64;   // cells per tile
 constexpr int BVC_AT = 32;   // agents per tile
 
 // One ray against all walls -> (distance to first wall, wall id).  Neurons.py:1655-1684.
-RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const double* __restrict__ walls, int W,
-                             double& dist, int& wall_id) {
+// wf: float32 copy of the walls as (ax, ay, sbx, sby) per wall (pre-filter only).
+RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const double* __restrict__ walls,
+                             const float4* __restrict__ wf, int W, double& dist, int& wall_id) {
   const D a0x(px), a0y(py);
   const D a1x = a0x + D(ux), a1y = a0y + D(uy);      // pos_line_segments[:, :, 1, :] += test_directions
   const D sax = a1x - a0x, say = a1y - a0y;
@@ -38,7 +39,24 @@ RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const d
   double best = -INFINITY;                           // running max of pref (np.argmax keeps the first max)
   int besti = 0;
   double best_la = 0.0;
+  const float pxf = (float)px, pyf = (float)py, sapxf = -(float)uy, sapyf = (float)ux;
   for (int w = 0; w < W; ++w) {
+    // float32 pre-filter: a wall whose l_b is outside [0,1] by a margin 1e-3 (>> float32 rounding of the
+    // quotient) is rejected without touching the float64 pipe -- the exact test below would reject it too
+    // (pref = -1).  Walls that are (nearly) parallel to the ray, or anywhere near the limits, fall through.
+    {
+      const float4 wl = wf[w];
+      const float d0xf = wl.x - pxf, d0yf = wl.y - pyf;
+      const float t1 = d0xf * sapxf, t2 = d0yf * sapyf, t3 = wl.z * sapxf, t4 = wl.w * sapyf;
+      const float nb = -(t1 + t2), db = t3 + t4;
+      const float tol = fmaf(1e-3f, fabsf(db), 1e-6f * (fabsf(t1) + fabsf(t2) + fabsf(t3) + fabsf(t4)));
+      const float s = (db >= 0.f) ? 1.f : -1.f;
+      const float nbs = nb * s, dbs = db * s;             // dbs >= 0 ;  l_b = nbs / dbs
+      if (nbs < -tol || nbs > dbs + tol) {
+        if (-1.0 > best) { best = -1.0; besti = w; best_la = 0.0; }
+        continue;
+      }
+    }
     const D bx0(walls[4 * w]), by0(walls[4 * w + 1]), bx1(walls[4 * w + 2]), by1(walls[4 * w + 3]);
     const D d0x = bx0 - a0x, d0y = by0 - a0y;
     const D sbx = bx1 - bx0, sby = by1 - by0;

@@ -57,11 +57,18 @@ def agent_normals(seed, step, agents):
 
 
 def spike_uniforms(seed, step, agents, n_cells, pop=0):
-    """(A, n_cells) float32 uniforms of the spike draw (Philox4x32-7, one call per 4 cells)."""
+    """(A, n_cells) float32 values m + v of the spike draw: spike <=> (m + v) < dt*65536*rate.
+    One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words
+    2h, 2h+1 as four 16-bit integers m; all share the dither v = ((r0^r1^r2^r3)>>8) * 2^-24."""
+    agents = np.asarray(agents, dtype=np.uint64)
     groups = (n_cells + 3) // 4
-    a = np.asarray(agents, dtype=np.uint64)[:, None]
+    a = (agents >> np.uint64(1))[:, None]
     g = np.arange(groups, dtype=np.uint64)[None, :]
-    r = philox4x32(counter(a, g, step, STREAM_SPIKES, pop), (seed & 0xFFFFFFFF, seed >> 32), rounds=7)
-    # device: fma(float32(x), 2^-32, 2^-33) -- float32(x) rounds to nearest, the fma rounds once more
-    u = (r.astype(np.float32).astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
+    r = philox4x32(counter(a, g, step, STREAM_SPIKES, pop), (seed & 0xFFFFFFFF, seed >> 32), rounds=7)   # (A,G,4)
+    v = ((r[..., 0] ^ r[..., 1] ^ r[..., 2] ^ r[..., 3]) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    h = (agents & np.uint64(1)).astype(np.int64)[:, None]
+    w0 = np.where(h == 1, r[..., 2], r[..., 0])
+    w1 = np.where(h == 1, r[..., 3], r[..., 1])
+    m = np.stack((w0 & np.uint32(0xFFFF), w0 >> np.uint32(16), w1 & np.uint32(0xFFFF), w1 >> np.uint32(16)), axis=-1)
+    u = (m.astype(np.float32) + v[..., None]).astype(np.float32)
     return u.reshape(len(agents), groups * 4)[:, :n_cells]

@@ -113,7 +113,7 @@ def test_spikes_match_numpy_philox():
     assert h["firingrate"].shape == (3, A, N) and h["spikes"].shape == (3, A, N) and h["spikes"].dtype == bool
     for s in range(3):
         u = spike_uniforms(11, s, np.arange(A), N, pop=0)
-        want = u < (np.float32(0.05) * h["firingrate"][s].astype(np.float32))
+        want = u < (np.float32(np.float32(0.05) * np.float32(65536.0)) * h["firingrate"][s].astype(np.float32))
         assert np.array_equal(h["spikes"][s], want), s
     assert 0.02 < h["spikes"].mean() < 0.6
 
@@ -205,8 +205,20 @@ def test_get_state_all_and_errors():
     # empty and ragged inputs
     assert PCs.get_state(evaluate_at=None, pos=np.zeros((0, 2))).shape == (30, 0)
     assert PCs.get_state(evaluate_at=None, pos=np.array([0.4, 0.6])).shape == (30, 1)
-    one_hot = rb.PlaceCells(Ag, {"n": 8, "description": "one_hot"})
+    # one_hot (arg-min across cells, np.argmin first-index ties) incl. the fused update path
+    one_hot = rb.PlaceCells(Ag, {"n": 40, "description": "one_hot", "wall_geometry": "line_of_sight"})
+    oh = one_hot.get_state(evaluate_at="all")
+    ref_oh = O.place_cells_get_state(env, one_hot.place_cell_centres, one_hot.place_cell_widths,
+                                     E.flattened_discrete_coords, O.TapeRNG(), "one_hot", "line_of_sight")
+    assert np.array_equal(oh, ref_oh)
+    Ag.update(); one_hot.update()
+    assert one_hot.firingrate.sum() == 1.0 and one_hot.firingrate.max() == 1.0
+    # more inner walls than the line-of-sight kernels hold in registers -> refused loudly, not silently wrong
+    E9 = rb.Environment()
+    for k in range(9):
+        E9.add_wall([[0.1 * (k + 1), 0.0], [0.1 * (k + 1), 0.3]])
+    Ag9 = rb.Agent(E9, {"dt": 0.01})
     with pytest.raises(RiabError):
-        one_hot.get_state(evaluate_at="all")
+        rb.PlaceCells(Ag9, {"n": 8, "wall_geometry": "line_of_sight"}).get_state(evaluate_at="all")
     with pytest.raises(NotImplementedError):
         rb.Environment({"boundary_conditions": "periodic"})

@@ -76,14 +76,14 @@ def test_place_cells_modeA_golden(golden):
     P = g["P"]
     E = _env(rb, g["box2_walls"])
     Ag = rb.Agent(E, {"dt": 0.01})
-    for desc in ("gaussian", "gaussian_threshold", "diff_of_gaussians", "top_hat"):
+    for desc in ("gaussian", "gaussian_threshold", "diff_of_gaussians", "top_hat", "one_hot"):
         for geom in ("euclidean", "line_of_sight"):
             c = g[f"pc_{desc}_{geom}_centres"]
             pc = rb.PlaceCells(Ag, {"place_cell_centres": c, "description": desc, "wall_geometry": geom,
                                     "widths": 0.2, "min_fr": 0.05, "max_fr": 3.0})
             got = pc.get_state(evaluate_at=None, pos=P)
             ref = g[f"pc_{desc}_{geom}"]
-            if desc == "top_hat":
+            if desc in ("top_hat", "one_hot"):
                 # discontinuous profile: the in/out classification must be identical, values float32-rounded
                 assert np.array_equal(got > 1.5, ref > 1.5), (desc, geom)
                 assert np.abs(got - ref).max() <= 1e-6
