@@ -30,40 +30,44 @@ constexpr int BVC_AT = 32;   // agents per tile
 
 // One ray against all walls -> (distance to first wall, wall id).  Neurons.py:1655-1684.
 // wf: float32 copy of the walls as (ax, ay, sbx, sby) per wall (pre-filter only).
+//
+// Two phases per ray so that the lanes of a warp (different agents / angles) do not serialise on each
+// other's walls: (1) a float32 pre-filter over all walls builds a bit mask of the walls whose l_b is
+// within [0,1] up to a margin 1e-3 (>> float32 rounding; anything it drops is rejected by the exact
+// test too, pref = -1); (2) each lane walks ITS OWN set bits in increasing wall order -- same code path
+// for every lane, different wall index as data -- and evaluates the reference's float64 expressions.
 RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const double* __restrict__ walls,
                              const float4* __restrict__ wf, int W, double& dist, int& wall_id) {
   const D a0x(px), a0y(py);
   const D a1x = a0x + D(ux), a1y = a0y + D(uy);      // pos_line_segments[:, :, 1, :] += test_directions
   const D sax = a1x - a0x, say = a1y - a0y;
   const D sapx = -say, sapy = sax;
-  double best = -INFINITY;                           // running max of pref (np.argmax keeps the first max)
-  int besti = 0;
-  double best_la = 0.0;
   const float pxf = (float)px, pyf = (float)py, sapxf = -(float)uy, sapyf = (float)ux;
+  unsigned long long mask = 0ull;
   for (int w = 0; w < W; ++w) {
-    // float32 pre-filter: a wall whose l_b is outside [0,1] by a margin 1e-3 (>> float32 rounding of the
-    // quotient) is rejected without touching the float64 pipe -- the exact test below would reject it too
-    // (pref = -1).  Walls that are (nearly) parallel to the ray, or anywhere near the limits, fall through.
-    {
-      const float4 wl = wf[w];
-      const float d0xf = wl.x - pxf, d0yf = wl.y - pyf;
-      const float t1 = d0xf * sapxf, t2 = d0yf * sapyf, t3 = wl.z * sapxf, t4 = wl.w * sapyf;
-      const float nb = -(t1 + t2), db = t3 + t4;
-      const float tol = fmaf(1e-3f, fabsf(db), 1e-6f * (fabsf(t1) + fabsf(t2) + fabsf(t3) + fabsf(t4)));
-      const float s = (db >= 0.f) ? 1.f : -1.f;
-      const float nbs = nb * s, dbs = db * s;             // dbs >= 0 ;  l_b = nbs / dbs
-      if (nbs < -tol || nbs > dbs + tol) {
-        if (-1.0 > best) { best = -1.0; besti = w; best_la = 0.0; }
-        continue;
-      }
-    }
+    const float4 wl = wf[w];
+    const float d0xf = wl.x - pxf, d0yf = wl.y - pyf;
+    const float t1 = d0xf * sapxf, t2 = d0yf * sapyf, t3 = wl.z * sapxf, t4 = wl.w * sapyf;
+    const float nb = -(t1 + t2), db = t3 + t4;
+    const float tol = fmaf(1e-3f, fabsf(db), 1e-6f * (fabsf(t1) + fabsf(t2) + fabsf(t3) + fabsf(t4)));
+    const float sgn = (db >= 0.f) ? 1.f : -1.f;
+    const float nbs = nb * sgn, dbs = db * sgn;          // dbs >= 0 ;  l_b = nbs / dbs
+    const bool rejected = (nbs < -tol) || (nbs > dbs + tol);
+    mask |= rejected ? 0ull : (1ull << w);
+  }
+  double best = -1.0;                                    // rejected walls all score -1; np.argmax keeps the first max
+  int besti = -1;
+  double best_la = 0.0;
+  while (mask) {
+    const int w = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
     const D bx0(walls[4 * w]), by0(walls[4 * w + 1]), bx1(walls[4 * w + 2]), by1(walls[4 * w + 3]);
     const D d0x = bx0 - a0x, d0y = by0 - a0y;
     const D sbx = bx1 - bx0, sby = by1 - by0;
     const D sbpx = -sby, sbpy = sbx;
     const D numB = (-d0x) * sapx + (-d0y) * sapy;
     const D denB = sbx * sapx + sby * sapy;
-    // l_b = numB/denB : decide (l_b < 0) || (l_b > 1) without dividing
+    // l_b = numB/denB : decide (l_b < 0) || (l_b > 1) without dividing (exact for IEEE division)
     bool rej;
     if (denB.v != 0.0 && numB.v == numB.v && fabs(denB.v) != INFINITY && fabs(numB.v) != INFINITY) {
       const bool same = (numB.v > 0.0) == (denB.v > 0.0);
@@ -72,20 +76,17 @@ RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const d
       const double lb = (numB / denB).v;
       rej = (lb < 0.0) || (lb > 1.0);
     }
-    double pref, la = 0.0;
-    if (rej) {
-      pref = -1.0;
-    } else {
-      const D numA = d0x * sbpx + d0y * sbpy;
-      const D denA = sax * sbpx + say * sbpy;
-      la = (numA / denA).v;
-      pref = (la > 0.0) ? __ddiv_rn(1.0, la) : ((la < 0.0) ? -1.0 : 0.0);
-    }
+    if (rej) continue;                                   // pref = -1: never beats the running maximum
+    const D numA = d0x * sbpx + d0y * sbpy;
+    const D denA = sax * sbpx + say * sbpy;
+    const double la = (numA / denA).v;
+    const double pref = (la > 0.0) ? __ddiv_rn(1.0, la) : ((la < 0.0) ? -1.0 : 0.0);
     if (pref > best) { best = pref; besti = w; best_la = la; }
   }
-  // if the arg-max wall was rejected (every pref == -1 -> wall 0) its l_a was not computed above
-  if (best == -1.0) {
-    const D bx0(walls[4 * besti]), by0(walls[4 * besti + 1]), bx1(walls[4 * besti + 2]), by1(walls[4 * besti + 3]);
+  if (besti < 0) {
+    // every wall scored -1: np.argmax returns wall 0, whose l_a is reported (Neurons.py:1677-1684)
+    besti = 0;
+    const D bx0(walls[0]), by0(walls[1]), bx1(walls[2]), by1(walls[3]);
     const D d0x = bx0 - a0x, d0y = by0 - a0y;
     const D sbx = bx1 - bx0, sby = by1 - by0;
     const D sbpx = -sby, sbpy = sbx;

@@ -1,0 +1,121 @@
+"""Edge cases the reference's usage implies: ragged sizes (agents not a multiple of the 32-agent tile,
+cells not a multiple of 4 / 128, more cells than one consumer pass holds), every register-template of the
+line-of-sight kernels (1, 2, 3..4, 5..8 inner walls), odd shard offsets, noise, populations sharing an
+Agent.  GPU only."""
+import numpy as np
+import pytest
+
+import riab_oracle as O
+from philox_np import spike_uniforms
+
+pytestmark = pytest.mark.gpu
+
+
+def _walls(k):
+    """k internal walls, alternately from floor and ceiling (none touches another)."""
+    out = []
+    for i in range(k):
+        x = (i + 1) / (k + 1)
+        out.append([[x, 0.0], [x, 0.45]] if i % 2 == 0 else [[x, 1.0], [x, 0.55]])
+    return out
+
+
+def _make(rb, A, walls, seed=4, **agent):
+    np.random.seed(seed)
+    E = rb.Environment()
+    for w in walls:
+        E.add_wall(w)
+    Ag = rb.Agent(E, dict({"dt": 0.01, "n_agents": A, "seed": 9}, **agent))
+    return E, Ag
+
+
+@pytest.mark.parametrize("A,N,k", [(1, 1, 0), (3, 5, 1), (33, 130, 2), (100, 1025, 3), (70, 2500, 0), (31, 257, 7)])
+def test_ragged_sizes_all_wall_templates(A, N, k):
+    import ratinabox_b200 as rb
+    walls = _walls(k)
+    E, Ag = _make(rb, A, walls)
+    geom = "line_of_sight" if k else "euclidean"
+    PCs = rb.PlaceCells(Ag, {"n": N, "wall_geometry": geom, "widths": 0.15, "max_fr": 4.0})
+    GCs = rb.GridCells(Ag, {"n": max(N // 3, 1)})
+    assert PCs.n == N
+    steps = 3
+    pos0 = np.array(Ag.pos, dtype=float).reshape(A, 2).copy()
+    Ag.run(steps)
+    pos = np.array(Ag.pos, dtype=float).reshape(A, 2)
+    env = O.OracleEnvironment(walls=walls)
+    ref = O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, pos, O.TapeRNG(),
+                                  "gaussian", geom, 0.0, 4.0).T
+    fr = np.array(PCs.firingrate, dtype=float).reshape(A, N)
+    assert np.abs(fr - ref).max() <= 4e-5            # 1e-5 of the rate scale (max_fr = 4)
+    refg = O.grid_cells_get_state(GCs.gridscales, GCs.phase_offsets, GCs.w, pos).T
+    assert np.abs(np.array(GCs.firingrate, dtype=float).reshape(A, GCs.n) - refg).max() <= 1e-5
+    h = PCs.get_history_arrays()
+    want = (steps, N) if A == 1 else (steps, A, N)
+    assert h["firingrate"].shape == want and h["spikes"].shape == want
+    # spikes of the last step against the NumPy mirror of the Philox stream (population 0)
+    u = spike_uniforms(9, steps - 1, np.arange(A), N, pop=0)
+    sp = h["spikes"][-1].reshape(A, N)
+    assert np.array_equal(sp, u < np.float32(0.01 * 65536.0) * fr.astype(np.float32))
+    assert np.isfinite(pos).all() and not np.array_equal(pos, pos0)
+
+
+def test_odd_shard_offsets_give_identical_results():
+    """Shards that start at odd global ids use the unpaired spike path and the same Philox streams."""
+    import ratinabox_b200 as rb
+    A = 77
+    E, Ag = _make(rb, A, _walls(2))
+    PCs = rb.PlaceCells(Ag, {"n": 96})
+    pos0, vel0 = Ag.pos.copy(), Ag.velocity.copy()
+    Ag.run(5)
+    full_pos, full_fr, full_sp = Ag.pos, PCs.firingrate, PCs.get_history_arrays()["spikes"]
+    for start, stop in ((0, 33), (33, 77)):
+        E2, Ag2 = _make(rb, stop - start, _walls(2), id_offset=start)
+        Ag2.pos, Ag2.velocity, Ag2.measured_velocity = pos0[start:stop], vel0[start:stop], vel0[start:stop]
+        P2 = rb.PlaceCells(Ag2, {"place_cell_centres": PCs.place_cell_centres})
+        Ag2.run(5)
+        assert np.array_equal(Ag2.pos, full_pos[start:stop])
+        assert np.array_equal(P2.firingrate, full_fr[start:stop])
+        assert np.array_equal(P2.get_history_arrays()["spikes"], full_sp[:, start:stop])
+
+
+def test_noise_is_ornstein_uhlenbeck_with_the_requested_std():
+    """Neurons.update's OU noise (Neurons.py:153-160): stationary std = noise_std, coherence noise_coherence_time."""
+    import ratinabox_b200 as rb
+    E, Ag = _make(rb, 64, [])
+    PCs = rb.PlaceCells(Ag, {"n": 64, "noise_std": 0.3, "noise_coherence_time": 0.05, "wall_geometry": "euclidean"})
+    clean = rb.PlaceCells(Ag, {"place_cell_centres": PCs.place_cell_centres, "wall_geometry": "euclidean"})
+    resid = []
+    for s in range(400):
+        Ag.update(); PCs.update(); clean.update()
+        if s >= 100:
+            resid.append(PCs.firingrate - clean.firingrate)
+    r = np.array(resid)
+    assert abs(r.mean()) < 0.01 and abs(r.std() - 0.3) < 0.02
+    lag = 5                                       # 5 steps = one coherence time -> correlation exp(-1)
+    c = np.mean(r[lag:] * r[:-lag]) / r.var()
+    assert abs(c - np.exp(-1.0)) < 0.06
+
+
+def test_three_populations_share_one_agent_in_run():
+    """config 5 in miniature: Place + Grid + BVC populations of one Agent stepped by riab_run all see the
+    positions of the same step (population 0 skewed, the others rate-only)."""
+    import ratinabox_b200 as rb
+    walls = _walls(2)
+    E, Ag = _make(rb, 48, walls)
+    PCs = rb.PlaceCells(Ag, {"n": 64})
+    GCs = rb.GridCells(Ag, {"n": 30})
+    BVCs = rb.BoundaryVectorCells(Ag, {"n": 20})
+    Ag.run(6)
+    pos = Ag.pos
+    env = O.OracleEnvironment(walls=walls)
+    rng = O.TapeRNG()
+    assert np.abs(PCs.firingrate - O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, pos, rng,
+                                                           "gaussian", "line_of_sight").T).max() <= 1e-5
+    assert np.abs(GCs.firingrate - O.grid_cells_get_state(GCs.gridscales, GCs.phase_offsets, GCs.w, pos).T).max() <= 1e-5
+    assert np.abs(BVCs.firingrate - O.bvc_get_state(env, BVCs.tuning_distances, BVCs.tuning_angles, BVCs.sigma_distances,
+                                                    BVCs.sigma_angles, pos, rng).T).max() <= 1e-5
+    hp = Ag.get_history_arrays()["pos"]
+    assert hp.shape == (6, 48, 2) and np.abs(hp[-1] - pos).max() <= 1e-6
+    # history rows of every population belong to the same 6 steps
+    for ns in (PCs, GCs, BVCs):
+        assert ns.get_history_arrays()["firingrate"].shape[0] == 6
