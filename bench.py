@@ -223,7 +223,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
+        # one single-threaded process per host core (the reference is single-threaded; BLAS/OpenMP pools
+        # in 128 workers would only oversubscribe the box)
+        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+            os.environ[v] = "1"
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
         per = {"c2": 300, "c2e": 400, "c3": 400, "c4": 60}[args.workload]
         vals = []
         for _ in range(max(1, min(args.warmup, 1))):
