@@ -172,6 +172,8 @@ typedef struct {
   const float* packed_dev;       /* riab_bvc_pack output (per-cell tuning + von Mises table tiles) */
   const double* test_dirs_dev;   /* (T,2) f64 test_directions (Neurons.py:1584-1596, duplicated-0 quirk kept) */
   int32_t n_pad;                 /* filled by riab_bvc_pack: n_cells rounded up to the cell tile (64) */
+  int32_t egocentric;            /* reference_frame == "egocentric" (Neurons.py:1693-1708, FieldOfViewBVCs :1847-1887):
+                                    test angles are measured from utils.get_angle(head_direction) */
 } riab_bvc_cells;
 int64_t riab_bvc_pack_floats(int32_t n_cells, int32_t n_test_angles);
 int riab_bvc_pack(const double* tuning_distances, const double* tuning_angles, const double* sigma_distances,
@@ -182,7 +184,9 @@ int riab_bvc_pack(const double* tuning_distances, const double* tuning_angles, c
  * [agent tile of 32][T][32] order; first_wall_dev optional (n_pos,T) int32 (argmax wall id, Neurons.py:1677-1679). */
 int64_t riab_bvc_scratch_floats(int64_t n_pos, int32_t n_test_angles);
 int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_bvc_cells* bvc,
-                   float* scratch_dev, int32_t* first_wall_dev, float* out_dev, int64_t ld_out, void* stream);
+                   float* scratch_dev, int32_t* first_wall_dev, const double* head_direction_dev /* (n_pos,2) f64 for
+                   egocentric cells; NULL = [1,0] (the reference's default, Neurons.py:1703) */,
+                   float* out_dev, int64_t ld_out, void* stream);
 
 /* ------------------------------------------------------- Neurons.update extras
  * OU noise (Neurons.py:153-160) and spikes (Neurons.py:681-684) for a block of

@@ -64,7 +64,7 @@ def main():
     assert riab is not None, "reference not present"
     from ratinabox.Environment import Environment
     from ratinabox.Agent import Agent
-    from ratinabox.Neurons import PlaceCells, GridCells, BoundaryVectorCells
+    from ratinabox.Neurons import PlaceCells, GridCells, BoundaryVectorCells, FieldOfViewBVCs
     os.makedirs(GOLD, exist_ok=True)
 
     # ------------------------------------------------------------ native_c1
@@ -243,6 +243,31 @@ def main():
                 res[f"bvc_{name}_{k}"] = np.array(getattr(bvc, k)).copy()
     res["box2_walls"] = Env.walls.copy()
     np.savez_compressed(os.path.join(GOLD, "modeA_rates.npz"), **res)
+
+    # ------------------------------------------------- modeA_fov (egocentric BVCs)
+    rs = np.random.RandomState(777)
+    Pe = rs.uniform(0.001, 0.999, size=(160, 2))
+    ang = rs.uniform(0, 2 * np.pi, size=160)
+    HD = np.stack((np.cos(ang), np.sin(ang)), axis=1) * rs.uniform(0.5, 1.5, size=(160, 1))
+    fov = {"P": Pe, "HD": HD}
+    with mode_a([]):
+        for name, walls in (("box2", BOX_WALLS), ("maze8", maze_walls())):
+            E = Environment()
+            for w in walls:
+                E.add_wall(w)
+            AgE = Agent(E, {"dt": 0.01})
+            f = FieldOfViewBVCs(AgE, {"min_fr": 0.0, "max_fr": 2.0})
+            out = np.zeros((f.n, len(Pe)))
+            for j in range(len(Pe)):
+                out[:, j] = f.get_state(evaluate_at=None, pos=Pe[j], head_direction=HD[j])[:, 0]
+            fov[f"fov_{name}"] = out
+            fov[f"fov_{name}_walls"] = E.walls.copy()
+            for k in ("tuning_distances", "tuning_angles", "sigma_distances", "sigma_angles", "cell_fr_norm"):
+                fov[f"fov_{name}_{k}"] = np.array(getattr(f, k)).copy()
+            # the Agent's own head direction (evaluate_at="agent")
+            AgE.pos, AgE.head_direction = Pe[0].copy(), HD[0] / np.linalg.norm(HD[0])
+            fov[f"fov_{name}_agent"] = f.get_state()[:, 0]
+    np.savez_compressed(os.path.join(GOLD, "modeA_fov.npz"), **fov)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 

@@ -511,8 +511,10 @@ def bvc_first_wall_distances(env, pos, test_directions, rng):
 
 
 def bvc_get_state(env, tuning_distances, tuning_angles, sigma_distances, sigma_angles, pos, rng,
-                  dtheta=2, min_fr=0.0, max_fr=1.0, return_aux=False):
-    """BoundaryVectorCells.get_state (allocentric), Neurons.py:1617-1744 -> (N, n_pos)."""
+                  dtheta=2, min_fr=0.0, max_fr=1.0, return_aux=False, head_direction=None):
+    """BoundaryVectorCells.get_state, Neurons.py:1617-1744 -> (N, n_pos).  ``head_direction`` None =
+    allocentric; a 2-vector = egocentric frame (Neurons.py:1693-1708: the test angles are shifted by
+    utils.get_angle(head_direction), one head direction for all positions of the call)."""
     dirs, angs = bvc_test_angles(dtheta)
     norm = bvc_cell_fr_norm(angs, sigma_angles)
     d, first = bvc_first_wall_distances(env, pos, dirs, rng)        # (n_pos,T)
@@ -521,12 +523,35 @@ def bvc_get_state(env, tuning_distances, tuning_angles, sigma_distances, sigma_a
     mu_t = np.asarray(tuning_angles, dtype=float)[:, None, None]
     sg_t = np.asarray(sigma_angles, dtype=float)[:, None, None]
     g = np.exp(-((d[None] - mu_d) ** 2) / (2 * sg_d ** 2))          # utils.gaussian(norm=1), utils.py:424-438
-    vm = von_mises_peak1(angs[None, None, :], mu_t, sg_t)
+    test_angles = np.tile(angs[None, None, :], (len(norm), d.shape[0], 1))
+    if head_direction is not None:
+        test_angles -= get_angle(head_direction)                    # Neurons.py:1707-1708
+    vm = von_mises_peak1(test_angles, mu_t, sg_t)
     fr = (g * vm).sum(axis=-1) / norm[:, None]
     fr = fr * (max_fr - min_fr) + min_fr
     if return_aux:
         return fr, d, first
     return fr
+
+
+def diverging_radial_assembly(distance_range=(0.01, 0.2), angle_range=(0, 90), spatial_resolution=0.04, beta=5):
+    """utils.create_diverging_radial_assembly, utils.py:1073-1112 -> (mu_d, mu_theta, sigma_d, sigma_theta)."""
+    fov = [a * np.pi / 180 for a in angle_range]
+    mu_d, mu_t, sg_d, sg_t = [], [], [], []
+    radius = max(0.01, distance_range[0])
+    xi = spatial_resolution - radius / beta
+    while radius < distance_range[1]:
+        res = xi + radius / beta
+        dth = res / radius
+        if dth / 2 > fov[1]:
+            right = np.array([fov[0] + dth / 2])
+        else:
+            right = np.arange(fov[0] + dth / 2, fov[1], dth)
+        thetas = np.concatenate((-right[::-1], right))
+        for th in thetas:
+            mu_d.append(radius); mu_t.append(th); sg_d.append(res); sg_t.append(res / radius)
+        radius = (2 * radius + res + xi) / (2 - 1 / beta)
+    return np.array(mu_d), np.array(mu_t), np.array(sg_d), np.array(sg_t)
 
 
 class OracleNeurons:

@@ -465,15 +465,26 @@ class BoundaryVectorCells(Neurons):
     _cells_kind = _lib.CELLS_BVC
 
     def __init__(self, Agent, params={}):
-        from .utils import create_random_assembly, rotate
+        from .utils import (create_random_assembly, create_uniform_radial_assembly,
+                            create_diverging_radial_assembly, rotate)
         super().__init__(Agent, params)
-        if self.reference_frame != "allocentric":
-            raise NotImplementedError("egocentric BVCs are outside the CUDA hot path (SURVEY.md section 2 row 15)")
-        if not (self.cell_arrangement is None or (isinstance(self.cell_arrangement, str) and self.cell_arrangement[:6] == "random")):
-            raise NotImplementedError("manifold cell arrangements are host set-up outside the hot path; pass "
-                                      "tuning arrays to the random assembly instead")
+        if self.reference_frame not in ("allocentric", "egocentric"):
+            raise ValueError(f"unknown reference_frame {self.reference_frame!r}")
+        arr = self.cell_arrangement                                   # VectorCells.set_tuning_parameters, Neurons.py:1388-1437
+        if callable(arr):
+            tuning = arr(**self.params)
+        elif arr is None or (isinstance(arr, str) and arr[:6] == "random"):
+            tuning = create_random_assembly(**self.params)
+        elif arr == "uniform_manifold":
+            tuning = create_uniform_radial_assembly(**self.params)
+        elif arr == "diverging_manifold":
+            tuning = create_diverging_radial_assembly(**self.params)
+        else:
+            raise ValueError("cell_arrangement must be either 'uniform_manifold' or 'diverging_manifold' or a function")
         (self.tuning_distances, self.tuning_angles, self.sigma_distances,
-         self.sigma_angles) = (np.array(x, dtype=float) for x in create_random_assembly(**self.params))
+         self.sigma_angles) = (np.array(x, dtype=float) for x in tuning)
+        assert len(self.tuning_distances) == len(self.tuning_angles) == len(self.sigma_distances) == len(self.sigma_angles), \
+            "All manifold tuning parameters must be of the same length"
         self.n = len(self.tuning_distances)
         test_direction = np.array([1, 0])                           # Neurons.py:1584-1596 (duplicated-0 quirk kept)
         dirs, angs = [test_direction], [0]
@@ -490,7 +501,7 @@ class BoundaryVectorCells(Neurons):
     def _signature(self):
         return tuple(hash(np.ascontiguousarray(a, dtype=np.float64).tobytes()) for a in (
             self.tuning_distances, self.tuning_angles, self.sigma_distances, self.sigma_angles, self.test_angles,
-            self.test_directions)) + (float(self.min_fr), float(self.max_fr))
+            self.test_directions)) + (float(self.min_fr), float(self.max_fr), self.reference_frame)
 
     def _pack(self):
         arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (
@@ -505,6 +516,7 @@ class BoundaryVectorCells(Neurons):
         self._packed = self._upload(host)
         self._dirs_dev = self._upload(np.ascontiguousarray(self.test_directions, dtype=np.float64))
         c.n_cells, c.n_test_angles = self.n, T
+        c.egocentric = 1 if self.reference_frame == "egocentric" else 0
         c.min_fr, c.max_fr = float(self.min_fr), float(self.max_fr)
         c.packed_dev, c.test_dirs_dev = self._packed.data_ptr(), self._dirs_dev.data_ptr()
         return c
@@ -518,10 +530,62 @@ class BoundaryVectorCells(Neurons):
     def _scratch_ptr(self, n):
         return self._scratch_for(n).data_ptr()
 
-    def _rates_from_positions(self, pos_dev, n_pos, out, first_wall=None):
+    def _rates_from_positions(self, pos_dev, n_pos, out, first_wall=None, head_dir=None):
         ag = self.Agent
         scratch = self._scratch_for(n_pos)
         _lib.check(self._lib.riab_bvc_rates(pos_dev.data_ptr(), n_pos, C.byref(ag._env_struct()),
                                             C.byref(self._cells()), scratch.data_ptr(),
                                             first_wall.data_ptr() if first_wall is not None else None,
+                                            head_dir.data_ptr() if head_dir is not None else None,
                                             out.data_ptr(), out.stride(0), ag._stream()))
+
+    def get_state(self, evaluate_at="agent", **kwargs):
+        """BoundaryVectorCells.get_state (Neurons.py:1617-1744).  Egocentric cells take the Agent's
+        head_direction with evaluate_at="agent", else the ``head_direction`` kwarg (one vector for all
+        positions, or one per position), else [1,0] with the reference's warning (Neurons.py:1693-1706)."""
+        if self.reference_frame != "egocentric":
+            return super().get_state(evaluate_at, **kwargs)
+        torch = self._torch
+        self._cells()
+        if evaluate_at == "agent":
+            self.Agent._flush_pending()
+            pos_dev, hd_dev = self.Agent._s["pos"], self.Agent._s["head_direction"]
+        else:
+            pos = self.Agent.Environment.flattened_discrete_coords if evaluate_at == "all" else kwargs["pos"]
+            pos_dev = torch.as_tensor(np.ascontiguousarray(np.asarray(pos, dtype=np.float64).reshape(-1, 2)), device=self.device)
+            if "head_direction" in kwargs:
+                hd = np.asarray(kwargs["head_direction"], dtype=np.float64)
+            elif "vel" in kwargs:
+                warnings.warn("'vel' kwarg deprecated in favour of 'head_direction'")
+                hd = np.asarray(kwargs["vel"], dtype=np.float64)
+            else:
+                warnings.warn("BVCs in egocentric plane require a head direction vector but none was passed. Using [1,0]")
+                hd = np.array([1.0, 0.0])
+            hd = np.ascontiguousarray(np.broadcast_to(hd.reshape(-1, 2), (pos_dev.shape[0], 2)))
+            hd_dev = torch.as_tensor(hd, device=self.device)
+        n_pos = int(pos_dev.shape[0])
+        out = torch.empty((n_pos, self._ld()), dtype=torch.float32, device=self.device)
+        if n_pos:
+            self._rates_from_positions(pos_dev, n_pos, out, head_dir=hd_dev)
+        if kwargs.get("return_tensor", False):
+            return out[:, : self.n]
+        return out[:, : self.n].T.contiguous().cpu().numpy().astype(np.float64)
+
+
+class FieldOfViewBVCs(BoundaryVectorCells):
+    """Egocentric BVCs tiling the agent's field of view (ratinabox/Neurons.py:1847-1887)."""
+    default_params = {
+        "distance_range": [0.02, 0.4],
+        "angle_range": [0, 75],
+        "spatial_resolution": 0.02,
+        "cell_arrangement": "diverging_manifold",
+        "beta": 5,
+        "color": [0.3, 0.3, 0.3, 1],
+    }
+
+    def __init__(self, Agent, params={}):
+        p = copy.deepcopy(__class__.default_params)
+        p.update(params)
+        p["reference_frame"] = "egocentric"
+        assert p["cell_arrangement"] is not None, "cell_arrangement must be set for FoV Neurons"
+        super().__init__(Agent, p)

@@ -10,6 +10,6 @@ verbose = False
 
 from .Environment import Environment          # noqa: E402
 from .Agent import Agent                      # noqa: E402
-from .Neurons import Neurons, PlaceCells, GridCells, BoundaryVectorCells   # noqa: E402
+from .Neurons import Neurons, PlaceCells, GridCells, BoundaryVectorCells, FieldOfViewBVCs   # noqa: E402
 
-__all__ = ["Environment", "Agent", "Neurons", "PlaceCells", "GridCells", "BoundaryVectorCells"]
+__all__ = ["Environment", "Agent", "Neurons", "PlaceCells", "GridCells", "BoundaryVectorCells", "FieldOfViewBVCs"]

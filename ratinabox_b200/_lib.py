@@ -56,7 +56,8 @@ class GridCells(C.Structure):
 
 class BvcCells(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("n_test_angles", C.c_int32), ("min_fr", C.c_float), ("max_fr", C.c_float),
-                ("packed_dev", C.c_void_p), ("test_dirs_dev", C.c_void_p), ("n_pad", C.c_int32)]
+                ("packed_dev", C.c_void_p), ("test_dirs_dev", C.c_void_p), ("n_pad", C.c_int32),
+                ("egocentric", C.c_int32)]
 
 
 class NeuronNoise(C.Structure):
@@ -103,7 +104,7 @@ SYMBOLS = {
     "riab_bvc_pack": (C.c_int, [c_double_p, c_double_p, c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32,
                                 C.POINTER(BvcCells), c_float_p]),
     "riab_bvc_rates": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Env), C.POINTER(BvcCells), C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_int64, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "riab_step_fused": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
                                   C.c_int32, C.c_void_p, C.POINTER(NeuronNoise), C.POINTER(RatesOut), C.c_void_p]),
     "riab_neurons_update": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.c_int32, C.c_void_p, C.POINTER(NeuronNoise),

@@ -717,6 +717,86 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
   }
 }
 
+// BVC phase B, egocentric frame: same tiling as k_bvc_integrate, no von Mises table.
+__global__ void __launch_bounds__(NT) k_bvc_integrate_ego(const BvcConst bc, const float* __restrict__ scratch,
+                                                          const long long n_rows, const long long n_tiles,
+                                                          const OutK out) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  const int T = bc.T;
+  float2* s_th = reinterpret_cast<float2*>(dyn);                    // [T] (cos, sin) of the test angles
+  float* s_d0 = reinterpret_cast<float*>(dyn) + 2 * (size_t)((T + 1) / 2 * 2);   // [T][32] x 2 buffers
+  float* s_d1 = s_d0 + (size_t)T * BVC_AT;
+  __shared__ uint64_t bar_d[2];
+  const int ct = blockIdx.x;
+  const int tid = threadIdx.x, cl = tid & 63, g = tid >> 6;
+  const int cell = ct * BVC_CT + cl;
+  const uint32_t d_bytes = (uint32_t)T * BVC_AT * 4u;
+  const float* base = bc.packed;
+  const size_t np = (size_t)bc.n_pad;
+  const float* ext = base + 3 * np + np * (size_t)T;               // kap | cmu | smu | cth | sth
+  for (int i = tid; i < T; i += blockDim.x) s_th[i] = make_float2(ext[3 * np + i], ext[3 * np + T + i]);
+  if (tid == 0) {
+    mbar_init(&bar_d[0], 1); mbar_init(&bar_d[1], 1);
+    mbar_fence_init();
+    long long t0 = blockIdx.y;
+    if (t0 < n_tiles) { mbar_expect_tx(&bar_d[0], d_bytes); tma_bulk_g2s(s_d0, scratch + (size_t)t0 * T * BVC_AT, d_bytes, &bar_d[0]); }
+  }
+  __syncthreads();
+  const float sc = base[cell], mc = base[np + cell], scale = base[2 * np + cell];
+  const float kap = ext[cell], cmu = ext[np + cell], smu = ext[2 * np + cell];
+  uint32_t phase[2] = {0u, 0u};
+  int buf = 0;
+  for (long long t = blockIdx.y; t < n_tiles; t += gridDim.y, buf ^= 1) {
+    const long long tn = t + gridDim.y;
+    if (tid == 0 && tn < n_tiles) {
+      mbar_expect_tx(&bar_d[buf ^ 1], d_bytes);
+      tma_bulk_g2s(buf ? s_d0 : s_d1, scratch + (size_t)tn * T * BVC_AT, d_bytes, &bar_d[buf ^ 1]);
+    }
+    // (cos, sin)(head bearing + mu_theta) for this thread's 8 agents
+    float cph[8], sph[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long row = t * BVC_AT + 8 * g + i;
+      float hx = 1.0f + 1e-6f, hy = 0.f;                            // default head direction [1,0] (Neurons.py:1703)
+      if (bc.head_dir != nullptr && row < n_rows) {
+        hx = (float)(bc.head_dir[2 * row] + 1e-6);                  // utils.get_angle: atan2(y, x + eps)
+        hy = (float)bc.head_dir[2 * row + 1];
+      }
+      const float rn = rsqrtf(fmaf(hx, hx, hy * hy));
+      const float ch = hx * rn, sh = hy * rn;
+      cph[i] = fmaf(-sh, smu, ch * cmu);
+      sph[i] = fmaf(ch, smu, sh * cmu);
+    }
+    mbar_wait(&bar_d[buf], phase[buf]);
+    phase[buf] ^= 1u;
+    const float* sd = (buf ? s_d1 : s_d0) + 8 * g;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int th = 0; th < T; ++th) {
+      const float2 cs = s_th[th];
+      const float4 da = *reinterpret_cast<const float4*>(sd + th * BVC_AT);
+      const float4 db = *reinterpret_cast<const float4*>(sd + th * BVC_AT + 4);
+      const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(dv[i], sc, -mc);                       // (d - mu_d) * s
+        const float c = fmaf(cs.y, sph[i], cs.x * cph[i]);          // cos(theta - bearing - mu_theta)
+        acc[i] += ex2f(fmaf(kap, c - 1.0f, -u * u));                // gaussian * von Mises in one ex2
+      }
+    }
+    if (cell < bc.n_cells) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long row = t * BVC_AT + 8 * g + i;
+        if (row < n_rows) st_cs_f1(out.rates + row * out.ld + cell, fmaf(acc[i] * scale, bc.span, bc.min_fr));
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host helpers
 int make_env(const riab_env* env, EnvK& k) {
@@ -889,7 +969,7 @@ int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_param
 template <bool FUSED>
 int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                const riab_bvc_cells* bvc, const OutK& out, const double* pos_in, long long n_rows, float* scratch,
-               int32_t* first_wall, cudaStream_t s) {
+               int32_t* first_wall, const double* head_dir, cudaStream_t s) {
   if (bvc == nullptr || bvc->packed_dev == nullptr || bvc->test_dirs_dev == nullptr)
     return fail(RIAB_ERR_INVALID, "bvc cells / packed_dev / test_dirs_dev NULL");
   if (scratch == nullptr) return fail(RIAB_ERR_INVALID, "bvc scratch NULL");
@@ -898,6 +978,7 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   bc.n_cells = bvc->n_cells; bc.n_pad = bvc->n_pad; bc.T = bvc->n_test_angles;
   bc.min_fr = bvc->min_fr; bc.span = bvc->max_fr - bvc->min_fr;
   bc.packed = bvc->packed_dev; bc.test_dirs = bvc->test_dirs_dev;
+  bc.ego = bvc->egocentric; bc.head_dir = head_dir;
   const long long n_tiles = (n_rows + BVC_AT - 1) / BVC_AT;
   const size_t smemA = (size_t)bc.T * 2 * sizeof(double);
   const size_t smemB = (size_t)bc.T * (BVC_CT + 2 * BVC_AT) * sizeof(float);
@@ -921,7 +1002,17 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   unsigned gy = (unsigned)((2 * 148 + cts - 1) / cts);           // ~2 CTAs per SM in total
   if (gy > n_tiles) gy = (unsigned)n_tiles;
   if (gy < 1) gy = 1;
-  k_bvc_integrate<<<dim3(cts, gy), NT, smemB, s>>>(bc, scratch, n_rows, n_tiles, out);
+  if (bc.ego) {
+    static bool attr_ego = false;
+    if (!attr_ego) {
+      RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate_ego, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_ego = true;
+    }
+    const size_t smemE = ((size_t)((bc.T + 1) / 2 * 2) * 2 + (size_t)bc.T * 2 * BVC_AT) * sizeof(float);
+    k_bvc_integrate_ego<<<dim3(cts, gy), NT, smemE, s>>>(bc, scratch, n_rows, n_tiles, out);
+  } else {
+    k_bvc_integrate<<<dim3(cts, gy), NT, smemB, s>>>(bc, scratch, n_rows, n_tiles, out);
+  }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   if (out.noise != nullptr || out.spikes != nullptr) {
@@ -1109,7 +1200,7 @@ static int bvc_n_pad(int n) { return (n + BVC_CT - 1) / BVC_CT * BVC_CT; }
 
 int64_t riab_bvc_pack_floats(int32_t n_cells, int32_t T) {
   const int64_t np = bvc_n_pad(n_cells);
-  return 3 * np + np * (int64_t)T;
+  return 3 * np + np * (int64_t)T + 3 * np + 2 * (int64_t)T;
 }
 int64_t riab_bvc_scratch_floats(int64_t n_pos, int32_t T) {
   return ((n_pos + BVC_AT - 1) / BVC_AT) * (int64_t)T * BVC_AT;
@@ -1134,12 +1225,23 @@ int riab_bvc_pack(const double* mu_d, const double* mu_t, const double* sg_d, co
     for (int t = 0; t < T; ++t)
       vm[((size_t)tile * T + t) * BVC_CT + cl] = (float)(exp(kappa * cos(test_angles[t] - mu_t[i])) * (1.0 / exp(kappa)));
   }
+  float* ext = vm + (size_t)np * T;                                  // egocentric: kap | cmu | smu | cth | sth
+  for (int i = 0; i < n; ++i) {
+    ext[i] = (float)(1.4426950408889634 / (sg_t[i] * sg_t[i]));
+    ext[np + i] = (float)cos(mu_t[i]);
+    ext[2 * np + i] = (float)sin(mu_t[i]);
+  }
+  for (int t = 0; t < T; ++t) {
+    ext[3 * (size_t)np + t] = (float)cos(test_angles[t]);
+    ext[3 * (size_t)np + T + t] = (float)sin(test_angles[t]);
+  }
   meta->n_pad = np;
   return 0;
 }
 
 int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_bvc_cells* bvc,
-                   float* scratch_dev, int32_t* first_wall_dev, float* out_dev, int64_t ld_out, void* stream) {
+                   float* scratch_dev, int32_t* first_wall_dev, const double* head_direction_dev, float* out_dev,
+                   int64_t ld_out, void* stream) {
   if (n_pos == 0) return 0;
   EnvK ek;
   OutK ok;
@@ -1154,7 +1256,8 @@ int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, co
   riab_agents ag; memset(&ag, 0, sizeof(ag));
   riab_motion_params mp; memset(&mp, 0, sizeof(mp));
   riab_step_io io; memset(&io, 0, sizeof(io));
-  return launch_bvc<false>(ek, ag, mp, io, bvc, ok, pos_dev, n_pos, scratch_dev, first_wall_dev, (cudaStream_t)stream);
+  return launch_bvc<false>(ek, ag, mp, io, bvc, ok, pos_dev, n_pos, scratch_dev, first_wall_dev, head_direction_dev,
+                           (cudaStream_t)stream);
 }
 
 // ----------------------------------------------------------------- fused step
@@ -1207,7 +1310,8 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
     // fusing the 128-register motion code into it halves its occupancy and adds a tail wave, so the
     // motion runs as its own (14 us) kernel first.
     if (MODE == 1 && (rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
-    return launch_bvc<false>(ek, *agents, mp0, io0, bvc, ok, agents->pos, agents->n_agents, out->bvc_scratch, nullptr, s);
+    return launch_bvc<false>(ek, *agents, mp0, io0, bvc, ok, agents->pos, agents->n_agents, out->bvc_scratch, nullptr,
+                             agents->head_direction, s);
   }
   return fail(RIAB_ERR_INVALID, "bad cells_kind %d", cells_kind);
 }

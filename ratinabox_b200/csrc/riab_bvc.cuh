@@ -17,8 +17,14 @@
 // shared memory by TMA bulk copies; the Gaussian is one FFMA + FMUL + MUFU.EX2.
 //
 // Packed block (float32, riab_bvc_pack), Np = n_cells rounded up to BVC_CT (64):
-//   s[Np] | m[Np] | scale[Np] | VM tiles: [Np/64][T][64]
-//   s = sqrt(log2(e)/2)/sigma_d, m = mu_d*s, scale = 1/cell_fr_norm
+//   s[Np] | m[Np] | scale[Np] | VM tiles: [Np/64][T][64] | kap[Np] | cmu[Np] | smu[Np] | cth[T] | sth[T]
+//   s = sqrt(log2(e)/2)/sigma_d, m = mu_d*s, scale = 1/cell_fr_norm,
+//   kap = log2(e)/sigma_theta^2, (cmu,smu) = (cos,sin)(mu_theta), (cth,sth) = (cos,sin)(test angle).
+// Egocentric cells (FieldOfViewBVCs): the von Mises argument is theta - head_bearing - mu_theta, which
+// depends on the agent, so no table: cos(theta - phi) = cth*cos(phi) + sth*sin(phi) with
+// (cos,sin)(phi = bearing + mu_theta) formed algebraically per (agent, cell) from the head direction
+// (cos(bearing), sin(bearing)) = (x+1e-6, y)/|(x+1e-6, y)|  -- utils.get_angle's eps quirk included --
+// and both exponentials share ONE ex2:  2^(kap*(cos-1) - u^2).
 // Scratch (phase A -> B): dist_to_first_wall as [agent tile of 32][T][32] float32.
 #pragma once
 #include "riab_common.cuh"
@@ -97,7 +103,8 @@ RIAB_DEV void bvc_first_wall(double px, double py, double ux, double uy, const d
 }
 
 struct BvcConst {
-  int n_cells, n_pad, T;
+  int n_cells, n_pad, T, ego;
+  const double* head_dir;    // device (n_rows,2) or NULL (egocentric only)
   float min_fr, span;
   const float* packed;
   const double* test_dirs;   // device (T,2)

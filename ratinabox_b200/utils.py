@@ -69,3 +69,34 @@ def create_random_assembly(tuning_distance_distribution="uniform", tuning_distan
     mu_t = draw(tuning_angle, tuning_angle_distribution) * (np.pi / 180)
     sg_t = draw(sigma_angle, sigma_angle_distribution) * (np.pi / 180)
     return mu_d, mu_t, sg_d, sg_t
+
+
+def create_uniform_radial_assembly(distance_range=(0.0, 0.2), angle_range=(0, 90), spatial_resolution=0.04, **kwargs):
+    """Concentric rows of equally sized receptive fields tiling a field of view (the reference's
+    utils.create_uniform_radial_assembly, ratinabox/utils.py:1033-1070)."""
+    lo, hi = (a * np.pi / 180 for a in angle_range)
+    mu_d, mu_t, sg_d, sg_t = [], [], [], []
+    for radius in np.arange(max(0.01, distance_range[0]), distance_range[1], spatial_resolution):
+        dtheta = spatial_resolution / radius
+        right = np.arange(lo + dtheta / 2, hi, dtheta)
+        for theta in np.concatenate((-right[::-1], right)):
+            mu_d.append(radius); mu_t.append(theta); sg_d.append(spatial_resolution); sg_t.append(spatial_resolution / radius)
+    return mu_d, mu_t, sg_d, sg_t
+
+
+def create_diverging_radial_assembly(distance_range=(0.01, 0.2), angle_range=(0, 90), spatial_resolution=0.04,
+                                     beta=5, **kwargs):
+    """Rows whose receptive fields grow with radius (Hartley et al. 2000): sigma_d = xi + radius/beta with xi fixed
+    by the innermost row (the reference's utils.create_diverging_radial_assembly, ratinabox/utils.py:1073-1112)."""
+    lo, hi = (a * np.pi / 180 for a in angle_range)
+    mu_d, mu_t, sg_d, sg_t = [], [], [], []
+    radius = max(0.01, distance_range[0])
+    xi = spatial_resolution - radius / beta
+    while radius < distance_range[1]:
+        res = xi + radius / beta
+        dtheta = res / radius
+        right = np.array([lo + dtheta / 2]) if dtheta / 2 > hi else np.arange(lo + dtheta / 2, hi, dtheta)
+        for theta in np.concatenate((-right[::-1], right)):
+            mu_d.append(radius); mu_t.append(theta); sg_d.append(res); sg_t.append(res / radius)
+        radius = (2 * radius + res + xi) / (2 - 1 / beta)      # next row just touches this one
+    return mu_d, mu_t, sg_d, sg_t

@@ -101,8 +101,12 @@ def test_grid_and_bvc_pack():
     np_ = bmeta.n_pad
     assert np_ == 64
     assert np.allclose(bout[2 * np_:2 * np_ + n], 1 / O.bvc_cell_fr_norm(angs, sg_t), rtol=1e-6)
-    vm = bout[3 * np_:].reshape(1, T, 64)[0, :, :n].T
+    vm = bout[3 * np_:3 * np_ + np_ * T].reshape(1, T, 64)[0, :, :n].T
     assert np.allclose(vm, O.von_mises_peak1(angs[None, :], mu_t[:, None], sg_t[:, None]), rtol=1e-6, atol=1e-30)
+    ext = bout[3 * np_ + np_ * T:]                      # egocentric extras: kap | cos mu | sin mu | cos theta | sin theta
+    assert np.allclose(ext[:n], np.log2(np.e) / sg_t ** 2, rtol=1e-6)
+    assert np.allclose(ext[np_:np_ + n], np.cos(mu_t), atol=1e-7) and np.allclose(ext[2 * np_:2 * np_ + n], np.sin(mu_t), atol=1e-7)
+    assert np.allclose(ext[3 * np_:3 * np_ + T], np.cos(angs), atol=1e-7) and len(ext) == 3 * np_ + 2 * T
     assert lib.riab_bvc_scratch_floats(33, T) == 2 * T * 32
 
 

@@ -130,3 +130,30 @@ def test_bvc_modeA_golden(golden, name):
     assert np.array_equal(bvc.test_angles, g[f"bvc_{name}_test_angles"])
     assert np.array_equal(bvc.test_directions, g[f"bvc_{name}_test_directions"])
     assert_rates_close(bvc.get_state(evaluate_at=None, pos=P), g[f"bvc_{name}"], 5.0, f"bvc {name}")
+
+
+@pytest.mark.parametrize("name", ["box2", "maze8"])
+def test_field_of_view_bvcs_egocentric_golden(golden, name):
+    """FieldOfViewBVCs (egocentric frame; Neurons.py:1693-1708, :1847-1887) against the live reference:
+    same manifold, rates at 160 positions each with its own head direction, and the Agent's own."""
+    import ratinabox_b200 as rb
+    g = golden("modeA_fov.npz")
+    P, HD = g["P"], g["HD"]
+    E = _env(rb, g[f"fov_{name}_walls"])
+    Ag = rb.Agent(E, {"dt": 0.01})
+    fov = rb.FieldOfViewBVCs(Ag, {"min_fr": 0.0, "max_fr": 2.0})
+    for k, attr in (("tuning_distances", "tuning_distances"), ("tuning_angles", "tuning_angles"),
+                    ("sigma_distances", "sigma_distances"), ("sigma_angles", "sigma_angles")):
+        assert np.array_equal(getattr(fov, attr), g[f"fov_{name}_{k}"]), k
+    assert np.allclose(fov.cell_fr_norm, g[f"fov_{name}_cell_fr_norm"], rtol=1e-14)
+    got = fov.get_state(evaluate_at=None, pos=P, head_direction=HD)
+    assert_rates_close(got, g[f"fov_{name}"], 2.0, f"fov {name}", pure_rel=False)
+    Ag.pos, Ag.head_direction = P[0], HD[0] / np.linalg.norm(HD[0])
+    assert_rates_close(fov.get_state()[:, 0], g[f"fov_{name}_agent"], 2.0, f"fov agent {name}", pure_rel=False)
+    # the update() path uses the Agent's (post-motion) head direction
+    Ag.update(); fov.update()
+    import riab_oracle as O
+    env = O.OracleEnvironment(walls=g[f"fov_{name}_walls"][4:])
+    ref = O.bvc_get_state(env, fov.tuning_distances, fov.tuning_angles, fov.sigma_distances, fov.sigma_angles,
+                          Ag.pos, O.TapeRNG(), min_fr=0.0, max_fr=2.0, head_direction=Ag.head_direction)[:, 0]
+    assert np.abs(fov.firingrate - ref).max() <= 2e-5

@@ -130,3 +130,26 @@ def test_modeA_rates(golden):
                              g[f"bvc_{name}_sigma_distances"], g[f"bvc_{name}_sigma_angles"], P, rng,
                              min_fr=0.0, max_fr=5.0)
         assert np.array_equal(fr, g[f"bvc_{name}"]), name
+
+
+def test_modeA_fov_egocentric_bvcs(golden):
+    """FieldOfViewBVCs (egocentric frame, diverging manifold) -- Neurons.py:1693-1708, :1847-1887,
+    utils.py:1073-1112 -- against the live reference."""
+    g = golden("modeA_fov.npz")
+    P, HD = g["P"], g["HD"]
+    mu_d, mu_t, sg_d, sg_t = O.diverging_radial_assembly(distance_range=[0.02, 0.4], angle_range=[0, 75],
+                                                         spatial_resolution=0.02, beta=5)
+    rng = O.TapeRNG()
+    for name in ("box2", "maze8"):
+        assert np.array_equal(mu_d, g[f"fov_{name}_tuning_distances"])
+        assert np.array_equal(mu_t, g[f"fov_{name}_tuning_angles"])
+        assert np.array_equal(sg_d, g[f"fov_{name}_sigma_distances"])
+        assert np.array_equal(sg_t, g[f"fov_{name}_sigma_angles"])
+        env = O.OracleEnvironment(walls=g[f"fov_{name}_walls"][4:])
+        ref = g[f"fov_{name}"]
+        for j in range(0, len(P), 3):
+            fr = O.bvc_get_state(env, mu_d, mu_t, sg_d, sg_t, P[j], rng, min_fr=0.0, max_fr=2.0, head_direction=HD[j])
+            assert np.array_equal(fr[:, 0], ref[:, j]), (name, j)
+        hd0 = HD[0] / np.linalg.norm(HD[0])
+        fr = O.bvc_get_state(env, mu_d, mu_t, sg_d, sg_t, P[0], rng, min_fr=0.0, max_fr=2.0, head_direction=hd0)
+        assert np.array_equal(fr[:, 0], g[f"fov_{name}_agent"])
