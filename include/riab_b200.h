@@ -45,12 +45,17 @@ const char* riab_last_error(void);
 
 /* ---------------------------------------------------------------- Environment
  * walls: (n_walls,2,2) float64, boundary walls first (Environment.py:137-144),
- * then user walls (add_wall, :330-342).  Solid rectangular 2D box only. */
+ * then user walls (add_wall, :330-342).  Rectangular 2D box, solid or periodic. */
 typedef struct {
   const double* walls_dev;     /* device, n_walls*4 doubles */
   int32_t n_walls;
   int32_t n_boundary_walls;    /* 4: Environment.py:715-717 `walls[4:]` */
   double extent[4];            /* left,right,bottom,top  (Environment.py:171-173) */
+  int32_t periodic;            /* boundary_conditions == "periodic" (rectangular box, no boundary walls built:
+                                  Environment.py:130-144); positions wrap (:877-879), displacement / distance
+                                  vectors take the short way round (:670-675) */
+  int32_t reserved;
+  double scale;                /* Environment.scale: the wrap threshold is scale/2 on both axes (:671) */
 } riab_env;
 
 /* ---------------------------------------------------------------------- Agent

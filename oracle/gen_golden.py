@@ -268,6 +268,56 @@ def main():
             AgE.pos, AgE.head_direction = Pe[0].copy(), HD[0] / np.linalg.norm(HD[0])
             fov[f"fov_{name}_agent"] = f.get_state()[:, 0]
     np.savez_compressed(os.path.join(GOLD, "modeA_fov.npz"), **fov)
+
+    # ------------------------------------------------- periodic boundary conditions
+    per = {}
+    for name, walls in (("open", []), ("wall", [[[0.5, 0.2], [0.5, 0.8]]])):
+        np.random.seed(11)
+        Env = Environment({"boundary_conditions": "periodic"})
+        for w in walls:
+            Env.add_wall(w)
+        Ag = Agent(Env, {"dt": 0.05, "speed_mean": 0.5})
+        PCs = PlaceCells(Ag, {"n": 30, "widths": 0.15})
+        GCs = GridCells(Ag, {"n": 9})
+        per[f"{name}_walls"] = Env.walls.copy()
+        per[f"{name}_pos0"], per[f"{name}_vel0"] = Ag.pos.copy(), Ag.velocity.copy()
+        per[f"{name}_centres"], per[f"{name}_widths"] = PCs.place_cell_centres.copy(), PCs.place_cell_widths.copy()
+        per[f"{name}_geom"] = np.array(PCs.wall_geometry)
+        per[f"{name}_gridscales"], per[f"{name}_phase"], per[f"{name}_w"] = GCs.gridscales.copy(), GCs.phase_offsets.copy(), GCs.w.copy()
+        st = np.random.get_state()
+        per[f"{name}_rng_keys"], per[f"{name}_rng_pos"], per[f"{name}_rng_has_gauss"], per[f"{name}_rng_cached"] = st[1], st[2], st[3], st[4]
+        for _ in range(800):
+            Ag.update(); PCs.update(); GCs.update()
+        pos = np.array(Ag.history["pos"])
+        wraps = int((np.abs(np.diff(pos, axis=0)) > 0.5).any(axis=1).sum())
+        print(f"periodic[{name}]: boundary crossings = {wraps}")
+        per[f"{name}_pos"], per[f"{name}_vel"] = pos, np.array(Ag.history["vel"])
+        per[f"{name}_rot_vel"], per[f"{name}_dist"] = np.array(Ag.history["rot_vel"]), np.array(Ag.history["distance_travelled"])
+        per[f"{name}_pc_fr"], per[f"{name}_gc_fr"] = np.array(PCs.history["firingrate"]), np.array(GCs.history["firingrate"])
+        # mode A single steps near / across the boundary + rates at positions
+        rs = np.random.RandomState(99)
+        A = 256
+        pos0 = rs.uniform(0.0, 1.0, size=(A, 2))
+        edge = rs.choice(A, A // 2, replace=False)
+        pos0[edge, rs.randint(0, 2, size=len(edge))] = rs.choice([0.002, 0.998], size=len(edge)) + rs.normal(scale=1e-3, size=len(edge))
+        pos0 = np.clip(pos0, 1e-4, 1 - 1e-4)
+        ang = rs.uniform(0, 2 * np.pi, size=A)
+        vel0 = rs.rayleigh(0.5, size=A)[:, None] * np.stack((np.cos(ang), np.sin(ang)), axis=1)
+        xi = rs.normal(size=(A, 2))
+        outp, outmv, outd = [], [], []
+        for a in range(A):
+            Ag.pos, Ag.velocity = pos0[a].copy(), vel0[a].copy()
+            Ag.rotational_velocity, Ag.measured_velocity = 0.0, vel0[a].copy()
+            Ag.head_direction, Ag.distance_travelled = vel0[a] / np.linalg.norm(vel0[a]), 0.0
+            with mode_a(list(xi[a])):
+                Ag.update()
+            outp.append(Ag.pos.copy()); outmv.append(Ag.measured_velocity.copy()); outd.append(Ag.distance_travelled)
+        per[f"{name}_A_pos0"], per[f"{name}_A_vel0"], per[f"{name}_A_xi"] = pos0, vel0, xi
+        per[f"{name}_A_pos"], per[f"{name}_A_mv"], per[f"{name}_A_dist"] = np.array(outp), np.array(outmv), np.array(outd)
+        print(f"periodic[{name}] mode A: wrapped = {int((np.abs(np.array(outp) - pos0) > 0.5).any(axis=1).sum())} / {A}")
+        with mode_a([]):
+            per[f"{name}_A_pc"] = PCs.get_state(evaluate_at=None, pos=pos0)
+    np.savez_compressed(os.path.join(GOLD, "periodic.npz"), **per)
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 

@@ -175,14 +175,17 @@ def rayleigh_to_normal(x, sigma=1.0):
 
 # ------------------------------------------------------------------ Environment
 class OracleEnvironment:
-    """The subset of Environment.__init__ (Environment.py:77-209) the path
-    needs: a solid rectangular 2D box, boundary walls first then user walls
-    (Environment.py:137-144, add_wall :330-342)."""
+    """The subset of Environment.__init__ (Environment.py:77-209) the path needs: a rectangular 2D box,
+    solid (boundary walls first, then user walls; Environment.py:137-144, add_wall :330-342) or periodic
+    (no boundary walls: only the `solid` branch builds them, Environment.py:130-144)."""
 
-    def __init__(self, scale=1.0, aspect=1.0, walls=()):
+    def __init__(self, scale=1.0, aspect=1.0, walls=(), boundary_conditions="solid"):
         b = [[0, 0], [aspect * scale, 0], [aspect * scale, scale], [0, scale]]
-        boundary_walls = np.array([[b[(i + 1) if (i + 1) < 4 else 0], b[i]] for i in range(4)], dtype=float)
-        self.walls = boundary_walls
+        self.boundary_conditions = boundary_conditions
+        if boundary_conditions == "solid":
+            self.walls = np.array([[b[(i + 1) if (i + 1) < 4 else 0], b[i]] for i in range(4)], dtype=float)
+        else:
+            self.walls = np.zeros((0, 2, 2))
         for w in walls:
             self.add_wall(w)
         self.extent = np.array([0.0, aspect * scale, 0.0, scale])
@@ -193,20 +196,36 @@ class OracleEnvironment:
         self.walls = np.concatenate((self.walls, np.asarray(wall, dtype=float).reshape(1, 2, 2)), axis=0)
 
     def contains(self, pos):
-        """Environment.py:781-818 for a rectangle without holes (the shapely
-        strict-interior test of a rectangle == four strict compares)."""
+        """Environment.py:781-818 for a rectangle without holes (the shapely strict-interior test of a
+        rectangle == four strict compares)."""
         e = self.extent
         return bool((pos[0] > e[0]) and (pos[0] < e[1]) and (pos[1] > e[2]) and (pos[1] < e[3]))
 
     def apply_boundary_conditions(self, pos):
-        """Environment.py:855-894, solid rectangular branch (:880-889)."""
+        """Environment.py:855-894, rectangular branch: solid clamp (:880-889) / periodic wrap (:877-879)."""
         if self.contains(pos):
             return pos
         e = self.extent
         pos = np.array(pos, dtype=float)
-        pos[0] = min(max(pos[0], e[0] + 0.01), e[1] - 0.01)
-        pos[1] = min(max(pos[1], e[2] + 0.01), e[3] - 0.01)
+        if self.boundary_conditions == "periodic":
+            pos[0] = pos[0] % e[1]
+            pos[1] = pos[1] % e[3]
+        else:
+            pos[0] = min(max(pos[0], e[0] + 0.01), e[1] - 0.01)
+            pos[1] = min(max(pos[1], e[2] + 0.01), e[3] - 0.01)
         return pos
+
+    def vectors_between(self, pos1, pos2):
+        """Environment.get_vectors_between___accounting_for_environment (Environment.py:657-675):
+        pairwise pos1 - pos2 (utils.py:213), wrapped through the boundary when periodic (note: the
+        reference compares against ``scale`` on both axes)."""
+        pos1 = np.asarray(pos1, dtype=float).reshape(-1, 2)
+        pos2 = np.asarray(pos2, dtype=float).reshape(-1, 2)
+        v = pos1[:, None, :] - pos2[None, :, :]
+        if self.boundary_conditions == "periodic":
+            flip = np.abs(v) > (self.scale / 2)
+            v[flip] = -np.sign(v[flip]) * (self.scale - np.abs(v[flip]))
+        return v
 
 
 # ------------------------------------------------------------------------ Agent
@@ -322,6 +341,8 @@ class OracleAgent:
     def _check_and_handle_wall_collisions(self, rng, info):
         """Agent.py:423-441 + Environment.check_wall_collisions (Environment.py:820-841)."""
         walls = self.env.walls
+        if len(walls) == 0:                                   # Environment.py:833-835: nothing to collide with
+            return
         while True:
             step = np.array([self.prev_pos, self.pos])
             hit = vector_intercepts(walls, step, rng, return_collisions=True).reshape(-1)
@@ -336,7 +357,7 @@ class OracleAgent:
 
     def _measure_velocity_of_step_taken(self, rng):
         """Agent.py:444-472."""
-        self.measured_velocity = (self.pos - self.prev_pos).reshape(-1) / self.dt
+        self.measured_velocity = self.env.vectors_between(self.pos, self.prev_pos).reshape(-1) / self.dt
         if np.linalg.norm(self.measured_velocity) == 0:
             self.measured_velocity = 1e-8 * rng.randn(2)
         now, before = get_angle(self.measured_velocity), get_angle(self.prev_measured_velocity)
@@ -354,7 +375,7 @@ class OracleAgent:
 
     def _update_distance_travelled(self):
         """Agent.py:502-507."""
-        self.distance_travelled += np.linalg.norm((self.pos - self.prev_pos).reshape(1, 1, 2), axis=-1)[0][0]
+        self.distance_travelled += np.linalg.norm(self.env.vectors_between(self.pos, self.prev_pos), axis=-1)[0][0]
 
     def _save_to_history(self):
         """Agent.py:509-521."""
@@ -372,7 +393,7 @@ def distances_accounting_for_environment(env, pos1, pos2, wall_geometry, rng):
     """Environment.py:677-779 for a solid 2D box -> (N1,N2) distances."""
     pos1 = np.asarray(pos1, dtype=float).reshape(-1, 2)
     pos2 = np.asarray(pos2, dtype=float).reshape(-1, 2)
-    vec = pos1[:, None, :] - pos2[None, :, :]                      # utils.py:213
+    vec = env.vectors_between(pos1, pos2)                          # utils.py:213 (+ periodic wrap, Environment.py:670-675)
     dist = np.linalg.norm(vec, axis=-1)
     if wall_geometry == "euclidean":
         return dist

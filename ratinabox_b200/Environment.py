@@ -1,10 +1,10 @@
 """Host mirror of ``ratinabox.Environment`` for the CUDA step engine.
 
-Only what the hot path needs lives here: a solid, rectangular 2D
-box with internal walls.  Construction semantics follow the reference:
+Only what the hot path needs lives here: a rectangular 2D box (solid
+or periodic) with internal walls.  Construction semantics follow the reference:
 boundary walls first, in the reference's corner order (ratinabox/Environment.py:118-144),
 then user walls in insertion order (``add_wall``, :330-342).  Anything outside
-that (1D, periodic, polygon boundaries, holes, objects) raises
+that (1D, polygon boundaries, holes, objects) raises
 ``NotImplementedError`` instead of silently taking a different path.
 """
 import copy
@@ -36,8 +36,8 @@ class Environment:
             setattr(self, k, v)
         if self.dimensionality != "2D":
             raise NotImplementedError("ratinabox_b200 accelerates 2D environments only (SURVEY.md section 2 row 9)")
-        if self.boundary_conditions != "solid":
-            raise NotImplementedError("periodic boundary conditions are outside the CUDA hot path (SURVEY.md section 2 row 10)")
+        if self.boundary_conditions not in ("solid", "periodic"):
+            raise ValueError(f"unknown boundary_conditions {self.boundary_conditions!r}")
         if self.boundary is not None or len(self.holes) > 0:
             raise NotImplementedError("polygon boundaries / holes are outside the CUDA hot path (SURVEY.md section 2 row 11)")
         if len(self.objects) > 0:
@@ -50,10 +50,14 @@ class Environment:
         self.agents_dict = {}
         b = [[0, 0], [self.aspect * self.scale, 0], [self.aspect * self.scale, self.scale], [0, self.scale]]
         self.boundary = b
-        boundary_walls = np.array([[b[(i + 1) if (i + 1) < len(b) else 0], b[i]] for i in range(len(b))], dtype=float)
         user_walls = np.array(self.walls, dtype=float).reshape(-1, 2, 2)
-        self.walls = np.vstack((boundary_walls, user_walls))
-        self.n_boundary_walls = 4
+        if self.boundary_conditions == "solid":                     # Environment.py:137-144
+            boundary_walls = np.array([[b[(i + 1) if (i + 1) < len(b) else 0], b[i]] for i in range(len(b))], dtype=float)
+            self.walls = np.vstack((boundary_walls, user_walls))
+            self.n_boundary_walls = 4
+        else:                                                       # periodic: no boundary walls are built
+            self.walls = user_walls
+            self.n_boundary_walls = 0
         left, right = min(c[0] for c in b), max(c[0] for c in b)
         bottom, top = min(c[1] for c in b), max(c[1] for c in b)
         self.centre = np.array([(left + right) / 2, (top + bottom) / 2])

@@ -303,6 +303,10 @@ class PlaceCells(Neurons):
         self.place_cell_widths = self.widths * np.ones(self.n)
         if self.description not in _lib.PC_DESCRIPTIONS:
             raise ValueError(f"unknown PlaceCells description {self.description!r}")
+        if self.wall_geometry in ("line_of_sight", "geodesic") and env.boundary_conditions == "periodic":   # Neurons.py:907-921
+            print(f"{self.wall_geometry} wall geometry only possible in 2D when the boundary conditions are solid. "
+                  "Using 'euclidean' instead.")
+            self.wall_geometry = "euclidean"
         if (self.wall_geometry == "geodesic") and (len(env.walls) > 5):   # Neurons.py:922-928
             print("'geodesic' wall geometry only supported for enivironments with 1 additional wall "
                   "(4 bounding walls + 1 additional). Sorry. Using 'line_of_sight' instead.")
@@ -468,6 +472,8 @@ class BoundaryVectorCells(Neurons):
         from .utils import (create_random_assembly, create_uniform_radial_assembly,
                             create_diverging_radial_assembly, rotate)
         super().__init__(Agent, params)
+        assert self.Agent.Environment.boundary_conditions == "solid", \
+            "boundary cells only possible with solid boundary conditions"      # Neurons.py:1580-1582
         if self.reference_frame not in ("allocentric", "egocentric"):
             raise ValueError(f"unknown reference_frame {self.reference_frame!r}")
         arr = self.cell_arrangement                                   # VectorCells.set_tuning_parameters, Neurons.py:1388-1437
@@ -554,7 +560,7 @@ class BoundaryVectorCells(Neurons):
             pos = self.Agent.Environment.flattened_discrete_coords if evaluate_at == "all" else kwargs["pos"]
             pos_dev = torch.as_tensor(np.ascontiguousarray(np.asarray(pos, dtype=np.float64).reshape(-1, 2)), device=self.device)
             if "head_direction" in kwargs:
-                hd = np.asarray(kwargs["head_direction"], dtype=np.float64)
+                hd = np.array(kwargs["head_direction"], dtype=np.float64)       # own, writable copy
             elif "vel" in kwargs:
                 warnings.warn("'vel' kwarg deprecated in favour of 'head_direction'")
                 hd = np.asarray(kwargs["vel"], dtype=np.float64)

@@ -18,7 +18,7 @@ class RiabError(RuntimeError):
 
 class Env(C.Structure):
     _fields_ = [("walls_dev", C.c_void_p), ("n_walls", C.c_int32), ("n_boundary_walls", C.c_int32),
-                ("extent", C.c_double * 4)]
+                ("extent", C.c_double * 4), ("periodic", C.c_int32), ("reserved", C.c_int32), ("scale", C.c_double)]
 
 
 class Agents(C.Structure):

@@ -46,9 +46,9 @@ constexpr int CELL_PAD = 128;  // packed per-cell arrays are padded to 4 cells x
 
 struct EnvK {
   const double* walls;
-  int W, nb, aligned;
+  int W, nb, aligned, periodic;
   double ext[4];
-  double cxm, cym;
+  double cxm, cym, scale;
 };
 
 struct OutK {
@@ -101,7 +101,8 @@ __device__ __forceinline__ void agent_update_one(const riab_agents& ag, const ri
   uint8_t* mask = (REC && io.collision_mask) ? io.collision_mask + (size_t)i * RIAB_MAX_REC_ITERS * env.W : nullptr;
   int32_t* fh = (REC && io.first_hit) ? io.first_hit + (size_t)i * RIAB_MAX_REC_ITERS : nullptr;
   int32_t* ni = (REC && io.n_iters) ? io.n_iters + i : nullptr;
-  motion_step<REC>(s, s_walls, env.W, mp, md, env.ext, n1, n2, has_drift, drx, dry, f1, f2, mask, fh, ni);
+  motion_step<REC>(s, s_walls, env.W, mp, md, env.ext, env.periodic != 0, env.scale, n1, n2, has_drift, drx, dry, f1, f2,
+                   mask, fh, ni);
   store_agent(ag, i, s);
   if (io.history_row != nullptr) store_history_row(io.history_row + 8 * (size_t)i, s);
 }
@@ -505,7 +506,11 @@ __device__ __forceinline__ double onehot_exact_dist(const PlaceConst& c, int cel
   const double cx = c.centres64[2 * cell], cy = c.centres64[2 * cell + 1];
   bool blocked = false;
   for (int j = 0; j < c.n_inner; ++j) blocked = blocked || los_blocked_exact(cx, cy, px, py, inner64 + 4 * j);
-  const D ex = D(cx) - D(px), ey = D(cy) - D(py);
+  D ex = D(cx) - D(px), ey = D(cy) - D(py);
+  if (c.periodic) {
+    if (fabs(ex.v) > c.scale / 2) ex = D(-copysign(1.0, ex.v)) * (D(c.scale) - D(fabs(ex.v)));
+    if (fabs(ey.v) > c.scale / 2) ey = D(-copysign(1.0, ey.v)) * (D(c.scale) - D(fabs(ey.v)));
+  }
   const double d = dsqrt(ex * ex + ey * ey).v;
   if (!blocked) return d;
   if (c.geometry == RIAB_GEOM_GEODESIC) {
@@ -544,7 +549,11 @@ __global__ void __launch_bounds__(NT) k_place_onehot(const EnvK env, const Place
   }
   const int np = pc.n_pad;
   auto d2_of = [&](int cell, bool& unsure) -> float {          // optimistic float32 squared distance of one cell
-    const float dx = pxf - pc.packed[cell], dy = pyf - pc.packed[np + cell];
+    float dx = fabsf(pxf - pc.packed[cell]), dy = fabsf(pyf - pc.packed[np + cell]);
+    if (pc.periodic) {
+      dx = (dx > pc.half_f) ? pc.scale_f - dx : dx;
+      dy = (dy > pc.half_f) ? pc.scale_f - dy : dy;
+    }
     float d2 = fmaf(dy, dy, dx * dx);
     bool hit = false;
     for (int j = 0; j < pc.n_inner; ++j) {
@@ -800,7 +809,7 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate_ego(const BvcConst bc, con
 // ---------------------------------------------------------------------------
 // host helpers
 int make_env(const riab_env* env, EnvK& k) {
-  if (env == nullptr || env->walls_dev == nullptr) return fail(RIAB_ERR_INVALID, "env / walls_dev is NULL");
+  if (env == nullptr || (env->walls_dev == nullptr && env->n_walls > 0)) return fail(RIAB_ERR_INVALID, "env / walls_dev is NULL");
   if (env->n_walls < 0 || env->n_walls > MAXW) return fail(RIAB_ERR_UNSUPPORTED, "n_walls=%d exceeds %d", env->n_walls, MAXW);
   if (env->n_boundary_walls < 0 || env->n_boundary_walls > env->n_walls)
     return fail(RIAB_ERR_INVALID, "n_boundary_walls=%d out of range", env->n_boundary_walls);
@@ -809,6 +818,9 @@ int make_env(const riab_env* env, EnvK& k) {
   for (int i = 0; i < 4; ++i) k.ext[i] = env->extent[i];
   k.cxm = 0.5 * (env->extent[0] + env->extent[1]);
   k.cym = 0.5 * (env->extent[2] + env->extent[3]);
+  k.periodic = env->periodic ? 1 : 0;
+  k.scale = env->scale;
+  if (k.periodic && !(env->scale > 0.0)) return fail(RIAB_ERR_INVALID, "periodic environment needs scale > 0");
   return 0;
 }
 
@@ -879,6 +891,9 @@ int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
   for (int j = 0; j < PLACE_MAX_WI; ++j) c.eps[j] = pc->eps[j];
   c.packed = pc->packed_dev; c.centres64 = pc->centres_dev;
   c.cxm = env.cxm; c.cym = env.cym;
+  c.periodic = env.periodic; c.scale = env.scale; c.scale_f = (float)env.scale; c.half_f = (float)(env.scale / 2);
+  if (env.periodic && pc->wall_geometry != RIAB_GEOM_EUCLIDEAN)
+    return fail(RIAB_ERR_INVALID, "line_of_sight / geodesic wall geometry only possible when the boundary conditions are solid (Neurons.py:907-921)");
   return 0;
 }
 
@@ -973,6 +988,7 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   if (bvc == nullptr || bvc->packed_dev == nullptr || bvc->test_dirs_dev == nullptr)
     return fail(RIAB_ERR_INVALID, "bvc cells / packed_dev / test_dirs_dev NULL");
   if (scratch == nullptr) return fail(RIAB_ERR_INVALID, "bvc scratch NULL");
+  if (env.periodic) return fail(RIAB_ERR_INVALID, "boundary cells only possible with solid boundary conditions (Neurons.py:1580-1582)");
   if (n_rows == 0) return 0;
   BvcConst bc;
   bc.n_cells = bvc->n_cells; bc.n_pad = bvc->n_pad; bc.T = bvc->n_test_angles;

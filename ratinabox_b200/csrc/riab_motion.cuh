@@ -90,7 +90,8 @@ RIAB_DEV double get_angle(double x, double y) {
 // REC: write the per-iteration collision masks (parity taps).
 template <bool REC>
 RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W, const riab_motion_params& p,
-                          const MotionDerived& m, const double* __restrict__ ext, double xi1, double xi2, bool has_drift, double drx,
+                          const MotionDerived& m, const double* __restrict__ ext, bool periodic, double scale,
+                          double xi1, double xi2, bool has_drift, double drx,
                           double dry, double fallback_n1, double fallback_n2, uint8_t* __restrict__ mask,
                           int32_t* __restrict__ first_hit, int32_t* __restrict__ n_iters_out) {
   const D dt(p.dt);
@@ -206,12 +207,24 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
 
   // ---- A7: still inside? else clamp (Environment.py:781-818, :880-889)
   if (!((px.v > ext[0]) && (px.v < ext[1]) && (py.v > ext[2]) && (py.v < ext[3]))) {
-    px = D(fmin(fmax(px.v, ext[0] + 0.01), ext[1] - 0.01));
-    py = D(fmin(fmax(py.v, ext[2] + 0.01), ext[3] - 0.01));
+    if (periodic) {                                     // pos % extent (Environment.py:877-879)
+      px = D(np_mod(px.v, ext[1]));
+      py = D(np_mod(py.v, ext[3]));
+    } else {
+      px = D(fmin(fmax(px.v, ext[0] + 0.01), ext[1] - 0.01));
+      py = D(fmin(fmax(py.v, ext[2] + 0.01), ext[3] - 0.01));
+    }
+  }
+  // displacement of the step; through the boundary when periodic (Environment.py:670-675)
+  D stx = px - ppx, sty = py - ppy;
+  if (periodic) {
+    const double half = scale / 2;
+    if (fabs(stx.v) > half) stx = D(-copysign(1.0, stx.v)) * (D(scale) - D(fabs(stx.v)));
+    if (fabs(sty.v) > half) sty = D(-copysign(1.0, sty.v)) * (D(scale) - D(fabs(sty.v)));
   }
 
   // ---- A8: measured velocity / rotational velocity (Agent.py:444-472)
-  D mvx = (px - ppx) / dt, mvy = (py - ppy) / dt;
+  D mvx = stx / dt, mvy = sty / dt;
   if (dsqrt(mvx * mvx + mvy * mvy).v == 0.0) {
     // 1e-8 * randn(2) in the reference; here a Philox draw keyed by the (bit-cast) seed / step^agent words
     uint32_t c[4] = {(uint32_t)__double_as_longlong(fallback_n2), (uint32_t)(__double_as_longlong(fallback_n2) >> 32),
@@ -246,8 +259,7 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
 
   // ---- A10: distance travelled (Agent.py:502-507)
   {
-    const D ex = px - ppx, ey = py - ppy;
-    s.dist = (D(s.dist) + dsqrt(ex * ex + ey * ey)).v;
+    s.dist = (D(s.dist) + dsqrt(stx * stx + sty * sty)).v;
   }
   s.px = px.v; s.py = py.v; s.vx = vx.v; s.vy = vy.v; s.rot = rot.v; s.mvx = mvx.v; s.mvy = mvy.v;
 }

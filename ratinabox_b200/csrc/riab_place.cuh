@@ -74,6 +74,9 @@ struct PlaceConst {                  // uniform per launch
   float eps[PLACE_MAX_WI];
   const float* packed;               // device
   const double* centres64;           // device (N,2)
+  int periodic;                      // wrap centre->agent vectors (Environment.py:670-675)
+  float scale_f, half_f;
+  double scale;
   double cxm, cym;
 };
 
@@ -155,10 +158,20 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
   const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, f_p0, t_p0
   float d2[4];
   bool unsure = false;
+  if (WI == 0 && c.periodic) {                           // warp-uniform
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float dx = r0.x - r.cx[i], dy = r0.y - r.cy[i];
-    d2[i] = fmaf(dy, dy, dx * dx);
+    for (int i = 0; i < 4; ++i) {
+      float dx = fabsf(r0.x - r.cx[i]), dy = fabsf(r0.y - r.cy[i]);
+      dx = (dx > c.half_f) ? c.scale_f - dx : dx;        // the short way round
+      dy = (dy > c.half_f) ? c.scale_f - dy : dy;
+      d2[i] = fmaf(dy, dy, dx * dx);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dx = r0.x - r.cx[i], dy = r0.y - r.cy[i];
+      d2[i] = fmaf(dy, dy, dx * dx);
+    }
   }
   // final squared distances (blocked pairs get distance 1000, Environment.py:730)
   float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
@@ -222,7 +235,11 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       if (fabsf(dv - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !blocked) {
         const int cell = cell0 + i;
         if (cell < c.n_cells) {
-          const D ex = D(c.centres64[2 * cell]) - D(pos64[0]), ey = D(c.centres64[2 * cell + 1]) - D(pos64[1]);
+          D ex = D(c.centres64[2 * cell]) - D(pos64[0]), ey = D(c.centres64[2 * cell + 1]) - D(pos64[1]);
+          if (c.periodic) {
+            if (fabs(ex.v) > c.scale / 2) ex = D(-copysign(1.0, ex.v)) * (D(c.scale) - D(fabs(ex.v)));
+            if (fabs(ey.v) > c.scale / 2) ey = D(-copysign(1.0, ey.v)) * (D(c.scale) - D(fabs(ey.v)));
+          }
           in = dsqrt(ex * ex + ey * ey).v < c.top_hat_w;
         }
       }

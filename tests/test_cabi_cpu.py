@@ -33,7 +33,7 @@ def test_struct_sizes_match_header():
     from ratinabox_b200 import _lib
     assert C.sizeof(_lib.MotionParams) == 14 * 8
     assert C.sizeof(_lib.Agents) == 10 * 8
-    assert C.sizeof(_lib.Env) == 8 + 4 + 4 + 32
+    assert C.sizeof(_lib.Env) == 8 + 4 + 4 + 32 + 4 + 4 + 8       # + periodic, reserved, scale
     assert C.sizeof(_lib.StepIO) == 8 * 8
 
 

@@ -221,4 +221,6 @@ def test_get_state_all_and_errors():
     with pytest.raises(RiabError):
         rb.PlaceCells(Ag9, {"n": 8, "wall_geometry": "line_of_sight"}).get_state(evaluate_at="all")
     with pytest.raises(NotImplementedError):
-        rb.Environment({"boundary_conditions": "periodic"})
+        rb.Environment({"dimensionality": "1D"})
+    with pytest.raises(AssertionError):          # boundary cells only possible with solid boundary conditions
+        rb.BoundaryVectorCells(rb.Agent(rb.Environment({"boundary_conditions": "periodic"})), {"n": 4})

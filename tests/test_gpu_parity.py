@@ -157,3 +157,36 @@ def test_field_of_view_bvcs_egocentric_golden(golden, name):
     ref = O.bvc_get_state(env, fov.tuning_distances, fov.tuning_angles, fov.sigma_distances, fov.sigma_angles,
                           Ag.pos, O.TapeRNG(), min_fr=0.0, max_fr=2.0, head_direction=Ag.head_direction)[:, 0]
     assert np.abs(fov.firingrate - ref).max() <= 2e-5
+
+
+@pytest.mark.parametrize("name,walls", [("open", []), ("wall", [[[0.5, 0.2], [0.5, 0.8]]])])
+def test_periodic_boundary_conditions_golden(golden, name, walls):
+    """Periodic box (Environment.py:130-136, :670-675, :877-879) against the live reference: teacher-forced
+    steps that cross the boundary (positions wrap, measured velocity / distance take the short way round)
+    and PlaceCells with wrapped distances."""
+    import ratinabox_b200 as rb
+    g = golden("periodic.npz")
+    E = rb.Environment({"boundary_conditions": "periodic"})
+    for w in walls:
+        E.add_wall(w)
+    assert np.array_equal(E.walls, g[f"{name}_walls"].reshape(-1, 2, 2))
+    A = len(g[f"{name}_A_pos0"])
+    Ag = rb.Agent(E, {"dt": 0.05, "speed_mean": 0.5, "n_agents": A})
+    v0 = g[f"{name}_A_vel0"]
+    Ag.pos, Ag.velocity, Ag.measured_velocity = g[f"{name}_A_pos0"], v0, v0
+    Ag.rotational_velocity = np.zeros(A)
+    Ag.head_direction = v0 / np.linalg.norm(v0, axis=1, keepdims=True)
+    Ag.distance_travelled = np.zeros(A)
+    PCs = rb.PlaceCells(Ag, {"place_cell_centres": g[f"{name}_centres"], "widths": 0.15})
+    assert PCs.wall_geometry == "euclidean"
+    assert_rates_close(PCs.get_state(evaluate_at=None, pos=g[f"{name}_A_pos0"]), g[f"{name}_A_pc"], 1.0, f"periodic pc {name}")
+    Ag.update(_xi=g[f"{name}_A_xi"])
+    assert np.abs(Ag.pos - g[f"{name}_A_pos"]).max() <= 1e-12
+    assert np.abs(Ag.measured_velocity - g[f"{name}_A_mv"]).max() <= 1e-10
+    assert np.abs(Ag.distance_travelled - g[f"{name}_A_dist"]).max() <= 1e-12
+    assert (np.abs(g[f"{name}_A_pos"] - g[f"{name}_A_pos0"]) > 0.5).any(axis=1).sum() > 20      # wraps are exercised
+    PCs.update()
+    import riab_oracle as O
+    env = O.OracleEnvironment(walls=walls, boundary_conditions="periodic")
+    ref = O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, Ag.pos, O.TapeRNG()).T
+    assert np.abs(PCs.firingrate - ref).max() <= 1e-5

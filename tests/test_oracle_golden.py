@@ -153,3 +153,35 @@ def test_modeA_fov_egocentric_bvcs(golden):
         hd0 = HD[0] / np.linalg.norm(HD[0])
         fr = O.bvc_get_state(env, mu_d, mu_t, sg_d, sg_t, P[0], rng, min_fr=0.0, max_fr=2.0, head_direction=hd0)
         assert np.array_equal(fr[:, 0], g[f"fov_{name}_agent"])
+
+
+@pytest.mark.parametrize("name,walls", [("open", []), ("wall", [[[0.5, 0.2], [0.5, 0.8]]])])
+def test_periodic_boundary_conditions(golden, name, walls):
+    """Periodic rectangular box (Environment.py:130-136, :670-675, :877-879): native 800-step run (global RNG,
+    jitter on, 26-35 boundary crossings) bit for bit, and teacher-forced single steps across the boundary."""
+    g = golden("periodic.npz")
+    env = O.OracleEnvironment(walls=walls, boundary_conditions="periodic")
+    assert np.array_equal(env.walls, g[f"{name}_walls"].reshape(-1, 2, 2))
+    assert str(g[f"{name}_geom"]) == "euclidean"
+    ag = O.OracleAgent(env, g[f"{name}_pos0"], g[f"{name}_vel0"], {"dt": 0.05, "speed_mean": 0.5})
+    rng = O.GlobalRNG()
+    pcs = O.OracleNeurons(ag, 30, lambda p, r: O.place_cells_get_state(env, g[f"{name}_centres"], g[f"{name}_widths"], p, r))
+    gcs = O.OracleNeurons(ag, 9, lambda p, r: O.grid_cells_get_state(g[f"{name}_gridscales"], g[f"{name}_phase"], g[f"{name}_w"], p))
+    np.random.set_state(("MT19937", g[f"{name}_rng_keys"], int(g[f"{name}_rng_pos"]), int(g[f"{name}_rng_has_gauss"]),
+                         float(g[f"{name}_rng_cached"])))
+    for _ in range(800):
+        ag.update(rng); pcs.update(rng); gcs.update(rng)
+    assert np.array_equal(np.array(ag.history["pos"]), g[f"{name}_pos"])
+    assert np.array_equal(np.array(ag.history["vel"]), g[f"{name}_vel"])
+    assert np.array_equal(np.array(ag.history["rot_vel"]), g[f"{name}_rot_vel"])
+    assert np.array_equal(np.array(ag.history["distance_travelled"]), g[f"{name}_dist"])
+    assert np.array_equal(np.array(pcs.history["firingrate"]), g[f"{name}_pc_fr"])
+    assert np.array_equal(np.array(gcs.history["firingrate"]), g[f"{name}_gc_fr"])
+    for a in range(len(g[f"{name}_A_pos0"])):
+        v0 = g[f"{name}_A_vel0"][a]
+        oa = O.OracleAgent(env, g[f"{name}_A_pos0"][a], v0, {"dt": 0.05, "speed_mean": 0.5})
+        oa.update(O.TapeRNG(agent_xi=g[f"{name}_A_xi"][a]))
+        assert np.array_equal(oa.pos, g[f"{name}_A_pos"][a]) and np.array_equal(oa.measured_velocity, g[f"{name}_A_mv"][a])
+        assert oa.distance_travelled == g[f"{name}_A_dist"][a]
+    fr = O.place_cells_get_state(env, g[f"{name}_centres"], g[f"{name}_widths"], g[f"{name}_A_pos0"], O.TapeRNG())
+    assert np.array_equal(fr, g[f"{name}_A_pc"])
