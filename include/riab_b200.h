@@ -196,7 +196,7 @@ int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, co
 /* ------------------------------------------------------- Neurons.update extras
  * OU noise (Neurons.py:153-160) and spikes (Neurons.py:681-684) for a block of
  * rates already written to rates_dev.  noise_dev (A,N) f32 state (NULL when
- * noise_std == 0); spikes (A, 4*ceil(N/32)) bytes, bit-packed little-endian (bit c of the row = cell c), NULL to skip. */
+ * noise_std == 0); spikes (A, 4*ceil(N/128)) uint32 words (layout: riab_rates_out.spikes_row), NULL to skip. */
 typedef struct {
   float noise_std, noise_coherence_time, dt;
   uint64_t seed, step;
@@ -212,7 +212,8 @@ typedef enum { RIAB_CELLS_PLACE = 0, RIAB_CELLS_GRID = 1, RIAB_CELLS_BVC = 2 } r
 typedef struct {
   float* rates_row;        /* (A, ld) f32: firing rates of this step (doubles as the history row) */
   int64_t ld;
-  uint32_t* spikes_row;    /* (A, ceil(N/32)) uint32 words, bit c%32 of word c/32 = cell c; or NULL */
+  uint32_t* spikes_row;    /* (A, 4*ceil(N/128)) uint32 words, 16-byte aligned, or NULL.  Bit L of word 4B+i =
+                            * spike of cell 128B + 4L + i (a warp's ballot of its lanes' i-th cell). */
   float* noise_state;      /* (A, ld) f32 OU noise state or NULL (noise_std == 0) */
   float* bvc_scratch;      /* (A, T) f32, BVC only */
 } riab_rates_out;
@@ -238,7 +239,7 @@ typedef struct {
   riab_neuron_noise noise;      /* seed/step base; step is advanced per step */
   riab_rates_out out;           /* ld, noise_state, bvc_scratch; rates_row/spikes_row are set from the rings */
   float* rates_ring;            /* (rows, A, ld) f32 */
-  uint32_t* spikes_ring;        /* (rows, A, ceil(N/32)) or NULL */
+  uint32_t* spikes_ring;        /* (rows, A, 4*ceil(N/128)) or NULL */
   int32_t ring_rows;
   int32_t ring_next;            /* in: first row to write */
 } riab_population;

@@ -111,7 +111,7 @@ class Neurons:
         """Next history row (rates [+ spikes]) on the device; grows / wraps like Agent's ring."""
         torch = self._torch
         A, ld = self.Agent.n_agents, self._ld()
-        words = (self.n + 31) // 32
+        words = 4 * ((self.n + 127) // 128)           # 4 ballot words per 128 cells (riab_b200.h, riab_rates_out)
         row_bytes = A * ld * 4
         if self._hist is None:
             cap = int(max(1, min(256, self.history_bytes_limit // row_bytes))) if self.save_history else 1
@@ -133,7 +133,7 @@ class Neurons:
         """Grow the ring (within history_bytes_limit) so n_more further rows fit without wrapping if possible."""
         torch = self._torch
         A, ld = self.Agent.n_agents, self._ld()
-        words = (self.n + 31) // 32
+        words = 4 * ((self.n + 127) // 128)           # 4 ballot words per 128 cells (riab_b200.h, riab_rates_out)
         row_bytes = A * ld * 4
         limit_rows = max(1, self.history_bytes_limit // row_bytes)
         need = self._hist_rows + n_more if self.save_history else 1
@@ -254,7 +254,9 @@ class Neurons:
                 idx = (torch.arange(n, device=self.device) + start) % self._hist_cap
                 fr = self._hist[idx][:, :, : self.n].cpu().numpy().astype(np.float64)
                 words = self._spk[idx].cpu().numpy().view(np.uint32)
+                # bit L of word 4B+i = cell 128B + 4L + i  (one warp ballot per cell slot i)
                 bits = np.unpackbits(words.view(np.uint8), axis=-1, bitorder="little")
+                bits = bits.reshape(n, A, -1, 4, 32).transpose(0, 1, 2, 4, 3).reshape(n, A, -1)
                 sp = bits[:, :, : self.n].astype(bool)
             if A == 1:
                 fr, sp = fr[:, 0], sp[:, 0]
@@ -567,7 +569,7 @@ class BoundaryVectorCells(Neurons):
             else:
                 warnings.warn("BVCs in egocentric plane require a head direction vector but none was passed. Using [1,0]")
                 hd = np.array([1.0, 0.0])
-            hd = np.ascontiguousarray(np.broadcast_to(hd.reshape(-1, 2), (pos_dev.shape[0], 2)))
+            hd = np.array(np.broadcast_to(hd.reshape(-1, 2), (pos_dev.shape[0], 2)))      # own, writable, contiguous
             hd_dev = torch.as_tensor(hd, device=self.device)
         n_pos = int(pos_dev.shape[0])
         out = torch.empty((n_pos, self._ld()), dtype=torch.float32, device=self.device)

@@ -136,7 +136,7 @@ struct TailCtx {
 struct RowCursor {
   float* dst;              // rates row + cell0
   float* nz;               // noise-state row + cell0 (or NULL)
-  uint8_t* spk;            // spikes row (bytes) + cell0/8
+  uint32_t* spk;           // spikes row + 4 * (cell0 / 128): the 4 ballot words of this warp's 128 cells
   unsigned long long gid;  // global agent id
 };
 
@@ -154,13 +154,13 @@ __device__ __forceinline__ void tail_init(TailCtx& t, const OutK& out, int cell0
 __device__ __forceinline__ void cursor_init(RowCursor& rc, const OutK& out, const TailCtx& t, long long row) {
   rc.dst = out.rates + row * out.ld + t.cell0;
   rc.nz = out.noise ? out.noise + row * out.ld + t.cell0 : nullptr;
-  rc.spk = out.spikes ? reinterpret_cast<uint8_t*>(out.spikes + row * out.spike_ld) + (t.cell0 >> 3) : nullptr;
+  rc.spk = out.spikes ? out.spikes + row * out.spike_ld + ((t.cell0 >> 7) << 2) : nullptr;
   rc.gid = (unsigned long long)(out.id_offset + row);
 }
 struct RowStride { long long rate, spk; int rows; };      // element strides for `rows` agents (warp-uniform)
 __device__ __forceinline__ RowStride make_stride(const OutK& out, int rows) {
   RowStride st;
-  st.rate = (long long)rows * out.ld; st.spk = (long long)rows * out.spike_ld * 4; st.rows = rows;
+  st.rate = (long long)rows * out.ld; st.spk = (long long)rows * out.spike_ld; st.rows = rows;
   return st;
 }
 __device__ __forceinline__ void cursor_advance(RowCursor& rc, const RowStride& st) {
@@ -213,47 +213,48 @@ __device__ __forceinline__ void store4(float (&o)[4], const OutK& out, const Tai
 // One Philox4x32-7 call serves the 4 cells of TWO agents (global ids 2k, 2k+1):
 //   r = Philox7(ctr = (gid >> 1, cell group, step, stream|population), key = seed)
 //   agent half h = gid & 1 takes words r[2h], r[2h+1]: four 16-bit integers m_i (cell i = half-word i);
-//   all eight share the dither v = ((r0^r1^r2^r3) >> 8) * 2^-24; uniform_i = (m_i + v) * 2^-16.
-// (m_i + v) is uniform on [0, 65536) with 40 random bits; sharing v only correlates the sub-2^-16
-// fractions of the eight uniforms (covariance < 6e-11).
+//   all eight share the dither v = ((r0^r2) >> 8) * 2^-24; uniform_i = (m_i + v) * 2^-16, and
+//   spike_i <=> m_i < fma(rate_i, dt*65536, -v)      (one FFMA, one I2F, one FSETP per rate).
+// (m_i + v) is uniform on [0, 65536) with 40 random bits and v is independent of every single m_i;
+// sharing v only correlates the sub-2^-16 fractions of the eight uniforms (covariance < 6e-11).
+// Layout of a spike row: a warp owns 128 consecutive cells (lane L holds cells 128B+4L .. +3) and
+// writes the four ballots of its cell slots as one 16-byte store:
+//   bit L of word 4B+i  =  spike of cell 128B + 4L + i.
 __device__ __forceinline__ void spike_words(uint32_t (&c)[4], const OutK& out, const TailCtx& t, unsigned long long gid) {
   const unsigned long long pair = gid >> 1;
   c[0] = (uint32_t)pair; c[1] = t.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = t.c2; c[3] = t.c3_spk;
   philox_keyed<7>(c, out.rk7);
 }
-__device__ __forceinline__ unsigned spike_nibble(uint32_t w0, uint32_t w1, float v, const float (&o)[4], float q) {
-  // q = dt * 65536
-  unsigned nib = 0;
-  nib |= (((float)(w0 & 0xffffu) + v) < q * o[0]) ? 1u : 0u;
-  nib |= (((float)(w0 >> 16) + v) < q * o[1]) ? 2u : 0u;
-  nib |= (((float)(w1 & 0xffffu) + v) < q * o[2]) ? 4u : 0u;
-  nib |= (((float)(w1 >> 16) + v) < q * o[3]) ? 8u : 0u;
-  return nib;
+__device__ __forceinline__ float spike_neg_dither(const uint32_t (&c)[4]) {
+  return (float)((c[0] ^ c[2]) >> 8) * -5.9604644775390625e-08f;
 }
-__device__ __forceinline__ float spike_dither(const uint32_t (&c)[4]) {
-  return (float)((c[0] ^ c[1] ^ c[2] ^ c[3]) >> 8) * 5.9604644775390625e-08f;
+// ballots of one agent's 4 cell slots; `ok` = this thread's cells exist (all 4 or none) when !MASKED
+template <bool MASKED>
+__device__ __forceinline__ void spike_ballots(uint32_t (&b)[4], uint32_t w0, uint32_t w1, float nv, const float (&o)[4],
+                                              float q /* dt * 65536 */, unsigned vmask, bool ok) {
+  bool s0 = (float)(w0 & 0xffffu) < fmaf(o[0], q, nv);
+  bool s1 = (float)(w0 >> 16) < fmaf(o[1], q, nv);
+  bool s2 = (float)(w1 & 0xffffu) < fmaf(o[2], q, nv);
+  bool s3 = (float)(w1 >> 16) < fmaf(o[3], q, nv);
+  if (MASKED) { s0 = s0 && (vmask & 1u); s1 = s1 && (vmask & 2u); s2 = s2 && (vmask & 4u); s3 = s3 && (vmask & 8u); }
+  else { s0 = s0 && ok; s1 = s1 && ok; s2 = s2 && ok; s3 = s3 && ok; }
+  b[0] = __ballot_sync(0xffffffffu, s0);
+  b[1] = __ballot_sync(0xffffffffu, s1);
+  b[2] = __ballot_sync(0xffffffffu, s2);
+  b[3] = __ballot_sync(0xffffffffu, s3);
 }
-__device__ __forceinline__ void spike_store(unsigned nib, const TailCtx& t, uint8_t* spk) {
-  nib &= t.vmask;
-  const unsigned hi = __shfl_down_sync(0xffffffffu, nib, 1);        // odd lane's nibble = cells 4..7 of the byte
-  if ((threadIdx.x & 1) == 0 && t.vmask != 0u) *spk = (uint8_t)(nib | (hi << 4));
+__device__ __forceinline__ void spike_store(const uint32_t (&b)[4], uint32_t* spk) {
+  if ((threadIdx.x & 31) == 0)
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(spk), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]) : "memory");
 }
-// one agent
+// one agent (whole warp must call)
 __device__ __forceinline__ void spikes1(const float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc) {
-  uint32_t c[4];
+  uint32_t c[4], b[4];
   spike_words(c, out, t, rc.gid);
-  const float v = spike_dither(c);
+  const float nv = spike_neg_dither(c);
   const unsigned h = (unsigned)(rc.gid & 1ull);
-  spike_store(spike_nibble(h ? c[2] : c[0], h ? c[3] : c[1], v, o, out.dt * 65536.0f), t, rc.spk);
-}
-// two agents with consecutive global ids, the first one even (rows rc and rc + 1)
-__device__ __forceinline__ void spikes2(const float (&oa)[4], const float (&ob)[4], const OutK& out, const TailCtx& t,
-                                        const RowCursor& rc) {
-  uint32_t c[4];
-  spike_words(c, out, t, rc.gid);
-  const float v = spike_dither(c), q = out.dt * 65536.0f;
-  spike_store(spike_nibble(c[0], c[1], v, oa, q), t, rc.spk);
-  spike_store(spike_nibble(c[2], c[3], v, ob, q), t, rc.spk + out.spike_ld * 4);
+  spike_ballots<true>(b, h ? c[2] : c[0], h ? c[3] : c[1], nv, o, out.dt * 65536.0f, t.vmask, true);
+  spike_store(b, rc.spk);
 }
 
 template <bool SPIKES, bool NOISE>
@@ -276,9 +277,8 @@ struct PlacePolicy {
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI>(r, c, cell0); }
   static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int cell0,
-                                                const float* rec, const double* pos64, const double* s_walls,
-                                                const EnvK& env) {
-    place_rates4<WI, DESC>(o, r, c, cell0, rec, pos64, s_walls + 4 * env.nb);
+                                                const float* rec, uint32_t inner_s) {
+    place_rates4<WI, DESC>(o, r, c, cell0, rec, inner_s);
   }
 };
 
@@ -294,7 +294,7 @@ struct GridPolicy {
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { grid_load_cells(r, c, cell0); }
   static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int, const float* rec,
-                                                const double*, const double*, const EnvK&) {
+                                                uint32_t) {
     grid_rates4(o, r, c, rec);
   }
 };
@@ -344,7 +344,6 @@ template <int N, int L> __device__ __forceinline__ void reg_set() {
 template <int REC>
 struct __align__(16) StepSlot {
   float rec[TA][REC];
-  double pos[TA][2];
   int na;
   int pad[3];
 };
@@ -384,8 +383,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
         if (lane < na) {
           const long long i = a0 + lane;
           const double px = ag.pos[2 * i], py = ag.pos[2 * i + 1];
-          s_slot[s].pos[lane][0] = px;
-          s_slot[s].pos[lane][1] = py;
           P::record(s_slot[s].rec[lane], px, py, s_walls, pc, env);
         }
         if (lane == 0) s_slot[s].na = na;
@@ -406,8 +403,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
         } else {
           px = pos_in[2 * i]; py = pos_in[2 * i + 1];
         }
-        s_slot[s].pos[lane][0] = px;
-        s_slot[s].pos[lane][1] = py;
         P::record(s_slot[s].rec[lane], px, py, s_walls, pc, env);
       }
       if (lane == 0) s_slot[s].na = na;
@@ -431,6 +426,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       P::load(regs, pc, cell0);
       tail_init(tc, out, cell0, pc.n_cells);
     }
+    const uint32_t inner_s = smem_u32(s_walls + 4 * env.nb);      // float64 inner walls (exact fall-back)
+    // Fast pair loop: rows are 16-byte aligned and every thread owns 4 existing cells or none, the
+    // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
+    const bool fast = (chunks == 1) && !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
+    const bool act = cell0 < pc.n_cells;
+    const long long pair_rate = 2ll * G * out.ld, pair_spk = 2ll * G * out.spike_ld;     // elements per pair step
+    const float q16 = out.dt * 65536.0f;
     for (long long q = 0; q < nq; ++q) {
       const int s = (int)(q % NS);
       mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
@@ -441,33 +443,71 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
           // agents are taken in pairs (2p, 2p+1) so that one Philox call feeds the spikes of both
           RowCursor rc;
           cursor_init(rc, out, tc, a0 + 2 * grp);
-          const RowStride stride = make_stride(out, 2 * G);
           const float* recp = s_slot[s].rec[2 * grp];
-          const double* posp = s_slot[s].pos[2 * grp];
+          int a = 2 * grp;
+          if (fast) {
+            float* dst = rc.dst;
+            uint32_t* spk = rc.spk;
+            unsigned long long pair = rc.gid >> 1;
+            for (; a + 1 < na; a += 2 * G) {
+              float o[4];
+              uint32_t c[4], bl[4];
+              P::rates4(o, regs, pc, cell0, recp, inner_s);
+              if (act) st_cs_f4(dst, o[0], o[1], o[2], o[3]);
+              float nv = 0.f;
+              if (SPIKES) {
+                c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
+                philox_keyed<7>(c, out.rk7);
+                nv = spike_neg_dither(c);
+                spike_ballots<false>(bl, c[0], c[1], nv, o, q16, 0u, act);
+                spike_store(bl, spk);
+              }
+              P::rates4(o, regs, pc, cell0, recp + P::REC, inner_s);
+              if (act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
+              if (SPIKES) {
+                spike_ballots<false>(bl, c[2], c[3], nv, o, q16, 0u, act);
+                spike_store(bl, spk + out.spike_ld);
+              }
+              dst += pair_rate;
+              spk += pair_spk;
+              pair += (unsigned long long)G;
+              recp += 2 * G * P::REC;
+            }
+            rc.dst = dst; rc.spk = spk; rc.gid = pair << 1;
+            if (NOISE) rc.nz = nullptr;            // (unreachable: fast implies !NOISE)
+          }
+          // general path: the last agent of an odd tile, odd shard offsets, OU noise, ragged cell counts
+          const RowStride stride = make_stride(out, 2 * G);
           const bool even = ((rc.gid & 1ull) == 0ull);      // uniform: a0 and 2*grp are even
-          for (int a = 2 * grp; a < na; a += 2 * G) {
+          for (; a < na; a += 2 * G) {
             float oa[4], ob[4];
             const bool has_b = (a + 1 < na);
-            P::rates4(oa, regs, pc, cell0, recp, posp, s_walls, env);
+            P::rates4(oa, regs, pc, cell0, recp, inner_s);
             store4<NOISE>(oa, out, tc, rc, 0);
             if (has_b) {
-              P::rates4(ob, regs, pc, cell0, recp + P::REC, posp + 2, s_walls, env);
+              P::rates4(ob, regs, pc, cell0, recp + P::REC, inner_s);
               store4<NOISE>(ob, out, tc, rc, out.ld);
             }
             if (SPIKES && (!NOISE || rc.spk != nullptr)) {
-              if (has_b && even) spikes2(oa, ob, out, tc, rc);
-              else {
+              if (has_b && even) {
+                uint32_t c[4], bl[4];
+                spike_words(c, out, tc, rc.gid);
+                const float nv = spike_neg_dither(c);
+                spike_ballots<true>(bl, c[0], c[1], nv, oa, q16, tc.vmask, true);
+                spike_store(bl, rc.spk);
+                spike_ballots<true>(bl, c[2], c[3], nv, ob, q16, tc.vmask, true);
+                spike_store(bl, rc.spk + out.spike_ld);
+              } else {
                 spikes1(oa, out, tc, rc);
                 if (has_b) {
                   RowCursor rb = rc;
-                  rb.gid += 1; rb.spk += out.spike_ld * 4;
+                  rb.gid += 1; rb.spk += out.spike_ld;
                   spikes1(ob, out, tc, rb);
                 }
               }
             }
             cursor_advance(rc, stride);
             recp += 2 * G * P::REC;
-            posp += 2 * G * 2;
           }
         }
       } else {
@@ -481,7 +521,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
             const RowStride stride = make_stride(out, 1);
             for (int a = 0; a < na; ++a) {
               float o[4];
-              P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], s_slot[s].pos[a], s_walls, env);
+              P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], inner_s);
               finish4<SPIKES, NOISE>(o, out, tc, rc);
               cursor_advance(rc, stride);
             }
@@ -845,7 +885,8 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
   if (o->ld < n_cells) return fail(RIAB_ERR_INVALID, "ld (%lld) < n_cells (%d)", (long long)o->ld, n_cells);
   memset(&k, 0, sizeof(k));
   k.rates = o->rates_row; k.ld = o->ld;
-  k.spikes = o->spikes_row; k.spike_ld = (n_cells + 31) / 32;
+  k.spikes = o->spikes_row; k.spike_ld = 4 * ((n_cells + 127) / 128);     // 4 ballot words per 128 cells
+  if (k.spikes != nullptr && (((uintptr_t)k.spikes) % 16 != 0)) return fail(RIAB_ERR_INVALID, "spikes_row must be 16-byte aligned");
   k.noise = nullptr;
   k.dt = (float)dt;
   k.id_offset = id_offset;
@@ -888,7 +929,8 @@ int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
   c.ep_valid = pc->ep_valid;
   c.min_fr = pc->min_fr; c.span = pc->max_fr - pc->min_fr;
   c.top_hat_w = pc->top_hat_width; c.top_hat_w2 = (float)(pc->top_hat_width * pc->top_hat_width);
-  for (int j = 0; j < PLACE_MAX_WI; ++j) c.eps[j] = pc->eps[j];
+  c.band = 0.f;
+  for (int j = 0; j < PLACE_MAX_WI; ++j) { c.eps[j] = pc->eps[j]; c.band = fmaxf(c.band, pc->eps[j]); }
   c.packed = pc->packed_dev; c.centres64 = pc->centres_dev;
   c.cxm = env.cxm; c.cym = env.cym;
   c.periodic = env.periodic; c.scale = env.scale; c.scale_f = (float)env.scale; c.half_f = (float)(env.scale / 2);
@@ -1121,9 +1163,9 @@ int riab_place_pack(const double* centres, const double* widths, int32_t n, cons
         double f, t;
         wall_coords(centres[2 * i], centres[2 * i + 1], w[0], w[1], w[2], w[3], f, t);
         fc[i] = (float)f; tc[i] = (float)t;
-        // a centre (numerically) on the wall's line: force the exact float64 path (NaN poisons the fast test)
-        if (fabs(f) < 1.0e-6 * (dmax + fcmax)) tc[i] = nanf("");
-      } else { fc[i] = 1.f; tc[i] = 0.f; }
+        // a centre (numerically) on the wall's line: (0,0) makes M' = 0, inside the band -> exact float64 path
+        if (fabs(f) < 1.0e-6 * (dmax + fcmax)) { fc[i] = 0.f; tc[i] = 0.f; }
+      } else { fc[i] = 1.f; tc[i] = -1.f; }
     }
     if (j < 8) meta->eps[j] = (float)band;
   }
@@ -1389,7 +1431,7 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
       if (pp.kind == RIAB_CELLS_PLACE) n_cells = ((const riab_place_cells*)pp.cells)->n_cells;
       else if (pp.kind == RIAB_CELLS_GRID) n_cells = ((const riab_grid_cells*)pp.cells)->n_cells;
       else if (pp.kind == RIAB_CELLS_BVC) n_cells = ((const riab_bvc_cells*)pp.cells)->n_cells;
-      ro.spikes_row = pp.spikes_ring ? pp.spikes_ring + slot * A * (size_t)((n_cells + 31) / 32) : nullptr;
+      ro.spikes_row = pp.spikes_ring ? pp.spikes_ring + slot * A * (size_t)(4 * ((n_cells + 127) / 128)) : nullptr;
       riab_neuron_noise nz = pp.noise;
       nz.step = pp.noise.step + (uint64_t)st;
       nz.dt = (float)prm->dt;

@@ -13,17 +13,20 @@
 // each inner wall with utils.vector_intercepts (utils.py:30-118): blocked iff
 // 0<l_a<1 and 0<l_b<1.  With f = signed distance to the wall's line and t = the
 // parameter along the wall, l_a = f_c/(f_c-f_p) and l_b = (f_c t_p - f_p t_c)/(f_c-f_p),
-// so per (agent, cell, wall) the float32 fast path is ~11 instructions on
-// per-cell registers and per-agent shared-memory broadcasts.  Results within a
-// relative band eps of 0 or 1 are re-evaluated in float64 with the reference's
-// exact expression (los_blocked_exact), so the decision equals the oracle's.
+// so per (agent, cell, wall) the float32 fast path is 9 instructions on
+// per-cell registers and per-agent shared-memory broadcasts (5 on the FMA pipe,
+// 2 three-input FMNMX3 on the half-rate ALU pipe, the select done arithmetically
+// with a saturating multiply).  Results within an absolute band of 0 or 1 are
+// re-evaluated in float64 with the reference's exact expression
+// (los_blocked_exact), so the decision equals the oracle's.
 #pragma once
 #include "riab_common.cuh"
 
 namespace riab {
 
 constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
-constexpr int PLACE_REC = 2 + 2 * PLACE_MAX_WI + 2;  // floats per agent record (px,py,(fp,tp)xWI,ep0,ep1)
+constexpr int PLACE_POS64 = 2 + 2 * PLACE_MAX_WI + 2;  // float index of the float64 position inside the record
+constexpr int PLACE_REC = PLACE_POS64 + 4;  // floats per agent record (px,py,(fp,tp)xWI,ep0,ep1, float64 px,py)
 
 RIAB_HD void wall_coords(double qx, double qy, double ax, double ay, double bx, double by, double& f, double& t) {
   const double sx = bx - ax, sy = by - ay;
@@ -34,9 +37,9 @@ RIAB_HD void wall_coords(double qx, double qy, double ax, double ay, double bx, 
 
 // The reference's exact float64 test for one (centre, pos, wall) triple:
 // a-list = segment centre->pos, b-list = wall  (Environment.py:718-721, utils.py:74-106)
-RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, const double* __restrict__ w) {
+RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, double w0, double w1, double w2, double w3) {
   const D ax(cx), ay(cy), bx(px), by(py);
-  const D wx0(w[0]), wy0(w[1]), wx1(w[2]), wy1(w[3]);
+  const D wx0(w0), wy0(w1), wx1(w2), wy1(w3);
   const D d0x = wx0 - ax, d0y = wy0 - ay;
   const D sax = bx - ax, say = by - ay;
   const D sbx = wx1 - wx0, sby = wy1 - wy0;
@@ -44,6 +47,9 @@ RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, cons
   const D la = (d0x * sbpx + d0y * sbpy) / (sax * sbpx + say * sbpy);
   const D lb = ((-d0x) * sapx + (-d0y) * sapy) / (sbx * sapx + sby * sapy);
   return (la.v > 0.0) && (la.v < 1.0) && (lb.v > 0.0) && (lb.v < 1.0);
+}
+RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, const double* __restrict__ w) {
+  return los_blocked_exact(cx, cy, px, py, w[0], w[1], w[2], w[3]);
 }
 
 // Per-agent record for the rate phase, from the float64 position.
@@ -55,10 +61,12 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
   for (int j = 0; j < n_inner && j < PLACE_MAX_WI; ++j) {
     double f, t;
     wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
-    rec[2 + 2 * j] = (float)f;
-    rec[3 + 2 * j] = (fabs(f) < 1e-9) ? nanf("") : (float)t;   // agent on the wall's line: exact path
+    const bool on_line = fabs(f) < 1e-9;      // agent on the wall's line: (0,0) makes M' = 0 -> exact path
+    rec[2 + 2 * j] = on_line ? 0.f : (float)f;
+    rec[3 + 2 * j] = on_line ? 0.f : (float)t;
   }
-  for (int j = n_inner; j < PLACE_MAX_WI; ++j) { rec[2 + 2 * j] = 1.f; rec[3 + 2 * j] = 0.f; }  // dummy walls never block
+  for (int j = n_inner; j < PLACE_MAX_WI; ++j) { rec[2 + 2 * j] = 1.f; rec[3 + 2 * j] = -1.f; }  // dummy walls: same side, M' = -2
+  *reinterpret_cast<double2*>(rec + PLACE_POS64) = make_double2(px, py);      // exact fall-back only
   if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
     // utils.get_distances_between(wall_edge, pos2)  (Environment.py:749-751)
     const double e0x = inner[0] - px, e0y = inner[1] - py, e1x = inner[2] - px, e1y = inner[3] - py;
@@ -72,6 +80,7 @@ struct PlaceConst {                  // uniform per launch
   float min_fr, span, top_hat_w2;
   double top_hat_w;
   float eps[PLACE_MAX_WI];
+  float band;                        // max of eps[]: one absolute band for all walls
   const float* packed;               // device
   const double* centres64;           // device (N,2)
   int periodic;                      // wrap centre->agent vectors (Environment.py:670-675)
@@ -100,7 +109,7 @@ RIAB_DEV void place_load_cells(PlaceCellRegs<WI>& r, const PlaceConst& c, int ce
   r.k[0] = k.x; r.k[1] = k.y; r.k[2] = k.z; r.k[3] = k.w;
 #pragma unroll
   for (int j = 0; j < WI; ++j) {
-    float4 f = make_float4(1.f, 1.f, 1.f, 1.f), t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 f = make_float4(1.f, 1.f, 1.f, 1.f), t = make_float4(-1.f, -1.f, -1.f, -1.f);   // dummy wall (see place_agent_record)
     if (j < c.n_inner) {
       f = *reinterpret_cast<const float4*>(base + (4 + 2 * j) * np + cell0);
       t = *reinterpret_cast<const float4*>(base + (5 + 2 * j) * np + cell0);
@@ -131,33 +140,40 @@ RIAB_DEV float place_profile(float d2, float k, int desc_rt) {
 }
 
 // Exact (float64) line-of-sight flags for this thread's 4 cells: the rare path taken when
-// any float32 predicate of the group fell inside its uncertainty band.
+// any float32 predicate of the group fell inside its uncertainty band.  Arguments are scalars and
+// shared-memory offsets (no generic pointers to materialise in the hot loop).
+RIAB_DEV double lds_f64(uint32_t saddr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+  return v;
+}
 template <int WI>
-__device__ __noinline__ unsigned place_blocked_exact4(const PlaceConst& c, int cell0, const double* __restrict__ pos64,
-                                                      const double* __restrict__ inner64) {
+__device__ __noinline__ unsigned place_blocked_exact4(const double* __restrict__ centres64, int n_cells, int n_inner,
+                                                      int cell0, uint32_t rec_s, uint32_t inner_s) {
+  const double px = lds_f64(rec_s + 4u * PLACE_POS64), py = lds_f64(rec_s + 4u * PLACE_POS64 + 8u);
   unsigned m = 0;
   for (int i = 0; i < 4; ++i) {
     const int cell = cell0 + i;
-    if (cell >= c.n_cells) continue;
-    const double cx = c.centres64[2 * cell], cy = c.centres64[2 * cell + 1];
+    if (cell >= n_cells) continue;
+    const double cx = centres64[2 * cell], cy = centres64[2 * cell + 1];
     bool b = false;
-    for (int j = 0; j < WI && j < c.n_inner; ++j) b = b || los_blocked_exact(cx, cy, pos64[0], pos64[1], inner64 + 4 * j);
+    for (int j = 0; j < WI && j < n_inner; ++j) {
+      const uint32_t w = inner_s + 32u * (uint32_t)j;
+      b = b || los_blocked_exact(cx, cy, px, py, lds_f64(w), lds_f64(w + 8u), lds_f64(w + 16u), lds_f64(w + 24u));
+    }
     m |= b ? (1u << i) : 0u;
   }
   return m;
 }
 
 // Rates of one agent for this thread's 4 cells (branch-free fast path; one rare branch).
-//   rec    : the agent's float32 record in shared memory (broadcast reads)
-//   pos64  : the agent's float64 position (exact fall-back only)
-//   inner64: float64 inner walls in shared memory (exact fall-back only)
+//   rec     : the agent's record in shared memory (broadcast reads); holds the float64 position too
+//   inner_s : shared-memory offset of the float64 inner walls (exact fall-back only)
 template <int WI, int DESC>
 RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0,
-                           const float* __restrict__ rec, const double* __restrict__ pos64,
-                           const double* __restrict__ inner64) {
+                           const float* __restrict__ rec, uint32_t inner_s) {
   const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, f_p0, t_p0
   float d2[4];
-  bool unsure = false;
   if (WI == 0 && c.periodic) {                           // warp-uniform
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -173,13 +189,17 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       d2[i] = fmaf(dy, dy, dx * dx);
     }
   }
-  // final squared distances (blocked pairs get distance 1000, Environment.py:730)
+  // final squared distances (blocked pairs get a distance >= 1000, Environment.py:730)
   float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
   if (WI > 0) {
-    // With s = sign(f_c) and the agent on the other side of the wall's line (opp):
-    //   |D| = |f_c| + |f_p|,  M' = s*M = |f_c| t_p + |f_p| t_c  (a convex combination of t_p, t_c),
-    //   blocked  <=>  opp and 0 < M' < |D|  <=>  opp and min(M', |D| - M') > 0.
-    // |min(..)| below the band => re-evaluate in float64 (conservatively, regardless of opp).
+    // With a = |f_c|, b = |f_p| and the agent on the other side of the wall's line (q = -f_c f_p > 0):
+    //   |D| = a + b,  M' = b t_c + a t_p  (a convex combination of t_p, t_c scaled by |D|),
+    //   blocked  <=>  q > 0 and 0 < M' < |D|  <=>  min(M', |D| - M', q) > 0.
+    // min(|M'|, ||D| - M'|) below the band => re-evaluate in float64 (conservatively, whatever q says).
+    // The select is arithmetic: pen = saturate(2^126 * max_j min3_j) is exactly 1 for a positive normal
+    // number and 0 otherwise (NaN included), and a blocked pair gets d^2 + 1e6.
+    float worst[4] = {-1.f, -1.f, -1.f, -1.f};            // max over walls of min3
+    float amin = 3.0e38f;
 #pragma unroll
     for (int j = 0; j < WI; ++j) {
       float fp, tp;
@@ -188,21 +208,23 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
         const float2 pw = *reinterpret_cast<const float2*>(rec + 2 + 2 * j);
         fp = pw.x; tp = pw.y;
       }
-      const float afp = fabsf(fp);
-      const float band = c.eps[j];                       // absolute band (eps * max |D| * max |t| over the box)
+      const float b = fabsf(fp);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float fc = r.fc[j][i];
-        const float Mp = fmaf(afp, r.tc[j][i], fabsf(fc) * tp);
-        const float Da = fabsf(fc) + afp;
-        const float mn = fminf(Mp, Da - Mp);
-        const bool opp = (fc * fp) < 0.f;                // strictly opposite sides of the wall's line (FMA pipe)
-        dd[i] = (opp & (mn > 0.f)) ? 1.0e6f : dd[i];
-        unsure = unsure | !(fabsf(mn) >= band);          // also true for NaN (degenerate centre / agent)
+        const float fc = r.fc[j][i], a = fabsf(fc);
+        const float Mp = fmaf(b, r.tc[j][i], a * tp);
+        const float Mq = (a + b) - Mp;
+        const float q = fc * -fp;
+        const float m3 = fminf(fminf(Mp, Mq), q);
+        worst[i] = (j == 0) ? m3 : fmaxf(worst[i], m3);
+        amin = fminf(fminf(amin, fabsf(Mp)), fabsf(Mq));
       }
     }
-    if (unsure) {                                        // rare: redo the group's flags with the reference's float64 test
-      const unsigned m = place_blocked_exact4<WI>(c, cell0, pos64, inner64);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dd[i] = fmaf(__saturatef(worst[i] * 8.5070591730234616e37f), 1.0e6f, d2[i]);
+    if (!(amin >= c.band)) {                             // rare: redo the group's flags with the reference's float64 test
+      const unsigned m = place_blocked_exact4<WI>(c.centres64, c.n_cells, c.n_inner, cell0,
+                                                  (uint32_t)__cvta_generic_to_shared(rec), inner_s);
 #pragma unroll
       for (int i = 0; i < 4; ++i) dd[i] = ((m >> i) & 1u) ? 1.0e6f : d2[i];
     }
@@ -235,7 +257,8 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       if (fabsf(dv - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !blocked) {
         const int cell = cell0 + i;
         if (cell < c.n_cells) {
-          D ex = D(c.centres64[2 * cell]) - D(pos64[0]), ey = D(c.centres64[2 * cell + 1]) - D(pos64[1]);
+          const double2 p64 = *reinterpret_cast<const double2*>(rec + PLACE_POS64);
+          D ex = D(c.centres64[2 * cell]) - D(p64.x), ey = D(c.centres64[2 * cell + 1]) - D(p64.y);
           if (c.periodic) {
             if (fabs(ex.v) > c.scale / 2) ex = D(-copysign(1.0, ex.v)) * (D(c.scale) - D(fabs(ex.v)));
             if (fabs(ey.v) > c.scale / 2) ey = D(-copysign(1.0, ey.v)) * (D(c.scale) - D(fabs(ey.v)));

@@ -56,19 +56,26 @@ def agent_normals(seed, step, agents):
                      (rad * np.sin(ang).astype(f32)).astype(np.float64)), axis=-1)
 
 
-def spike_uniforms(seed, step, agents, n_cells, pop=0):
-    """(A, n_cells) float32 values m + v of the spike draw: spike <=> (m + v) < dt*65536*rate.
-    One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words
-    2h, 2h+1 as four 16-bit integers m; all share the dither v = ((r0^r1^r2^r3)>>8) * 2^-24."""
+def expected_spikes(seed, step, agents, fr, dt, pop=0):
+    """(A, n_cells) bool spikes of one step given the float32 rates `fr` (A, n_cells):
+        spike <=> m < fma(rate, dt*65536, -v)      (riab_b200.cu: spike_ballots)
+    One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words 2h, 2h+1 as four
+    16-bit integers m; all eight share the dither v = ((r0^r2)>>8) * 2^-24.  The float32 fma is mirrored
+    in float64: the 48-bit product and the 24-bit dither add exactly, so the sum rounds to float32 once."""
     agents = np.asarray(agents, dtype=np.uint64)
+    fr = np.asarray(fr, dtype=np.float32)
+    n_cells = fr.shape[1]
     groups = (n_cells + 3) // 4
     a = (agents >> np.uint64(1))[:, None]
     g = np.arange(groups, dtype=np.uint64)[None, :]
     r = philox4x32(counter(a, g, step, STREAM_SPIKES, pop), (seed & 0xFFFFFFFF, seed >> 32), rounds=7)   # (A,G,4)
-    v = ((r[..., 0] ^ r[..., 1] ^ r[..., 2] ^ r[..., 3]) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)
+    v = ((r[..., 0] ^ r[..., 2]) >> np.uint32(8)).astype(np.float64) * 2.0 ** -24
     h = (agents & np.uint64(1)).astype(np.int64)[:, None]
     w0 = np.where(h == 1, r[..., 2], r[..., 0])
     w1 = np.where(h == 1, r[..., 3], r[..., 1])
     m = np.stack((w0 & np.uint32(0xFFFF), w0 >> np.uint32(16), w1 & np.uint32(0xFFFF), w1 >> np.uint32(16)), axis=-1)
-    u = (m.astype(np.float32) + v[..., None]).astype(np.float32)
-    return u.reshape(len(agents), groups * 4)[:, :n_cells]
+    m = m.astype(np.float32).reshape(len(agents), groups * 4)[:, :n_cells]
+    vv = np.repeat(v, 4, axis=1)[:, :n_cells]
+    q = np.float64(np.float32(np.float32(dt) * np.float32(65536.0)))
+    thr = (fr.astype(np.float64) * q - vv).astype(np.float32)
+    return m < thr

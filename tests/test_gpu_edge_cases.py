@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import riab_oracle as O
-from philox_np import spike_uniforms
+from philox_np import expected_spikes
 
 pytestmark = pytest.mark.gpu
 
@@ -53,9 +53,8 @@ def test_ragged_sizes_all_wall_templates(A, N, k):
     want = (steps, N) if A == 1 else (steps, A, N)
     assert h["firingrate"].shape == want and h["spikes"].shape == want
     # spikes of the last step against the NumPy mirror of the Philox stream (population 0)
-    u = spike_uniforms(9, steps - 1, np.arange(A), N, pop=0)
     sp = h["spikes"][-1].reshape(A, N)
-    assert np.array_equal(sp, u < np.float32(0.01 * 65536.0) * fr.astype(np.float32))
+    assert np.array_equal(sp, expected_spikes(9, steps - 1, np.arange(A), fr, 0.01, pop=0))
     assert np.isfinite(pos).all() and not np.array_equal(pos, pos0)
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import riab_oracle as O
-from philox_np import agent_normals, spike_uniforms
+from philox_np import agent_normals, expected_spikes
 
 pytestmark = pytest.mark.gpu
 
@@ -112,8 +112,7 @@ def test_spikes_match_numpy_philox():
     h = PCs.get_history_arrays()
     assert h["firingrate"].shape == (3, A, N) and h["spikes"].shape == (3, A, N) and h["spikes"].dtype == bool
     for s in range(3):
-        u = spike_uniforms(11, s, np.arange(A), N, pop=0)
-        want = u < (np.float32(np.float32(0.05) * np.float32(65536.0)) * h["firingrate"][s].astype(np.float32))
+        want = expected_spikes(11, s, np.arange(A), h["firingrate"][s], 0.05, pop=0)
         assert np.array_equal(h["spikes"][s], want), s
     assert 0.02 < h["spikes"].mean() < 0.6
 
