@@ -244,8 +244,12 @@ __device__ __forceinline__ void spike_ballots(uint32_t (&b)[4], uint32_t w0, uin
   b[3] = __ballot_sync(0xffffffffu, s3);
 }
 __device__ __forceinline__ void spike_store(const uint32_t (&b)[4], uint32_t* spk) {
-  if ((threadIdx.x & 31) == 0)
-    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(spk), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]) : "memory");
+  // every lane holds the same four words: one elected lane stores them (whole warp must call)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(spk), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3])
+      : "memory");
 }
 // one agent (whole warp must call)
 __device__ __forceinline__ void spikes1(const float (&o)[4], const OutK& out, const TailCtx& t, const RowCursor& rc) {
@@ -276,10 +280,13 @@ struct PlacePolicy {
     place_agent_record(rec, px, py, s_walls + 4 * env.nb, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym);
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI>(r, c, cell0); }
+  template <bool DEFER>
   static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int cell0,
-                                                const float* rec, uint32_t inner_s) {
-    place_rates4<WI, DESC>(o, r, c, cell0, rec, inner_s);
+                                                const float* rec, uint32_t inner_s, float& amin) {
+    place_rates4<WI, DESC, DEFER>(o, r, c, cell0, rec, inner_s, amin);
   }
+  // deferred band test of the line-of-sight predicate (see place_rates4)
+  static __device__ __forceinline__ bool unsure(float amin, const Const& c) { return (WI > 0) && !(amin >= c.band); }
 };
 
 struct GridPolicy {
@@ -293,10 +300,12 @@ struct GridPolicy {
     rec[1] = (float)(py - env.cym);
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { grid_load_cells(r, c, cell0); }
+  template <bool DEFER>
   static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int, const float* rec,
-                                                uint32_t) {
+                                                uint32_t, float&) {
     grid_rates4(o, r, c, rec);
   }
+  static __device__ __forceinline__ bool unsure(float, const Const&) { return false; }
 };
 
 // ---------------------------------------------------------------------------
@@ -347,6 +356,50 @@ struct __align__(16) StepSlot {
   int na;
   int pad[3];
 };
+
+// The consumers' hot loop: agent pairs (2p, 2p+1) of one ring slot, 4 cells per thread, no OU noise,
+// 16-byte aligned rows, even first global id.  FULL: every cell-thread owns 4 existing cells (no
+// predicate on the stores).  The line-of-sight band test is deferred: a pair whose float32 decision fell
+// inside the band only sets its bit in `redo`; the caller redoes those pairs through the general path
+// (per-agent exact float64 fall-back) after the loop -- no call and no branch in here.
+template <class P, bool SPIKES, bool FULL>
+__device__ __forceinline__ void consume_pairs(int& a, const int na, const int G, const typename P::Regs& regs,
+                                              const typename P::Const& pc, const OutK& out, const TailCtx& tc,
+                                              const int cell0, const float*& recp, const uint32_t inner_s, RowCursor& rc,
+                                              const bool act, const float q16, uint32_t& redo) {
+  float* dst = rc.dst;
+  uint32_t bit = 1u;
+  uint32_t* spk = rc.spk;
+  unsigned long long pair = rc.gid >> 1;
+  const long long pair_rate = 2ll * G * out.ld, pair_spk = 2ll * G * out.spike_ld;     // elements per pair step
+  for (; a + 1 < na; a += 2 * G) {
+    float o[4], amin = 3.0e38f;
+    uint32_t c[4], bl[4];
+    P::template rates4<true>(o, regs, pc, cell0, recp, inner_s, amin);
+    if (FULL || act) st_cs_f4(dst, o[0], o[1], o[2], o[3]);
+    float nv = 0.f;
+    if (SPIKES) {
+      c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
+      philox_keyed<7>(c, out.rk7);
+      nv = spike_neg_dither(c);
+      spike_ballots<false>(bl, c[0], c[1], nv, o, q16, 0u, FULL || act);
+      spike_store(bl, spk);
+    }
+    P::template rates4<true>(o, regs, pc, cell0, recp + P::REC, inner_s, amin);
+    if (FULL || act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
+    if (SPIKES) {
+      spike_ballots<false>(bl, c[2], c[3], nv, o, q16, 0u, FULL || act);
+      spike_store(bl, spk + out.spike_ld);
+    }
+    redo |= P::unsure(amin, pc) ? bit : 0u;
+    bit <<= 1;
+    dst += pair_rate;
+    spk += pair_spk;
+    pair += (unsigned long long)G;
+    recp += 2 * G * P::REC;
+  }
+  rc.dst = dst; rc.spk = spk; rc.gid = pair << 1;
+}
 
 template <class P, int MODE, bool SPIKES, bool NOISE, class C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const riab_agents ag,
@@ -431,7 +484,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
     // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
     const bool fast = (chunks == 1) && !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
     const bool act = cell0 < pc.n_cells;
-    const long long pair_rate = 2ll * G * out.ld, pair_spk = 2ll * G * out.spike_ld;     // elements per pair step
+    const bool full = (pc.n_cells == pc.n_pad);          // no padding cells at all
     const float q16 = out.dt * 65536.0f;
     for (long long q = 0; q < nq; ++q) {
       const int s = (int)(q % NS);
@@ -445,47 +498,37 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
           cursor_init(rc, out, tc, a0 + 2 * grp);
           const float* recp = s_slot[s].rec[2 * grp];
           int a = 2 * grp;
+          uint32_t only = 0xffffffffu;       // pairs (by iteration index) the general loop below evaluates
           if (fast) {
-            float* dst = rc.dst;
-            uint32_t* spk = rc.spk;
-            unsigned long long pair = rc.gid >> 1;
-            for (; a + 1 < na; a += 2 * G) {
-              float o[4];
-              uint32_t c[4], bl[4];
-              P::rates4(o, regs, pc, cell0, recp, inner_s);
-              if (act) st_cs_f4(dst, o[0], o[1], o[2], o[3]);
-              float nv = 0.f;
-              if (SPIKES) {
-                c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
-                philox_keyed<7>(c, out.rk7);
-                nv = spike_neg_dither(c);
-                spike_ballots<false>(bl, c[0], c[1], nv, o, q16, 0u, act);
-                spike_store(bl, spk);
-              }
-              P::rates4(o, regs, pc, cell0, recp + P::REC, inner_s);
-              if (act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
-              if (SPIKES) {
-                spike_ballots<false>(bl, c[2], c[3], nv, o, q16, 0u, act);
-                spike_store(bl, spk + out.spike_ld);
-              }
-              dst += pair_rate;
-              spk += pair_spk;
-              pair += (unsigned long long)G;
-              recp += 2 * G * P::REC;
+            uint32_t redo = 0u;
+            if (full) consume_pairs<P, SPIKES, true>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
+            else consume_pairs<P, SPIKES, false>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
+            redo = __reduce_or_sync(0xffffffffu, redo);
+            if (redo != 0u) {
+              // some float32 line-of-sight decision was inside the band: redo those pairs through the
+              // general path (the stores are idempotent); complete pairs not in `redo` are skipped
+              only = redo;
+              a = 2 * grp;
+              cursor_init(rc, out, tc, a0 + 2 * grp);
+              recp = s_slot[s].rec[2 * grp];
             }
-            rc.dst = dst; rc.spk = spk; rc.gid = pair << 1;
-            if (NOISE) rc.nz = nullptr;            // (unreachable: fast implies !NOISE)
           }
           // general path: the last agent of an odd tile, odd shard offsets, OU noise, ragged cell counts
           const RowStride stride = make_stride(out, 2 * G);
           const bool even = ((rc.gid & 1ull) == 0ull);      // uniform: a0 and 2*grp are even
-          for (; a < na; a += 2 * G) {
+          for (uint32_t it = 0; a < na; a += 2 * G, ++it) {
             float oa[4], ob[4];
             const bool has_b = (a + 1 < na);
-            P::rates4(oa, regs, pc, cell0, recp, inner_s);
+            if (has_b && !((only >> (it & 31u)) & 1u)) {      // warp-uniform
+              cursor_advance(rc, stride);
+              recp += 2 * G * P::REC;
+              continue;
+            }
+            float dummy = 0.f;
+            P::template rates4<false>(oa, regs, pc, cell0, recp, inner_s, dummy);
             store4<NOISE>(oa, out, tc, rc, 0);
             if (has_b) {
-              P::rates4(ob, regs, pc, cell0, recp + P::REC, inner_s);
+              P::template rates4<false>(ob, regs, pc, cell0, recp + P::REC, inner_s, dummy);
               store4<NOISE>(ob, out, tc, rc, out.ld);
             }
             if (SPIKES && (!NOISE || rc.spk != nullptr)) {
@@ -520,8 +563,8 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
             cursor_init(rc, out, tc, a0);
             const RowStride stride = make_stride(out, 1);
             for (int a = 0; a < na; ++a) {
-              float o[4];
-              P::rates4(o, regs, pc, cell0, s_slot[s].rec[a], inner_s);
+              float o[4], dummy = 0.f;
+              P::template rates4<false>(o, regs, pc, cell0, s_slot[s].rec[a], inner_s, dummy);
               finish4<SPIKES, NOISE>(o, out, tc, rc);
               cursor_advance(rc, stride);
             }

@@ -25,8 +25,11 @@
 namespace riab {
 
 constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
-constexpr int PLACE_POS64 = 2 + 2 * PLACE_MAX_WI + 2;  // float index of the float64 position inside the record
-constexpr int PLACE_REC = PLACE_POS64 + 4;  // floats per agent record (px,py,(fp,tp)xWI,ep0,ep1, float64 px,py)
+// Agent record (floats): [px, py, ep0, ep1] [f_p, t_p, -f_p * 2^20, 0] x PLACE_MAX_WI [float64 px, py]
+constexpr int PLACE_WALL0 = 4;                               // float index of wall 0's (f_p, t_p, q-factor, 0)
+constexpr int PLACE_POS64 = PLACE_WALL0 + 4 * PLACE_MAX_WI;  // float index of the float64 position
+constexpr int PLACE_REC = PLACE_POS64 + 4;                   // 40 floats = 160 B per agent
+constexpr float PLACE_QSCALE = 1048576.0f;                   // 2^20: q' = f_c * (-f_p * 2^20) never enters the band by magnitude
 
 RIAB_HD void wall_coords(double qx, double qy, double ax, double ay, double bx, double by, double& f, double& t) {
   const double sx = bx - ax, sy = by - ay;
@@ -56,23 +59,26 @@ RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, cons
 // inner = walls + 4*n_boundary (float64 endpoints), cxm/cym = box centre.
 RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, const double* __restrict__ inner,
                                  int n_inner, int geometry, double cxm, double cym) {
-  rec[0] = (float)(px - cxm);
-  rec[1] = (float)(py - cym);
-  for (int j = 0; j < n_inner && j < PLACE_MAX_WI; ++j) {
-    double f, t;
-    wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
-    const bool on_line = fabs(f) < 1e-9;      // agent on the wall's line: (0,0) makes M' = 0 -> exact path
-    rec[2 + 2 * j] = on_line ? 0.f : (float)f;
-    rec[3 + 2 * j] = on_line ? 0.f : (float)t;
-  }
-  for (int j = n_inner; j < PLACE_MAX_WI; ++j) { rec[2 + 2 * j] = 1.f; rec[3 + 2 * j] = -1.f; }  // dummy walls: same side, M' = -2
-  *reinterpret_cast<double2*>(rec + PLACE_POS64) = make_double2(px, py);      // exact fall-back only
+  float ep0 = 0.f, ep1 = 0.f;
   if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
     // utils.get_distances_between(wall_edge, pos2)  (Environment.py:749-751)
     const double e0x = inner[0] - px, e0y = inner[1] - py, e1x = inner[2] - px, e1y = inner[3] - py;
-    rec[2 + 2 * PLACE_MAX_WI] = (float)sqrt(e0x * e0x + e0y * e0y);
-    rec[3 + 2 * PLACE_MAX_WI] = (float)sqrt(e1x * e1x + e1y * e1y);
+    ep0 = (float)sqrt(e0x * e0x + e0y * e0y);
+    ep1 = (float)sqrt(e1x * e1x + e1y * e1y);
   }
+  *reinterpret_cast<float4*>(rec) = make_float4((float)(px - cxm), (float)(py - cym), ep0, ep1);
+  for (int j = 0; j < PLACE_MAX_WI; ++j) {
+    float4 w = make_float4(1.f, -1.f, -PLACE_QSCALE, 0.f);        // dummy wall: same side (q' < 0), M' = -2
+    if (j < n_inner) {
+      double f, t;
+      wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
+      const bool on_line = fabs(f) < 1e-9;      // agent on the wall's line: (0,0,0) makes M' = q' = 0 -> exact path
+      const float ff = on_line ? 0.f : (float)f;
+      w = make_float4(ff, on_line ? 0.f : (float)t, -ff * PLACE_QSCALE, 0.f);
+    }
+    *reinterpret_cast<float4*>(rec + PLACE_WALL0 + 4 * j) = w;
+  }
+  *reinterpret_cast<double2*>(rec + PLACE_POS64) = make_double2(px, py);      // exact fall-back only
 }
 
 struct PlaceConst {                  // uniform per launch
@@ -166,13 +172,16 @@ __device__ __noinline__ unsigned place_blocked_exact4(const double* __restrict__
   return m;
 }
 
-// Rates of one agent for this thread's 4 cells (branch-free fast path; one rare branch).
+// Rates of one agent for this thread's 4 cells (branch-free fast path).
 //   rec     : the agent's record in shared memory (broadcast reads); holds the float64 position too
 //   inner_s : shared-memory offset of the float64 inner walls (exact fall-back only)
-template <int WI, int DESC>
+//   amin    : running minimum of |min3| (the quantity compared with the band).  DEFER = true only
+//             accumulates it -- the caller checks `amin >= band` later and redoes the agents it covers
+//             with DEFER = false, which tests per agent and takes the exact float64 path at once.
+template <int WI, int DESC, bool DEFER>
 RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0,
-                           const float* __restrict__ rec, uint32_t inner_s) {
-  const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, f_p0, t_p0
+                           const float* __restrict__ rec, uint32_t inner_s, float& amin_io) {
+  const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, ep0, ep1
   float d2[4];
   if (WI == 0 && c.periodic) {                           // warp-uniform
 #pragma unroll
@@ -192,37 +201,34 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
   // final squared distances (blocked pairs get a distance >= 1000, Environment.py:730)
   float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
   if (WI > 0) {
-    // With a = |f_c|, b = |f_p| and the agent on the other side of the wall's line (q = -f_c f_p > 0):
+    // With a = |f_c|, b = |f_p| and q' = -f_c f_p 2^20 (> 0 iff the agent is on the other side of the wall's line):
     //   |D| = a + b,  M' = b t_c + a t_p  (a convex combination of t_p, t_c scaled by |D|),
-    //   blocked  <=>  q > 0 and 0 < M' < |D|  <=>  min(M', |D| - M', q) > 0.
-    // min(|M'|, ||D| - M'|) below the band => re-evaluate in float64 (conservatively, whatever q says).
-    // The select is arithmetic: pen = saturate(2^126 * max_j min3_j) is exactly 1 for a positive normal
+    //   blocked  <=>  q' > 0 and 0 < M' < |D|  <=>  m3 = min(M', |D| - M', q') > 0.
+    // |m3| below the band => the sign of m3 is not certain in float32: re-evaluate in float64.
+    // The select is arithmetic: pen = saturate(2^126 * max_j m3_j) is exactly 1 for a positive normal
     // number and 0 otherwise (NaN included), and a blocked pair gets d^2 + 1e6.
-    float worst[4] = {-1.f, -1.f, -1.f, -1.f};            // max over walls of min3
-    float amin = 3.0e38f;
+    float worst[4] = {-1.f, -1.f, -1.f, -1.f};            // max over walls of m3
+    float amin = DEFER ? amin_io : 3.0e38f;
 #pragma unroll
     for (int j = 0; j < WI; ++j) {
-      float fp, tp;
-      if (j == 0) { fp = r0.z; tp = r0.w; }
-      else {
-        const float2 pw = *reinterpret_cast<const float2*>(rec + 2 + 2 * j);
-        fp = pw.x; tp = pw.y;
-      }
-      const float b = fabsf(fp);
+      const float4 pw = *reinterpret_cast<const float4*>(rec + PLACE_WALL0 + 4 * j);   // f_p, t_p, -f_p 2^20
+      const float b = fabsf(pw.x);
+      float m3[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float fc = r.fc[j][i], a = fabsf(fc);
-        const float Mp = fmaf(b, r.tc[j][i], a * tp);
+        const float Mp = fmaf(b, r.tc[j][i], a * pw.y);
         const float Mq = (a + b) - Mp;
-        const float q = fc * -fp;
-        const float m3 = fminf(fminf(Mp, Mq), q);
-        worst[i] = (j == 0) ? m3 : fmaxf(worst[i], m3);
-        amin = fminf(fminf(amin, fabsf(Mp)), fabsf(Mq));
+        m3[i] = fminf(fminf(Mp, Mq), fc * pw.z);
+        worst[i] = (j == 0) ? m3[i] : fmaxf(worst[i], m3[i]);
       }
+      amin = fminf(fminf(amin, fabsf(m3[0])), fabsf(m3[1]));
+      amin = fminf(fminf(amin, fabsf(m3[2])), fabsf(m3[3]));
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) dd[i] = fmaf(__saturatef(worst[i] * 8.5070591730234616e37f), 1.0e6f, d2[i]);
-    if (!(amin >= c.band)) {                             // rare: redo the group's flags with the reference's float64 test
+    if (DEFER) amin_io = amin;
+    else if (!(amin >= c.band)) {                        // rare: redo the group's flags with the reference's float64 test
       const unsigned m = place_blocked_exact4<WI>(c.centres64, c.n_cells, c.n_inner, cell0,
                                                   (uint32_t)__cvta_generic_to_shared(rec), inner_s);
 #pragma unroll
@@ -237,8 +243,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       out[i] = fmaf(place_profile<DESC>(dd[i], r.k[i], c.desc), c.span, c.min_fr);   // Neurons.py:978-980
     return;
   }
-  float2 ep = make_float2(0.f, 0.f);
-  if (geodesic) ep = *reinterpret_cast<const float2*>(rec + 2 + 2 * PLACE_MAX_WI);
+  const float2 ep = make_float2(r0.z, r0.w);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const bool blocked = (WI > 0) && (dd[i] != d2[i]);
