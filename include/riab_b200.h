@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RIAB_ABI_VERSION 1
+#define RIAB_ABI_VERSION 2
 
 typedef enum {
   RIAB_OK = 0,
@@ -135,6 +135,8 @@ typedef struct {
   float eps[8];            /* relative uncertainty band of the float32 line-of-sight predicate, per inner wall */
   int32_t ep_valid;        /* geodesic: bit k set iff end k of walls[4] lies strictly inside the box (Environment.py:748) */
   int32_t n_pad;           /* n_cells rounded up to a multiple of 4 */
+  float k_uniform;         /* log2(e)/(2 w^2) when every cell has the same width w, else 0 */
+  float r2_max;            /* max squared distance of a centre or box corner from the box centre */
 } riab_place_cells;
 
 /* Host-side packing of PlaceCells parameters (place_cell_centres (N,2) f64,

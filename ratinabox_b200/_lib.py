@@ -46,7 +46,8 @@ class PlaceCells(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("description", C.c_int32), ("wall_geometry", C.c_int32),
                 ("n_inner_walls", C.c_int32), ("min_fr", C.c_float), ("max_fr", C.c_float),
                 ("top_hat_width", C.c_double), ("packed_dev", C.c_void_p), ("centres_dev", C.c_void_p),
-                ("eps", C.c_float * 8), ("ep_valid", C.c_int32), ("n_pad", C.c_int32)]
+                ("eps", C.c_float * 8), ("ep_valid", C.c_int32), ("n_pad", C.c_int32),
+                ("k_uniform", C.c_float), ("r2_max", C.c_float)]
 
 
 class GridCells(C.Structure):
@@ -138,7 +139,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.riab_abi_version() != 1:
+    if lib.riab_abi_version() != 2:
         raise ImportError("libriab_b200.so ABI version mismatch")
     _lib = lib
     return lib

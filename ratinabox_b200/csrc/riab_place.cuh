@@ -3,7 +3,8 @@
 // (ratinabox/Environment.py:677-779) for euclidean / line_of_sight / geodesic.
 //
 // Layout of the packed per-population block (float32, written by riab_place_pack):
-//   cx[Np] | cy[Np] | k[Np] | (spare)[Np] | per inner wall j: fc_j[Np], tc_j[Np] | ce0[Np] | ce1[Np]
+//   cx[Np] | cy[Np] | k[Np] | a[Np] | per inner wall j: fc_j[Np], tc_j[Np] | ce0[Np] | ce1[Np]
+//   a = -k |c|^2 (expanded Gaussian form, see place_rates4), only when all widths are equal.
 //   Np = n_cells rounded up to a multiple of 4 (padding cells sit far away, k = 0).
 //   Coordinates are relative to the box centre (halves the float32 rounding error).
 //   fc_j = signed distance of the centre to wall j's line, tc_j = its parameter
@@ -25,8 +26,8 @@
 namespace riab {
 
 constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
-// Agent record (floats): [px, py, ep0, ep1] [f_p, t_p, -f_p * 2^20, 0] x PLACE_MAX_WI [float64 px, py]
-constexpr int PLACE_WALL0 = 4;                               // float index of wall 0's (f_p, t_p, q-factor, 0)
+// Agent record (floats): [px, py, ep0, ep1] [t_p/|f_p|, (1-t_p)/|f_p|, -f_p * 2^20, band/|f_p|] x PLACE_MAX_WI [float64 px, py]
+constexpr int PLACE_WALL0 = 4;                               // float index of wall 0's float4
 constexpr int PLACE_POS64 = PLACE_WALL0 + 4 * PLACE_MAX_WI;  // float index of the float64 position
 constexpr int PLACE_REC = PLACE_POS64 + 4;                   // 40 floats = 160 B per agent
 constexpr float PLACE_QSCALE = 1048576.0f;                   // 2^20: q' = f_c * (-f_p * 2^20) never enters the band by magnitude
@@ -58,7 +59,7 @@ RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, cons
 // Per-agent record for the rate phase, from the float64 position.
 // inner = walls + 4*n_boundary (float64 endpoints), cxm/cym = box centre.
 RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, const double* __restrict__ inner,
-                                 int n_inner, int geometry, double cxm, double cym) {
+                                 int n_inner, int geometry, double cxm, double cym, float band, int expanded, float kx) {
   float ep0 = 0.f, ep1 = 0.f;
   if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
     // utils.get_distances_between(wall_edge, pos2)  (Environment.py:749-751)
@@ -66,15 +67,17 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
     ep0 = (float)sqrt(e0x * e0x + e0y * e0y);
     ep1 = (float)sqrt(e1x * e1x + e1y * e1y);
   }
-  *reinterpret_cast<float4*>(rec) = make_float4((float)(px - cxm), (float)(py - cym), ep0, ep1);
+  const float pxf = (float)(px - cxm), pyf = (float)(py - cym);
+  if (expanded) ep0 = (float)((double)kx * ((double)pxf * pxf + (double)pyf * pyf));    // -k |p|^2 of the rounded position
+  *reinterpret_cast<float4*>(rec) = make_float4(pxf, pyf, ep0, ep1);
   for (int j = 0; j < PLACE_MAX_WI; ++j) {
-    float4 w = make_float4(1.f, -1.f, -PLACE_QSCALE, 0.f);        // dummy wall: same side (q' < 0), M' = -2
+    float4 w = make_float4(-1.f, 2.f, -PLACE_QSCALE, 1.0e-6f);    // dummy wall: same side (q' < 0), X = -2, Y = 4
     if (j < n_inner) {
       double f, t;
       wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
-      const bool on_line = fabs(f) < 1e-9;      // agent on the wall's line: (0,0,0) makes M' = q' = 0 -> exact path
-      const float ff = on_line ? 0.f : (float)f;
-      w = make_float4(ff, on_line ? 0.f : (float)t, -ff * PLACE_QSCALE, 0.f);
+      const double b = fabs(f);
+      if (b < 1e-9) w = make_float4(0.f, 0.f, 0.f, 3.0e38f);      // agent on the wall's line: every decision -> exact path
+      else w = make_float4((float)(t / b), (float)((1.0 - t) / b), (float)(-f) * PLACE_QSCALE, (float)((double)band / b));
     }
     *reinterpret_cast<float4*>(rec + PLACE_WALL0 + 4 * j) = w;
   }
@@ -87,6 +90,8 @@ struct PlaceConst {                  // uniform per launch
   double top_hat_w;
   float eps[PLACE_MAX_WI];
   float band;                        // max of eps[]: one absolute band for all walls
+  int expanded;                      // Gaussian with one common width: -k d^2 = a_c + (2k c).p - k|p|^2 (3 FMA-pipe ops)
+  float kx;                          // -k = -log2(e)/(2 w^2) of that common width
   const float* packed;               // device
   const double* centres64;           // device (N,2)
   int periodic;                      // wrap centre->agent vectors (Environment.py:670-675)
@@ -99,7 +104,7 @@ struct PlaceConst {                  // uniform per launch
 template <int WI>
 struct PlaceCellRegs {
   float cx[4], cy[4], k[4];
-  float fc[WI > 0 ? WI : 1][4], tc[WI > 0 ? WI : 1][4];
+  float fc[WI > 0 ? WI : 1][4], tc[WI > 0 ? WI : 1][4], tq[WI > 0 ? WI : 1][4];   // tq = 1 - tc
   float ce0[4], ce1[4];
 };
 
@@ -113,6 +118,13 @@ RIAB_DEV void place_load_cells(PlaceCellRegs<WI>& r, const PlaceConst& c, int ce
   r.cx[0] = x.x; r.cx[1] = x.y; r.cx[2] = x.z; r.cx[3] = x.w;
   r.cy[0] = y.x; r.cy[1] = y.y; r.cy[2] = y.z; r.cy[3] = y.w;
   r.k[0] = k.x; r.k[1] = k.y; r.k[2] = k.z; r.k[3] = k.w;
+  if (c.expanded) {                                      // registers hold (2k cx, 2k cy, -k|c|^2) instead of (cx, cy, k)
+    const float4 a = *reinterpret_cast<const float4*>(base + 3 * np + cell0);
+    const float k2 = -2.f * c.kx;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r.cx[i] *= k2; r.cy[i] *= k2; }
+    r.k[0] = a.x; r.k[1] = a.y; r.k[2] = a.z; r.k[3] = a.w;
+  }
 #pragma unroll
   for (int j = 0; j < WI; ++j) {
     float4 f = make_float4(1.f, 1.f, 1.f, 1.f), t = make_float4(-1.f, -1.f, -1.f, -1.f);   // dummy wall (see place_agent_record)
@@ -122,6 +134,7 @@ RIAB_DEV void place_load_cells(PlaceCellRegs<WI>& r, const PlaceConst& c, int ce
     }
     r.fc[j][0] = f.x; r.fc[j][1] = f.y; r.fc[j][2] = f.z; r.fc[j][3] = f.w;
     r.tc[j][0] = t.x; r.tc[j][1] = t.y; r.tc[j][2] = t.z; r.tc[j][3] = t.w;
+    r.tq[j][0] = 1.f - t.x; r.tq[j][1] = 1.f - t.y; r.tq[j][2] = 1.f - t.z; r.tq[j][3] = 1.f - t.w;
   }
   if (WI > 0 && c.geometry == RIAB_GEOM_GEODESIC) {
     const float4 a = *reinterpret_cast<const float4*>(base + (4 + 2 * c.n_inner) * np + cell0);
@@ -175,13 +188,66 @@ __device__ __noinline__ unsigned place_blocked_exact4(const double* __restrict__
 // Rates of one agent for this thread's 4 cells (branch-free fast path).
 //   rec     : the agent's record in shared memory (broadcast reads); holds the float64 position too
 //   inner_s : shared-memory offset of the float64 inner walls (exact fall-back only)
-//   amin    : running minimum of |min3| (the quantity compared with the band).  DEFER = true only
-//             accumulates it -- the caller checks `amin >= band` later and redoes the agents it covers
-//             with DEFER = false, which tests per agent and takes the exact float64 path at once.
-template <int WI, int DESC, bool DEFER>
+//   unsure  : DEFER = true only ORs the band test into it -- the caller redoes the agents it covers
+//             later with DEFER = false, which tests per agent and takes the exact float64 path at once.
+//   EXP     : 1 = the expanded Gaussian form is known to be on (no branch), 0 = known off, -1 = test c.expanded
+template <int WI, int DESC, bool DEFER, int EXP = -1>
 RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0,
-                           const float* __restrict__ rec, uint32_t inner_s, float& amin_io) {
-  const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, ep0, ep1
+                           const float* __restrict__ rec, uint32_t inner_s, bool& unsure_io) {
+  const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, ep0 | -k|p|^2, ep1
+  // ---- line of sight: pen[i] = 1 if the segment centre_i -> agent crosses an inner wall, else 0
+  float pen[4] = {0.f, 0.f, 0.f, 0.f};
+  if (WI > 0) {
+    // With a = |f_c|, b = |f_p| and q' = -f_c f_p 2^20 (> 0 iff the agent is on the other side of the wall's line):
+    //   |D| = a + b,  M' = b t_c + a t_p  (a convex combination of t_p, t_c scaled by |D|),
+    //   blocked  <=>  q' > 0 and 0 < M' < |D|.
+    // Everything is divided by b on the agent side (record: t_p/b, (1-t_p)/b, band/b), so per pair
+    //   X = M'/b = fma(a, t_p/b, t_c),  Y = (|D|-M')/b = fma(a, (1-t_p)/b, 1-t_c),  m3 = min(X, Y, q')
+    // is 2 FFMA + 1 FMUL + 1 FMNMX3, and blocked <=> m3 > 0.
+    // |m3| below band/b => the sign of m3 is not certain in float32: re-evaluate in float64.
+    // The select is arithmetic: pen = saturate(2^126 * max_j m3_j) is exactly 1 for a positive normal
+    // number and 0 otherwise (NaN included).
+    float worst[4] = {-1.f, -1.f, -1.f, -1.f};            // max over walls of m3
+    bool unsure = DEFER ? unsure_io : false;
+#pragma unroll
+    for (int j = 0; j < WI; ++j) {
+      const float4 pw = *reinterpret_cast<const float4*>(rec + PLACE_WALL0 + 4 * j);
+      float m3[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float fc = r.fc[j][i], a = fabsf(fc);
+        const float X = fmaf(a, pw.x, r.tc[j][i]);
+        const float Y = fmaf(a, pw.y, r.tq[j][i]);
+        m3[i] = fminf(fminf(X, Y), fc * pw.z);
+        worst[i] = (j == 0) ? m3[i] : fmaxf(worst[i], m3[i]);
+      }
+      const float am = fminf(fminf(fminf(fabsf(m3[0]), fabsf(m3[1])), fabsf(m3[2])), fabsf(m3[3]));
+      unsure = unsure || (am < pw.w);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pen[i] = __saturatef(worst[i] * 8.5070591730234616e37f);
+    if (DEFER) unsure_io = unsure;
+    else if (unsure) {                                   // rare: redo the group's flags with the reference's float64 test
+      const unsigned m = place_blocked_exact4<WI>(c.centres64, c.n_cells, c.n_inner, cell0,
+                                                  (uint32_t)__cvta_generic_to_shared(rec), inner_s);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pen[i] = ((m >> i) & 1u) ? 1.f : 0.f;
+    }
+  }
+  // ---- Gaussian with one common width, expanded:  -k|c-p|^2 = (-k|c|^2 - k|p|^2) + (2k cx) px + (2k cy) py.
+  // 1 FADD + 2 FFMA per rate on per-cell registers (2k cx, 2k cy, -k|c|^2); only used when k * r2_max <= 10,
+  // where the cancellation costs < 4e-6 relative (make_place).  Blocked pairs: exponent - 1e5 -> rate 0 (d = 1000).
+  if (DESC == RIAB_PC_GAUSSIAN && (EXP == 1 || (EXP < 0 && c.expanded))) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t = r.k[i] + r0.z;
+      t = fmaf(r.cx[i], r0.x, t);
+      t = fmaf(r.cy[i], r0.y, t);
+      if (WI > 0) t = fmaf(pen[i], -1.0e5f, t);
+      out[i] = fmaf(ex2f(t), c.span, c.min_fr);          // Neurons.py:978-980
+    }
+    return;
+  }
   float d2[4];
   if (WI == 0 && c.periodic) {                           // warp-uniform
 #pragma unroll
@@ -199,42 +265,9 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     }
   }
   // final squared distances (blocked pairs get a distance >= 1000, Environment.py:730)
-  float dd[4] = {d2[0], d2[1], d2[2], d2[3]};
-  if (WI > 0) {
-    // With a = |f_c|, b = |f_p| and q' = -f_c f_p 2^20 (> 0 iff the agent is on the other side of the wall's line):
-    //   |D| = a + b,  M' = b t_c + a t_p  (a convex combination of t_p, t_c scaled by |D|),
-    //   blocked  <=>  q' > 0 and 0 < M' < |D|  <=>  m3 = min(M', |D| - M', q') > 0.
-    // |m3| below the band => the sign of m3 is not certain in float32: re-evaluate in float64.
-    // The select is arithmetic: pen = saturate(2^126 * max_j m3_j) is exactly 1 for a positive normal
-    // number and 0 otherwise (NaN included), and a blocked pair gets d^2 + 1e6.
-    float worst[4] = {-1.f, -1.f, -1.f, -1.f};            // max over walls of m3
-    float amin = DEFER ? amin_io : 3.0e38f;
+  float dd[4];
 #pragma unroll
-    for (int j = 0; j < WI; ++j) {
-      const float4 pw = *reinterpret_cast<const float4*>(rec + PLACE_WALL0 + 4 * j);   // f_p, t_p, -f_p 2^20
-      const float b = fabsf(pw.x);
-      float m3[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float fc = r.fc[j][i], a = fabsf(fc);
-        const float Mp = fmaf(b, r.tc[j][i], a * pw.y);
-        const float Mq = (a + b) - Mp;
-        m3[i] = fminf(fminf(Mp, Mq), fc * pw.z);
-        worst[i] = (j == 0) ? m3[i] : fmaxf(worst[i], m3[i]);
-      }
-      amin = fminf(fminf(amin, fabsf(m3[0])), fabsf(m3[1]));
-      amin = fminf(fminf(amin, fabsf(m3[2])), fabsf(m3[3]));
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dd[i] = fmaf(__saturatef(worst[i] * 8.5070591730234616e37f), 1.0e6f, d2[i]);
-    if (DEFER) amin_io = amin;
-    else if (!(amin >= c.band)) {                        // rare: redo the group's flags with the reference's float64 test
-      const unsigned m = place_blocked_exact4<WI>(c.centres64, c.n_cells, c.n_inner, cell0,
-                                                  (uint32_t)__cvta_generic_to_shared(rec), inner_s);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) dd[i] = ((m >> i) & 1u) ? 1.0e6f : d2[i];
-    }
-  }
+  for (int i = 0; i < 4; ++i) dd[i] = (WI > 0) ? fmaf(pen[i], 1.0e6f, d2[i]) : d2[i];
   const bool geodesic = (DESC < 0) && (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
   const int desc = (DESC >= 0) ? DESC : c.desc;
   if (desc != RIAB_PC_TOP_HAT && !geodesic) {
