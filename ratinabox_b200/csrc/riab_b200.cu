@@ -228,13 +228,22 @@ __device__ __forceinline__ void spike_words(uint32_t (&c)[4], const OutK& out, c
 __device__ __forceinline__ float spike_neg_dither(const uint32_t (&c)[4]) {
   return (float)((c[0] ^ c[2]) >> 8) * -5.9604644775390625e-08f;
 }
-// ballots of one agent's 4 cell slots; `ok` = this thread's cells exist (all 4 or none) when !MASKED
-template <bool MASKED>
+// ballots of one agent's 4 cell slots; `ok` = this thread's cells exist (all 4 or none) when !MASKED.
+// XU_BOUND: for a cell type that saturates the XU pipe the four integer -> float conversions can be done as
+// as_float(0x4B000000 | m) - 2^23  (PRMT + FADD, exact, same bits) instead of I2F; no current policy needs it.
+template <bool MASKED, bool XU_BOUND = false>
 __device__ __forceinline__ void spike_ballots(uint32_t (&b)[4], uint32_t w0, uint32_t w1, float nv, const float (&o)[4],
                                               float q /* dt * 65536 */, unsigned vmask, bool ok) {
-  float m0, m1, m2, m3;           // the four 16-bit integers as floats: I2F.U16 reads either half-word directly
-  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.u16 %0, l;\n\tcvt.rn.f32.u16 %1, h;\n\t}" : "=f"(m0), "=f"(m1) : "r"(w0));
-  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.u16 %0, l;\n\tcvt.rn.f32.u16 %1, h;\n\t}" : "=f"(m2), "=f"(m3) : "r"(w1));
+  float m0, m1, m2, m3;           // the four 16-bit integers as floats
+  if (XU_BOUND) {
+    m0 = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7610)) - 8388608.0f;
+    m1 = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7632)) - 8388608.0f;
+    m2 = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7610)) - 8388608.0f;
+    m3 = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7632)) - 8388608.0f;
+  } else {                        // I2F.U16 reads either half-word directly
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.u16 %0, l;\n\tcvt.rn.f32.u16 %1, h;\n\t}" : "=f"(m0), "=f"(m1) : "r"(w0));
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.u16 %0, l;\n\tcvt.rn.f32.u16 %1, h;\n\t}" : "=f"(m2), "=f"(m3) : "r"(w1));
+  }
   bool s0 = m0 < fmaf(o[0], q, nv);
   bool s1 = m1 < fmaf(o[1], q, nv);
   bool s2 = m2 < fmaf(o[2], q, nv);
@@ -278,6 +287,7 @@ struct PlacePolicy {
   using Regs = PlaceCellRegs<WI>;
   static constexpr int REC = PLACE_REC;
   static constexpr bool LIGHT = (WI == 0) && (DESC >= 0);   // few instructions per rate: HBM-bound consumers
+  static constexpr bool XU_BOUND = false;
   static __device__ __forceinline__ void record(float* rec, double px, double py, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
     place_agent_record(rec, px, py, s_walls + 4 * env.nb, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx);
@@ -296,6 +306,7 @@ struct GridPolicy {
   using Regs = GridCellRegs;
   static constexpr int REC = 4;
   static constexpr bool LIGHT = false;    // 36 cell registers per thread do not fit StepCfg<8>'s 56-register consumers
+  static constexpr bool XU_BOUND = false; // 3 MUFU.COS per rate, yet issue-bound: PRMT+FADD instead of I2F measured slower (95.6 vs 91.3 us, c3)
   static __device__ __forceinline__ void record(float* rec, double px, double py, const double*, const Const&,
                                                 const EnvK& env) {
     rec[0] = (float)(px - env.cxm);
@@ -385,13 +396,13 @@ __device__ __forceinline__ void consume_pairs(int& a, const int na, const int G,
       c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
       philox_keyed<7>(c, out.rk7);
       nv = spike_neg_dither(c);
-      spike_ballots<false>(bl, c[0], c[1], nv, o, q16, 0u, FULL || act);
+      spike_ballots<false, P::XU_BOUND>(bl, c[0], c[1], nv, o, q16, 0u, FULL || act);
       spike_store(bl, spk);
     }
     P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
     if (FULL || act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
     if (SPIKES) {
-      spike_ballots<false>(bl, c[2], c[3], nv, o, q16, 0u, FULL || act);
+      spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, FULL || act);
       spike_store(bl, spk + out.spike_ld);
     }
     redo |= unsure ? bit : 0u;

@@ -118,3 +118,45 @@ def test_three_populations_share_one_agent_in_run():
     # history rows of every population belong to the same 6 steps
     for ns in (PCs, GCs, BVCs):
         assert ns.get_history_arrays()["firingrate"].shape[0] == 6
+
+
+@pytest.mark.parametrize("widths", ["uniform", "mixed"])
+def test_line_of_sight_on_the_decision_boundary(widths):
+    """Adversarial geometry for the float32 line-of-sight predicate: positions chosen so that the segment
+    centre -> position grazes a wall END POINT (l_b = 0 or 1 up to rounding), runs ALONG the wall's line, or starts
+    on it.  Those pairs fall inside the float32 band and must be decided by the exact float64 path exactly like
+    utils.vector_intercepts (utils.py:96-106): a single misclassified pair changes a rate by O(1).
+    `uniform` widths take the expanded-exponent kernel, `mixed` the direct one."""
+    import ratinabox_b200 as rb
+    rng = np.random.default_rng(3)
+    walls = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+    N = 256
+    centres = rng.uniform(0.02, 0.98, size=(N, 2))
+    centres[:8, 0] = 0.3                               # centres ON the first wall's line (above and on the wall)
+    centres[8:12, 0] = 0.7
+    w = np.full(N, 0.2) if widths == "uniform" else rng.uniform(0.1, 0.3, size=N)
+    ends = np.array([[0.3, 0.5], [0.7, 0.5]])
+    pos = []
+    for k in range(1500):                              # through a wall end: p = e + s (e - c)
+        c, e = centres[rng.integers(N)], ends[rng.integers(2)]
+        s = rng.uniform(0.05, 3.0)
+        pos.append(e + s * (e - c))
+    for k in range(250):                               # on a wall's line (blocked-ness of centres on the other line)
+        pos.append([0.3 if k % 2 else 0.7, rng.uniform(0.02, 0.98)])
+    pos = np.array(pos)
+    pos = pos[(pos[:, 0] > 0.01) & (pos[:, 0] < 0.99) & (pos[:, 1] > 0.01) & (pos[:, 1] < 0.99)]
+    assert len(pos) > 600
+    np.random.seed(1)
+    E = rb.Environment()
+    for wl in walls:
+        E.add_wall(wl)
+    Ag = rb.Agent(E, {"dt": 0.01, "n_agents": 4})
+    PCs = rb.PlaceCells(Ag, {"place_cell_centres": centres, "widths": w if widths == "mixed" else 0.2,
+                             "wall_geometry": "line_of_sight"})
+    got = PCs.get_state(evaluate_at=None, pos=pos)     # (N, n_pos)
+    env = O.OracleEnvironment(walls=walls)
+    ref = O.place_cells_get_state(env, centres, w, pos, O.TapeRNG(), "gaussian", "line_of_sight")
+    dist = O.distances_accounting_for_environment(env, centres, pos, "line_of_sight", O.TapeRNG())
+    assert 0.05 < (dist >= 1000).mean() < 0.8          # both outcomes are well represented
+    bad = np.abs(got - ref) > 1e-5
+    assert not bad.any(), (int(bad.sum()), np.argwhere(bad)[:5], got[bad][:5], ref[bad][:5])
