@@ -48,7 +48,20 @@ WORKLOADS = {
                desc="configs[2]: 65536 agents, 1024 GridCells, box"),
     "c4": dict(agents=16384, walls=maze_walls(), cells=("bvc", 512, None),
                desc="configs[3]: 16384 agents, 512 BVCs, 8-wall maze (4 boundary + 8 internal)"),
+    # configs[4] is a STRONG-scaling case: 262144 agents in total, divided over the ranks
+    "c5": dict(agents=262144, strong=True, walls=BOX_WALLS,
+               cells=[("place", 512, "line_of_sight"), ("grid", 512, None), ("bvc", 256, None)],
+               desc="configs[4]: 262144 agents in total, 512 Place + 512 Grid + 256 BVC populations, box+2 walls"),
 }
+
+
+def cells_of(wl):
+    c = wl["cells"]
+    return list(c) if isinstance(c, list) else [c]
+
+
+def agents_per_rank(wl, world):
+    return wl["agents"] // world if wl.get("strong") else wl["agents"]
 
 
 def synthetic_cells(kind, n, seed):
@@ -143,24 +156,29 @@ def _oracle_worker(args):
     env = O.OracleEnvironment(walls=wl["walls"])
     pos, vel = synthetic_agents(1, wl["walls"], seed)
     ag = O.OracleAgent(env, pos[0], vel[0], {"dt": 0.01})
-    kind, n, geom = wl["cells"]
-    cp = synthetic_cells(kind, n, 0)
     rng = O.GlobalRNG()
-    if kind == "place":
-        ns = O.OracleNeurons(ag, n, lambda p, r: O.place_cells_get_state(env, cp["centres"], cp["widths"], p, r,
-                                                                         "gaussian", geom))
-    elif kind == "grid":
-        w = O.grid_cells_w(cp["orientations"])
-        ns = O.OracleNeurons(ag, n, lambda p, r: O.grid_cells_get_state(cp["gridscales"], cp["phase_offsets"], w, p))
-    else:
-        ns = O.OracleNeurons(ag, n, lambda p, r: O.bvc_get_state(env, cp["mu_d"], np.radians(cp["mu_t"]), cp["sg_d"],
-                                                                 np.radians(cp["sg_t"]), p, r))
+
+    def population(kind, n, geom, k):
+        cp = synthetic_cells(kind, n, k)
+        if kind == "place":
+            return O.OracleNeurons(ag, n, lambda p, r: O.place_cells_get_state(env, cp["centres"], cp["widths"], p, r,
+                                                                               "gaussian", geom))
+        if kind == "grid":
+            w = O.grid_cells_w(cp["orientations"])
+            return O.OracleNeurons(ag, n, lambda p, r: O.grid_cells_get_state(cp["gridscales"], cp["phase_offsets"], w, p))
+        return O.OracleNeurons(ag, n, lambda p, r: O.bvc_get_state(env, cp["mu_d"], np.radians(cp["mu_t"]), cp["sg_d"],
+                                                                   np.radians(cp["sg_t"]), p, r))
+
+    pops = [population(kind, n, geom, k) for k, (kind, n, geom) in enumerate(cells_of(wl))]
     for _ in range(5):
-        ag.update(rng); ns.update(rng)
+        ag.update(rng)
+        for ns in pops:
+            ns.update(rng)
     t0 = time.perf_counter()
     for _ in range(n_steps):
         ag.update(rng)
-        ns.update(rng)
+        for ns in pops:
+            ns.update(rng)
     return n_steps, time.perf_counter() - t0
 
 
@@ -179,9 +197,12 @@ def cpu_port_rate(wl_name, n_steps, procs):
 
 
 # -------------------------------------------------------------------------------- main
-def build_population(rb, Ag, wl):
-    kind, n, geom = wl["cells"]
-    cp = synthetic_cells(kind, n, 0)
+def build_populations(rb, Ag, wl):
+    return [build_population(rb, Ag, kind, n, geom, k) for k, (kind, n, geom) in enumerate(cells_of(wl))]
+
+
+def build_population(rb, Ag, kind, n, geom, k=0):
+    cp = synthetic_cells(kind, n, k)
     if kind == "place":
         return rb.PlaceCells(Ag, {"place_cell_centres": cp["centres"], "widths": 0.2, "description": "gaussian",
                                   "wall_geometry": geom})
@@ -212,8 +233,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    kind, n_cells, geom = wl["cells"]
-    config = {"workload": f"{args.workload}: {wl['desc']}", "agents_per_gpu": wl["agents"], "n_cells": n_cells,
+    cl = cells_of(wl)
+    n_cells = sum(n for _, n, _ in cl)
+    kind = "+".join(k for k, _, _ in cl)
+    geom = cl[0][2]
+    A_rank = agents_per_rank(wl, world)
+    scaling = "strong" if wl.get("strong") else "weak"
+    config = {"workload": f"{args.workload}: {wl['desc']}", "agents_per_gpu": A_rank, "n_cells": n_cells,
               "cells": kind, "wall_geometry": geom, "n_walls": 4 + len(wl["walls"]), "dt": 0.01,
               "spikes": not args.no_spikes, "history": "device rings (rates: last rows within 8 GiB; agent rows: all)",
               "l2": "each step writes >= 2x L2 of fresh rate rows (inputs larger than L2)",
@@ -231,7 +257,7 @@ def main():
             cores = len(os.sched_getaffinity(0))
         except Exception:
             cores = os.cpu_count() or 1
-        per = {"c2": 300, "c2e": 400, "c3": 400, "c4": 60}[args.workload]
+        per = {"c2": 300, "c2e": 400, "c3": 400, "c4": 60, "c5": 60}[args.workload]
         vals = []
         for _ in range(max(1, min(args.warmup, 1))):
             cpu_port_rate(args.workload, max(10, per // 10), cores)
@@ -242,7 +268,7 @@ def main():
         value = float(np.mean(vals))
         line = {"impl": "reference", "metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * wl["agents"] / value, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * A_rank * world / value, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
                                  "sample": f"{cores} processes x 1 agent x {per} steps of the NumPy port (oracle/riab_oracle.py), "
@@ -261,7 +287,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    A = wl["agents"]
+    A = A_rank
     np.random.seed(1234 + rank)
     Env = rb.Environment()
     for w in wl["walls"]:
@@ -270,9 +296,10 @@ def main():
     pos, vel = synthetic_agents(A, wl["walls"], 100 + rank)
     Ag.pos, Ag.velocity = pos, vel
     Ag.measured_velocity = vel
-    Ns = build_population(rb, Ag, wl)
+    pops = build_populations(rb, Ag, wl)
     if args.no_spikes:
-        Ns.save_spikes = False
+        for ns in pops:
+            ns.save_spikes = False
     lib = _lib.load()
 
     def barrier():
@@ -305,12 +332,16 @@ def main():
     e2e_steps = max(10, min(args.steps, 500))
     drift = (0.05 * torch.randn((A, 2), dtype=torch.float64)).pin_memory()       # a policy's velocity commands
     for _ in range(3):
-        Ag.update(drift_velocity=drift); Ns.update(); _ = Ag.pos
+        Ag.update(drift_velocity=drift)
+        for ns in pops:
+            ns.update()
+        _ = Ag.pos
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         Ag.update(drift_velocity=drift)          # H2D: A*2*8 B from pinned host memory, every step
-        Ns.update()                              # fused motion + rates kernel
+        for ns in pops:
+            ns.update()                          # first population: fused motion + rates kernel; others: rates
         p = Ag.pos                               # D2H: A*2*8 B (the step's result), blocking
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -347,13 +378,13 @@ def main():
             pass
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        per = {"c2": 4000, "c2e": 5000, "c3": 5000, "c4": 800}[args.workload]
+        per = {"c2": 4000, "c2e": 5000, "c3": 5000, "c4": 800, "c5": 600}[args.workload]
         v, wall = cpu_port_rate(args.workload, per, 1)
         cpu_baseline = {"value": v, "unit": "agent-steps/s", "cores": 1, "kind": "port",
                         "sample": f"1 agent x {per} steps of oracle/riab_oracle.py (NumPy port, same cost structure as the "
                                   f"reference's per-agent Python loop), {wall:.1f} s"}
     line = {"metric": "agent-steps/sec", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32 rates / f64 agent state", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline}

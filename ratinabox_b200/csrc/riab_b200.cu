@@ -712,8 +712,8 @@ __global__ void __launch_bounds__(NT) k_place_onehot(const EnvK env, const Place
 // Noise + spikes post-pass over rate rows that a kernel without finish4 produced (BVC).
 __global__ void __launch_bounds__(NT) k_finish_rows(const OutK out, const int n_cells, const int n_pad128,
                                                     const long long n_rows) {
-  const long long row = blockIdx.y;
-  const int cell0 = (blockIdx.x * NT + threadIdx.x) * 4;
+  const long long row = blockIdx.x;                        // rows on x: gridDim.y stops at 65535
+  const int cell0 = (blockIdx.y * NT + threadIdx.x) * 4;
   if (row >= n_rows || cell0 >= n_pad128) return;          // warp-uniform: a warp covers 128 consecutive cells
   float o[4];
 #pragma unroll
@@ -1080,7 +1080,7 @@ int launch_onehot(const EnvK& env, const PlaceConst& pc, const OutK& out, const 
   RIAB_CUDA_OK(cudaGetLastError());
   if (out.noise != nullptr || out.spikes != nullptr) {
     const int np128 = (pc.n_cells + CELL_PAD - 1) / CELL_PAD * CELL_PAD;
-    k_finish_rows<<<dim3((unsigned)((np128 / 4 + NT - 1) / NT), (unsigned)n_rows), NT, 0, s>>>(out, pc.n_cells, np128, n_rows);
+    k_finish_rows<<<dim3((unsigned)n_rows, (unsigned)((np128 / 4 + NT - 1) / NT)), NT, 0, s>>>(out, pc.n_cells, np128, n_rows);
     g_launches++;
     RIAB_CUDA_OK(cudaGetLastError());
   }
@@ -1152,7 +1152,7 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   RIAB_CUDA_OK(cudaGetLastError());
   if (out.noise != nullptr || out.spikes != nullptr) {
     const int np128 = (bc.n_cells + CELL_PAD - 1) / CELL_PAD * CELL_PAD;
-    k_finish_rows<<<dim3((unsigned)((np128 / 4 + NT - 1) / NT), (unsigned)n_rows), NT, 0, s>>>(out, bc.n_cells, np128, n_rows);
+    k_finish_rows<<<dim3((unsigned)n_rows, (unsigned)((np128 / 4 + NT - 1) / NT)), NT, 0, s>>>(out, bc.n_cells, np128, n_rows);
     g_launches++;
     RIAB_CUDA_OK(cudaGetLastError());
   }

@@ -160,3 +160,22 @@ def test_line_of_sight_on_the_decision_boundary(widths):
     assert 0.05 < (dist >= 1000).mean() < 0.8          # both outcomes are well represented
     bad = np.abs(got - ref) > 1e-5
     assert not bad.any(), (int(bad.sum()), np.argwhere(bad)[:5], got[bad][:5], ref[bad][:5])
+
+
+def test_more_rows_than_a_grid_dimension():
+    """70 000 agents (> 65 535, the y/z grid limit): every per-row kernel (BVC rays / integration / spike post-pass,
+    one_hot) must index rows on the x dimension."""
+    import ratinabox_b200 as rb
+    A = 70000
+    E, Ag = _make(rb, A, _walls(1))
+    BVCs = rb.BoundaryVectorCells(Ag, {"n": 8})
+    OH = rb.PlaceCells(Ag, {"n": 16, "description": "one_hot", "wall_geometry": "euclidean"})
+    Ag.update(); BVCs.update(); OH.update()
+    pos = Ag.pos
+    sel = np.array([0, 1, 65534, 65535, 65536, A - 1])
+    env = O.OracleEnvironment(walls=_walls(1))
+    ref = O.bvc_get_state(env, BVCs.tuning_distances, BVCs.tuning_angles, BVCs.sigma_distances, BVCs.sigma_angles,
+                          pos[sel], O.TapeRNG()).T
+    assert np.abs(BVCs.firingrate[sel] - ref).max() <= 1e-5
+    assert np.array_equal(OH.firingrate.sum(axis=1), np.ones(A))
+    assert BVCs.get_history_arrays()["spikes"].shape == (1, A, 8)

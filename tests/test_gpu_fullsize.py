@@ -106,3 +106,41 @@ def test_config4_16384_agents_512_bvcs_maze():
     ref = O.bvc_get_state(env, BVCs.tuning_distances, BVCs.tuning_angles, BVCs.sigma_distances, BVCs.sigma_angles,
                           pos[sample], O.TapeRNG()).T
     assert np.abs(fr[sample] - ref).max() <= 1e-5
+
+
+def test_config5_shard_32768_agents_three_populations():
+    """configs[4] (262 144 agents over 8 GPUs) as one GPU sees it: a 32 768-agent shard with global ids
+    32768..65535 and 512 Place (line_of_sight) + 512 Grid + 256 BVC populations on one Agent."""
+    import ratinabox_b200 as rb
+    A, steps, off = 32768, 3, 32768
+    np.random.seed(8)
+    E = rb.Environment()
+    for w in BOX_WALLS:
+        E.add_wall(w)
+    Ag = rb.Agent(E, {"dt": 0.01, "n_agents": A, "seed": 5, "id_offset": off})
+    pos0, vel0 = Ag.pos.copy(), Ag.velocity.copy()
+    PCs = rb.PlaceCells(Ag, {"n": 512})
+    GCs = rb.GridCells(Ag, {"n": 512})
+    BVCs = rb.BoundaryVectorCells(Ag, {"n": 256})
+    Ag.run(steps)
+    pos = Ag.pos
+    sample = np.random.RandomState(4).choice(A, 160, replace=False)
+    env = O.OracleEnvironment(walls=BOX_WALLS)
+    ref_pos = np.zeros((len(sample), 2))
+    for k, a in enumerate(sample):                         # Philox streams are keyed on the GLOBAL agent id
+        oa = O.OracleAgent(env, pos0[a], vel0[a], {"dt": 0.01})
+        for s in range(steps):
+            oa.update(O.TapeRNG(agent_xi=agent_normals(5, s, np.array([off + a]))[0]))
+        ref_pos[k] = oa.pos
+    assert np.abs(pos[sample] - ref_pos).max() <= 1e-6
+    rng = O.TapeRNG()
+    ps = pos[sample]
+    assert np.abs(PCs.firingrate[sample] - O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, ps, rng,
+                                                                   "gaussian", "line_of_sight").T).max() <= 1e-5
+    assert np.abs(GCs.firingrate[sample] - O.grid_cells_get_state(GCs.gridscales, GCs.phase_offsets, GCs.w, ps).T).max() <= 1e-5
+    assert np.abs(BVCs.firingrate[sample] - O.bvc_get_state(env, BVCs.tuning_distances, BVCs.tuning_angles,
+                                                            BVCs.sigma_distances, BVCs.sigma_angles, ps, rng).T).max() <= 1e-5
+    for ns in (PCs, GCs, BVCs):
+        h = ns.get_history_arrays()
+        assert h["firingrate"].shape == (steps, A, ns.n) and h["spikes"].shape == (steps, A, ns.n)
+        assert np.array_equal(h["firingrate"][-1], ns.firingrate)
