@@ -43,19 +43,29 @@ typedef enum {
 int riab_abi_version(void);
 const char* riab_last_error(void);
 
+/* RIAB_BOUNDARY_SOLID_BOX: strict 4-compare in-environment test and clamp (Environment.py:793-806, :880-889).
+ * RIAB_BOUNDARY_PERIODIC_BOX: no boundary walls are built (:130-144); positions wrap (:877-879), displacement /
+ *   distance vectors take the short way round (:670-675).
+ * RIAB_BOUNDARY_POLYGON: polygon boundary and / or holes, solid.  In the environment <=> strictly inside the boundary
+ *   polygon and not strictly inside a hole (:807-817, shapely `contains`), decided by an even-odd ray cast over the
+ *   boundary / hole walls; a position outside after the bounce loop is re-drawn uniformly inside (:892-893, the
+ *   reference draws from np.random there; here a Philox stream keyed by seed / step / agent). */
+typedef enum { RIAB_BOUNDARY_SOLID_BOX = 0, RIAB_BOUNDARY_PERIODIC_BOX = 1, RIAB_BOUNDARY_POLYGON = 2 } riab_boundary_mode;
+
 /* ---------------------------------------------------------------- Environment
  * walls: (n_walls,2,2) float64, boundary walls first (Environment.py:137-144),
- * then user walls (add_wall, :330-342).  Rectangular 2D box, solid or periodic. */
+ * then user walls (add_wall, :330-342), then the walls of the holes (:147-160).  2D: rectangular box (solid or
+ * periodic), or a polygon boundary and / or holes (solid). */
 typedef struct {
   const double* walls_dev;     /* device, n_walls*4 doubles */
   int32_t n_walls;
-  int32_t n_boundary_walls;    /* 4: Environment.py:715-717 `walls[4:]` */
+  int32_t n_boundary_walls;    /* the first n_boundary_walls walls are the closed boundary polygon (4 for the box) */
   double extent[4];            /* left,right,bottom,top  (Environment.py:171-173) */
-  int32_t periodic;            /* boundary_conditions == "periodic" (rectangular box, no boundary walls built:
-                                  Environment.py:130-144); positions wrap (:877-879), displacement / distance
-                                  vectors take the short way round (:670-675) */
-  int32_t reserved;
+  int32_t boundary_mode;       /* riab_boundary_mode */
+  int32_t n_hole_walls;        /* RIAB_BOUNDARY_POLYGON: walls [hole_wall0, hole_wall0 + n_hole_walls) are the edges of the holes */
   double scale;                /* Environment.scale: the wrap threshold is scale/2 on both axes (:671) */
+  int32_t hole_wall0;
+  int32_t reserved;
 } riab_env;
 
 /* ---------------------------------------------------------------------- Agent

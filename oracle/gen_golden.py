@@ -322,5 +322,84 @@ def main():
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 
 
+LROOM = [[0, 0], [1, 0], [1, 0.5], [0.5, 0.5], [0.5, 1], [0, 1]]          # an L-shaped room (6 boundary walls)
+HOLE = [[0.4, 0.4], [0.6, 0.4], [0.6, 0.6], [0.4, 0.6]]
+
+
+def gen_polygon():
+    """Polygon boundary / holes (Environment.py:112-160, :807-817): the walls are the polygon's and the holes' edges,
+    PlaceCells keep the hard-coded `walls[4:]` (Environment.py:715-717).  shapely is absent here: the in-environment
+    test comes from oracle/ref_shim.py's stub, everything else is the unmodified reference."""
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox.Environment import Environment
+    from ratinabox.Agent import Agent
+    from ratinabox.Neurons import PlaceCells, BoundaryVectorCells
+    out = {}
+    cases = (("lroom", {"boundary": LROOM, "walls": [[[0.25, 0.0], [0.25, 0.3]]]}),
+             ("holed", {"holes": [HOLE], "walls": [[[0.8, 0.0], [0.8, 0.35]]]}))
+    for name, params in cases:
+        np.random.seed(23)
+        Env = Environment(dict(params))
+        Ag = Agent(Env, {"dt": 0.02, "speed_mean": 0.25})
+        PCs = PlaceCells(Ag, {"n": 24, "widths": 0.15})
+        BVCs = BoundaryVectorCells(Ag, {"n": 6})
+        out[f"{name}_walls"] = Env.walls.copy()
+        out[f"{name}_extent"] = np.array(Env.extent, dtype=float)
+        out[f"{name}_pos0"], out[f"{name}_vel0"] = Ag.pos.copy(), Ag.velocity.copy()
+        out[f"{name}_centres"], out[f"{name}_widths"] = PCs.place_cell_centres.copy(), PCs.place_cell_widths.copy()
+        out[f"{name}_geom"] = np.array(PCs.wall_geometry)
+        out[f"{name}_bvc"] = np.stack((BVCs.tuning_distances, BVCs.tuning_angles, BVCs.sigma_distances, BVCs.sigma_angles))
+        st = np.random.get_state()
+        out[f"{name}_rng_keys"], out[f"{name}_rng_pos"], out[f"{name}_rng_has_gauss"], out[f"{name}_rng_cached"] = st[1], st[2], st[3], st[4]
+        for _ in range(1000):
+            Ag.update(); PCs.update(); BVCs.update()
+        out[f"{name}_pos"], out[f"{name}_vel"] = np.array(Ag.history["pos"]), np.array(Ag.history["vel"])
+        out[f"{name}_pc_fr"], out[f"{name}_bvc_fr"] = np.array(PCs.history["firingrate"]), np.array(BVCs.history["firingrate"])
+        inside = all(Env.check_if_position_is_in_environment(p) for p in out[f"{name}_pos"])
+        print(f"polygon[{name}]: {len(Env.walls)} walls, geometry {PCs.wall_geometry}, trajectory inside: {inside}")
+        # mode A single steps from positions inside the environment, half of them hugging a wall at speed
+        rs = np.random.RandomState(5)
+        A = 384
+        np.random.seed(77)
+        pos0 = Env.sample_positions(n=A, method="random")
+        wl = Env.walls
+        for a in range(A // 2):
+            w = wl[rs.randint(len(wl))]
+            q = w[0] + rs.uniform(0.05, 0.95) * (w[1] - w[0])
+            nrm = np.array([-(w[1] - w[0])[1], (w[1] - w[0])[0]]); nrm /= np.linalg.norm(nrm)
+            for sgn in (1.0, -1.0):
+                cand = q + sgn * rs.uniform(0.002, 0.02) * nrm
+                if Env.check_if_position_is_in_environment(cand):
+                    pos0[a] = cand
+                    break
+        ang = rs.uniform(0, 2 * np.pi, size=A)
+        vel0 = rs.rayleigh(0.4, size=A)[:, None] * np.stack((np.cos(ang), np.sin(ang)), axis=1)
+        xi = rs.normal(size=(A, 2))
+        outp, outv, outmv = [], [], []
+        for a in range(A):
+            Ag.pos, Ag.velocity = pos0[a].copy(), vel0[a].copy()
+            Ag.rotational_velocity, Ag.measured_velocity = 0.0, vel0[a].copy()
+            Ag.head_direction, Ag.distance_travelled = vel0[a] / np.linalg.norm(vel0[a]), 0.0
+            with mode_a(list(xi[a])):
+                Ag.update()
+            outp.append(Ag.pos.copy()); outv.append(Ag.velocity.copy()); outmv.append(Ag.measured_velocity.copy())
+        out[f"{name}_A_pos0"], out[f"{name}_A_vel0"], out[f"{name}_A_xi"] = pos0, vel0, xi
+        out[f"{name}_A_pos"], out[f"{name}_A_vel"], out[f"{name}_A_mv"] = np.array(outp), np.array(outv), np.array(outmv)
+        bounced = int((np.abs(np.linalg.norm(np.array(outv), axis=1) - 0.5 * 0.25) < 1e-12).sum())
+        print(f"polygon[{name}] mode A: {bounced} / {A} steps bounced")
+        with mode_a([]):
+            out[f"{name}_A_pc"] = PCs.get_state(evaluate_at=None, pos=pos0)
+            out[f"{name}_A_bvc"] = BVCs.get_state(evaluate_at=None, pos=pos0)
+        np.random.seed(3)
+        out[f"{name}_samples_uj"] = Env.sample_positions(n=50, method="uniform_jitter")
+    np.savez_compressed(os.path.join(GOLD, "polygon.npz"), **out)
+    print("polygon.npz", os.path.getsize(os.path.join(GOLD, "polygon.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["polygon"]:
+        gen_polygon()
+    else:
+        main()
+        gen_polygon()

@@ -174,21 +174,51 @@ def rayleigh_to_normal(x, sigma=1.0):
 
 
 # ------------------------------------------------------------------ Environment
-class OracleEnvironment:
-    """The subset of Environment.__init__ (Environment.py:77-209) the path needs: a rectangular 2D box,
-    solid (boundary walls first, then user walls; Environment.py:137-144, add_wall :330-342) or periodic
-    (no boundary walls: only the `solid` branch builds them, Environment.py:130-144)."""
+def polygon_contains_strict(verts, p):
+    """shapely ``Polygon(verts).contains(Point(p))`` (Environment.py:810-817) restated as an even-odd ray cast;
+    points on an edge or a vertex are not inside.  shapely / GEOS is a third-party dependency absent from
+    /root/reference and from this image, so this predicate is pinned only by oracle/ref_shim.py's identical stub
+    ("parity unpinned" for points within rounding of an edge; the path never evaluates such points in the fixtures)."""
+    x, y = float(p[0]), float(p[1])
+    n = len(verts)
+    inside = False
+    for i in range(n):
+        x0, y0 = float(verts[i][0]), float(verts[i][1])
+        x1, y1 = float(verts[(i + 1) % n][0]), float(verts[(i + 1) % n][1])
+        cross = (x1 - x0) * (y - y0) - (y1 - y0) * (x - x0)
+        if cross == 0.0 and min(x0, x1) <= x <= max(x0, x1) and min(y0, y1) <= y <= max(y0, y1):
+            return False
+        if (y0 > y) != (y1 > y):
+            xi = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+            if x < xi:
+                inside = not inside
+    return inside
 
-    def __init__(self, scale=1.0, aspect=1.0, walls=(), boundary_conditions="solid"):
-        b = [[0, 0], [aspect * scale, 0], [aspect * scale, scale], [0, scale]]
+
+class OracleEnvironment:
+    """The subset of Environment.__init__ (Environment.py:77-209) the path needs: a 2D environment, either the
+    rectangular box -- solid (boundary walls first, then user walls; Environment.py:137-144, add_wall :330-342) or
+    periodic (no boundary walls: only the `solid` branch builds them, :130-144) -- or a polygon `boundary` with
+    optional `holes` (solid; hole walls after the `walls` param, :146-160)."""
+
+    def __init__(self, scale=1.0, aspect=1.0, walls=(), boundary_conditions="solid", boundary=None, holes=()):
+        self.is_rectangular = boundary is None
+        b = [[0, 0], [aspect * scale, 0], [aspect * scale, scale], [0, scale]] if boundary is None else [list(v) for v in boundary]
+        self.boundary = b
+        self.holes = [[list(v) for v in h] for h in holes]
         self.boundary_conditions = boundary_conditions
         if boundary_conditions == "solid":
-            self.walls = np.array([[b[(i + 1) if (i + 1) < 4 else 0], b[i]] for i in range(4)], dtype=float)
+            self.walls = np.array([[b[(i + 1) if (i + 1) < len(b) else 0], b[i]] for i in range(len(b))], dtype=float)
         else:
+            assert self.is_rectangular and not self.holes
             self.walls = np.zeros((0, 2, 2))
         for w in walls:
             self.add_wall(w)
-        self.extent = np.array([0.0, aspect * scale, 0.0, scale])
+        for h in self.holes:
+            for i in range(len(h)):
+                self.add_wall([h[(i + 1) if (i + 1) < len(h) else 0], h[i]])
+        xs, ys = [c[0] for c in b], [c[1] for c in b]
+        self.extent = np.array([min(xs), max(xs), min(ys), max(ys)], dtype=float)
         self.scale = scale
         self.aspect = aspect
 
@@ -196,15 +226,24 @@ class OracleEnvironment:
         self.walls = np.concatenate((self.walls, np.asarray(wall, dtype=float).reshape(1, 2, 2)), axis=0)
 
     def contains(self, pos):
-        """Environment.py:781-818 for a rectangle without holes (the shapely strict-interior test of a
-        rectangle == four strict compares)."""
-        e = self.extent
-        return bool((pos[0] > e[0]) and (pos[0] < e[1]) and (pos[1] > e[2]) and (pos[1] < e[3]))
+        """Environment.py:781-818: four strict compares for a rectangle without holes (:793-806), else strictly
+        inside the boundary polygon and strictly inside no hole (:807-817)."""
+        if self.is_rectangular and not self.holes:
+            e = self.extent
+            return bool((pos[0] > e[0]) and (pos[0] < e[1]) and (pos[1] > e[2]) and (pos[1] < e[3]))
+        is_in = polygon_contains_strict(self.boundary, pos)
+        for h in self.holes:
+            is_in = is_in and not polygon_contains_strict(h, pos)
+        return bool(is_in)
 
     def apply_boundary_conditions(self, pos):
-        """Environment.py:855-894, rectangular branch: solid clamp (:880-889) / periodic wrap (:877-879)."""
+        """Environment.py:855-894, rectangular branch: solid clamp (:880-889) / periodic wrap (:877-879).
+        Holes / polygon boundary: the reference re-draws a random position (:890-893) -- "in theory, this isn't
+        used"; the fixtures never reach it and the oracle refuses to guess the RNG tape."""
         if self.contains(pos):
             return pos
+        if not (self.is_rectangular and not self.holes):
+            raise RuntimeError("position left a polygon / holed environment: the reference would re-draw it at random")
         e = self.extent
         pos = np.array(pos, dtype=float)
         if self.boundary_conditions == "periodic":

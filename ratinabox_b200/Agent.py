@@ -165,7 +165,8 @@ class Agent:
         e.n_boundary_walls = int(env.n_boundary_walls)
         for i in range(4):
             e.extent[i] = float(env.extent[i])
-        e.periodic = 1 if env.boundary_conditions == "periodic" else 0
+        e.boundary_mode = 1 if env.boundary_conditions == "periodic" else (2 if env.is_polygonal else 0)
+        e.n_hole_walls, e.hole_wall0 = env.n_hole_walls, env.hole_wall0
         e.scale = float(env.scale)
         self._walls_keepalive = walls
         return e

@@ -1,10 +1,10 @@
 """Host mirror of ``ratinabox.Environment`` for the CUDA step engine.
 
-Only what the hot path needs lives here: a rectangular 2D box (solid
-or periodic) with internal walls.  Construction semantics follow the reference:
-boundary walls first, in the reference's corner order (ratinabox/Environment.py:118-144),
-then user walls in insertion order (``add_wall``, :330-342).  Anything outside
-that (1D, polygon boundaries, holes, objects) raises
+Only what the hot path needs lives here: a 2D environment -- the rectangular
+box (solid or periodic) or a polygon ``boundary`` with optional ``holes`` (solid) -- with internal walls.
+Construction semantics follow the reference: boundary walls first, in the reference's corner order
+(ratinabox/Environment.py:118-144), then the ``walls`` param, the walls of the holes (:147-160), and
+later ``add_wall`` calls in insertion order (:330-342).  Anything outside that (1D, objects) raises
 ``NotImplementedError`` instead of silently taking a different path.
 """
 import copy
@@ -38,26 +38,42 @@ class Environment:
             raise NotImplementedError("ratinabox_b200 accelerates 2D environments only (SURVEY.md section 2 row 9)")
         if self.boundary_conditions not in ("solid", "periodic"):
             raise ValueError(f"unknown boundary_conditions {self.boundary_conditions!r}")
-        if self.boundary is not None or len(self.holes) > 0:
-            raise NotImplementedError("polygon boundaries / holes are outside the CUDA hot path (SURVEY.md section 2 row 11)")
         if len(self.objects) > 0:
             raise NotImplementedError("objects are outside the CUDA hot path (SURVEY.md section 2 row 13)")
 
         self.D = 2
-        self.is_rectangular = True
-        self.has_holes = False
         self.Agents = []
         self.agents_dict = {}
-        b = [[0, 0], [self.aspect * self.scale, 0], [self.aspect * self.scale, self.scale], [0, self.scale]]
-        self.boundary = b
+        if self.boundary is None:                                   # Environment.py:112-125
+            self.is_rectangular = True
+            self.boundary = [[0, 0], [self.aspect * self.scale, 0], [self.aspect * self.scale, self.scale], [0, self.scale]]
+        else:
+            self.is_rectangular = False
+        b = self.boundary
         user_walls = np.array(self.walls, dtype=float).reshape(-1, 2, 2)
+        if self.boundary_conditions == "periodic" and not self.is_rectangular:      # Environment.py:129-135
+            # the reference warns and only rewrites params["boundary_conditions"]: the attribute stays "periodic" and
+            # no boundary walls are built -- that combination is outside the hot path
+            raise NotImplementedError("periodic boundary conditions need the rectangular box (Environment.py:129-135)")
         if self.boundary_conditions == "solid":                     # Environment.py:137-144
             boundary_walls = np.array([[b[(i + 1) if (i + 1) < len(b) else 0], b[i]] for i in range(len(b))], dtype=float)
             self.walls = np.vstack((boundary_walls, user_walls))
-            self.n_boundary_walls = 4
+            self.n_boundary_walls = len(b)
         else:                                                       # periodic: no boundary walls are built
             self.walls = user_walls
             self.n_boundary_walls = 0
+        self.has_holes = len(self.holes) > 0                        # Environment.py:146-160
+        self.hole_wall0, self.n_hole_walls = len(self.walls), 0     # the hole walls are walls[hole_wall0 : +n_hole_walls]
+        if self.has_holes:
+            assert np.array(self.holes).ndim == 3, ("Incorrect dimensionality for holes list. It must be a list of "
+                                                    "lists of coordinates")
+            if self.boundary_conditions != "solid":
+                raise NotImplementedError("holes need solid boundary conditions")
+            for h in self.holes:
+                hole_walls = np.array([[h[(i + 1) if (i + 1) < len(h) else 0], h[i]] for i in range(len(h))], dtype=float)
+                self.walls = np.vstack((self.walls, hole_walls))
+                self.n_hole_walls += len(h)
+        self.is_polygonal = (not self.is_rectangular) or self.has_holes
         left, right = min(c[0] for c in b), max(c[0] for c in b)
         bottom, top = min(c[1] for c in b), max(c[1] for c in b)
         self.centre = np.array([(left + right) / 2, (top + bottom) / 2])
@@ -66,6 +82,12 @@ class Environment:
         self.flattened_discrete_coords = self.discrete_coords.reshape(-1, self.discrete_coords.shape[-1])
         self._walls_version = 0
         self._dev = {}          # device -> (version, tensor)
+
+    @property
+    def los_skip(self):
+        """How many leading walls the line_of_sight / geodesic distances ignore: the reference hard-codes
+        ``walls[4:]`` (Environment.py:715-717) whatever the boundary polygon's vertex count."""
+        return 0 if self.boundary_conditions == "periodic" else min(4, len(self.walls))
 
     # ------------------------------------------------------------------ registry
     def add_agent(self, agent=None):                                # Environment.py:220-250
@@ -95,19 +117,28 @@ class Environment:
         return hit[1]
 
     # ------------------------------------------------------------------ sampling
-    def sample_positions(self, n=10, method="uniform_jitter"):      # Environment.py:560-633 (2D, rectangular)
+    def sample_positions(self, n=10, method="uniform_jitter"):      # Environment.py:560-633 (2D)
         ex = self.extent
         if method == "random":
             positions = np.zeros((n, 2))
             positions[:, 0] = np.random.uniform(ex[0], ex[1], size=n)
             positions[:, 1] = np.random.uniform(ex[2], ex[3], size=n)
+            if self.is_polygonal:                                   # :592-600 brute-force resampling
+                for i, pos in enumerate(positions):
+                    if self.check_if_position_is_in_environment(pos) == False:
+                        positions[i] = self.sample_positions(n=1, method="random").reshape(-1)
             return positions
         if method[:7] == "uniform":
             area = (ex[1] - ex[0]) * (ex[3] - ex[2])
+            if self.has_holes:
+                area -= sum(_polygon_area(h) for h in self.holes)
             delta = np.sqrt(area / n)
             x = np.linspace(ex[0] + delta / 2, ex[1] - delta / 2, int((ex[1] - ex[0]) / delta))
             y = np.linspace(ex[2] + delta / 2, ex[3] - delta / 2, int((ex[3] - ex[2]) / delta))
             positions = np.array(np.meshgrid(x, y)).reshape(2, -1).T
+            if self.is_polygonal:                                   # :612-615 drop the illegal grid points
+                delpos = [i for (i, pos) in enumerate(positions) if self.check_if_position_is_in_environment(pos) == False]
+                positions = np.delete(positions, delpos, axis=0)
             n_uniform = positions.shape[0]
             if method[7:] == "_jitter":
                 positions = positions + np.random.uniform(-0.45 * delta, 0.45 * delta, positions.shape)
@@ -128,7 +159,36 @@ class Environment:
         xm, ym = np.meshgrid(self.x_array, self.y_array)
         return np.stack((xm, ym), axis=-1)
 
-    def check_if_position_is_in_environment(self, pos):             # Environment.py:781-818 (rectangle, no holes)
+    def check_if_position_is_in_environment(self, pos):             # Environment.py:781-818
         pos = np.asarray(pos, dtype=float).reshape(-1)
-        e = self.extent
-        return bool((pos[0] > e[0]) and (pos[0] < e[1]) and (pos[1] > e[2]) and (pos[1] < e[3]))
+        if not self.is_polygonal:
+            e = self.extent
+            return bool((pos[0] > e[0]) and (pos[0] < e[1]) and (pos[1] > e[2]) and (pos[1] < e[3]))
+        is_in = _polygon_contains_strict(self.boundary, pos)        # shapely `contains`: strict interior
+        for h in self.holes:
+            is_in = is_in and not _polygon_contains_strict(h, pos)
+        return bool(is_in)
+
+
+def _polygon_contains_strict(verts, p):
+    """Even-odd ray cast; points on an edge or a vertex are NOT inside (shapely ``contains``,
+    Environment.py:810-817).  Same arithmetic as ``edges_contain`` in csrc/riab_motion.cuh."""
+    x, y = float(p[0]), float(p[1])
+    n = len(verts)
+    inside = False
+    for i in range(n):
+        x0, y0 = float(verts[i][0]), float(verts[i][1])
+        x1, y1 = float(verts[(i + 1) % n][0]), float(verts[(i + 1) % n][1])
+        cross = (x1 - x0) * (y - y0) - (y1 - y0) * (x - x0)
+        if cross == 0.0 and min(x0, x1) <= x <= max(x0, x1) and min(y0, y1) <= y <= max(y0, y1):
+            return False
+        if (y0 > y) != (y1 > y):
+            xi = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+            if x < xi:
+                inside = not inside
+    return inside
+
+
+def _polygon_area(verts):
+    v = np.asarray(verts, dtype=float)
+    return 0.5 * abs(np.dot(v[:, 0], np.roll(v[:, 1], -1)) - np.dot(v[:, 1], np.roll(v[:, 0], -1)))

@@ -315,10 +315,12 @@ class PlaceCells(Neurons):
             self.wall_geometry = "line_of_sight"
 
     def _effective_geometry(self):
-        n_inner = len(self.Agent.Environment.walls) - self.Agent.Environment.n_boundary_walls
+        n_inner = len(self.Agent.Environment.walls) - self.Agent.Environment.los_skip
         if self.wall_geometry not in _lib.WALL_GEOMETRIES:
             raise ValueError(f"unknown wall_geometry {self.wall_geometry!r}")
         if self.wall_geometry == "geodesic":
+            if self.Agent.Environment.is_polygonal:
+                raise NotImplementedError("geodesic distances in polygon / holed environments are outside the CUDA hot path")
             assert n_inner <= 1, ("unfortunately geodesic geometry is only defined in closed rooms with one "
                                   "additional wall (Environment.py:736-739)")
         if n_inner == 0:
@@ -340,13 +342,13 @@ class PlaceCells(Neurons):
         assert widths.shape[0] == self.n
         geom = _lib.WALL_GEOMETRIES[self._effective_geometry()]
         walls = np.ascontiguousarray(env.walls, dtype=np.float64)
-        n_inner = 0 if geom == 0 else walls.shape[0] - env.n_boundary_walls
+        n_inner = 0 if geom == 0 else walls.shape[0] - env.los_skip
         c = _lib.PlaceCells()
         nfl = self._lib.riab_place_pack_floats(self.n, n_inner)
         host = np.zeros(nfl, dtype=np.float32)
         ext = np.ascontiguousarray(env.extent, dtype=np.float64)
         _lib.check(self._lib.riab_place_pack(_f64p(centres), _f64p(widths), self.n, _f64p(walls), walls.shape[0],
-                                             env.n_boundary_walls, _f64p(ext), geom, C.byref(c),
+                                             env.los_skip, _f64p(ext), geom, C.byref(c),
                                              host.ctypes.data_as(_lib.c_float_p)))
         self._packed = self._upload(host)
         self._centres_dev = self._upload(centres)

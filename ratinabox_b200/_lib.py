@@ -18,7 +18,8 @@ class RiabError(RuntimeError):
 
 class Env(C.Structure):
     _fields_ = [("walls_dev", C.c_void_p), ("n_walls", C.c_int32), ("n_boundary_walls", C.c_int32),
-                ("extent", C.c_double * 4), ("periodic", C.c_int32), ("reserved", C.c_int32), ("scale", C.c_double)]
+                ("extent", C.c_double * 4), ("boundary_mode", C.c_int32), ("n_hole_walls", C.c_int32), ("scale", C.c_double),
+                ("hole_wall0", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Agents(C.Structure):

@@ -47,6 +47,7 @@ constexpr int CELL_PAD = 128;  // packed per-cell arrays are padded to 4 cells x
 struct EnvK {
   const double* walls;
   int W, nb, aligned, periodic;
+  int polygon, nh, h0;      // RIAB_BOUNDARY_POLYGON: even-odd in-environment test over walls [0,nb) and [h0,h0+nh)
   double ext[4];
   double cxm, cym, scale;
 };
@@ -101,7 +102,8 @@ __device__ __forceinline__ void agent_update_one(const riab_agents& ag, const ri
   uint8_t* mask = (REC && io.collision_mask) ? io.collision_mask + (size_t)i * RIAB_MAX_REC_ITERS * env.W : nullptr;
   int32_t* fh = (REC && io.first_hit) ? io.first_hit + (size_t)i * RIAB_MAX_REC_ITERS : nullptr;
   int32_t* ni = (REC && io.n_iters) ? io.n_iters + i : nullptr;
-  motion_step<REC>(s, s_walls, env.W, mp, md, env.ext, env.periodic != 0, env.scale, n1, n2, has_drift, drx, dry, f1, f2,
+  motion_step<REC>(s, s_walls, env.W, mp, md, env.ext, env.periodic != 0, env.scale, env.polygon != 0, env.nb, env.h0, env.nh,
+                   n1, n2, has_drift, drx, dry, f1, f2,
                    mask, fh, ni);
   store_agent(ag, i, s);
   if (io.history_row != nullptr) store_history_row(io.history_row + 8 * (size_t)i, s);
@@ -290,7 +292,7 @@ struct PlacePolicy {
   static constexpr bool XU_BOUND = false;
   static __device__ __forceinline__ void record(float* rec, double px, double py, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
-    place_agent_record(rec, px, py, s_walls + 4 * env.nb, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx);
+    place_agent_record(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx);
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI>(r, c, cell0); }
   template <bool DEFER, int EXP = -1>
@@ -299,6 +301,7 @@ struct PlacePolicy {
     place_rates4<WI, DESC, DEFER, EXP>(o, r, c, cell0, rec, inner_s, unsure);
   }
   static __device__ __forceinline__ bool expanded(const Const& c) { return DESC == RIAB_PC_GAUSSIAN && c.expanded; }
+  static __device__ __forceinline__ int wall0(const Const& c) { return c.wall0; }
 };
 
 struct GridPolicy {
@@ -319,6 +322,7 @@ struct GridPolicy {
     grid_rates4(o, r, c, rec);
   }
   static __device__ __forceinline__ bool expanded(const Const&) { return false; }
+  static __device__ __forceinline__ int wall0(const Const&) { return 0; }
 };
 
 // ---------------------------------------------------------------------------
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       P::load(regs, pc, cell0);
       tail_init(tc, out, cell0, pc.n_cells);
     }
-    const uint32_t inner_s = smem_u32(s_walls + 4 * env.nb);      // float64 inner walls (exact fall-back)
+    const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);   // float64 inner walls (exact fall-back)
     // Fast pair loop: rows are 16-byte aligned and every thread owns 4 existing cells or none, the
     // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
     const bool fast = (chunks == 1) && !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
@@ -648,7 +652,7 @@ __global__ void __launch_bounds__(NT) k_place_onehot(const EnvK env, const Place
   const long long row = (long long)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const double px = pos[2 * row], py = pos[2 * row + 1];
-  const double* inner = s_walls + 4 * env.nb;
+  const double* inner = s_walls + 4 * pc.wall0;
   const float pxf = (float)(px - env.cxm), pyf = (float)(py - env.cym);
   float fp[PLACE_MAX_WI], tp[PLACE_MAX_WI];
   for (int j = 0; j < PLACE_MAX_WI; ++j) {
@@ -930,7 +934,14 @@ int make_env(const riab_env* env, EnvK& k) {
   for (int i = 0; i < 4; ++i) k.ext[i] = env->extent[i];
   k.cxm = 0.5 * (env->extent[0] + env->extent[1]);
   k.cym = 0.5 * (env->extent[2] + env->extent[3]);
-  k.periodic = env->periodic ? 1 : 0;
+  if (env->boundary_mode < 0 || env->boundary_mode > RIAB_BOUNDARY_POLYGON) return fail(RIAB_ERR_INVALID, "bad boundary_mode %d", env->boundary_mode);
+  k.periodic = env->boundary_mode == RIAB_BOUNDARY_PERIODIC_BOX ? 1 : 0;
+  k.polygon = env->boundary_mode == RIAB_BOUNDARY_POLYGON ? 1 : 0;
+  k.nh = k.polygon ? env->n_hole_walls : 0;
+  k.h0 = k.polygon ? env->hole_wall0 : 0;
+  if (k.nh < 0 || k.h0 < 0 || (k.nh > 0 && (k.h0 < k.nb || k.h0 + k.nh > k.W)))
+    return fail(RIAB_ERR_INVALID, "hole walls [%d, %d) out of range", env->hole_wall0, env->hole_wall0 + env->n_hole_walls);
+  if (k.polygon && k.nb < 3) return fail(RIAB_ERR_INVALID, "a polygon boundary needs at least 3 boundary walls");
   k.scale = env->scale;
   if (k.periodic && !(env->scale > 0.0)) return fail(RIAB_ERR_INVALID, "periodic environment needs scale > 0");
   return 0;
@@ -986,7 +997,11 @@ int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
   if (pc == nullptr || pc->packed_dev == nullptr) return fail(RIAB_ERR_INVALID, "place cells / packed_dev NULL");
   if (pc->description < 0 || pc->description > RIAB_PC_ONE_HOT) return fail(RIAB_ERR_INVALID, "bad description %d", pc->description);
   if (pc->wall_geometry < 0 || pc->wall_geometry > RIAB_GEOM_GEODESIC) return fail(RIAB_ERR_INVALID, "bad wall_geometry");
-  const int n_inner = env.W - env.nb;
+  // Environment.py:715-717 hard-codes `walls[4:]`: with a polygon boundary the walls after the first FOUR count as
+  // "inner" walls whatever the polygon's vertex count; the box has exactly its 4 boundary walls first
+  const int skip = env.polygon ? (env.W < 4 ? env.W : 4) : env.nb;
+  const int n_inner = env.W - skip;
+  c.wall0 = skip;
   if (pc->wall_geometry != RIAB_GEOM_EUCLIDEAN) {
     if (pc->n_inner_walls != n_inner) return fail(RIAB_ERR_INVALID, "packed for %d inner walls, env has %d (re-pack after add_wall)", pc->n_inner_walls, n_inner);
     if (n_inner > PLACE_MAX_WI) return fail(RIAB_ERR_UNSUPPORTED, "line_of_sight supports at most %d inner walls (got %d)", PLACE_MAX_WI, n_inner);

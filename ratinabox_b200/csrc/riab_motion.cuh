@@ -86,12 +86,36 @@ RIAB_DEV double get_angle(double x, double y) {
   return np_mod(atan2(y, __dadd_rn(x, 1e-6)), 2.0 * M_PI);
 }
 
+// Even-odd ray cast over `count` polygon edges stored as walls (wall i = [v_{i+1}, v_i], Environment.py:137-144):
+// strictly inside <=> odd number of crossings and not on an edge (shapely `contains`, Environment.py:810-817).
+RIAB_DEV bool edges_contain(double x, double y, const double* __restrict__ w, int count) {
+  bool inside = false;
+  for (int i = 0; i < count; ++i) {
+    const D x1(w[4 * i]), y1(w[4 * i + 1]), x0(w[4 * i + 2]), y0(w[4 * i + 3]);
+    const D cross = (x1 - x0) * (D(y) - y0) - (y1 - y0) * (D(x) - x0);
+    if (cross.v == 0.0 && fmin(x0.v, x1.v) <= x && x <= fmax(x0.v, x1.v) && fmin(y0.v, y1.v) <= y && y <= fmax(y0.v, y1.v))
+      return false;                                                   // on an edge or a vertex: not inside
+    if ((y0.v > y) != (y1.v > y)) {
+      const D xi = x0 + (D(y) - y0) * (x1 - x0) / (y1 - y0);
+      if (x < xi.v) inside = !inside;
+    }
+  }
+  return inside;
+}
+// In the environment: inside the boundary polygon (first n_poly walls) and in no hole (walls [hole0, hole0+n_hole)).
+RIAB_DEV bool env_contains(double x, double y, const double* __restrict__ walls, int n_poly, int hole0, int n_hole) {
+  if (!edges_contain(x, y, walls, n_poly)) return false;
+  // the holes are disjoint polygons: strictly inside one of them <=> odd crossings over all their edges.
+  // A point on a hole's edge is not in that hole (nor in another one), so it is in the environment.
+  return (n_hole == 0) || !edges_contain(x, y, walls + 4 * hole0, n_hole);
+}
+
 // walls: shared/global array of W*(ax,ay,bx,by) doubles.
 // REC: write the per-iteration collision masks (parity taps).
 template <bool REC>
 RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W, const riab_motion_params& p,
                           const MotionDerived& m, const double* __restrict__ ext, bool periodic, double scale,
-                          double xi1, double xi2, bool has_drift, double drx,
+                          bool polygon, int n_poly, int hole0, int n_hole, double xi1, double xi2, bool has_drift, double drx,
                           double dry, double fallback_n1, double fallback_n2, uint8_t* __restrict__ mask,
                           int32_t* __restrict__ first_hit, int32_t* __restrict__ n_iters_out) {
   const D dt(p.dt);
@@ -206,7 +230,20 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
   if (REC && n_iters_out != nullptr) *n_iters_out = iters;
 
   // ---- A7: still inside? else clamp (Environment.py:781-818, :880-889)
-  if (!((px.v > ext[0]) && (px.v < ext[1]) && (py.v > ext[2]) && (py.v < ext[3]))) {
+  if (polygon) {
+    if (!env_contains(px.v, py.v, walls, n_poly, hole0, n_hole)) {
+      // Environment.py:890-893: "just resample random position" -- uniform in the extent until inside
+      // (the reference draws from np.random; a Philox stream keyed like the zero-displacement fall-back here)
+      const long long k1 = __double_as_longlong(fallback_n1), k2 = __double_as_longlong(fallback_n2);
+      for (uint32_t t = 0; t < 1024u; ++t) {
+        uint32_t c[4] = {(uint32_t)k2, (uint32_t)(k2 >> 32), 0x52534d50u + t, RIAB_STREAM_MEASURE << 24};
+        philox4x32_10(c, (uint32_t)k1, (uint32_t)(k1 >> 32));
+        const double qx = ext[0] + u01_53(c[0], c[1]) * (ext[1] - ext[0]);
+        const double qy = ext[2] + u01_53(c[2], c[3]) * (ext[3] - ext[2]);
+        if (env_contains(qx, qy, walls, n_poly, hole0, n_hole)) { px = D(qx); py = D(qy); break; }
+      }
+    }
+  } else if (!((px.v > ext[0]) && (px.v < ext[1]) && (py.v > ext[2]) && (py.v < ext[3]))) {
     if (periodic) {                                     // pos % extent (Environment.py:877-879)
       px = D(np_mod(px.v, ext[1]));
       py = D(np_mod(py.v, ext[3]));

@@ -86,6 +86,7 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
 
 struct PlaceConst {                  // uniform per launch
   int desc, geometry, n_cells, n_pad, n_inner, ep_valid;
+  int wall0;                         // index of the first wall the line-of-sight / geodesic tests use (Environment.py:715-717: 4)
   float min_fr, span, top_hat_w2;
   double top_hat_w;
   float eps[PLACE_MAX_WI];

@@ -33,7 +33,7 @@ def test_struct_sizes_match_header():
     from ratinabox_b200 import _lib
     assert C.sizeof(_lib.MotionParams) == 14 * 8
     assert C.sizeof(_lib.Agents) == 10 * 8
-    assert C.sizeof(_lib.Env) == 8 + 4 + 4 + 32 + 4 + 4 + 8       # + periodic, reserved, scale
+    assert C.sizeof(_lib.Env) == 8 + 4 + 4 + 32 + 4 + 4 + 8 + 4 + 4   # + boundary_mode, n_hole_walls, scale, hole_wall0, reserved
     assert C.sizeof(_lib.StepIO) == 8 * 8
 
 
@@ -199,3 +199,29 @@ def test_sharding_and_history_gather_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_environment_mirror_polygon_and_holes_host_logic(golden):
+    """Host side of polygon boundaries / holes: wall order (boundary, `walls`, holes, later add_wall), the strict
+    in-environment test and sample_positions (Environment.py:560-633) -- the latter bit-equal to the live reference
+    under the same np.random seed (tests/golden/polygon.npz)."""
+    from ratinabox_b200.Environment import Environment
+    g = golden("polygon.npz")
+    cases = {"lroom": {"boundary": [[0, 0], [1, 0], [1, 0.5], [0.5, 0.5], [0.5, 1], [0, 1]], "walls": [[[0.25, 0.0], [0.25, 0.3]]]},
+             "holed": {"holes": [[[0.4, 0.4], [0.6, 0.4], [0.6, 0.6], [0.4, 0.6]]], "walls": [[[0.8, 0.0], [0.8, 0.35]]]}}
+    for name, params in cases.items():
+        E = Environment(dict(params))
+        assert np.array_equal(E.walls, g[f"{name}_walls"]) and E.is_polygonal
+        assert E.los_skip == 4                                  # Environment.py:715-717
+        np.random.seed(3)
+        assert np.array_equal(E.sample_positions(n=50, method="uniform_jitter"), g[f"{name}_samples_uj"])
+        assert all(E.check_if_position_is_in_environment(p) for p in g[f"{name}_pos"][::25])
+    E = Environment(dict(cases["holed"]))
+    assert (E.hole_wall0, E.n_hole_walls, E.n_boundary_walls) == (5, 4, 4)
+    E.add_wall([[0.1, 0.1], [0.2, 0.1]])                        # appended AFTER the hole walls, like the reference
+    assert len(E.walls) == 10 and (E.hole_wall0, E.n_hole_walls) == (5, 4)
+    assert not E.check_if_position_is_in_environment([0.5, 0.5])        # in the hole
+    assert E.check_if_position_is_in_environment([0.4, 0.5])            # on the hole's edge: not strictly inside the hole
+    L = Environment(dict(cases["lroom"]))
+    assert L.check_if_position_is_in_environment([0.25, 0.75]) and not L.check_if_position_is_in_environment([0.75, 0.75])
+    assert not L.check_if_position_is_in_environment([0.5, 0.75])       # exactly on a boundary edge: not inside

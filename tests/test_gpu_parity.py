@@ -190,3 +190,38 @@ def test_periodic_boundary_conditions_golden(golden, name, walls):
     env = O.OracleEnvironment(walls=walls, boundary_conditions="periodic")
     ref = O.place_cells_get_state(env, PCs.place_cell_centres, PCs.place_cell_widths, Ag.pos, O.TapeRNG()).T
     assert np.abs(PCs.firingrate - ref).max() <= 1e-5
+
+
+@pytest.mark.parametrize("name,params", [
+    ("lroom", {"boundary": [[0, 0], [1, 0], [1, 0.5], [0.5, 0.5], [0.5, 1], [0, 1]], "walls": [[[0.25, 0.0], [0.25, 0.3]]]}),
+    ("holed", {"holes": [[[0.4, 0.4], [0.6, 0.4], [0.6, 0.6], [0.4, 0.6]]], "walls": [[[0.8, 0.0], [0.8, 0.35]]]})])
+def test_polygon_boundary_and_holes_golden(golden, name, params):
+    """Polygon boundary / holes against the live reference (tests/golden/polygon.npz): teacher-forced steps started
+    next to boundary, hole and inner walls (repulsion + bounces off every kind of wall), line_of_sight PlaceCells with
+    the reference's hard-coded `walls[4:]`, BVCs over all walls; then a free run that must stay in the environment."""
+    import ratinabox_b200 as rb
+    g = golden("polygon.npz")
+    E = rb.Environment(dict(params))
+    assert np.array_equal(E.walls, g[f"{name}_walls"]) and np.array_equal(E.extent, g[f"{name}_extent"])
+    A = len(g[f"{name}_A_pos0"])
+    Ag = rb.Agent(E, {"dt": 0.02, "speed_mean": 0.25, "n_agents": A})
+    v0 = g[f"{name}_A_vel0"]
+    Ag.pos, Ag.velocity, Ag.measured_velocity = g[f"{name}_A_pos0"], v0, v0
+    Ag.rotational_velocity = np.zeros(A)
+    Ag.head_direction = v0 / np.linalg.norm(v0, axis=1, keepdims=True)
+    PCs = rb.PlaceCells(Ag, {"place_cell_centres": g[f"{name}_centres"], "widths": 0.15})
+    assert PCs.wall_geometry == "line_of_sight"
+    td, ta, sd, sa = g[f"{name}_bvc"]
+    BVCs = rb.BoundaryVectorCells(Ag, {"tuning_distance": td, "tuning_angle": np.degrees(ta), "sigma_distance": sd,
+                                       "sigma_angle": np.degrees(sa)})
+    assert_rates_close(PCs.get_state(evaluate_at=None, pos=g[f"{name}_A_pos0"]), g[f"{name}_A_pc"], 1.0, f"polygon pc {name}")
+    assert_rates_close(BVCs.get_state(evaluate_at=None, pos=g[f"{name}_A_pos0"]), g[f"{name}_A_bvc"], 1.0, f"polygon bvc {name}")
+    Ag.update(_xi=g[f"{name}_A_xi"])
+    assert np.abs(Ag.pos - g[f"{name}_A_pos"]).max() <= 1e-12
+    assert np.abs(Ag.velocity - g[f"{name}_A_vel"]).max() <= 1e-12
+    assert np.abs(Ag.measured_velocity - g[f"{name}_A_mv"]).max() <= 1e-10
+    Ag.run(300)                                            # Philox-driven: every agent stays strictly inside
+    pos = Ag.pos
+    assert all(E.check_if_position_is_in_environment(p) for p in pos)
+    hp = Ag.get_history_arrays()["pos"]
+    assert np.isfinite(hp).all()

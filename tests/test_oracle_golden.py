@@ -185,3 +185,44 @@ def test_periodic_boundary_conditions(golden, name, walls):
         assert oa.distance_travelled == g[f"{name}_A_dist"][a]
     fr = O.place_cells_get_state(env, g[f"{name}_centres"], g[f"{name}_widths"], g[f"{name}_A_pos0"], O.TapeRNG())
     assert np.array_equal(fr, g[f"{name}_A_pc"])
+
+
+POLY_CASES = {"lroom": dict(boundary=[[0, 0], [1, 0], [1, 0.5], [0.5, 0.5], [0.5, 1], [0, 1]], walls=[[[0.25, 0.0], [0.25, 0.3]]]),
+              "holed": dict(holes=[[[0.4, 0.4], [0.6, 0.4], [0.6, 0.6], [0.4, 0.6]]], walls=[[[0.8, 0.0], [0.8, 0.35]]])}
+
+
+@pytest.mark.parametrize("name", sorted(POLY_CASES))
+def test_polygon_boundary_and_holes(golden, name):
+    """Polygon boundary / holes (Environment.py:112-160, :807-817): wall list, a native 1000-step run (global RNG,
+    jitter on) with line_of_sight PlaceCells (the hard-coded `walls[4:]`, Environment.py:715-717) and BVCs bit for
+    bit, and 384 teacher-forced single steps started next to boundary / hole / inner walls."""
+    g = golden("polygon.npz")
+    env = O.OracleEnvironment(**POLY_CASES[name])
+    assert np.array_equal(env.walls, g[f"{name}_walls"]) and np.array_equal(env.extent, g[f"{name}_extent"])
+    assert str(g[f"{name}_geom"]) == "line_of_sight"
+    prm = {"dt": 0.02, "speed_mean": 0.25}
+    ag = O.OracleAgent(env, g[f"{name}_pos0"], g[f"{name}_vel0"], prm)
+    rng = O.GlobalRNG()
+    td, ta, sd, sa = g[f"{name}_bvc"]
+    pcs = O.OracleNeurons(ag, 24, lambda p, r: O.place_cells_get_state(env, g[f"{name}_centres"], g[f"{name}_widths"], p, r,
+                                                                       "gaussian", "line_of_sight"))
+    bvcs = O.OracleNeurons(ag, 6, lambda p, r: O.bvc_get_state(env, td, ta, sd, sa, p, r))
+    np.random.set_state(("MT19937", g[f"{name}_rng_keys"], int(g[f"{name}_rng_pos"]), int(g[f"{name}_rng_has_gauss"]),
+                         float(g[f"{name}_rng_cached"])))
+    for _ in range(1000):
+        ag.update(rng); pcs.update(rng); bvcs.update(rng)
+    assert np.array_equal(np.array(ag.history["pos"]), g[f"{name}_pos"])
+    assert np.array_equal(np.array(ag.history["vel"]), g[f"{name}_vel"])
+    assert np.array_equal(np.array(pcs.history["firingrate"]), g[f"{name}_pc_fr"])
+    assert np.array_equal(np.array(bvcs.history["firingrate"]), g[f"{name}_bvc_fr"])
+    assert all(env.contains(p) for p in g[f"{name}_pos"][::10])
+    for a in range(len(g[f"{name}_A_pos0"])):
+        assert env.contains(g[f"{name}_A_pos0"][a])
+        oa = O.OracleAgent(env, g[f"{name}_A_pos0"][a], g[f"{name}_A_vel0"][a], prm)
+        oa.update(O.TapeRNG(agent_xi=g[f"{name}_A_xi"][a]))
+        assert np.array_equal(oa.pos, g[f"{name}_A_pos"][a]) and np.array_equal(oa.velocity, g[f"{name}_A_vel"][a])
+        assert np.array_equal(oa.measured_velocity, g[f"{name}_A_mv"][a])
+    fr = O.place_cells_get_state(env, g[f"{name}_centres"], g[f"{name}_widths"], g[f"{name}_A_pos0"], O.TapeRNG(),
+                                 "gaussian", "line_of_sight")
+    assert np.array_equal(fr, g[f"{name}_A_pc"])
+    assert np.array_equal(O.bvc_get_state(env, td, ta, sd, sa, g[f"{name}_A_pos0"], O.TapeRNG()), g[f"{name}_A_bvc"])
