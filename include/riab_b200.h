@@ -205,6 +205,34 @@ int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, co
                    egocentric cells; NULL = [1,0] (the reference's default, Neurons.py:1703) */,
                    float* out_dev, int64_t ld_out, void* stream);
 
+/* --------------------------------------------------------- ObjectVectorCells
+ * Neurons.py:1892-2113.  Objects live in the Environment (Environment.add_object, Environment.py:366-395): up to
+ * RIAB_MAX_OBJECTS positions with an integer type each.  Cell i fires for the objects whose type equals
+ * tuning_types[i]: sum of gaussian(distance) * von_mises(bearing), both with peak 1 (Neurons.py:2090-2104); with
+ * walls_occlude the distance is the `line_of_sight` one (1000 behind an inner wall, Environment.py:710-730);
+ * egocentric cells measure bearings from the head direction (Neurons.py:2030-2047). */
+#define RIAB_MAX_OBJECTS 9
+typedef struct {
+  int32_t n_cells;
+  int32_t n_objects;
+  double objects[2 * RIAB_MAX_OBJECTS];     /* Environment.objects["objects"], (n_objects,2) */
+  int32_t object_types[RIAB_MAX_OBJECTS];   /* Environment.objects["object_types"] */
+  int32_t walls_occlude;                    /* 1: wall_geometry "line_of_sight", 0: "euclidean" (Neurons.py:1937-1940) */
+  int32_t egocentric;                       /* reference_frame == "egocentric" */
+  float min_fr, max_fr;
+  const float* packed_dev;                  /* device block written by riab_ovc_pack (riab_ovc_pack_floats floats) */
+  int32_t n_pad;                            /* filled by riab_ovc_pack */
+  int32_t reserved;
+} riab_ovc_cells;
+int64_t riab_ovc_pack_floats(int32_t n_cells);
+/* tuning_angles / sigma_angles in radians (VectorCells attributes), tuning_types (n_cells) int32 */
+int riab_ovc_pack(const double* tuning_distances, const double* tuning_angles, const double* sigma_distances,
+                  const double* sigma_angles, const int32_t* tuning_types, int32_t n_cells, riab_ovc_cells* meta_out,
+                  float* out_host);
+/* ObjectVectorCells.get_state at given positions; head_direction_dev (n_pos,2) for egocentric cells, NULL = [1,0]. */
+int riab_ovc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_ovc_cells* ovc,
+                   const double* head_direction_dev, float* out_dev, int64_t ld_out, void* stream);
+
 /* ------------------------------------------------------- Neurons.update extras
  * OU noise (Neurons.py:153-160) and spikes (Neurons.py:681-684) for a block of
  * rates already written to rates_dev.  noise_dev (A,N) f32 state (NULL when
@@ -219,8 +247,8 @@ typedef struct {
 /* --------------------------------------------------------------- fused step
  * One launch = Agent.update for every agent + Neurons.update of ONE population
  * (motion -> rates [-> noise] [-> spikes] -> history row).  `cells_kind` selects
- * which of pc / gc / bvc is read. */
-typedef enum { RIAB_CELLS_PLACE = 0, RIAB_CELLS_GRID = 1, RIAB_CELLS_BVC = 2 } riab_cells_kind;
+ * which of pc / gc / bvc / ovc is read. */
+typedef enum { RIAB_CELLS_PLACE = 0, RIAB_CELLS_GRID = 1, RIAB_CELLS_BVC = 2, RIAB_CELLS_OVC = 3 } riab_cells_kind;
 typedef struct {
   float* rates_row;        /* (A, ld) f32: firing rates of this step (doubles as the history row) */
   int64_t ld;
@@ -247,7 +275,7 @@ int riab_neurons_update(const riab_agents* agents, const riab_env* env, int32_t 
  * History rows go to device rings: row (next + s) % rows for step s. */
 typedef struct {
   int32_t kind;                 /* riab_cells_kind */
-  const void* cells;            /* riab_place_cells* / riab_grid_cells* / riab_bvc_cells* */
+  const void* cells;            /* riab_place_cells* / riab_grid_cells* / riab_bvc_cells* / riab_ovc_cells* */
   riab_neuron_noise noise;      /* seed/step base; step is advanced per step */
   riab_rates_out out;           /* ld, noise_state, bvc_scratch; rates_row/spikes_row are set from the rings */
   float* rates_ring;            /* (rows, A, ld) f32 */

@@ -397,9 +397,65 @@ def gen_polygon():
     print("polygon.npz", os.path.getsize(os.path.join(GOLD, "polygon.npz")) // 1024, "KiB")
 
 
+OVC_WALLS = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+OVC_OBJECTS = [([0.15, 0.2], 0), ([0.5, 0.8], "same"), ([0.85, 0.3], "new"), ([0.5, 0.25], "new"), ([0.9, 0.9], 1)]
+
+
+def gen_ovc():
+    """ObjectVectorCells / FieldOfViewOVCs (Neurons.py:1892-2160): five objects of three types in the two-wall box."""
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox.Environment import Environment
+    from ratinabox.Agent import Agent
+    from ratinabox.Neurons import ObjectVectorCells, FieldOfViewOVCs
+    out = {}
+    np.random.seed(31)
+    Env = Environment()
+    for w in OVC_WALLS:
+        Env.add_wall(w)
+    for o, t in OVC_OBJECTS:
+        Env.add_object(o, type=t)
+    out["objects"], out["object_types"] = Env.objects["objects"].copy(), Env.objects["object_types"].copy()
+    Ag = Agent(Env, {"dt": 0.02})
+    pops = {"allo": ObjectVectorCells(Ag, {"n": 12}),
+            "eucl": ObjectVectorCells(Ag, {"n": 6, "walls_occlude": False, "object_tuning_type": 1}),
+            "fov": FieldOfViewOVCs(Ag, {"object_tuning_type": 0, "spatial_resolution": 0.05})}
+    for k, P in pops.items():
+        out[f"{k}_tuning"] = np.stack((P.tuning_distances, P.tuning_angles, P.sigma_distances, P.sigma_angles))
+        out[f"{k}_types"] = np.array(P.tuning_types)
+        out[f"{k}_geom"] = np.array(P.wall_geometry)
+        print(f"ovc[{k}]: n = {P.n}, frame {P.reference_frame}, geometry {P.wall_geometry}")
+    out["pos0"], out["vel0"] = Ag.pos.copy(), Ag.velocity.copy()
+    st = np.random.get_state()
+    out["rng_keys"], out["rng_pos"], out["rng_has_gauss"], out["rng_cached"] = st[1], st[2], st[3], st[4]
+    for _ in range(400):
+        Ag.update()
+        for P in pops.values():
+            P.update()
+    out["pos"], out["head"] = np.array(Ag.history["pos"]), np.array(Ag.history["head_direction"])
+    for k, P in pops.items():
+        out[f"{k}_fr"] = np.array(P.history["firingrate"])
+    rs = np.random.RandomState(17)
+    A = 384
+    pos = rs.uniform(0.02, 0.98, size=(A, 2))
+    ang = rs.uniform(0, 2 * np.pi, size=A)
+    hd = np.stack((np.cos(ang), np.sin(ang)), axis=1)
+    out["A_pos"], out["A_hd"] = pos, hd
+    with mode_a([]):
+        out["A_allo"] = pops["allo"].get_state(evaluate_at=None, pos=pos)
+        out["A_eucl"] = pops["eucl"].get_state(evaluate_at=None, pos=pos)
+        out["A_fov"] = np.stack([pops["fov"].get_state(evaluate_at=None, pos=pos[a], head_direction=hd[a])[:, 0] for a in range(A)], axis=1)
+    print("ovc: max rates", out["A_allo"].max(), out["A_eucl"].max(), out["A_fov"].max())
+    np.savez_compressed(os.path.join(GOLD, "ovc.npz"), **out)
+    print("ovc.npz", os.path.getsize(os.path.join(GOLD, "ovc.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["polygon"]:
         gen_polygon()
+    elif sys.argv[1:] == ["ovc"]:
+        gen_ovc()
     else:
         main()
         gen_polygon()
+        gen_ovc()

@@ -96,7 +96,10 @@ def install():
         colors.to_rgba = _to_rgba
         path.Path = _Path
         mpl.pyplot, mpl.collections, mpl.colors, mpl.path, mpl.cm = plt, coll, colors, path, cm
-        mpl.colormaps = {}
+        class _Colormaps(dict):                     # matplotlib.colormaps[name](x) -> RGBA (plot colours only)
+            def __missing__(self, name):
+                return lambda x: (0.0, 0.0, 0.0, 1.0)
+        mpl.colormaps = _Colormaps()
         mpl.rcParams = {}
         for name, mod in [("matplotlib", mpl), ("matplotlib.pyplot", plt),
                           ("matplotlib.collections", coll), ("matplotlib.colors", colors),

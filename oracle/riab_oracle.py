@@ -594,6 +594,36 @@ def bvc_get_state(env, tuning_distances, tuning_angles, sigma_distances, sigma_a
     return fr
 
 
+def ovc_get_state(env, objects, object_types, tuning_distances, tuning_angles, sigma_distances, sigma_angles,
+                  tuning_types, pos, rng, wall_geometry="line_of_sight", head_direction=None, min_fr=0.0, max_fr=1.0):
+    """ObjectVectorCells.get_state, Neurons.py:1989-2113 -> (N_cells, N_pos).  `head_direction` (2,) or (N_pos,2)
+    makes the cells egocentric (Neurons.py:2030-2047); angles in radians."""
+    objects = np.asarray(objects, dtype=float).reshape(-1, 2)
+    pos = np.asarray(pos, dtype=float).reshape(-1, 2)
+    n_pos, n_cells, n_obj = len(pos), len(tuning_distances), len(objects)
+    if n_obj == 0:
+        return np.zeros((n_cells, n_pos))
+    dist = distances_accounting_for_environment(env, pos, objects, wall_geometry, rng)           # (N_pos, N_obj)
+    vec = env.vectors_between(pos, objects)                                                      # pos1 - pos2
+    flat = -1 * vec.reshape(-1, 2)
+    bearings = np.mod(np.arctan2(flat[:, 1], flat[:, 0] + 1e-6), 2 * np.pi).reshape(n_pos, n_obj)   # utils.get_angle, is_array
+    if head_direction is not None:
+        hd = np.asarray(head_direction, dtype=float)
+        if hd.ndim == 1:
+            bearings = bearings - get_angle(hd)
+        else:                                                       # one head direction per position (batched agents)
+            bearings = bearings - np.mod(np.arctan2(hd[:, 1], hd[:, 0] + 1e-6), 2 * np.pi)[:, None]
+    d = dist[:, :, None]
+    b = bearings[:, :, None]
+    td, ta = np.asarray(tuning_distances, dtype=float)[None, None, :], np.asarray(tuning_angles, dtype=float)[None, None, :]
+    sd, sa = np.asarray(sigma_distances, dtype=float)[None, None, :], np.asarray(sigma_angles, dtype=float)[None, None, :]
+    g = np.exp(-((d - td) ** 2) / (2 * sd ** 2)) * 1                 # utils.gaussian(..., norm=1), utils.py:424-438
+    fr = g * von_mises_peak1(b, ta, sa)                              # utils.von_mises(..., norm=1), utils.py:441-457
+    mask = (np.asarray(object_types)[:, None] == np.asarray(tuning_types)[None, :]).astype(int)[None, :, :]
+    fr = (fr * mask).sum(axis=1).T
+    return fr * (max_fr - min_fr) + min_fr
+
+
 def diverging_radial_assembly(distance_range=(0.01, 0.2), angle_range=(0, 90), spatial_resolution=0.04, beta=5):
     """utils.create_diverging_radial_assembly, utils.py:1073-1112 -> (mu_d, mu_theta, sigma_d, sigma_theta)."""
     fov = [a * np.pi / 180 for a in angle_range]

@@ -38,9 +38,6 @@ class Environment:
             raise NotImplementedError("ratinabox_b200 accelerates 2D environments only (SURVEY.md section 2 row 9)")
         if self.boundary_conditions not in ("solid", "periodic"):
             raise ValueError(f"unknown boundary_conditions {self.boundary_conditions!r}")
-        if len(self.objects) > 0:
-            raise NotImplementedError("objects are outside the CUDA hot path (SURVEY.md section 2 row 13)")
-
         self.D = 2
         self.Agents = []
         self.agents_dict = {}
@@ -74,6 +71,12 @@ class Environment:
                 self.walls = np.vstack((self.walls, hole_walls))
                 self.n_hole_walls += len(h)
         self.is_polygonal = (not self.is_rectangular) or self.has_holes
+        self.passed_in_objects = copy.deepcopy(self.objects)         # Environment.py:175-187
+        self.objects = {"objects": np.empty((0, self.D)), "object_types": np.empty(0, int)}
+        self.n_object_types = 0
+        self.object_colormap = "rainbow_r"
+        for o in self.passed_in_objects:
+            self.add_object(o, type=0)
         left, right = min(c[0] for c in b), max(c[0] for c in b)
         bottom, top = min(c[1] for c in b), max(c[1] for c in b)
         self.centre = np.array([(left + right) / 2, (top + bottom) / 2])
@@ -101,6 +104,22 @@ class Environment:
         wall = np.asarray(wall, dtype=float).reshape(1, 2, 2)
         self.walls = np.concatenate((self.walls, wall), axis=0)
         self._walls_version += 1
+
+    def add_object(self, object, type="new"):                        # Environment.py:366-395
+        object = np.array(object, dtype=float).reshape(1, -1)
+        assert object.shape[1] == self.D
+        if type == "new":
+            type = self.n_object_types
+        elif type == "same":
+            type = 0 if len(self.objects["object_types"]) == 0 else self.objects["object_types"][-1]
+        else:
+            assert type <= self.n_object_types, (
+                f"Newly added object must be one of the existing types (currently {np.unique(self.objects['object_types'])}) "
+                f"or the next one along ({self.n_object_types}), not {type}")
+        type = np.array([type], int)
+        self.objects["objects"] = np.append(self.objects["objects"], object, axis=0)
+        self.objects["object_types"] = np.append(self.objects["object_types"], type, axis=0)
+        self.n_object_types = len(np.unique(self.objects["object_types"]))
 
     def _walls_signature(self):
         return (self._walls_version, self.walls.shape[0], hash(self.walls.tobytes()))

@@ -471,13 +471,13 @@ class BoundaryVectorCells(Neurons):
         "min_fr": 0.0,
     }
     _cells_kind = _lib.CELLS_BVC
+    _egocentric_warning = "BVCs in egocentric plane require a head direction vector but none was passed. Using [1,0]"
 
-    def __init__(self, Agent, params={}):
+    def _init_vector_tuning(self):
+        """VectorCells.set_tuning_parameters (Neurons.py:1388-1437): tuning_distances / tuning_angles /
+        sigma_distances / sigma_angles from ``cell_arrangement``."""
         from .utils import (create_random_assembly, create_uniform_radial_assembly,
-                            create_diverging_radial_assembly, rotate)
-        super().__init__(Agent, params)
-        assert self.Agent.Environment.boundary_conditions == "solid", \
-            "boundary cells only possible with solid boundary conditions"      # Neurons.py:1580-1582
+                            create_diverging_radial_assembly)
         if self.reference_frame not in ("allocentric", "egocentric"):
             raise ValueError(f"unknown reference_frame {self.reference_frame!r}")
         arr = self.cell_arrangement                                   # VectorCells.set_tuning_parameters, Neurons.py:1388-1437
@@ -496,6 +496,13 @@ class BoundaryVectorCells(Neurons):
         assert len(self.tuning_distances) == len(self.tuning_angles) == len(self.sigma_distances) == len(self.sigma_angles), \
             "All manifold tuning parameters must be of the same length"
         self.n = len(self.tuning_distances)
+
+    def __init__(self, Agent, params={}):
+        from .utils import rotate
+        super().__init__(Agent, params)
+        assert self.Agent.Environment.boundary_conditions == "solid", \
+            "boundary cells only possible with solid boundary conditions"      # Neurons.py:1580-1582
+        self._init_vector_tuning()
         test_direction = np.array([1, 0])                           # Neurons.py:1584-1596 (duplicated-0 quirk kept)
         dirs, angs = [test_direction], [0]
         self.n_test_angles = int(360 / self.dtheta)
@@ -569,7 +576,7 @@ class BoundaryVectorCells(Neurons):
                 warnings.warn("'vel' kwarg deprecated in favour of 'head_direction'")
                 hd = np.asarray(kwargs["vel"], dtype=np.float64)
             else:
-                warnings.warn("BVCs in egocentric plane require a head direction vector but none was passed. Using [1,0]")
+                warnings.warn(self._egocentric_warning)
                 hd = np.array([1.0, 0.0])
             hd = np.array(np.broadcast_to(hd.reshape(-1, 2), (pos_dev.shape[0], 2)))      # own, writable, contiguous
             hd_dev = torch.as_tensor(hd, device=self.device)
@@ -598,4 +605,117 @@ class FieldOfViewBVCs(BoundaryVectorCells):
         p.update(params)
         p["reference_frame"] = "egocentric"
         assert p["cell_arrangement"] is not None, "cell_arrangement must be set for FoV Neurons"
+        super().__init__(Agent, p)
+
+
+class ObjectVectorCells(BoundaryVectorCells):
+    """ratinabox.ObjectVectorCells (Neurons.py:1892-2113): vector cells tuned to the objects of the Environment.
+    Same tuning machinery as the other VectorCells (cell_arrangement, tuning_distance, ...); each cell responds to the
+    objects of ONE type (``object_tuning_type``: "random", an int, or one int per cell).  The rates are evaluated by
+    ``riab_ovc_*`` (csrc/riab_ovc.cuh): exact float64 agent-object geometry per agent, float32 tuning per cell."""
+    default_params = {
+        "n": 10,
+        "name": "ObjectVectorCell",
+        "walls_occlude": True,          # objects behind walls cannot be seen
+        "object_tuning_type": "random",
+    }
+    _cells_kind = _lib.CELLS_OVC
+
+    def __init__(self, Agent, params={}):
+        p = copy.deepcopy(__class__.default_params)
+        p.update(params)
+        env = Agent.Environment
+        if len(env.objects["objects"]) == 0:                       # Neurons.py:1921-1923
+            raise RuntimeError(f"Cannot initialize {p['name']}, as there are no objects in the environment.")
+        if len(env.objects["objects"]) > _lib.MAX_OBJECTS:
+            raise NotImplementedError(f"at most {_lib.MAX_OBJECTS} objects per environment on the CUDA path")
+        Neurons.__init__(self, Agent, p)
+        self._init_vector_tuning()
+        self.object_locations = env.objects["objects"]
+        self.tuning_types = None
+        self.set_tuning_types(self.object_tuning_type)
+        self.wall_geometry = "line_of_sight" if self.walls_occlude == True else "euclidean"      # Neurons.py:1937-1940
+
+    def set_tuning_types(self, tuning_types=None):                  # Neurons.py:1962-1986
+        if isinstance(tuning_types, str) and tuning_types == "random":
+            self.object_types = self.Agent.Environment.objects["object_types"]
+            self.tuning_types = np.random.choice(np.unique(self.object_types), replace=True, size=(self.n,))
+        else:
+            if isinstance(tuning_types, (int, np.integer)):
+                tuning_types = np.repeat(tuning_types, self.n)
+            elif isinstance(tuning_types, list):
+                tuning_types = np.array(tuning_types)
+            assert isinstance(tuning_types, np.ndarray), "tuning_types must be an integer, list or numpy array"
+            assert tuning_types.shape[0] == self.n, \
+                f"Tuning types must be a vector of length of the number of neurons: ({self.n},)"
+            self.tuning_types = tuning_types
+
+    def _signature(self):
+        env = self.Agent.Environment
+        return tuple(hash(np.ascontiguousarray(a, dtype=np.float64).tobytes()) for a in (
+            self.tuning_distances, self.tuning_angles, self.sigma_distances, self.sigma_angles,
+            np.asarray(self.tuning_types, dtype=np.float64), env.objects["objects"],
+            np.asarray(env.objects["object_types"], dtype=np.float64))) + (
+            float(self.min_fr), float(self.max_fr), self.reference_frame, self.wall_geometry)
+
+    def _pack(self):
+        env = self.Agent.Environment
+        arrs = [np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (
+            self.tuning_distances, self.tuning_angles, self.sigma_distances, self.sigma_angles)]
+        self.n = arrs[0].shape[0]
+        types = np.ascontiguousarray(self.tuning_types, dtype=np.int32).reshape(-1)
+        assert types.shape[0] == self.n
+        objs = np.ascontiguousarray(env.objects["objects"], dtype=np.float64).reshape(-1, 2)
+        otypes = np.asarray(env.objects["object_types"], dtype=np.int32).reshape(-1)
+        if len(objs) > _lib.MAX_OBJECTS:
+            raise NotImplementedError(f"at most {_lib.MAX_OBJECTS} objects per environment on the CUDA path")
+        c = _lib.OvcCells()
+        host = np.zeros(self._lib.riab_ovc_pack_floats(self.n), dtype=np.float32)
+        _lib.check(self._lib.riab_ovc_pack(*[_f64p(a) for a in arrs], types.ctypes.data_as(C.POINTER(C.c_int32)), self.n,
+                                           C.byref(c), host.ctypes.data_as(_lib.c_float_p)))
+        self._packed = self._upload(host)
+        c.n_cells, c.n_objects = self.n, len(objs)
+        for o in range(len(objs)):
+            c.objects[2 * o], c.objects[2 * o + 1] = float(objs[o, 0]), float(objs[o, 1])
+            c.object_types[o] = int(otypes[o])
+        c.walls_occlude = 1 if self.wall_geometry == "line_of_sight" else 0
+        c.egocentric = 1 if self.reference_frame == "egocentric" else 0
+        c.min_fr, c.max_fr = float(self.min_fr), float(self.max_fr)
+        c.packed_dev = self._packed.data_ptr()
+        return c
+
+    def _scratch_ptr(self, n):
+        return None
+
+    def _rates_from_positions(self, pos_dev, n_pos, out, first_wall=None, head_dir=None):
+        ag = self.Agent
+        _lib.check(self._lib.riab_ovc_rates(pos_dev.data_ptr(), n_pos, C.byref(ag._env_struct()), C.byref(self._cells()),
+                                            head_dir.data_ptr() if head_dir is not None else None,
+                                            out.data_ptr(), out.stride(0), ag._stream()))
+
+    _egocentric_warning = "OVCs in egocentric plane require a head direction vector but none was passed. Using [1,0]"
+
+
+class FieldOfViewOVCs(ObjectVectorCells):
+    """Egocentric ObjectVectorCells tiling the agent's field of view (ratinabox/Neurons.py:2116-2160)."""
+    default_params = {
+        "distance_range": [0.02, 0.4],
+        "angle_range": [0, 75],
+        "spatial_resolution": 0.02,
+        "beta": 5,
+        "cell_arrangement": "diverging_manifold",
+        "object_tuning_type": None,
+    }
+
+    def __init__(self, Agent, params={}):
+        p = copy.deepcopy(__class__.default_params)
+        p.update(params)
+        if p["object_tuning_type"] is None:
+            warnings.warn("For FieldOfViewOVCs you must specify the object type they are selective for with the "
+                          "'object_tuning_type' parameter. This can be 'random' (each cell in the field of view chooses a "
+                          "random object type) or any integer (all cells have the same preference for this type). For now "
+                          "defaulting to params['object_tuning_type'] = 0.")
+            p["object_tuning_type"] = 0
+        p["reference_frame"] = "egocentric"
+        assert p["cell_arrangement"] is not None, "cell_arrangement must be set for FOV Neurons"
         super().__init__(Agent, p)

@@ -10,6 +10,8 @@ verbose = False
 
 from .Environment import Environment          # noqa: E402
 from .Agent import Agent                      # noqa: E402
-from .Neurons import Neurons, PlaceCells, GridCells, BoundaryVectorCells, FieldOfViewBVCs   # noqa: E402
+from .Neurons import (Neurons, PlaceCells, GridCells, BoundaryVectorCells, FieldOfViewBVCs,   # noqa: E402
+                      ObjectVectorCells, FieldOfViewOVCs)
 
-__all__ = ["Environment", "Agent", "Neurons", "PlaceCells", "GridCells", "BoundaryVectorCells", "FieldOfViewBVCs"]
+__all__ = ["Environment", "Agent", "Neurons", "PlaceCells", "GridCells", "BoundaryVectorCells", "FieldOfViewBVCs",
+           "ObjectVectorCells", "FieldOfViewOVCs"]

@@ -62,6 +62,16 @@ class BvcCells(C.Structure):
                 ("egocentric", C.c_int32)]
 
 
+MAX_OBJECTS = 9
+
+
+class OvcCells(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("n_objects", C.c_int32), ("objects", C.c_double * (2 * MAX_OBJECTS)),
+                ("object_types", C.c_int32 * MAX_OBJECTS), ("walls_occlude", C.c_int32), ("egocentric", C.c_int32),
+                ("min_fr", C.c_float), ("max_fr", C.c_float), ("packed_dev", C.c_void_p), ("n_pad", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class NeuronNoise(C.Structure):
     _fields_ = [("noise_std", C.c_float), ("noise_coherence_time", C.c_float), ("dt", C.c_float),
                 ("seed", C.c_uint64), ("step", C.c_uint64), ("id_offset", C.c_int64), ("population_id", C.c_int32)]
@@ -85,7 +95,7 @@ class AgentHistory(C.Structure):
 PC_DESCRIPTIONS = {"gaussian": 0, "gaussian_threshold": 1, "diff_of_gaussians": 2, "top_hat": 3, "one_hot": 4}
 WALL_GEOMETRIES = {"euclidean": 0, "line_of_sight": 1, "geodesic": 2}
 GC_DESCRIPTIONS = {"rectified_cosines": 0, "shifted_cosines": 1}
-CELLS_PLACE, CELLS_GRID, CELLS_BVC = 0, 1, 2
+CELLS_PLACE, CELLS_GRID, CELLS_BVC, CELLS_OVC = 0, 1, 2, 3
 MAX_REC_ITERS = 4
 
 # name -> (restype, argtypes); every symbol include/riab_b200.h declares
@@ -107,6 +117,11 @@ SYMBOLS = {
                                 C.POINTER(BvcCells), c_float_p]),
     "riab_bvc_rates": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Env), C.POINTER(BvcCells), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "riab_ovc_pack_floats": (C.c_int64, [C.c_int32]),
+    "riab_ovc_pack": (C.c_int, [c_double_p, c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int32), C.c_int32,
+                                C.POINTER(OvcCells), c_float_p]),
+    "riab_ovc_rates": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(Env), C.POINTER(OvcCells), C.c_void_p, C.c_void_p,
+                                 C.c_int64, C.c_void_p]),
     "riab_step_fused": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
                                   C.c_int32, C.c_void_p, C.POINTER(NeuronNoise), C.POINTER(RatesOut), C.c_void_p]),
     "riab_neurons_update": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.c_int32, C.c_void_p, C.POINTER(NeuronNoise),

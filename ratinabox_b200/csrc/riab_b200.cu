@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "riab_bvc.cuh"
+#include "riab_ovc.cuh"
 #include "riab_grid.cuh"
 #include "riab_motion.cuh"
 #include "riab_place.cuh"
@@ -290,7 +291,8 @@ struct PlacePolicy {
   static constexpr int REC = PLACE_REC;
   static constexpr bool LIGHT = (WI == 0) && (DESC >= 0);   // few instructions per rate: HBM-bound consumers
   static constexpr bool XU_BOUND = false;
-  static __device__ __forceinline__ void record(float* rec, double px, double py, const double* s_walls,
+  static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
+  static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
     place_agent_record(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx);
   }
@@ -310,7 +312,8 @@ struct GridPolicy {
   static constexpr int REC = 4;
   static constexpr bool LIGHT = false;    // 36 cell registers per thread do not fit StepCfg<8>'s 56-register consumers
   static constexpr bool XU_BOUND = false; // 3 MUFU.COS per rate, yet issue-bound: PRMT+FADD instead of I2F measured slower (95.6 vs 91.3 us, c3)
-  static __device__ __forceinline__ void record(float* rec, double px, double py, const double*, const Const&,
+  static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
+  static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double*, const Const&,
                                                 const EnvK& env) {
     rec[0] = (float)(px - env.cxm);
     rec[1] = (float)(py - env.cym);
@@ -320,6 +323,27 @@ struct GridPolicy {
   static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int, const float* rec,
                                                 uint32_t, bool&) {
     grid_rates4(o, r, c, rec);
+  }
+  static __device__ __forceinline__ bool expanded(const Const&) { return false; }
+  static __device__ __forceinline__ int wall0(const Const&) { return 0; }
+};
+
+struct OvcPolicy {
+  using Const = OvcConst;
+  using Regs = OvcCellRegs;
+  static constexpr int REC = OVC_REC;
+  static constexpr bool LIGHT = false;
+  static constexpr bool XU_BOUND = false;
+  static __device__ __forceinline__ const double* head_dir(const Const& c) { return c.head_dir; }
+  static __device__ __forceinline__ void record(float* rec, double px, double py, double hdx, double hdy,
+                                                const double* s_walls, const Const& c, const EnvK&) {
+    ovc_agent_record(rec, px, py, hdx, hdy, s_walls, c);
+  }
+  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { ovc_load_cells(r, c, cell0); }
+  template <bool DEFER, int EXP = -1>
+  static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int, const float* rec,
+                                                uint32_t, bool&) {
+    ovc_rates4(o, r, c, rec);
   }
   static __device__ __forceinline__ bool expanded(const Const&) { return false; }
   static __device__ __forceinline__ int wall0(const Const&) { return 0; }
@@ -463,7 +487,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
         if (lane < na) {
           const long long i = a0 + lane;
           const double px = ag.pos[2 * i], py = ag.pos[2 * i + 1];
-          P::record(s_slot[s].rec[lane], px, py, s_walls, pc, env);
+          P::record(s_slot[s].rec[lane], px, py, ag.head_direction[2 * i], ag.head_direction[2 * i + 1], s_walls, pc, env);
         }
         if (lane == 0) s_slot[s].na = na;
         __syncwarp();
@@ -476,14 +500,17 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       }
       if (lane < na) {
         const long long i = a0 + lane;
-        double px, py;
-        if (MODE == 1) {          AgentState st;
+        double px, py, hdx = 1.0, hdy = 0.0;
+        if (MODE == 1) {
+          AgentState st;
           agent_update_one<false>(ag, mp, md, io, env, s_walls, i, st);
-          px = st.px; py = st.py;
+          px = st.px; py = st.py; hdx = st.hdx; hdy = st.hdy;
         } else {
           px = pos_in[2 * i]; py = pos_in[2 * i + 1];
+          const double* hd = P::head_dir(pc);                 // egocentric cells evaluated at given positions
+          if (hd != nullptr) { hdx = hd[2 * i]; hdy = hd[2 * i + 1]; }
         }
-        P::record(s_slot[s].rec[lane], px, py, s_walls, pc, env);
+        P::record(s_slot[s].rec[lane], px, py, hdx, hdy, s_walls, pc, env);
       }
       if (lane == 0) s_slot[s].na = na;
       __syncwarp();
@@ -1048,6 +1075,25 @@ int make_grid(const riab_grid_cells* gc, const EnvK& env, GridConst& c) {
   return 0;
 }
 
+int make_ovc(const riab_ovc_cells* oc, const EnvK& env, const double* head_dir, OvcConst& c) {
+  if (oc == nullptr || oc->packed_dev == nullptr) return fail(RIAB_ERR_INVALID, "object vector cells / packed_dev NULL");
+  if (oc->n_objects < 0 || oc->n_objects > RIAB_MAX_OBJECTS)
+    return fail(RIAB_ERR_UNSUPPORTED, "n_objects=%d exceeds %d", oc->n_objects, RIAB_MAX_OBJECTS);
+  if (env.periodic) return fail(RIAB_ERR_UNSUPPORTED, "object vector cells need solid boundary conditions here");
+  memset(&c, 0, sizeof(c));
+  c.n_cells = oc->n_cells; c.n_pad = oc->n_pad; c.n_obj = oc->n_objects;
+  c.ego = oc->egocentric ? 1 : 0; c.occlude = oc->walls_occlude ? 1 : 0;
+  c.wall0 = env.W < 4 ? env.W : 4;                       // Environment.py:715-717: walls[4:]
+  c.n_inner = env.W - c.wall0;
+  c.min_fr = oc->min_fr; c.span = oc->max_fr - oc->min_fr;
+  c.packed = oc->packed_dev; c.head_dir = head_dir;
+  for (int o = 0; o < oc->n_objects; ++o) {
+    c.obj[2 * o] = oc->objects[2 * o]; c.obj[2 * o + 1] = oc->objects[2 * o + 1];
+    c.type[o] = (float)oc->object_types[o];
+  }
+  return 0;
+}
+
 int g_num_sms = 0;
 
 // MODE 0: rates for given positions; 1: motion -> rates (one step); 2: skewed (rates of the current
@@ -1424,6 +1470,48 @@ int riab_bvc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, co
                            (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------ ObjectVectorCells
+int64_t riab_ovc_pack_floats(int32_t n_cells) { return (int64_t)place_n_pad(n_cells) * 6; }
+
+int riab_ovc_pack(const double* tuning_distances, const double* tuning_angles, const double* sigma_distances,
+                  const double* sigma_angles, const int32_t* tuning_types, int32_t n, riab_ovc_cells* meta, float* out) {
+  if (!tuning_distances || !tuning_angles || !sigma_distances || !sigma_angles || !tuning_types || !meta || !out || n <= 0)
+    return fail(RIAB_ERR_INVALID, "riab_ovc_pack: bad argument");
+  const int np = place_n_pad(n);
+  const double log2e = 1.4426950408889634;
+  for (int i = 0; i < np; ++i) {
+    const bool in = i < n;
+    const double kappa = in ? 1.0 / (sigma_angles[i] * sigma_angles[i]) : 0.0;       // utils.von_mises (utils.py:441-457)
+    out[i] = in ? (float)tuning_distances[i] : 0.f;
+    out[(size_t)np + i] = in ? (float)(sqrt(0.5 * log2e) / sigma_distances[i]) : 0.f;  // utils.gaussian (utils.py:424-438)
+    out[(size_t)2 * np + i] = in ? (float)cos(0.5 * tuning_angles[i]) : 1.f;
+    out[(size_t)3 * np + i] = in ? (float)sin(0.5 * tuning_angles[i]) : 0.f;
+    out[(size_t)4 * np + i] = (float)sqrt(2.0 * kappa * log2e);
+    out[(size_t)5 * np + i] = in ? (float)tuning_types[i] : -2.f;                     // padding cells match no object
+  }
+  meta->n_pad = np;
+  return 0;
+}
+
+int riab_ovc_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, const riab_ovc_cells* ovc,
+                   const double* head_direction_dev, float* out_dev, int64_t ld_out, void* stream) {
+  if (n_pos == 0) return 0;
+  EnvK ek;
+  OvcConst c;
+  OutK ok;
+  int rc;
+  if ((rc = make_env(env, ek)) || (rc = make_ovc(ovc, ek, head_direction_dev, c))) return rc;
+  if (n_pos > 0 && pos_dev == nullptr) return fail(RIAB_ERR_INVALID, "pos_dev NULL");
+  riab_rates_out ro;
+  memset(&ro, 0, sizeof(ro));
+  ro.rates_row = out_dev; ro.ld = ld_out;
+  if ((rc = make_out(&ro, nullptr, ovc->n_cells, 1.0, 0, ok))) return rc;
+  riab_agents ag; memset(&ag, 0, sizeof(ag));
+  riab_motion_params mp; memset(&mp, 0, sizeof(mp));
+  riab_step_io io; memset(&io, 0, sizeof(io));
+  return launch_tile<OvcPolicy, 0>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+}
+
 // ----------------------------------------------------------------- fused step
 // MODE 1: motion + rates of one population; 0: rates for agents->pos as it is; 2: skewed (riab_run).
 }  // extern "C"
@@ -1476,6 +1564,12 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
     if (MODE == 1 && (rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
     return launch_bvc<false>(ek, *agents, mp0, io0, bvc, ok, agents->pos, agents->n_agents, out->bvc_scratch, nullptr,
                              agents->head_direction, s);
+  }
+  if (cells_kind == RIAB_CELLS_OVC) {
+    const riab_ovc_cells* oc = (const riab_ovc_cells*)cells;
+    OvcConst c;
+    if ((rc = make_ovc(oc, ek, agents->head_direction, c)) || (rc = make_out(out, noise, oc->n_cells, dt, agents->id_offset, ok))) return rc;
+    return launch_tile<OvcPolicy, MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   return fail(RIAB_ERR_INVALID, "bad cells_kind %d", cells_kind);
 }
@@ -1537,6 +1631,7 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
       if (pp.kind == RIAB_CELLS_PLACE) n_cells = ((const riab_place_cells*)pp.cells)->n_cells;
       else if (pp.kind == RIAB_CELLS_GRID) n_cells = ((const riab_grid_cells*)pp.cells)->n_cells;
       else if (pp.kind == RIAB_CELLS_BVC) n_cells = ((const riab_bvc_cells*)pp.cells)->n_cells;
+      else if (pp.kind == RIAB_CELLS_OVC) n_cells = ((const riab_ovc_cells*)pp.cells)->n_cells;
       ro.spikes_row = pp.spikes_ring ? pp.spikes_ring + slot * A * (size_t)(4 * ((n_cells + 127) / 128)) : nullptr;
       riab_neuron_noise nz = pp.noise;
       nz.step = pp.noise.step + (uint64_t)st;

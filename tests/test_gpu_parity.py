@@ -225,3 +225,79 @@ def test_polygon_boundary_and_holes_golden(golden, name, params):
     assert all(E.check_if_position_is_in_environment(p) for p in pos)
     hp = Ag.get_history_arrays()["pos"]
     assert np.isfinite(hp).all()
+
+
+OVC_WALLS = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+OVC_OBJECTS = [([0.15, 0.2], 0), ([0.5, 0.8], "same"), ([0.85, 0.3], "new"), ([0.5, 0.25], "new"), ([0.9, 0.9], 1)]
+
+
+def _ovc_setup(rb, g, A):
+    E = rb.Environment()
+    for w in OVC_WALLS:
+        E.add_wall(w)
+    for o, t in OVC_OBJECTS:
+        E.add_object(o, type=t)
+    assert np.array_equal(E.objects["objects"], g["objects"]) and np.array_equal(E.objects["object_types"], g["object_types"])
+    Ag = rb.Agent(E, {"dt": 0.02, "n_agents": A, "seed": 3})
+    pops = {}
+    for k, cls, extra in (("allo", rb.ObjectVectorCells, {}), ("eucl", rb.ObjectVectorCells, {"walls_occlude": False}),
+                          ("fov", rb.FieldOfViewOVCs, {"spatial_resolution": 0.05})):
+        td, ta, sd, sa = g[f"{k}_tuning"]
+        P = cls(Ag, dict({"object_tuning_type": [int(t) for t in g[f"{k}_types"]], "tuning_distance": td,
+                          "tuning_angle": np.degrees(ta), "sigma_distance": sd, "sigma_angle": np.degrees(sa),
+                          "cell_arrangement": "random"}, **extra))
+        # the manifold's tuning is pinned to the fixture's (field-of-view cells come from diverging_manifold there)
+        P.tuning_distances, P.tuning_angles, P.sigma_distances, P.sigma_angles = td.copy(), ta.copy(), sd.copy(), sa.copy()
+        assert P.n == len(td) and P.wall_geometry == str(g[f"{k}_geom"])
+        pops[k] = P
+    assert pops["fov"].reference_frame == "egocentric"
+    return E, Ag, pops
+
+
+def test_object_vector_cells_golden(golden):
+    """ObjectVectorCells (allocentric, occluding walls / euclidean) and FieldOfViewOVCs (egocentric) against the live
+    reference at 384 positions / head directions (tests/golden/ovc.npz)."""
+    import ratinabox_b200 as rb
+    g = golden("ovc.npz")
+    E, Ag, pops = _ovc_setup(rb, g, 4)
+    for k in ("allo", "eucl"):
+        assert_rates_close(pops[k].get_state(evaluate_at=None, pos=g["A_pos"]), g[f"A_{k}"], 1.0, f"ovc {k}")
+    assert_rates_close(pops["fov"].get_state(evaluate_at=None, pos=g["A_pos"], head_direction=g["A_hd"]), g["A_fov"], 1.0, "ovc fov")
+    one = pops["fov"].get_state(evaluate_at=None, pos=g["A_pos"][:5], head_direction=g["A_hd"][2])   # one direction for all
+    import riab_oracle as O
+    env = O.OracleEnvironment(walls=OVC_WALLS)
+    td, ta, sd, sa = g["fov_tuning"]
+    ref = O.ovc_get_state(env, g["objects"], g["object_types"], td, ta, sd, sa, g["fov_types"], g["A_pos"][:5], O.TapeRNG(),
+                          "line_of_sight", head_direction=g["A_hd"][2])
+    assert np.abs(one - ref).max() <= 1e-5
+
+
+def test_object_vector_cells_stepped_with_the_agent(golden):
+    """Agent.update + three ObjectVectorCells populations: the fused step (first population), riab_neurons_update
+    (the others) and riab_run all see the positions / head directions of the same step; spikes and history rows."""
+    import ratinabox_b200 as rb
+    import riab_oracle as O
+    g = golden("ovc.npz")
+    A = 96
+    E, Ag, pops = _ovc_setup(rb, g, A)
+    env = O.OracleEnvironment(walls=OVC_WALLS)
+
+    def check(tag):
+        pos, hd = Ag.pos, Ag.head_direction
+        for k, ego in (("allo", False), ("eucl", False), ("fov", True)):
+            td, ta, sd, sa = g[f"{k}_tuning"]
+            ref = O.ovc_get_state(env, g["objects"], g["object_types"], td, ta, sd, sa, g[f"{k}_types"], pos, O.TapeRNG(),
+                                  str(g[f"{k}_geom"]), head_direction=(hd if ego else None)).T
+            assert np.abs(pops[k].firingrate - ref).max() <= 1e-5, (tag, k)
+
+    for _ in range(3):
+        Ag.update()
+        for P in pops.values():
+            P.update()
+    check("stepped")
+    Ag.run(5)
+    check("run")
+    for k, P in pops.items():
+        h = P.get_history_arrays()
+        assert h["firingrate"].shape == (8, A, P.n) and h["spikes"].shape == (8, A, P.n)
+        assert np.array_equal(h["firingrate"][-1], P.firingrate)

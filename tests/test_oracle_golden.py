@@ -226,3 +226,40 @@ def test_polygon_boundary_and_holes(golden, name):
                                  "gaussian", "line_of_sight")
     assert np.array_equal(fr, g[f"{name}_A_pc"])
     assert np.array_equal(O.bvc_get_state(env, td, ta, sd, sa, g[f"{name}_A_pos0"], O.TapeRNG()), g[f"{name}_A_bvc"])
+
+
+OVC_WALLS = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+
+
+def test_object_vector_cells(golden):
+    """ObjectVectorCells / FieldOfViewOVCs (Neurons.py:1892-2160) against the live reference: a native 400-step
+    run (global RNG, jitter on; allocentric + euclidean + egocentric field-of-view populations on one Agent) bit
+    for bit, and get_state at 384 positions / head directions in zero-jitter mode."""
+    g = golden("ovc.npz")
+    env = O.OracleEnvironment(walls=OVC_WALLS)
+    obj, otypes = g["objects"], g["object_types"]
+    assert list(otypes) == [0, 0, 1, 2, 1]
+    ag = O.OracleAgent(env, g["pos0"], g["vel0"], {"dt": 0.02})
+    rng = O.GlobalRNG()
+
+    def pop(k, ego):
+        td, ta, sd, sa = g[f"{k}_tuning"]
+        geom = str(g[f"{k}_geom"])
+        return O.OracleNeurons(ag, len(td), lambda p, r: O.ovc_get_state(
+            env, obj, otypes, td, ta, sd, sa, g[f"{k}_types"], p, r, geom, head_direction=(ag.head_direction if ego else None)))
+
+    pops = {"allo": pop("allo", False), "eucl": pop("eucl", False), "fov": pop("fov", True)}
+    np.random.set_state(("MT19937", g["rng_keys"], int(g["rng_pos"]), int(g["rng_has_gauss"]), float(g["rng_cached"])))
+    for _ in range(400):
+        ag.update(rng)
+        for P in pops.values():
+            P.update(rng)
+    assert np.array_equal(np.array(ag.history["pos"]), g["pos"])
+    for k, P in pops.items():
+        assert np.array_equal(np.array(P.history["firingrate"]), g[f"{k}_fr"]), k
+    for k, ego in (("allo", False), ("eucl", False), ("fov", True)):
+        td, ta, sd, sa = g[f"{k}_tuning"]
+        fr = O.ovc_get_state(env, obj, otypes, td, ta, sd, sa, g[f"{k}_types"], g["A_pos"], O.TapeRNG(), str(g[f"{k}_geom"]),
+                             head_direction=(g["A_hd"] if ego else None))
+        assert np.array_equal(fr, g[f"A_{k}"]), k
+    assert (g["A_allo"] > 0.05).mean() > 0.01 and (g["A_fov"] > 0.05).mean() > 0.002
