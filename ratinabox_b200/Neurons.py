@@ -578,7 +578,7 @@ class BoundaryVectorCells(Neurons):
             else:
                 warnings.warn(self._egocentric_warning)
                 hd = np.array([1.0, 0.0])
-            hd = np.array(np.broadcast_to(hd.reshape(-1, 2), (pos_dev.shape[0], 2)))      # own, writable, contiguous
+            hd = np.array(np.broadcast_to(hd.reshape(-1, 2), (pos_dev.shape[0], 2)), order="C")   # own, writable, C-contiguous
             hd_dev = torch.as_tensor(hd, device=self.device)
         n_pos = int(pos_dev.shape[0])
         out = torch.empty((n_pos, self._ld()), dtype=torch.float32, device=self.device)

@@ -1115,8 +1115,11 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   if (MODE != 0) derive_motion(mp, md);
   if (noise) k_step<P, MODE, true, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   else if (spikes) k_step<P, MODE, true, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else if (P::LIGHT && MODE != 0) k_step<P, MODE, false, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else k_step<P, MODE, false, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else {
+    // light consumers without spikes run at the HBM write rate: twice the producer warps (only instantiated for them)
+    if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, false, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+    else k_step<P, MODE, false, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   return 0;
