@@ -339,10 +339,11 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        Ag.update(drift_velocity=drift)          # H2D: A*2*8 B from pinned host memory, every step
+        Ag.update(drift_velocity=drift)          # H2D: A*2*8 B read from pinned host memory by the motion kernel, every step
         for ns in pops:
             ns.update()                          # first population: fused motion + rates kernel; others: rates
-        p = Ag.pos                               # D2H: A*2*8 B (the step's result), blocking
+        p = Ag.pos                               # D2H: A*2*8 B posted to pinned host memory by the motion kernel; blocks
+                                                 # until the whole step (motion + rates) has finished
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist is not None:

@@ -105,7 +105,9 @@ typedef struct {
   double drift_to_random_strength_ratio;        /* Agent.update arg */
 } riab_motion_params;
 
-/* Optional per-step inputs / parity taps (device pointers, may be NULL). */
+/* Optional per-step inputs / parity taps (device pointers, may be NULL).  drift_velocity and pos_mirror may
+ * also point to page-locked HOST memory (unified addressing): the motion step then reads the commands and posts the
+ * new positions over the bus itself, without separate copies (1 MB each way at 65 536 agents). */
 typedef struct {
   const double* drift_velocity;   /* (A,2) Agent.update(drift_velocity=...), Agent.py:324-341 */
   const double* xi;               /* (A,2) injected standard normals for the two OU draws
@@ -118,6 +120,7 @@ typedef struct {
   int32_t* n_iters;               /* (A) number of collision-loop iterations executed */
   float* history_row;             /* (A,8) float32: pos.xy, vel.xy (measured), head_direction.xy,
                                      rot_vel, distance_travelled -- Agent.save_to_history, Agent.py:509-521 */
+  double* pos_mirror;             /* (A,2) second copy of the new positions (e.g. a pinned host buffer) or NULL */
 } riab_step_io;
 
 #define RIAB_MAX_REC_ITERS 4

@@ -118,6 +118,8 @@ class Agent:
         self._pending = None
         self._tape = None
         self._rec = None
+        self._pos_mirror_current = False
+        self._drift_keep = None
 
         # ---- initial state (Agent.py:523-535, :136-141), sampled on the host like the reference
         pos = Environment.sample_positions(n=A, method="random")
@@ -195,7 +197,10 @@ class Agent:
             buf = self._pinned.get(name)
             if buf is None:
                 buf = self._pinned[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            buf.copy_(t, non_blocking=True)
+            if not (name == "pos" and self._pos_mirror_current):
+                # (the motion kernels post the new positions straight into the pinned `pos` buffer:
+                # riab_step_io.pos_mirror -- no copy needed while that mirror is current)
+                buf.copy_(t, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             arr = buf.numpy()
             arr.flags.writeable = False
@@ -210,6 +215,8 @@ class Agent:
         import torch
         self._flush_pending()
         self._shadow.pop(name, None)
+        if name == "pos":
+            self._pos_mirror_current = False
         arr = np.asarray(value, dtype=np.float64)
         if name in _VEC:
             arr = np.broadcast_to(arr.reshape(-1, 2) if arr.size == 2 * self.n_agents else arr, (self.n_agents, 2))
@@ -270,9 +277,15 @@ class Agent:
             assert tuple(d.shape) in ((2,), (self.n_agents, 2)), "drift_velocity must have shape (Env.D,) or (n_agents, Env.D)"
             if d.dtype != torch.float64:
                 d = d.to(torch.float64)
-            # host -> device on the current stream (asynchronous when the host buffer is pinned)
-            self._drift_dev.copy_(d.expand(self.n_agents, 2), non_blocking=True)
-            io.drift_velocity = self._drift_dev.data_ptr()
+            if (not d.is_cuda) and d.is_pinned() and d.is_contiguous() and tuple(d.shape) == (self.n_agents, 2):
+                # page-locked host commands: the motion kernel reads them over the bus itself (unified addressing),
+                # no staging copy.  Like a non_blocking copy, the buffer must not change before the step has run.
+                self._drift_keep = d
+                io.drift_velocity = d.data_ptr()
+            else:
+                # host -> device on the current stream (asynchronous when the host buffer is pinned)
+                self._drift_dev.copy_(d.expand(self.n_agents, 2), non_blocking=True)
+                io.drift_velocity = self._drift_dev.data_ptr()
         io.xi = None
         self._tape = None
         xi = kwargs.get("_xi", None)          # parity tap: injected standard normals (oracle mode A)
@@ -297,6 +310,15 @@ class Agent:
         if self.save_history:
             io.history_row = self._history_row_ptr()
             self._t_hist.append(self.t)
+        io.pos_mirror = None
+        if self.n_agents > self._SHADOW_MAX:
+            # large batches: the motion step also posts the new positions into the pinned host buffer that
+            # `Ag.pos` hands out, so reading them back after the step costs a stream sync and no copy
+            buf = self._pinned.get("pos")
+            if buf is None:
+                buf = self._pinned["pos"] = torch.empty((self.n_agents, 2), dtype=torch.float64).pin_memory()
+            io.pos_mirror = buf.data_ptr()
+            self._pos_mirror_current = True
         self._pending = True
         self._step += 1
 
@@ -328,6 +350,10 @@ class Agent:
         # stage everything exactly like one update() would, then hand the loop to C
         self.update(**kwargs)
         self._pending = None
+        # a device-resident loop needs no per-step host mirror of the positions (1 MB of bus writes per step at
+        # 65 536 agents); reads after the run copy once
+        self._io.pos_mirror = None
+        self._pos_mirror_current = False
         dt = self.dt
         first_step = self._step - 1
         A = self.n_agents

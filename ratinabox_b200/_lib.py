@@ -40,7 +40,7 @@ class MotionParams(C.Structure):
 class StepIO(C.Structure):
     _fields_ = [("drift_velocity", C.c_void_p), ("xi", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("collision_mask", C.c_void_p), ("first_hit", C.c_void_p), ("n_iters", C.c_void_p),
-                ("history_row", C.c_void_p)]
+                ("history_row", C.c_void_p), ("pos_mirror", C.c_void_p)]
 
 
 class PlaceCells(C.Structure):

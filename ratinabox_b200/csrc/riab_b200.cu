@@ -107,6 +107,7 @@ __device__ __forceinline__ void agent_update_one(const riab_agents& ag, const ri
                    n1, n2, has_drift, drx, dry, f1, f2,
                    mask, fh, ni);
   store_agent(ag, i, s);
+  if (io.pos_mirror != nullptr) *reinterpret_cast<double2*>(io.pos_mirror + 2 * (size_t)i) = make_double2(s.px, s.py);
   if (io.history_row != nullptr) store_history_row(io.history_row + 8 * (size_t)i, s);
 }
 

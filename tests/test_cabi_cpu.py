@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.MotionParams) == 14 * 8
     assert C.sizeof(_lib.Agents) == 10 * 8
     assert C.sizeof(_lib.Env) == 8 + 4 + 4 + 32 + 4 + 4 + 8 + 4 + 4   # + boundary_mode, n_hole_walls, scale, hole_wall0, reserved
-    assert C.sizeof(_lib.StepIO) == 8 * 8
+    assert C.sizeof(_lib.StepIO) == 9 * 8
 
 
 def test_place_pack_matches_numpy():

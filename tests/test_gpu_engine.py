@@ -223,3 +223,78 @@ def test_get_state_all_and_errors():
         rb.Environment({"dimensionality": "1D"})
     with pytest.raises(AssertionError):          # boundary cells only possible with solid boundary conditions
         rb.BoundaryVectorCells(rb.Agent(rb.Environment({"boundary_conditions": "periodic"})), {"n": 4})
+
+
+def test_mode_b_statistics_of_the_production_stream(golden):
+    """SURVEY section 8(c) mode B: the Philox-driven GPU motion is compared STATISTICALLY with the reference's
+    process (config 1: default box, defaults, dt = 10 ms): Rayleigh speeds with scale speed_mean, an
+    Ornstein-Uhlenbeck rotational velocity with std 120 deg/s and coherence 0.08 s, the speed process's coherence
+    0.7 s, uniform-ish occupancy; the live reference's own 600-step run (native_c1.npz) lies within the batch's spread."""
+    import ratinabox_b200 as rb
+    np.random.seed(2)
+    A, steps = 2048, 1500
+    E = rb.Environment()
+    Ag = rb.Agent(E, {"dt": 0.01, "n_agents": A, "seed": 77})
+    Ag.run(steps)
+    h = Ag.get_history_arrays()
+    vel, rot, pos = h["vel"][300:], h["rot_vel"][300:], h["pos"][300:]
+    speed = np.linalg.norm(vel, axis=-1)
+    far = (np.minimum(pos, 1 - pos).min(axis=-1) > 0.15)               # away from walls: no repulsion / bounce effects
+    # Rayleigh(sigma = speed_mean = 0.08) away from the walls: mean sigma*sqrt(pi/2), second moment 2 sigma^2 (Agent.py:298-312)
+    assert abs(speed[far].mean() - 0.08 * np.sqrt(np.pi / 2)) < 0.002
+    assert abs(np.sqrt((speed[far] ** 2).mean() / 2) - 0.08) < 0.002
+    # over the whole box the walls slow the agents (repulsion, bounces at half speed): the NumPy port of the reference
+    # measures 0.0937 +- 0.003 (12 agents x 2200 steps); the batch 0.0917
+    assert 0.088 < speed.mean() < 0.098
+    # OU rotational velocity: std sigma = 120 deg/s, autocorrelation exp(-lag/tau), tau = 0.08 s   (Agent.py:287-296)
+    r = rot[:-8][far[:-8] & far[8:]]
+    r8 = rot[8:][far[:-8] & far[8:]]
+    assert abs(r.std() - np.radians(120)) < 0.05 * np.radians(120)
+    assert abs(np.mean(r * r8) / r.var() - np.exp(-0.08 / 0.08)) < 0.05
+    # speed coherence 0.7 s: correlation of the underlying normal at lag 0.7 s is exp(-1); the Rayleigh transform
+    # keeps it close to that
+    s0, s1 = speed[:-70], speed[70:]
+    c = np.mean((s0 - s0.mean()) * (s1 - s1.mean())) / speed.var()
+    assert 0.25 < c < 0.45
+    # occupancy: inside, thigmotaxis 0.5 keeps a bias to the walls but no cell of a 5 x 5 grid is empty or dominant
+    assert (pos > 0).all() and (pos < 1).all()
+    H, _, _ = np.histogram2d(pos[..., 0].ravel(), pos[..., 1].ravel(), bins=5, range=[[0, 1], [0, 1]])
+    H = H / H.sum()
+    assert H.min() > 0.02 and H.max() < 0.08
+    # the live reference's own run (600 steps of ONE agent): its mean speed lies within the spread of the batch's agents
+    g = golden("native_c1.npz")
+    ref_speed = np.linalg.norm(g["vel"], axis=-1).mean()
+    per_agent = speed[:600].mean(axis=0)
+    assert per_agent.min() < ref_speed < per_agent.max()
+
+
+def test_zero_copy_host_io_equals_staged_copies():
+    """Page-locked host buffers: a pinned drift_velocity tensor is read by the motion kernel directly and, for batches
+    above the shadow limit, the new positions are posted into the pinned buffer `Ag.pos` hands out
+    (riab_step_io.pos_mirror).  Both must equal the staged-copy path bit for bit, step after step."""
+    import torch
+    import ratinabox_b200 as rb
+    A = 5000                                      # > Agent._SHADOW_MAX: pinned read-only views
+    outs = []
+    for pinned in (False, True):
+        np.random.seed(12)
+        E = rb.Environment()
+        E.add_wall([[0.5, 0.0], [0.5, 0.6]])
+        Ag = rb.Agent(E, {"dt": 0.02, "n_agents": A, "seed": 4})
+        PCs = rb.PlaceCells(Ag, {"n": 32})
+        rs = np.random.RandomState(0)
+        traj = []
+        for s in range(6):
+            cmd = 0.2 * rs.standard_normal((A, 2))
+            d = torch.as_tensor(cmd).pin_memory() if pinned else cmd
+            Ag.update(drift_velocity=d, drift_to_random_strength_ratio=2.0)
+            PCs.update()
+            p = Ag.pos
+            assert np.array_equal(p, Ag._s["pos"].cpu().numpy())        # the mirror IS the device state
+            traj.append(p.copy())
+        Ag.pos = traj[0]                                                  # a user write invalidates the mirror
+        assert np.array_equal(Ag.pos, traj[0])
+        Ag.update(); PCs.update()
+        traj.append(Ag.pos.copy())
+        outs.append((np.array(traj), PCs.firingrate.copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
