@@ -537,8 +537,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
     const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);   // float64 inner walls (exact fall-back)
     // Fast pair loop: rows are 16-byte aligned and every thread owns 4 existing cells or none, the
     // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
-    const bool fast = (chunks == 1) && !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
-    const bool act = cell0 < pc.n_cells;
+    const bool fast = !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
     const bool full = (pc.n_cells == pc.n_pad);          // no padding cells at all
     const float q16 = out.dt * 65536.0f;
     for (long long q = 0; q < nq; ++q) {
@@ -546,8 +545,19 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
       const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * TA;
       const int na = s_slot[s].na;
-      if (chunks == 1) {
-        if (!idle) {
+      // chunks == 1: the cell registers loaded above serve every slot; more than 2048 cells: the 16 warps walk
+      // the cells in chunks of 2048 and reload their registers per chunk (G = 1, all warps on the same agents)
+      for (int ch = 0; ch < chunks; ++ch) {
+        if (chunks > 1) {
+          cell0 = (ch * NC + ctid) * 4;
+          if (cell0 >= pc.n_pad) continue;              // warp-uniform (n_pad is a multiple of 128)
+          P::load(regs, pc, cell0);
+          tail_init(tc, out, cell0, pc.n_cells);
+        } else if (idle) {
+          continue;
+        }
+        const bool act = cell0 < pc.n_cells;
+        {
           // agents are taken in pairs (2p, 2p+1) so that one Philox call feeds the spikes of both
           RowCursor rc;
           cursor_init(rc, out, tc, a0 + 2 * grp);
@@ -611,24 +621,6 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
             }
             cursor_advance(rc, stride);
             recp += 2 * G * P::REC;
-          }
-        }
-      } else {
-        for (int ch = 0; ch < chunks; ++ch) {
-          cell0 = (ch * NC + ctid) * 4;
-          if (cell0 < pc.n_pad) {                       // warp-uniform (n_pad is a multiple of 128)
-            P::load(regs, pc, cell0);
-            tail_init(tc, out, cell0, pc.n_cells);
-            RowCursor rc;
-            cursor_init(rc, out, tc, a0);
-            const RowStride stride = make_stride(out, 1);
-            for (int a = 0; a < na; ++a) {
-              float o[4];
-              bool dummy = false;
-              P::template rates4<false>(o, regs, pc, cell0, s_slot[s].rec[a], inner_s, dummy);
-              finish4<SPIKES, NOISE>(o, out, tc, rc);
-              cursor_advance(rc, stride);
-            }
           }
         }
       }

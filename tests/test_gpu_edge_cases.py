@@ -29,7 +29,7 @@ def _make(rb, A, walls, seed=4, **agent):
     return E, Ag
 
 
-@pytest.mark.parametrize("A,N,k", [(1, 1, 0), (3, 5, 1), (33, 130, 2), (100, 1025, 3), (70, 2500, 0), (31, 257, 7)])
+@pytest.mark.parametrize("A,N,k", [(1, 1, 0), (3, 5, 1), (33, 130, 2), (100, 1025, 3), (70, 2500, 0), (31, 257, 7), (64, 4096, 2)])
 def test_ragged_sizes_all_wall_templates(A, N, k):
     import ratinabox_b200 as rb
     walls = _walls(k)
