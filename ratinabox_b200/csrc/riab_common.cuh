@@ -148,6 +148,21 @@ RIAB_DEV float ex2f(float x) {
   return y;
 }
 
+// 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5*2^23 trick,
+// degree-5 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.5e-7, ex2.approx's own is ~2e-7), exponent
+// added in the integer domain.  11 instructions; used next to MUFU.EX2 where the MUFU pipe is the limit.
+RIAB_DEV float ex2_fma(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(1.3400433e-3f, f, 9.6760374e-3f);
+  p = fmaf(p, f, 5.5503272e-2f);
+  p = fmaf(p, f, 2.4022107e-1f);
+  p = fmaf(p, f, 6.9314718e-1f);
+  p = fmaf(p, f, 1.0000001f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // NumPy's floating remainder (result takes the sign of the divisor) -- np.mod
 RIAB_DEV double np_mod(double x, double m) {
   double r = fmod(x, m);
