@@ -299,6 +299,8 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
 
 /* Number of kernels launched by the library since load (bench.py "gpu_launches"). */
 int64_t riab_launch_count(void);
+/* cudaStreamSynchronize(stream): lets a host binding wait for its steps without another CUDA binding. */
+int riab_stream_synchronize(void* stream);
 
 /* -------------------------------------------------- host-buffer (e2e) entry
  * The reference-facing call with HOST buffers: copies drift (may be NULL) to the

@@ -120,6 +120,7 @@ class Agent:
         self._rec = None
         self._pos_mirror_current = False
         self._drift_keep = None
+        self._env_key = None
 
         # ---- initial state (Agent.py:523-535, :136-141), sampled on the host like the reference
         pos = Environment.sample_positions(n=A, method="random")
@@ -160,6 +161,10 @@ class Agent:
 
     def _env_struct(self):
         env = self.Environment
+        key = (env._walls_signature(), env.boundary_conditions)
+        if key == self._env_key:
+            return self._env_c
+        self._env_key = key
         walls = env.walls_device(self.device)
         e = self._env_c
         e.walls_dev = walls.data_ptr()
@@ -174,8 +179,16 @@ class Agent:
         return e
 
     def _stream(self):
+        """The caller's current CUDA stream on this device (raw handle; torch's C accessor is ~20x cheaper than
+        building a torch.cuda.Stream object on the per-step path)."""
         import torch
+        raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if raw is not None:
+            return C.c_void_p(raw(self.device.index))
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _sync_stream(self):
+        _lib.check(self._lib.riab_stream_synchronize(self._stream()))
 
     def _squeeze(self, name, arr):
         if self.n_agents != 1:
@@ -201,7 +214,7 @@ class Agent:
                 # (the motion kernels post the new positions straight into the pinned `pos` buffer:
                 # riab_step_io.pos_mirror -- no copy needed while that mirror is current)
                 buf.copy_(t, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
+            self._sync_stream()
             arr = buf.numpy()
             arr.flags.writeable = False
             return arr
@@ -392,7 +405,7 @@ class Agent:
         for ns in self.Neurons:
             last = (ns._hist_rows + n_steps - 1) % ns._hist_cap
             ns._hist_rows += n_steps
-            ns._last_row = ns._hist[last]
+            ns._last_slot = last
             if ns.save_history:
                 ns._t_hist.extend(ts)
 

@@ -73,7 +73,7 @@ class Neurons:
         self._spk = None
         self._noise = None
         self._t_hist = []
-        self._last_row = None
+        self._last_slot = None
         self._history_view = _HistoryView(self)
         self._last_history_array_cache_time = None
         self._history_arrays = {}
@@ -127,7 +127,9 @@ class Neurons:
             self._hist, self._spk, self._hist_cap = new, spk, 2 * cap
         slot = self._hist_rows % self._hist_cap
         self._hist_rows += 1
-        return self._hist[slot], self._spk[slot]
+        self._last_slot = slot
+        # raw pointers of the slot (no tensor views on the per-step path)
+        return (self._hist.data_ptr() + slot * row_bytes, self._spk.data_ptr() + slot * A * words * 4)
 
     def _reserve_history(self, n_more):
         """Grow the ring (within history_bytes_limit) so n_more further rows fit without wrapping if possible."""
@@ -155,10 +157,10 @@ class Neurons:
     def _fill_out_structs(self, row, spk):
         ag = self.Agent
         out, nz = self._out, self._nz
-        out.rates_row = row.data_ptr() if row is not None else None
+        out.rates_row = row
         out.ld = self._ld()
         want_spikes = bool(self.save_history and self.save_spikes)
-        out.spikes_row = spk.data_ptr() if (want_spikes and spk is not None) else None
+        out.spikes_row = spk if (want_spikes and spk is not None) else None
         out.noise_state = None
         if self.noise_std != 0:
             if self._noise is None:
@@ -179,7 +181,6 @@ class Neurons:
         ag = self.Agent
         cells = self._cells()
         row, spk = self._row_buffers()
-        self._last_row = row
         out, nz = self._fill_out_structs(row, spk)
         if ag._take_pending():
             _lib.check(self._lib.riab_step_fused(C.byref(ag._agents_c), C.byref(ag._env_struct()), C.byref(ag._mp),
@@ -226,9 +227,9 @@ class Neurons:
     # ------------------------------------------------------------------ firingrate
     @property
     def firingrate(self):
-        if self._last_row is None:
+        if self._last_slot is None:
             return np.zeros(self.n)
-        r = self._last_row[:, : self.n].cpu().numpy().astype(np.float64)
+        r = self._hist[self._last_slot][:, : self.n].cpu().numpy().astype(np.float64)
         return r[0] if self.Agent.n_agents == 1 else r
 
     # --------------------------------------------------------------------- history
@@ -329,8 +330,8 @@ class PlaceCells(Neurons):
 
     def _signature(self):
         env = self.Agent.Environment
-        return (hash(np.ascontiguousarray(self.place_cell_centres, dtype=np.float64).tobytes()),
-                hash(np.ascontiguousarray(self.place_cell_widths, dtype=np.float64).tobytes()),
+        return (np.ascontiguousarray(self.place_cell_centres, dtype=np.float64).tobytes(),
+                np.ascontiguousarray(self.place_cell_widths, dtype=np.float64).tobytes(),
                 env._walls_signature(), self.description, self.wall_geometry, float(self.min_fr), float(self.max_fr),
                 float(self.widths) if np.isscalar(self.widths) else None, self.n)
 
@@ -423,9 +424,9 @@ class GridCells(Neurons):
             raise ValueError(f"unknown GridCells description {self.description!r}")
 
     def _signature(self):
-        return (hash(np.ascontiguousarray(self.gridscales, dtype=np.float64).tobytes()),
-                hash(np.ascontiguousarray(self.phase_offsets, dtype=np.float64).tobytes()),
-                hash(np.ascontiguousarray(self.w, dtype=np.float64).tobytes()),
+        return (np.ascontiguousarray(self.gridscales, dtype=np.float64).tobytes(),
+                np.ascontiguousarray(self.phase_offsets, dtype=np.float64).tobytes(),
+                np.ascontiguousarray(self.w, dtype=np.float64).tobytes(),
                 self.description, float(self.width_ratio), float(self.min_fr), float(self.max_fr))
 
     def _pack(self):
@@ -516,7 +517,7 @@ class BoundaryVectorCells(Neurons):
         self._scratch = None
 
     def _signature(self):
-        return tuple(hash(np.ascontiguousarray(a, dtype=np.float64).tobytes()) for a in (
+        return tuple(np.ascontiguousarray(a, dtype=np.float64).tobytes() for a in (
             self.tuning_distances, self.tuning_angles, self.sigma_distances, self.sigma_angles, self.test_angles,
             self.test_directions)) + (float(self.min_fr), float(self.max_fr), self.reference_frame)
 
@@ -652,7 +653,7 @@ class ObjectVectorCells(BoundaryVectorCells):
 
     def _signature(self):
         env = self.Agent.Environment
-        return tuple(hash(np.ascontiguousarray(a, dtype=np.float64).tobytes()) for a in (
+        return tuple(np.ascontiguousarray(a, dtype=np.float64).tobytes() for a in (
             self.tuning_distances, self.tuning_angles, self.sigma_distances, self.sigma_angles,
             np.asarray(self.tuning_types, dtype=np.float64), env.objects["objects"],
             np.asarray(env.objects["object_types"], dtype=np.float64))) + (

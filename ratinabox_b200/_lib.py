@@ -103,6 +103,7 @@ SYMBOLS = {
     "riab_abi_version": (C.c_int, []),
     "riab_last_error": (C.c_char_p, []),
     "riab_launch_count": (C.c_int64, []),
+    "riab_stream_synchronize": (C.c_int, [C.c_void_p]),
     "riab_agent_update": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO), C.c_void_p]),
     "riab_place_pack_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "riab_place_pack": (C.c_int, [c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32, C.c_int32, c_double_p,

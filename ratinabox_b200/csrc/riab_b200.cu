@@ -1232,6 +1232,10 @@ extern "C" {
 int riab_abi_version(void) { return RIAB_ABI_VERSION; }
 const char* riab_last_error(void) { return g_err; }
 int64_t riab_launch_count(void) { return (int64_t)g_launches.load(); }
+int riab_stream_synchronize(void* stream) {
+  RIAB_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
 
 int riab_agent_update(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
                       const riab_step_io* io, void* stream) {
