@@ -378,7 +378,7 @@ def main():
         except Exception:
             pass
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # a reported baseline, timed at N=1 only
         per = {"c2": 4000, "c2e": 5000, "c3": 5000, "c4": 800, "c5": 600}[args.workload]
         v, wall = cpu_port_rate(args.workload, per, 1)
         cpu_baseline = {"value": v, "unit": "agent-steps/s", "cores": 1, "kind": "port",
