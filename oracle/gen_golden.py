@@ -450,8 +450,86 @@ def gen_ovc():
     print("ovc.npz", os.path.getsize(os.path.join(GOLD, "ovc.npz")) // 1024, "KiB")
 
 
+# Agent parameter / keyword variants of Agent.update (Agent.py:268-521): (constructor params, update kwargs)
+PARAM_VARIANTS = {
+    "speed_std0": ({"speed_std": 0.0}, {}),                                   # Agent.py:310-311: s' = speed_mean
+    "thigmotaxis0": ({"thigmotaxis": 0.0}, {}),                               # spring only
+    "thigmotaxis1": ({"thigmotaxis": 1.0}, {}),                               # conveyor belt only
+    "no_repel": ({"wall_repel_strength": 0.0}, {}),                           # Agent.py:359-360: skipped
+    "strong_repel": ({"wall_repel_strength": 2.5, "wall_repel_distance": 0.2}, {}),
+    "fast_head": ({"head_direction_smoothing_timescale": 0.005}, {}),         # tau_h <= dt: head = measured direction
+    "timescales": ({"speed_coherence_time": 0.1, "rotational_velocity_coherence_time": 0.3,
+                    "rotational_velocity_std": 3.0, "speed_mean": 0.2}, {}),
+    "kwargs": ({}, {"speed_mean": 0.3, "speed_coherence_time": 0.2, "rotational_velocity_std": 1.0,
+                    "rotational_velocity_coherence_time": 0.05, "rotational_velocity_drift": 0.7,
+                    "thigmotaxis": 0.8, "wall_repel_distance": 0.15, "wall_repel_strength": 1.5,
+                    "head_direction_smoothing_timescale": 0.4}),             # the kwarg quirks of :280-285, :302-311, :483-489
+    "kw_std0": ({"speed_std": 0.0}, {"speed_mean": 0.3}),                     # attribute speed_std, kwarg speed_mean
+    "dt_arg": ({}, {"dt": 0.05}),                                             # dt persists (:193-194)
+    "drift_weak": ({}, {"drift_ratio": 0.5}),
+    "drift_strong": ({"speed_mean": 0.15}, {"drift_ratio": 5.0}),
+}
+
+
+def gen_params():
+    """Single teacher-forced steps (zero jitter, injected normals) of the unmodified reference for every parameter /
+    keyword variant in PARAM_VARIANTS, 160 agents each in the two-wall box, half of them next to a wall."""
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox.Environment import Environment
+    from ratinabox.Agent import Agent
+    out = {}
+    rs = np.random.RandomState(77)
+    A = 160
+    Env0 = Environment()
+    for w in BOX_WALLS:
+        Env0.add_wall(w)
+    pos0 = rs.uniform(0.002, 0.998, size=(A, 2))
+    near = rs.choice(A, A // 2, replace=False)
+    wl = Env0.walls[rs.randint(0, len(Env0.walls), size=len(near))]
+    lam = rs.uniform(0, 1, size=(len(near), 1))
+    pos0[near] = np.clip(wl[:, 0] + lam * (wl[:, 1] - wl[:, 0]) + rs.normal(scale=4e-3, size=(len(near), 2)), 0.0005, 0.9995)
+    speed = rs.rayleigh(0.1, size=A) * rs.choice([1.0, 1.0, 5.0], size=A)
+    ang = rs.uniform(0, 2 * np.pi, size=A)
+    vel0 = speed[:, None] * np.stack((np.cos(ang), np.sin(ang)), axis=1)
+    rot0 = rs.normal(scale=2.0, size=A)
+    mv0 = vel0 + rs.normal(scale=0.01, size=(A, 2))
+    hd0 = mv0 / np.linalg.norm(mv0, axis=1, keepdims=True)
+    xi = rs.normal(size=(A, 2))
+    drift = rs.normal(scale=0.15, size=(A, 2))
+    out.update(pos0=pos0, vel0=vel0, rot0=rot0, mv0=mv0, hd0=hd0, xi=xi, drift=drift, walls=Env0.walls)
+    for name, (params, kw) in PARAM_VARIANTS.items():
+        Env = Environment()
+        for w in BOX_WALLS:
+            Env.add_wall(w)
+        Ag = Agent(Env, dict({"dt": 0.01}, **params))
+        kw = dict(kw)
+        ratio = kw.pop("drift_ratio", None)
+        res = {k: [] for k in ("pos", "vel", "rot", "mv", "mrot", "hd", "dist", "dclose")}
+        for a in range(A):
+            Ag.pos, Ag.velocity = pos0[a].copy(), vel0[a].copy()
+            Ag.rotational_velocity, Ag.measured_velocity = float(rot0[a]), mv0[a].copy()
+            Ag.head_direction, Ag.distance_travelled, Ag.t, Ag.dt = hd0[a].copy(), 0.0, 0.0, 0.01
+            with mode_a(list(xi[a])):
+                if ratio is not None:
+                    Ag.update(drift_velocity=drift[a].copy(), drift_to_random_strength_ratio=ratio, **kw)
+                else:
+                    Ag.update(**kw)
+            res["pos"].append(Ag.pos.copy()); res["vel"].append(Ag.velocity.copy()); res["rot"].append(Ag.rotational_velocity)
+            res["mv"].append(Ag.measured_velocity.copy()); res["mrot"].append(Ag.measured_rotational_velocity)
+            res["hd"].append(Ag.head_direction.copy()); res["dist"].append(Ag.distance_travelled)
+            res["dclose"].append(Ag.distance_to_closest_wall)
+        for k, v in res.items():
+            out[f"{name}_{k}"] = np.array(v)
+        print(f"params[{name}]: dt after = {Ag.dt}, max speed out = {np.linalg.norm(np.array(res['vel']), axis=1).max():.3f}")
+    np.savez_compressed(os.path.join(GOLD, "modeA_params.npz"), **out)
+    print("modeA_params.npz", os.path.getsize(os.path.join(GOLD, "modeA_params.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["polygon"]:
+    if sys.argv[1:] == ["params"]:
+        gen_params()
+    elif sys.argv[1:] == ["polygon"]:
         gen_polygon()
     elif sys.argv[1:] == ["ovc"]:
         gen_ovc()
@@ -459,3 +537,4 @@ if __name__ == "__main__":
         main()
         gen_polygon()
         gen_ovc()
+        gen_params()

@@ -301,3 +301,44 @@ def test_object_vector_cells_stepped_with_the_agent(golden):
         h = P.get_history_arrays()
         assert h["firingrate"].shape == (8, A, P.n) and h["spikes"].shape == (8, A, P.n)
         assert np.array_equal(h["firingrate"][-1], P.firingrate)
+
+
+def _param_variants():
+    import test_oracle_golden as T
+    return T.PARAM_VARIANTS
+
+
+@pytest.mark.parametrize("name", sorted(_param_variants()))
+def test_agent_parameter_and_keyword_variants_golden(golden, name):
+    """The CUDA motion step against the live reference for every motion parameter / Agent.update keyword
+    (tests/golden/modeA_params.npz; same table as the oracle's test): positions and velocities to 1e-12."""
+    import ratinabox_b200 as rb
+    g = golden("modeA_params.npz")
+    params, kw = _param_variants()[name]
+    kw = dict(kw)
+    ratio = kw.pop("drift_ratio", None)
+    A = len(g["pos0"])
+    E = rb.Environment()
+    for w in OVC_WALLS:                                # the two-wall box of config 2
+        E.add_wall(w)
+    assert np.array_equal(E.walls, g["walls"])
+    Ag = rb.Agent(E, dict({"dt": 0.01, "n_agents": A}, **params))
+    Ag.pos, Ag.velocity, Ag.measured_velocity = g["pos0"], g["vel0"], g["mv0"]
+    Ag.rotational_velocity, Ag.head_direction = g["rot0"], g["hd0"]
+    Ag.distance_travelled = np.zeros(A)
+    if ratio is not None:
+        Ag.update(drift_velocity=g["drift"], drift_to_random_strength_ratio=ratio, _xi=g["xi"], **kw)
+    else:
+        Ag.update(_xi=g["xi"], **kw)
+    tol = {"pos": 1e-12, "vel": 1e-12, "rot": 1e-10, "mv": 1e-9, "mrot": 1e-6, "hd": 1e-10, "dist": 1e-12, "dclose": 1e-12}
+    got = {"pos": Ag.pos, "vel": Ag.velocity, "rot": Ag.rotational_velocity, "mv": Ag.measured_velocity,
+           "mrot": Ag.measured_rotational_velocity, "hd": Ag.head_direction, "dist": Ag.distance_travelled,
+           "dclose": Ag.distance_to_closest_wall}
+    for key in tol:
+        ref = g[f"{name}_{key}"]
+        if key == "dclose" and name == "no_repel":
+            continue                                   # Agent.py:359-360 returns before distance_to_closest_wall is set
+        err = np.abs(np.asarray(got[key]).reshape(ref.shape) - ref).max()
+        assert err <= tol[key], (name, key, err)
+    if name == "dt_arg":
+        assert Ag.dt == 0.05

@@ -263,3 +263,53 @@ def test_object_vector_cells(golden):
                              head_direction=(g["A_hd"] if ego else None))
         assert np.array_equal(fr, g[f"A_{k}"]), k
     assert (g["A_allo"] > 0.05).mean() > 0.01 and (g["A_fov"] > 0.05).mean() > 0.002
+
+
+BOX_WALLS = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]]]
+
+PARAM_VARIANTS = {          # (constructor params, update kwargs); same table as oracle/gen_golden.py
+    "speed_std0": ({"speed_std": 0.0}, {}),
+    "thigmotaxis0": ({"thigmotaxis": 0.0}, {}),
+    "thigmotaxis1": ({"thigmotaxis": 1.0}, {}),
+    "no_repel": ({"wall_repel_strength": 0.0}, {}),
+    "strong_repel": ({"wall_repel_strength": 2.5, "wall_repel_distance": 0.2}, {}),
+    "fast_head": ({"head_direction_smoothing_timescale": 0.005}, {}),
+    "timescales": ({"speed_coherence_time": 0.1, "rotational_velocity_coherence_time": 0.3,
+                    "rotational_velocity_std": 3.0, "speed_mean": 0.2}, {}),
+    "kwargs": ({}, {"speed_mean": 0.3, "speed_coherence_time": 0.2, "rotational_velocity_std": 1.0,
+                    "rotational_velocity_coherence_time": 0.05, "rotational_velocity_drift": 0.7,
+                    "thigmotaxis": 0.8, "wall_repel_distance": 0.15, "wall_repel_strength": 1.5,
+                    "head_direction_smoothing_timescale": 0.4}),
+    "kw_std0": ({"speed_std": 0.0}, {"speed_mean": 0.3}),
+    "dt_arg": ({}, {"dt": 0.05}),
+    "drift_weak": ({}, {"drift_ratio": 0.5}),
+    "drift_strong": ({"speed_mean": 0.15}, {"drift_ratio": 5.0}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PARAM_VARIANTS))
+def test_agent_parameter_and_keyword_variants(golden, name):
+    """Every motion parameter / Agent.update keyword the reference reads (Agent.py:280-285, :302-311, :353-355,
+    :483-489), including its quirks -- the attribute speed_std with the kwarg speed_mean, the overwritten
+    head_direction_smoothing_timescale kwarg, dt that persists: 160 teacher-forced steps per variant, bit for bit."""
+    g = golden("modeA_params.npz")
+    params, kw = PARAM_VARIANTS[name]
+    kw = dict(kw)
+    ratio = kw.pop("drift_ratio", None)
+    env = O.OracleEnvironment(walls=BOX_WALLS)
+    assert np.array_equal(env.walls, g["walls"])
+    for a in range(len(g["pos0"])):
+        oa = O.OracleAgent(env, g["pos0"][a], g["vel0"][a], dict({"dt": 0.01}, **params))
+        oa.rotational_velocity, oa.measured_velocity = float(g["rot0"][a]), g["mv0"][a].copy()
+        oa.head_direction = g["hd0"][a].copy()
+        rng = O.TapeRNG(agent_xi=g["xi"][a])
+        if ratio is not None:
+            oa.update(rng, drift_velocity=g["drift"][a].copy(), drift_to_random_strength_ratio=ratio, **kw)
+        else:
+            oa.update(rng, **kw)
+        for key, val in (("pos", oa.pos), ("vel", oa.velocity), ("rot", oa.rotational_velocity), ("mv", oa.measured_velocity),
+                         ("mrot", oa.measured_rotational_velocity), ("hd", oa.head_direction), ("dist", oa.distance_travelled),
+                         ("dclose", oa.distance_to_closest_wall)):
+            assert np.array_equal(np.asarray(val), g[f"{name}_{key}"][a]), (name, a, key)
+        if name == "dt_arg":
+            assert oa.dt == 0.05
