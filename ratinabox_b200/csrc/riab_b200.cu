@@ -299,7 +299,7 @@ struct PlacePolicy {
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
   static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
-    place_agent_record(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx);
+    place_agent_record(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx, c.fold ? c.lspan : 0.f);
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI>(r, c, cell0); }
   template <bool DEFER, int EXP = -1>
@@ -307,7 +307,8 @@ struct PlacePolicy {
                                                 const float* rec, uint32_t inner_s, bool& unsure) {
     place_rates4<WI, DESC, DEFER, EXP>(o, r, c, cell0, rec, inner_s, unsure);
   }
-  static __device__ __forceinline__ bool expanded(const Const& c) { return DESC == RIAB_PC_GAUSSIAN && c.expanded; }
+  // 0: direct form, 1: expanded exponent, 2: expanded with the [0, max_fr] scale folded into the exponent
+  static __device__ __forceinline__ int expanded(const Const& c) { return (DESC == RIAB_PC_GAUSSIAN && c.expanded) ? 1 + c.fold : 0; }
   static __device__ __forceinline__ int wall0(const Const& c) { return c.wall0; }
 };
 
@@ -329,7 +330,7 @@ struct GridPolicy {
                                                 uint32_t, bool&) {
     grid_rates4(o, r, c, rec);
   }
-  static __device__ __forceinline__ bool expanded(const Const&) { return false; }
+  static __device__ __forceinline__ int expanded(const Const&) { return 0; }
   static __device__ __forceinline__ int wall0(const Const&) { return 0; }
 };
 
@@ -350,7 +351,7 @@ struct OvcPolicy {
                                                 uint32_t, bool&) {
     ovc_rates4(o, r, c, rec);
   }
-  static __device__ __forceinline__ bool expanded(const Const&) { return false; }
+  static __device__ __forceinline__ int expanded(const Const&) { return 0; }
   static __device__ __forceinline__ int wall0(const Const&) { return 0; }
 };
 
@@ -570,7 +571,11 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
           uint32_t only = 0xffffffffu;       // pairs (by iteration index) the general loop below evaluates
           if (fast) {
             uint32_t redo = 0u;
-            if (P::expanded(pc)) {
+            const int ex = P::expanded(pc);
+            if (ex == 2) {
+              if (full) consume_pairs<P, SPIKES, true, 2>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
+              else consume_pairs<P, SPIKES, false, 2>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
+            } else if (ex == 1) {
               if (full) consume_pairs<P, SPIKES, true, 1>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
               else consume_pairs<P, SPIKES, false, 1>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
             } else {
@@ -1053,6 +1058,8 @@ int make_place(const riab_place_cells* pc, const EnvK& env, PlaceConst& c) {
   c.expanded = (pc->description == RIAB_PC_GAUSSIAN && pc->wall_geometry != RIAB_GEOM_GEODESIC && !env.periodic &&
                 pc->k_uniform > 0.f && pc->k_uniform * pc->r2_max <= 10.0f) ? 1 : 0;
   c.kx = -pc->k_uniform;
+  c.fold = (c.expanded && pc->min_fr == 0.f && c.span > 0.f) ? 1 : 0;
+  c.lspan = c.fold ? log2f(c.span) : 0.f;
   c.periodic = env.periodic; c.scale = env.scale; c.scale_f = (float)env.scale; c.half_f = (float)(env.scale / 2);
   if (env.periodic && pc->wall_geometry != RIAB_GEOM_EUCLIDEAN)
     return fail(RIAB_ERR_INVALID, "line_of_sight / geodesic wall geometry only possible when the boundary conditions are solid (Neurons.py:907-921)");

@@ -30,6 +30,7 @@ constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
 constexpr int PLACE_WALL0 = 4;                               // float index of wall 0's float4
 constexpr int PLACE_POS64 = PLACE_WALL0 + 4 * PLACE_MAX_WI;  // float index of the float64 position
 constexpr int PLACE_REC = PLACE_POS64 + 4;                   // 40 floats = 160 B per agent
+constexpr float PLACE_PEN = 1.2676506002282294e30f;          // 2^100: pen * PLACE_PEN is >= 1e24 for every certain blocked pair
 constexpr float PLACE_QSCALE = 1048576.0f;                   // 2^20: q' = f_c * (-f_p * 2^20) never enters the band by magnitude
 
 RIAB_HD void wall_coords(double qx, double qy, double ax, double ay, double bx, double by, double& f, double& t) {
@@ -59,7 +60,8 @@ RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, cons
 // Per-agent record for the rate phase, from the float64 position.
 // inner = walls + 4*n_boundary (float64 endpoints), cxm/cym = box centre.
 RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, const double* __restrict__ inner,
-                                 int n_inner, int geometry, double cxm, double cym, float band, int expanded, float kx) {
+                                 int n_inner, int geometry, double cxm, double cym, float band, int expanded, float kx,
+                                 float lfold /* log2(span) when the scale is folded into the exponent, else 0 */) {
   float ep0 = 0.f, ep1 = 0.f;
   if (geometry == RIAB_GEOM_GEODESIC && n_inner >= 1) {
     // utils.get_distances_between(wall_edge, pos2)  (Environment.py:749-751)
@@ -68,7 +70,7 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
     ep1 = (float)sqrt(e1x * e1x + e1y * e1y);
   }
   const float pxf = (float)(px - cxm), pyf = (float)(py - cym);
-  if (expanded) ep0 = (float)((double)kx * ((double)pxf * pxf + (double)pyf * pyf));    // -k |p|^2 of the rounded position
+  if (expanded) ep0 = (float)((double)kx * ((double)pxf * pxf + (double)pyf * pyf) + (double)lfold);   // -k |p|^2 [+ log2 span]
   *reinterpret_cast<float4*>(rec) = make_float4(pxf, pyf, ep0, ep1);
   for (int j = 0; j < PLACE_MAX_WI; ++j) {
     float4 w = make_float4(-1.f, 2.f, -PLACE_QSCALE, 1.0e-6f);    // dummy wall: same side (q' < 0), X = -2, Y = 4
@@ -93,6 +95,8 @@ struct PlaceConst {                  // uniform per launch
   float band;                        // max of eps[]: one absolute band for all walls
   int expanded;                      // Gaussian with one common width: -k d^2 = a_c + (2k c).p - k|p|^2 (3 FMA-pipe ops)
   float kx;                          // -k = -log2(e)/(2 w^2) of that common width
+  int fold;                          // expanded and min_fr == 0: log2(max_fr) is added to the agent's -k|p|^2 term, no final FFMA
+  float lspan;                       // log2(max_fr - min_fr)
   const float* packed;               // device
   const double* centres64;           // device (N,2)
   int periodic;                      // wrap centre->agent vectors (Environment.py:670-675)
@@ -206,10 +210,11 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     //   X = M'/b = fma(a, t_p/b, t_c),  Y = (|D|-M')/b = fma(a, (1-t_p)/b, 1-t_c),  m3 = min(X, Y, q')
     // is 2 FFMA + 1 FMUL + 1 FMNMX3, and blocked <=> m3 > 0.
     // |m3| below band/b => the sign of m3 is not certain in float32: re-evaluate in float64.
-    // The select is arithmetic: pen = saturate(2^126 * max_j m3_j) is exactly 1 for a positive normal
-    // number and 0 otherwise (NaN included).
-    float worst[4] = {-1.f, -1.f, -1.f, -1.f};            // max over walls of m3
+    // The select is arithmetic: pen = max(0, max_j m3_j) (one FMNMX3 for two walls; NaN -> 0) enters the exponent /
+    // the squared distance multiplied by 2^100: any pen above the band (>= ~1e-6 / b) makes the rate exactly 0.
+    float worst[4] = {0.f, 0.f, 0.f, 0.f};                // max(0, max over walls of m3)
     bool unsure = DEFER ? unsure_io : false;
+    float m3_prev[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < WI; ++j) {
       const float4 pw = *reinterpret_cast<const float4*>(rec + PLACE_WALL0 + 4 * j);
@@ -220,13 +225,15 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
         const float X = fmaf(a, pw.x, r.tc[j][i]);
         const float Y = fmaf(a, pw.y, r.tq[j][i]);
         m3[i] = fminf(fminf(X, Y), fc * pw.z);
-        worst[i] = (j == 0) ? m3[i] : fmaxf(worst[i], m3[i]);
+        if ((j & 1) == 1) worst[i] = fmaxf(fmaxf(worst[i], m3[i]), m3_prev[i]);   // pairs of walls: one FMNMX3
+        else if (j == WI - 1) worst[i] = fmaxf(worst[i], m3[i]);                                    // odd wall count: the last one
+        m3_prev[i] = m3[i];
       }
       const float am = fminf(fminf(fminf(fabsf(m3[0]), fabsf(m3[1])), fabsf(m3[2])), fabsf(m3[3]));
       unsure = unsure || (am < pw.w);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pen[i] = __saturatef(worst[i] * 8.5070591730234616e37f);
+    for (int i = 0; i < 4; ++i) pen[i] = worst[i];
     if (DEFER) unsure_io = unsure;
     else if (unsure) {                                   // rare: redo the group's flags with the reference's float64 test
       const unsigned m = place_blocked_exact4<WI>(c.centres64, c.n_cells, c.n_inner, cell0,
@@ -238,14 +245,15 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
   // ---- Gaussian with one common width, expanded:  -k|c-p|^2 = (-k|c|^2 - k|p|^2) + (2k cx) px + (2k cy) py.
   // 1 FADD + 2 FFMA per rate on per-cell registers (2k cx, 2k cy, -k|c|^2); only used when k * r2_max <= 10,
   // where the cancellation costs < 4e-6 relative (make_place).  Blocked pairs: exponent - 1e5 -> rate 0 (d = 1000).
-  if (DESC == RIAB_PC_GAUSSIAN && (EXP == 1 || (EXP < 0 && c.expanded))) {
+  if (DESC == RIAB_PC_GAUSSIAN && (EXP >= 1 || (EXP < 0 && c.expanded))) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float t = r.k[i] + r0.z;
       t = fmaf(r.cx[i], r0.x, t);
       t = fmaf(r.cy[i], r0.y, t);
-      if (WI > 0) t = fmaf(pen[i], -1.0e5f, t);
-      out[i] = fmaf(ex2f(t), c.span, c.min_fr);          // Neurons.py:978-980
+      if (WI > 0) t = fmaf(pen[i], -PLACE_PEN, t);
+      // Neurons.py:978-980; EXP == 2: min_fr == 0 and log2(span) already sits in the agent's -k|p|^2 term
+      out[i] = (EXP == 2 || (EXP < 0 && c.fold)) ? ex2f(t) : fmaf(ex2f(t), c.span, c.min_fr);
     }
     return;
   }
@@ -268,7 +276,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
   // final squared distances (blocked pairs get a distance >= 1000, Environment.py:730)
   float dd[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dd[i] = (WI > 0) ? fmaf(pen[i], 1.0e6f, d2[i]) : d2[i];
+  for (int i = 0; i < 4; ++i) dd[i] = (WI > 0) ? fmaf(pen[i], PLACE_PEN, d2[i]) : d2[i];
   const bool geodesic = (DESC < 0) && (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
   const int desc = (DESC >= 0) ? DESC : c.desc;
   if (desc != RIAB_PC_TOP_HAT && !geodesic) {

@@ -179,3 +179,31 @@ def test_more_rows_than_a_grid_dimension():
     assert np.abs(BVCs.firingrate[sel] - ref).max() <= 1e-5
     assert np.array_equal(OH.firingrate.sum(axis=1), np.ones(A))
     assert BVCs.get_history_arrays()["spikes"].shape == (1, A, 8)
+
+
+def test_population_parameters_beyond_the_defaults():
+    """Neurons-level parameters the fixtures keep at their defaults: BVC dtheta (T = 72 and 360 test angles),
+    GridCells width_ratio / shifted_cosines and PlaceCells profiles with [min_fr, max_fr] != [0, 1]."""
+    import ratinabox_b200 as rb
+    walls = _walls(3)
+    E, Ag = _make(rb, 40, walls)
+    pos = np.random.RandomState(2).uniform(0.03, 0.97, size=(300, 2))
+    env = O.OracleEnvironment(walls=walls)
+    rng = O.TapeRNG()
+    for dtheta in (5, 1):
+        B = rb.BoundaryVectorCells(Ag, {"n": 24, "dtheta": dtheta, "min_fr": 0.5, "max_fr": 3.0})
+        assert len(B.test_angles) == 360 // dtheta
+        ref = O.bvc_get_state(env, B.tuning_distances, B.tuning_angles, B.sigma_distances, B.sigma_angles, pos, rng,
+                              dtheta=dtheta, min_fr=0.5, max_fr=3.0)
+        assert np.abs(B.get_state(evaluate_at=None, pos=pos) - ref).max() <= 2.5e-5      # 1e-5 of the 2.5 Hz span
+    for desc in ("rectified_cosines", "shifted_cosines"):
+        G = rb.GridCells(Ag, {"n": 30, "description": desc, "width_ratio": 0.5, "min_fr": -1.0, "max_fr": 2.0})
+        ref = O.grid_cells_get_state(G.gridscales, G.phase_offsets, G.w, pos, desc, 0.5, -1.0, 2.0)
+        assert np.abs(G.get_state(evaluate_at=None, pos=pos) - ref).max() <= 3e-5
+    for desc in ("gaussian_threshold", "diff_of_gaussians", "top_hat"):
+        P = rb.PlaceCells(Ag, {"n": 40, "description": desc, "widths": 0.25, "min_fr": 1.0, "max_fr": 5.0,
+                               "wall_geometry": "line_of_sight"})
+        ref = O.place_cells_get_state(env, P.place_cell_centres, P.place_cell_widths, pos, rng, desc, "line_of_sight",
+                                      1.0, 5.0, scalar_width=0.25)
+        err = np.abs(P.get_state(evaluate_at=None, pos=pos) - ref)
+        assert err.max() <= 4e-5, (desc, err.max())
