@@ -45,7 +45,7 @@ constexpr int NT = 256;     // threads per CTA in the tile kernels
 constexpr int MAXW = 64;    // walls staged in shared memory
 constexpr int CELL_PAD = 128;  // packed per-cell arrays are padded to 4 cells x 32 lanes
 #ifndef RIAB_BVC_MUFU_TERMS
-#define RIAB_BVC_MUFU_TERMS 7
+#define RIAB_BVC_MUFU_TERMS 8
 #endif
 constexpr int BVC_MUFU_TERMS = RIAB_BVC_MUFU_TERMS;   // of 8 agents per thread: exponentials on the MUFU pipe (rest: ex2_fma)
 
@@ -858,8 +858,9 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
       for (int i = 0; i < 8; ++i) {
         const float u = fmaf(dv[i], sc, -mc);                    // (d - mu_d) * s
         // gaussian * von Mises.  The loop is bound by MUFU.EX2 (one warp instruction per 8 cycles against 4 issue
-        // slots per term): one of the eight agents takes the 11-instruction FMA-pipe exponential instead.
-        // Measured on c4 (us/step): 8 MUFU 558, 7+1 545, 6+2 580, 5+3 602.
+        // slots per term).  Moving some of the eight exponentials to the 11-instruction FMA-pipe form (ex2_fma,
+        // -DRIAB_BVC_MUFU_TERMS=7) measured 545 vs 558 us/step on c4 in a --split-compile build but 572 vs 559 in the
+        // default build (register allocation of the unrolled loop decides): all eight stay on MUFU.
         const float e = (i < BVC_MUFU_TERMS) ? ex2f(-u * u) : ex2_fma(-u * u);
         acc[i] = fmaf(e, vm, acc[i]);
       }
