@@ -371,6 +371,14 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_agent_step": bytes_unit, "kernel_ms": kernel_ms}
+    n_bvc = sum(n for k, n, _ in cl if k == "bvc")
+    if n_bvc:
+        # BoundaryVectorCells are bound by the special-function unit, not by HBM: one ex2 per (agent, cell, test angle)
+        # in the angular integral (T = 180) against 16 MUFU results per clock per SM (148 SMs at the sampled SM clock)
+        ex2 = A * n_bvc * 180 / (kernel_ms * 1e-3)
+        peak_ex2 = 148 * 16 * (clocks.get("sm_mhz") or 1965.0) * 1e6
+        roofline["mufu"] = {"achieved_ex2_per_s": ex2, "peak_ex2_per_s": peak_ex2, "frac": ex2 / peak_ex2,
+                            "note": "share of the whole step (motion, rays, other populations included) spent at the ex2 rate"}
     prof = os.path.join(ROOT, "profiles", f"traffic_{args.workload}.json")
     if os.path.exists(prof):
         try:
