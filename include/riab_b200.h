@@ -297,6 +297,28 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
              const riab_population* pops, int32_t n_pops, const riab_agent_history* hist, int64_t n_steps,
              void* stream);
 
+/* ------------------------------------------------------------ history analytics
+ * utils.bin_data_for_histogramming (utils.py:544-589) over the device history rings, pooled over agents and steps:
+ * count[ix, iy] = number of (step, agent) samples whose position falls into bin (ix, iy) -- np.histogram2d with the
+ * explicit edges np.arange(extent[0], extent[1] + dx, dx) (right-most edge inclusive, outside samples dropped) --
+ * and sum[(ix, iy), c] = the sum of cell c's rates over those samples.  rate map = sum / max(count, 1), laid out
+ * `.T[::-1, :]` by the host like the reference (Neurons.py:483-490 plot_rate_map(method="history"),
+ * Agent.py:956 plot_position_heatmap). */
+typedef struct {
+  const float* agent_ring;     /* (agent_ring_rows, A, 8) f32 history rows (pos.xy first), riab_agent_history.ring */
+  int32_t agent_ring_rows;
+  int32_t agent_row0;          /* ring row of the first step to use */
+  const float* rates_ring;     /* (rates_ring_rows, A, ld) f32 or NULL (occupancy only) */
+  int32_t rates_ring_rows;
+  int32_t rates_row0;
+  int64_t n_steps, n_agents, ld;
+  int32_t n_cells;
+  int32_t reserved;
+} riab_history_view;
+int riab_history_rate_maps(const riab_history_view* h, const double* edges_x_dev, int32_t n_edges_x,
+                           const double* edges_y_dev, int32_t n_edges_y, float* sum_dev /* ((nx*ny), ld), zeroed here */,
+                           float* count_dev /* (nx*ny), zeroed here */, void* stream);
+
 /* Number of kernels launched by the library since load (bench.py "gpu_launches"). */
 int64_t riab_launch_count(void);
 /* cudaStreamSynchronize(stream): lets a host binding wait for its steps without another CUDA binding. */

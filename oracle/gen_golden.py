@@ -526,8 +526,29 @@ def gen_params():
     print("modeA_params.npz", os.path.getsize(os.path.join(GOLD, "modeA_params.npz")) // 1024, "KiB")
 
 
+def gen_histogram():
+    """utils.bin_data_for_histogramming (utils.py:544-589) on random 2D data: plain, weighted and bin-count-normalised."""
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox import utils
+    rs = np.random.RandomState(8)
+    data = rs.uniform(-0.02, 1.52, size=(4000, 2)) * np.array([1.0, 0.66])        # some samples fall outside the extent
+    data[:5] = [[0.0, 0.0], [1.5, 1.0], [1.5, 0.3], [0.7, 1.0], [0.75, 0.5]]      # on edges / the right-most edges
+    w = rs.uniform(0, 3, size=4000)
+    extent, dx = [0.0, 1.5, 0.0, 1.0], 0.05
+    out = {"data": data, "weights": w, "extent": np.array(extent), "dx": dx}
+    out["plain"] = utils.bin_data_for_histogramming(data, extent, dx)
+    out["weighted"] = utils.bin_data_for_histogramming(data, extent, dx, weights=w)
+    hm, zb = utils.bin_data_for_histogramming(data, extent, dx, weights=w, norm_by_bincount=True, return_zero_bins=True)
+    out["normed"], out["zero_bins"] = hm, zb
+    np.savez_compressed(os.path.join(GOLD, "histogram.npz"), **out)
+    print("histogram.npz", out["plain"].shape, int(out["plain"].sum()), "of", len(data), "samples inside")
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["params"]:
+    if sys.argv[1:] == ["histogram"]:
+        gen_histogram()
+    elif sys.argv[1:] == ["params"]:
         gen_params()
     elif sys.argv[1:] == ["polygon"]:
         gen_polygon()
@@ -538,3 +559,4 @@ if __name__ == "__main__":
         gen_polygon()
         gen_ovc()
         gen_params()
+        gen_histogram()

@@ -624,6 +624,24 @@ def ovc_get_state(env, objects, object_types, tuning_distances, tuning_angles, s
     return fr * (max_fr - min_fr) + min_fr
 
 
+def bin_data_for_histogramming(data, extent, dx, weights=None, norm_by_bincount=False, return_zero_bins=False):
+    """utils.bin_data_for_histogramming, 2D branch (utils.py:574-589)."""
+    data = np.asarray(data, dtype=float)
+    bins_x = np.arange(extent[0], extent[1] + dx, dx)
+    bins_y = np.arange(extent[2], extent[3] + dx, dx)
+    heatmap, xedges, yedges = np.histogram2d(data[:, 0], data[:, 1], bins=[bins_x, bins_y], weights=weights)
+    zero_bins = None
+    if norm_by_bincount:
+        bincount, xedges, yedges = np.histogram2d(data[:, 0], data[:, 1], bins=[bins_x, bins_y])
+        zero_bins = (bincount == 0)
+        bincount[zero_bins] = 1
+        heatmap = heatmap / bincount
+    heatmap = heatmap.T[::-1, :]
+    if return_zero_bins:
+        return (heatmap, zero_bins.T[::-1, :])
+    return heatmap
+
+
 def diverging_radial_assembly(distance_range=(0.01, 0.2), angle_range=(0, 90), spatial_resolution=0.04, beta=5):
     """utils.create_diverging_radial_assembly, utils.py:1073-1112 -> (mu_d, mu_theta, sigma_d, sigma_theta)."""
     fov = [a * np.pi / 180 for a in angle_range]

@@ -487,6 +487,50 @@ class Agent:
             }
         return self._history_arrays
 
+    def _history_maps(self, dx, neurons=None):
+        """Occupancy counts (nx, ny) [and rate sums (nx*ny, ld)] of the history rings, binned on the device
+        (riab_history_rate_maps); the last min(rows available) steps of both rings are used."""
+        import torch
+        self._flush_pending()
+        env = self.Environment
+        dx = env.dx * 5 if dx is None else dx
+        ex = np.arange(env.extent[0], env.extent[1] + dx, dx)
+        ey = np.arange(env.extent[2], env.extent[3] + dx, dx)
+        n = min(self._hist_rows, self._hist_cap) if self._hist is not None else 0
+        if neurons is not None:
+            n = min(n, min(neurons._hist_rows, neurons._hist_cap) if neurons._hist is not None else 0)
+        nx, ny = len(ex) - 1, len(ey) - 1
+        count = torch.zeros(nx * ny, dtype=torch.float32, device=self.device)
+        ssum = None
+        if n > 0:
+            h = _lib.HistoryView()
+            h.agent_ring, h.agent_ring_rows = self._hist.data_ptr(), int(self._hist_cap)
+            h.agent_row0 = int((self._hist_rows - n) % self._hist_cap)
+            h.n_steps, h.n_agents = n, self.n_agents
+            if neurons is not None:
+                ssum = torch.zeros((nx * ny, neurons._ld()), dtype=torch.float32, device=self.device)
+                h.rates_ring, h.rates_ring_rows = neurons._hist.data_ptr(), int(neurons._hist_cap)
+                h.rates_row0 = int((neurons._hist_rows - n) % neurons._hist_cap)
+                h.ld, h.n_cells = neurons._ld(), neurons.n
+            exd = torch.as_tensor(ex, device=self.device)
+            eyd = torch.as_tensor(ey, device=self.device)
+            _lib.check(self._lib.riab_history_rate_maps(C.byref(h), exd.data_ptr(), len(ex), eyd.data_ptr(), len(ey),
+                                                        ssum.data_ptr() if ssum is not None else None, count.data_ptr(),
+                                                        self._stream()))
+        count = count.cpu().numpy().astype(np.float64).reshape(nx, ny)
+        if ssum is not None:
+            ssum = ssum.cpu().numpy().astype(np.float64)[:, : neurons.n].reshape(nx, ny, neurons.n)
+        elif neurons is not None:
+            ssum = np.zeros((nx, ny, neurons.n))
+        return count, ssum
+
+    def get_position_heatmap(self, dx=None):
+        """The occupancy heat-map of Agent.plot_position_heatmap (Agent.py:950-957):
+        ``utils.bin_data_for_histogramming(history positions, extent, dx)`` pooled over all agents, binned on the device.
+        dx defaults to 5 x Environment.dx like the reference."""
+        count, _ = self._history_maps(dx)
+        return count.T[::-1, :]
+
     def reset_history(self):                                        # Agent.py:537-541
         self._flush_pending()
         self._hist_rows = 0

@@ -265,6 +265,19 @@ class Neurons:
             self._history_arrays = {"t": np.array(self._t_hist[len(self._t_hist) - n:]), "firingrate": fr, "spikes": sp}
         return self._history_arrays
 
+    def get_history_rate_maps(self, dx=None, return_zero_bins=False):
+        """Rate maps from the history, the data of ``plot_rate_map(method="history")`` (Neurons.py:470-490): for every
+        cell ``utils.bin_data_for_histogramming(pos, extent, dx, weights=rate, norm_by_bincount=True)`` over the history of
+        ALL agents, binned on the device (riab_history_rate_maps).  Returns (n_cells, ny, nx) [and the empty-bin mask]."""
+        count, ssum = self.Agent._history_maps(dx, neurons=self)
+        zero = (count == 0)
+        c = count.copy()
+        c[zero] = 1
+        maps = (ssum / c[:, :, None]).transpose(2, 1, 0)[:, ::-1, :]            # per cell: heatmap.T[::-1, :]
+        if return_zero_bins:
+            return maps, zero.T[::-1, :]
+        return maps
+
     def reset_history(self):                                        # Neurons.py:689-692
         self._hist_rows = 0
         self._t_hist = []

@@ -72,6 +72,13 @@ class OvcCells(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class HistoryView(C.Structure):
+    _fields_ = [("agent_ring", C.c_void_p), ("agent_ring_rows", C.c_int32), ("agent_row0", C.c_int32),
+                ("rates_ring", C.c_void_p), ("rates_ring_rows", C.c_int32), ("rates_row0", C.c_int32),
+                ("n_steps", C.c_int64), ("n_agents", C.c_int64), ("ld", C.c_int64), ("n_cells", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class NeuronNoise(C.Structure):
     _fields_ = [("noise_std", C.c_float), ("noise_coherence_time", C.c_float), ("dt", C.c_float),
                 ("seed", C.c_uint64), ("step", C.c_uint64), ("id_offset", C.c_int64), ("population_id", C.c_int32)]
@@ -104,6 +111,8 @@ SYMBOLS = {
     "riab_last_error": (C.c_char_p, []),
     "riab_launch_count": (C.c_int64, []),
     "riab_stream_synchronize": (C.c_int, [C.c_void_p]),
+    "riab_history_rate_maps": (C.c_int, [C.POINTER(HistoryView), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "riab_agent_update": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO), C.c_void_p]),
     "riab_place_pack_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "riab_place_pack": (C.c_int, [c_double_p, c_double_p, C.c_int32, c_double_p, C.c_int32, C.c_int32, c_double_p,

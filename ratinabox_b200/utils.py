@@ -100,3 +100,25 @@ def create_diverging_radial_assembly(distance_range=(0.01, 0.2), angle_range=(0,
             mu_d.append(radius); mu_t.append(theta); sg_d.append(res); sg_t.append(res / radius)
         radius = (2 * radius + res + xi) / (2 - 1 / beta)      # next row just touches this one
     return mu_d, mu_t, sg_d, sg_t
+
+
+def bin_data_for_histogramming(data, extent, dx, weights=None, norm_by_bincount=False, return_zero_bins=False):
+    """ratinabox.utils.bin_data_for_histogramming, 2D branch (utils.py:544-589): np.histogram2d over
+    np.arange(extent[0], extent[1] + dx, dx) x np.arange(extent[2], extent[3] + dx, dx), optionally weighted and
+    divided by the bin count, returned `.T[::-1, :]`.  Host NumPy; the device path over the history rings is
+    ``Agent.get_position_heatmap`` / ``Neurons.get_history_rate_maps``."""
+    assert len(extent) == 4, "2D only"
+    data = np.asarray(data, dtype=float)
+    bins_x = np.arange(extent[0], extent[1] + dx, dx)
+    bins_y = np.arange(extent[2], extent[3] + dx, dx)
+    heatmap, _, _ = np.histogram2d(data[:, 0], data[:, 1], bins=[bins_x, bins_y], weights=weights)
+    zero_bins = None
+    if norm_by_bincount:
+        bincount, _, _ = np.histogram2d(data[:, 0], data[:, 1], bins=[bins_x, bins_y])
+        zero_bins = (bincount == 0)
+        bincount[zero_bins] = 1
+        heatmap = heatmap / bincount
+    heatmap = heatmap.T[::-1, :]
+    if return_zero_bins:
+        return (heatmap, zero_bins.T[::-1, :])
+    return heatmap

@@ -298,3 +298,31 @@ def test_zero_copy_host_io_equals_staged_copies():
         traj.append(Ag.pos.copy())
         outs.append((np.array(traj), PCs.firingrate.copy()))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_history_rate_maps_on_the_device():
+    """riab_history_rate_maps: occupancy and rate maps binned from the device history rings equal
+    utils.bin_data_for_histogramming (utils.py:544-589) applied to the same history on the host -- counts exactly
+    (same np.histogram2d edge semantics), rate sums to float32 atomics' accuracy."""
+    import ratinabox_b200 as rb
+    A, steps = 300, 40
+    E, Ag = make(rb, A, dt=0.05)
+    PCs = rb.PlaceCells(Ag, {"n": 20, "widths": 0.3})
+    GCs = rb.GridCells(Ag, {"n": 6})
+    Ag.run(steps)
+    hp = Ag.get_history_arrays()["pos"].reshape(-1, 2)                # (steps*A, 2), float32-rounded positions
+    dx = 0.1
+    heat = Ag.get_position_heatmap(dx=dx)
+    ref = O.bin_data_for_histogramming(hp, list(E.extent), dx)
+    assert heat.shape == ref.shape and np.array_equal(heat, ref) and heat.sum() == steps * A
+    for Ns in (PCs, GCs):
+        fr = Ns.get_history_arrays()["firingrate"].reshape(-1, Ns.n)
+        maps, zero = Ns.get_history_rate_maps(dx=dx, return_zero_bins=True)
+        assert maps.shape == (Ns.n,) + ref.shape
+        for c in range(Ns.n):
+            m, zb = O.bin_data_for_histogramming(hp, list(E.extent), dx, weights=fr[:, c], norm_by_bincount=True,
+                                                 return_zero_bins=True)
+            assert np.array_equal(zero, zb)
+            assert np.abs(maps[c] - m).max() <= 1e-5 * max(1.0, np.abs(m).max())
+    # the default bin width is 5 x Environment.dx like the reference's plots
+    assert Ag.get_position_heatmap().shape == (20, 20)

@@ -313,3 +313,17 @@ def test_agent_parameter_and_keyword_variants(golden, name):
             assert np.array_equal(np.asarray(val), g[f"{name}_{key}"][a]), (name, a, key)
         if name == "dt_arg":
             assert oa.dt == 0.05
+
+
+def test_bin_data_for_histogramming(golden):
+    """utils.bin_data_for_histogramming (utils.py:544-589) -- the oracle's restatement and the host mirror in
+    ratinabox_b200.utils against the live reference: plain, weighted, bin-count-normalised, zero-bin mask; samples on
+    bin edges, on the right-most edges and outside the extent."""
+    from ratinabox_b200 import utils as U
+    g = golden("histogram.npz")
+    data, w, extent, dx = g["data"], g["weights"], list(g["extent"]), float(g["dx"])
+    for f in (O.bin_data_for_histogramming, U.bin_data_for_histogramming):
+        assert np.array_equal(f(data, extent, dx), g["plain"])
+        assert np.array_equal(f(data, extent, dx, weights=w), g["weighted"])
+        hm, zb = f(data, extent, dx, weights=w, norm_by_bincount=True, return_zero_bins=True)
+        assert np.array_equal(hm, g["normed"]) and np.array_equal(zb, g["zero_bins"])
