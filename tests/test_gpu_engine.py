@@ -326,3 +326,42 @@ def test_history_rate_maps_on_the_device():
             assert np.abs(maps[c] - m).max() <= 1e-5 * max(1.0, np.abs(m).max())
     # the default bin width is 5 x Environment.dx like the reference's plots
     assert Ag.get_position_heatmap().shape == (20, 20)
+
+
+def test_step_fused_host_entry_point():
+    """riab_step_fused_host (the C-ABI e2e entry: HOST drift in, fused step, HOST positions out) equals the Python
+    API's own step bit for bit."""
+    import ctypes as C
+    import torch
+    import ratinabox_b200 as rb
+    from ratinabox_b200 import _lib
+    lib = _lib.load()
+    A = 200
+    res = []
+    for use_host_entry in (False, True):
+        E, Ag = make(rb, A)
+        PCs = rb.PlaceCells(Ag, {"n": 48})
+        rs = np.random.RandomState(5)
+        for s in range(3):
+            cmd = 0.1 * rs.standard_normal((A, 2))
+            if not use_host_entry:
+                Ag.update(drift_velocity=cmd); PCs.update()
+                pos = Ag.pos.copy()
+            else:
+                Ag.update()                                   # stages params / io exactly like a normal step
+                assert Ag._take_pending()
+                cells = PCs._cells()
+                row, spk = PCs._row_buffers()
+                out, nz = PCs._fill_out_structs(row, spk)
+                drift_host = torch.as_tensor(cmd).pin_memory()
+                staging = torch.empty((A, 2), dtype=torch.float64, device=Ag.device)
+                pos_host = torch.empty((A, 2), dtype=torch.float64).pin_memory()
+                _lib.check(lib.riab_step_fused_host(C.byref(Ag._agents_c), C.byref(Ag._env_struct()), C.byref(Ag._mp),
+                                                    C.byref(Ag._io), PCs._cells_kind, C.byref(cells), C.byref(nz), C.byref(out),
+                                                    drift_host.data_ptr(), staging.data_ptr(), pos_host.data_ptr(), Ag._stream()))
+                torch.cuda.synchronize()
+                PCs._t_hist.append(Ag.t)
+                pos = pos_host.numpy().copy()
+                assert np.array_equal(pos, Ag.pos)
+        res.append((pos, PCs.firingrate.copy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
