@@ -156,11 +156,19 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or (os.path.isdir(_build.CSRC) and _build.needs_build() and _have_nvcc()):
+    if not os.path.exists(path):
         if not _have_nvcc():
             raise ImportError(f"{path} is missing and nvcc is not available to build it: "
                               "ratinabox_b200 has no CPU fallback")
         _build.build()
+    elif os.path.isdir(_build.CSRC) and _build.needs_build():
+        # sources newer than the library (or file times scrambled by a copy): rebuilding takes minutes, so it is only
+        # done on request (__graft_entry__.build(), `python ratinabox_b200/_build.py`, RIAB_AUTO_REBUILD=1)
+        if os.environ.get("RIAB_AUTO_REBUILD") == "1" and _have_nvcc():
+            _build.build()
+        else:
+            import warnings
+            warnings.warn(f"{path} is older than its CUDA sources; run __graft_entry__.build() to rebuild")
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported

@@ -372,6 +372,8 @@ struct OvcPolicy {
 //   StepCfg<4>: 4 producer + 16 consumer warps (640 threads x 96 regs): heavy consumers
 //               (line-of-sight / spikes / noise) set the pace, so they get 104 registers and the 4
 //               producers run (spilling) in 64 -- their latency stays hidden (measured: r104 > r96 > r88).
+//               Do NOT raise the consumers to 112 (producers 56): the setmaxnreg.inc of the 16 consumer warps
+//               never completes (the kernel hangs) although 16*32*112 + 4*32*56 <= 65536 on paper.
 //   StepCfg<8>: 8 producer + 16 consumer warps (768 threads x 80 regs): light consumers (Euclidean
 //               Gaussian / grid cells without spikes) run at the HBM write rate, so the float64
 //               motion chain (~14 us per 32-agent tile) needs twice the producer warps to keep up.
