@@ -545,8 +545,44 @@ def gen_histogram():
     print("histogram.npz", out["plain"].shape, int(out["plain"].sum()), "of", len(data), "samples inside")
 
 
+def gen_api_defaults():
+    """default_params of the reference's classes on the path -> tests/golden/api_defaults.json (the host mirror must
+    accept the same keys with the same defaults)."""
+    import json
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox.Environment import Environment
+    from ratinabox.Agent import Agent
+    import importlib
+    RN = importlib.import_module("ratinabox.Neurons")      # (the package attribute `Neurons` is the class)
+
+    def clean(d):
+        out = {}
+        for k, v in d.items():
+            if isinstance(v, np.ndarray):
+                v = v.tolist()
+            elif isinstance(v, tuple):
+                v = list(v)
+            try:
+                json.dumps(v)
+            except TypeError:
+                v = repr(v)
+            out[k] = v
+        return out
+
+    ref = {"Environment": clean(Environment.default_params), "Agent": clean(Agent.default_params)}
+    for name in ("Neurons", "PlaceCells", "GridCells", "VectorCells", "BoundaryVectorCells", "FieldOfViewBVCs",
+                 "ObjectVectorCells", "FieldOfViewOVCs"):
+        ref[name] = clean(getattr(RN, name).default_params)
+    with open(os.path.join(GOLD, "api_defaults.json"), "w") as f:
+        json.dump(ref, f, indent=1, sort_keys=True)
+    print("api_defaults.json", {k: len(v) for k, v in ref.items()})
+
+
 if __name__ == "__main__":
-    if sys.argv[1:] == ["histogram"]:
+    if sys.argv[1:] == ["api"]:
+        gen_api_defaults()
+    elif sys.argv[1:] == ["histogram"]:
         gen_histogram()
     elif sys.argv[1:] == ["params"]:
         gen_params()
@@ -560,3 +596,4 @@ if __name__ == "__main__":
         gen_ovc()
         gen_params()
         gen_histogram()
+        gen_api_defaults()

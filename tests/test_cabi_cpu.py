@@ -225,3 +225,46 @@ def test_environment_mirror_polygon_and_holes_host_logic(golden):
     L = Environment(dict(cases["lroom"]))
     assert L.check_if_position_is_in_environment([0.25, 0.75]) and not L.check_if_position_is_in_environment([0.75, 0.75])
     assert not L.check_if_position_is_in_environment([0.5, 0.75])       # exactly on a boundary edge: not inside
+
+
+def test_mirror_default_params_match_the_reference():
+    """Every default_params key of the reference's classes on the path exists in the host mirror with the same default
+    (tests/golden/api_defaults.json, written from the live reference by oracle/gen_golden.py api); the mirror only ADDS
+    the batch-engine knobs."""
+    import json
+    import ratinabox_b200 as rb
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "api_defaults.json")))
+
+    def merged(cls):
+        d = {}
+        for c in reversed(cls.__mro__):
+            d.update(getattr(c, "default_params", {}))
+        return d
+
+    def same(a, b):
+        if isinstance(a, (list, tuple, np.ndarray)) or isinstance(b, (list, tuple, np.ndarray)):
+            return np.allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+        return a == b
+
+    pairs = {"Environment": (rb.Environment, ["Environment"]), "Agent": (rb.Agent, ["Agent"]),
+             "PlaceCells": (rb.PlaceCells, ["Neurons", "PlaceCells"]), "GridCells": (rb.GridCells, ["Neurons", "GridCells"]),
+             "BoundaryVectorCells": (rb.BoundaryVectorCells, ["Neurons", "VectorCells", "BoundaryVectorCells"]),
+             "FieldOfViewBVCs": (rb.FieldOfViewBVCs, ["Neurons", "VectorCells", "BoundaryVectorCells", "FieldOfViewBVCs"]),
+             "ObjectVectorCells": (rb.ObjectVectorCells, ["Neurons", "VectorCells", "ObjectVectorCells"]),
+             "FieldOfViewOVCs": (rb.FieldOfViewOVCs, ["Neurons", "VectorCells", "ObjectVectorCells", "FieldOfViewOVCs"])}
+    added = {"Agent": {"n_agents", "seed", "id_offset", "history_bytes_limit"}, "Neurons": {"save_spikes", "history_bytes_limit"}}
+    for name, (cls, chain) in pairs.items():
+        want = {}
+        for c in chain:
+            want.update(ref[c])
+        have = merged(cls)
+        for k, v in want.items():
+            if k == "color":
+                continue                                   # plotting only
+            assert k in have, (name, k)
+            assert same(have[k], v), (name, k, have[k], v)
+        extra = set(have) - set(want) - {"color"}
+        allowed = added.get(name, set()) | added["Neurons"] | {"dtheta", "name", "n", "min_fr", "max_fr"}
+        if name in ("Environment", "Agent"):
+            allowed = added.get(name, set())
+        assert extra <= allowed | set(ref.get("BoundaryVectorCells", {})), (name, sorted(extra - allowed))
