@@ -579,9 +579,38 @@ def gen_api_defaults():
     print("api_defaults.json", {k: len(v) for k, v in ref.items()})
 
 
+def gen_host_utils():
+    """Host-side helpers the mirror re-implements: Environment.sample_positions (box), utils.distribution_sampler and the
+    three vector-cell assemblies, each under a fixed np.random seed -> tests/golden/host_utils.npz."""
+    riab = ref_shim.import_reference()
+    assert riab is not None, "reference not present"
+    from ratinabox.Environment import Environment
+    from ratinabox import utils
+    out = {}
+    Env = Environment({"aspect": 2, "scale": 0.8})
+    for method in ("random", "uniform", "uniform_jitter"):
+        for n in (7, 40, 100):
+            np.random.seed(5)
+            out[f"sample_{method}_{n}"] = Env.sample_positions(n=n, method=method)
+    for k, (name, prm) in enumerate((("uniform", (0.1, 0.4)), ("rayleigh", (0.2,)), ("normal", (1.0, 0.3)), ("logarithmic", (0.05, 1.0)),
+                                     ("delta", (0.7,)), ("modules", (0.3, 0.5, 0.8)), ("truncnorm", (0.0, 1.0, 0.5, 0.2)))):
+        np.random.seed(9)
+        out[f"dist_{name}"] = np.asarray(utils.distribution_sampler(name, prm, (23,)))
+    np.random.seed(4)
+    out["assembly_random"] = np.stack(utils.create_random_assembly(n=17))
+    np.random.seed(4)
+    out["assembly_random_lists"] = np.stack(utils.create_random_assembly(tuning_distance=[0.1, 0.2, 0.3], sigma_angle=[10.0, 20.0, 30.0]))
+    out["assembly_uniform"] = np.stack(utils.create_uniform_radial_assembly(distance_range=[0.02, 0.3], angle_range=[0, 60], spatial_resolution=0.04))
+    out["assembly_diverging"] = np.stack(utils.create_diverging_radial_assembly(distance_range=[0.02, 0.4], angle_range=[0, 75], spatial_resolution=0.02, beta=5))
+    np.savez_compressed(os.path.join(GOLD, "host_utils.npz"), **out)
+    print("host_utils.npz", {k: v.shape for k, v in out.items() if k.startswith("assembly")})
+
+
 if __name__ == "__main__":
     if sys.argv[1:] == ["api"]:
         gen_api_defaults()
+    elif sys.argv[1:] == ["host"]:
+        gen_host_utils()
     elif sys.argv[1:] == ["histogram"]:
         gen_histogram()
     elif sys.argv[1:] == ["params"]:
@@ -597,3 +626,4 @@ if __name__ == "__main__":
         gen_params()
         gen_histogram()
         gen_api_defaults()
+        gen_host_utils()

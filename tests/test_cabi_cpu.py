@@ -268,3 +268,30 @@ def test_mirror_default_params_match_the_reference():
         if name in ("Environment", "Agent"):
             allowed = added.get(name, set())
         assert extra <= allowed | set(ref.get("BoundaryVectorCells", {})), (name, sorted(extra - allowed))
+
+
+def test_host_helpers_match_the_reference(golden):
+    """Host-side helpers the mirror re-implements, under the same np.random seeds as the live reference
+    (tests/golden/host_utils.npz): Environment.sample_positions in a 1.6 x 0.8 box, utils.distribution_sampler, and the
+    random / uniform / diverging vector-cell assemblies."""
+    from ratinabox_b200.Environment import Environment
+    from ratinabox_b200 import utils as U
+    g = golden("host_utils.npz")
+    Env = Environment({"aspect": 2, "scale": 0.8})
+    for method in ("random", "uniform", "uniform_jitter"):
+        for n in (7, 40, 100):
+            np.random.seed(5)
+            assert np.array_equal(Env.sample_positions(n=n, method=method), g[f"sample_{method}_{n}"]), (method, n)
+    for name, prm in (("uniform", (0.1, 0.4)), ("rayleigh", (0.2,)), ("normal", (1.0, 0.3)), ("logarithmic", (0.05, 1.0)),
+                      ("delta", (0.7,)), ("modules", (0.3, 0.5, 0.8)), ("truncnorm", (0.0, 1.0, 0.5, 0.2))):
+        np.random.seed(9)
+        assert np.array_equal(np.asarray(U.distribution_sampler(name, prm, (23,))), g[f"dist_{name}"]), name
+    np.random.seed(4)
+    assert np.array_equal(np.stack(U.create_random_assembly(n=17)), g["assembly_random"])
+    np.random.seed(4)
+    assert np.array_equal(np.stack(U.create_random_assembly(tuning_distance=[0.1, 0.2, 0.3], sigma_angle=[10.0, 20.0, 30.0])),
+                          g["assembly_random_lists"])
+    assert np.array_equal(np.stack(U.create_uniform_radial_assembly(distance_range=[0.02, 0.3], angle_range=[0, 60],
+                                                                    spatial_resolution=0.04)), g["assembly_uniform"])
+    assert np.array_equal(np.stack(U.create_diverging_radial_assembly(distance_range=[0.02, 0.4], angle_range=[0, 75],
+                                                                      spatial_resolution=0.02, beta=5)), g["assembly_diverging"])
