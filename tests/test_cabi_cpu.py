@@ -295,3 +295,20 @@ def test_host_helpers_match_the_reference(golden):
                                                                     spatial_resolution=0.04)), g["assembly_uniform"])
     assert np.array_equal(np.stack(U.create_diverging_radial_assembly(distance_range=[0.02, 0.4], angle_range=[0, 75],
                                                                       spatial_resolution=0.02, beta=5)), g["assembly_diverging"])
+
+
+def test_environment_mirror_like_the_reference_suite():
+    """The 2D cases of the reference's own tests/test_environment.py (:20-23 add_wall, :31-36 sample_positions,
+    :38-41 discretise_environment) against the host mirror; 1D is refused loudly."""
+    from ratinabox_b200.Environment import Environment
+    Env2D = Environment(params={"dimensionality": "2D"})
+    assert type(Env2D) == Environment
+    n_walls = len(Env2D.walls)
+    Env2D.add_wall([[0.2, 0.2], [0.2, 0.2]])                 # the reference's test adds this zero-length wall
+    assert len(Env2D.walls) == n_walls + 1
+    for method_ in ["uniform", "random", "uniform_random"]:
+        assert Env2D.sample_positions(5, method=method_).shape == (5, 2)
+    coords = Env2D.discretise_environment(dx=0.01)
+    assert type(coords) is np.ndarray and coords.shape == (100, 100, 2)
+    with pytest.raises(NotImplementedError):
+        Environment(params={"dimensionality": "1D"})
