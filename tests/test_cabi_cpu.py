@@ -312,3 +312,34 @@ def test_environment_mirror_like_the_reference_suite():
     assert type(coords) is np.ndarray and coords.shape == (100, 100, 2)
     with pytest.raises(NotImplementedError):
         Environment(params={"dimensionality": "1D"})
+
+
+def test_ctypes_structs_have_the_headers_layout(tmp_path):
+    """Compile a C program against include/riab_b200.h (gcc: the header is plain C) that prints sizeof / selected
+    offsetof of every POD struct, and compare with the ctypes mirrors in ratinabox_b200/_lib.py."""
+    import shutil
+    import subprocess
+    from ratinabox_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = {"riab_env": _lib.Env, "riab_agents": _lib.Agents, "riab_motion_params": _lib.MotionParams,
+             "riab_step_io": _lib.StepIO, "riab_place_cells": _lib.PlaceCells, "riab_grid_cells": _lib.GridCells,
+             "riab_bvc_cells": _lib.BvcCells, "riab_ovc_cells": _lib.OvcCells, "riab_neuron_noise": _lib.NeuronNoise,
+             "riab_rates_out": _lib.RatesOut, "riab_population": _lib.Population, "riab_agent_history": _lib.AgentHistory,
+             "riab_history_view": _lib.HistoryView}
+    last = {name: cls._fields_[-1][0] for name, cls in pairs.items()}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "riab_b200.h"', "int main(void) {"]
+    for name in pairs:
+        src.append(f'  printf("{name} %zu %zu\\n", sizeof({name}), offsetof({name}, {last[name]}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "sizes.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-std=c11", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        name, size, off = line.split()
+        cls = pairs[name]
+        assert C.sizeof(cls) == int(size), (name, C.sizeof(cls), size)
+        assert getattr(cls, last[name]).offset == int(off), (name, last[name])
