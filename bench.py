@@ -335,15 +335,15 @@ def main():
         Ag.update(drift_velocity=drift)
         for ns in pops:
             ns.update()
-        _ = Ag.pos
+        _ = Ag.state_view("pos")
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         Ag.update(drift_velocity=drift)          # H2D: A*2*8 B read from pinned host memory by the motion kernel, every step
         for ns in pops:
             ns.update()                          # first population: fused motion + rates kernel; others: rates
-        p = Ag.pos                               # D2H: A*2*8 B posted to pinned host memory by the motion kernel; blocks
-                                                 # until the whole step (motion + rates) has finished
+        p = Ag.state_view("pos")                 # D2H: A*2*8 B posted to pinned host memory by the motion kernel; blocks until
+                                                 # the whole step (motion + rates) has finished (`Ag.pos` = a private copy of it)
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -353,7 +353,7 @@ def main():
     clocks = sampler.stop()        # sampled across the device-resident and the e2e timed regions
     e2e = {"value": world * A * e2e_steps / e2e_s, "unit": "agent-steps/s", "h2d_bytes_per_step": A * 16,
            "d2h_bytes_per_step": A * 16, "steps": e2e_steps,
-           "api": "Agent.update(drift_velocity=<pinned host tensor>) + Neurons.update() + read Agent.pos, per step"}
+           "api": "Agent.update(drift_velocity=<pinned host tensor>) + Neurons.update() + Agent.state_view('pos') (host positions), per step; rates stay in the device history ring (268 MB/step at c2 cannot cross PCIe)"}
 
     if rank != 0:
         if dist is not None:

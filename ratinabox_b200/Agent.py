@@ -195,18 +195,19 @@ class Agent:
             return arr
         return arr[0].copy() if name in _VEC else arr[0].item()
 
-    _SHADOW_MAX = 4096      # above this many agents state reads are read-only views (no write tracking)
+    _SHADOW_MAX = 4096      # above this many agents state reads are plain copies (no in-place write tracking)
 
-    def _get_state(self, name):
+    def _get_state(self, name, view=False):
         self._flush_pending()
-        if name in self._shadow:
+        if name in self._shadow and not view:
             return self._shadow[name][0]
         import torch
         t = self._s[name]
-        if self.n_agents > self._SHADOW_MAX:
+        if self.n_agents > self._SHADOW_MAX or view:
             # large batches: one pinned staging buffer per state array, asynchronous D2H on the current
-            # stream + one stream sync; the returned array is a read-only view (assign to write:
-            # ``Ag.pos = new_positions``)
+            # stream + one stream sync.  `Ag.pos` hands out a fresh COPY of it (reference-style code keeps
+            # such arrays: `traj.append(Ag.pos)`); in-place edits of that copy are not tracked -- assign to
+            # write (``Ag.pos = new_positions``).  state_view() returns the staging buffer itself.
             buf = self._pinned.get(name)
             if buf is None:
                 buf = self._pinned[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
@@ -216,13 +217,25 @@ class Agent:
                 buf.copy_(t, non_blocking=True)
             self._sync_stream()
             arr = buf.numpy()
-            arr.flags.writeable = False
-            return arr
+            if view:
+                arr = arr.view()
+                arr.flags.writeable = False
+                return arr
+            return arr.copy()
         host = t.cpu().numpy()
         val = self._squeeze(name, host)
         if isinstance(val, np.ndarray):
             self._shadow[name] = (val, val.copy())
         return val
+
+    def state_view(self, name="pos"):
+        """Zero-copy, READ-ONLY view of a state array in page-locked host memory, shape (n_agents, ...) -- the opt-in
+        fast path for per-step control loops (`Ag.pos` returns a private copy instead).  The view ALIASES a buffer the
+        engine reuses: it is valid until the next ``update()`` / ``run()`` of this Agent (the next motion kernel posts
+        the new positions into the same memory, asynchronously); copy what you need to keep."""
+        if name not in _STATE:
+            raise KeyError(name)
+        return self._get_state(name, view=True)
 
     def _set_state(self, name, value):
         import torch
@@ -383,7 +396,7 @@ class Agent:
             cells = ns._cells()
             ns._reserve_history(n_steps)
             out, nz = ns._fill_out_structs(None, None)
-            nz.step = first_step
+            nz.step = ns._upd
             p = pops[i]
             p.kind, p.cells = ns._cells_kind, C.cast(C.pointer(cells), C.c_void_p)
             p.noise, p.out = nz, out
@@ -405,6 +418,7 @@ class Agent:
         for ns in self.Neurons:
             last = (ns._hist_rows + n_steps - 1) % ns._hist_cap
             ns._hist_rows += n_steps
+            ns._upd += n_steps
             ns._last_slot = last
             if ns.save_history:
                 ns._t_hist.extend(ts)

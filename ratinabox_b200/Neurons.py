@@ -74,6 +74,7 @@ class Neurons:
         self._noise = None
         self._t_hist = []
         self._last_slot = None
+        self._upd = 0              # updates of THIS population so far: keys its OU-noise / spike Philox streams
         self._history_view = _HistoryView(self)
         self._last_history_array_cache_time = None
         self._history_arrays = {}
@@ -171,7 +172,7 @@ class Neurons:
         nz.noise_coherence_time = float(self.noise_coherence_time)
         nz.dt = float(ag.dt)
         nz.seed = int(ag.seed) & 0xFFFFFFFFFFFFFFFF
-        nz.step = max(ag._step - 1, 0)
+        nz.step = self._upd
         nz.id_offset = int(ag.id_offset)
         nz.population_id = self._population_id
         return out, nz
@@ -180,15 +181,25 @@ class Neurons:
         """Neurons.update (ratinabox/Neurons.py:145-171)."""
         ag = self.Agent
         cells = self._cells()
+        ag._sync_user_writes()                 # in-place edits of Ag.pos etc. since they were read
+        saved = (self._hist_rows, self._last_slot)
         row, spk = self._row_buffers()
         out, nz = self._fill_out_structs(row, spk)
-        if ag._take_pending():
-            _lib.check(self._lib.riab_step_fused(C.byref(ag._agents_c), C.byref(ag._env_struct()), C.byref(ag._mp),
-                                                 C.byref(ag._io), self._cells_kind, C.byref(cells), C.byref(nz),
-                                                 C.byref(out), ag._stream()))
-        else:
-            ag._flush_pending()
-            self._update_unfused(cells, out, nz)
+        fused = ag._take_pending()
+        try:
+            if fused:
+                _lib.check(self._lib.riab_step_fused(C.byref(ag._agents_c), C.byref(ag._env_struct()), C.byref(ag._mp),
+                                                     C.byref(ag._io), self._cells_kind, C.byref(cells), C.byref(nz),
+                                                     C.byref(out), ag._stream()))
+            else:
+                self._update_unfused(cells, out, nz)
+        except Exception:
+            # the library refused the call (validation): nothing ran -- keep the queued motion step and the ring as they were
+            self._hist_rows, self._last_slot = saved
+            if fused:
+                ag._pending = True
+            raise
+        self._upd += 1
         if self.save_history:
             self._t_hist.append(ag.t)
 
@@ -209,6 +220,7 @@ class Neurons:
         self._cells()
         if evaluate_at == "agent":
             self.Agent._flush_pending()
+            self.Agent._sync_user_writes()
             pos_dev = self.Agent._s["pos"]
         else:
             pos = self.Agent.Environment.flattened_discrete_coords if evaluate_at == "all" else kwargs["pos"]

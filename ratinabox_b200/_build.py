@@ -8,20 +8,24 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("RIAB_LIB", os.path.join(HERE, "libriab_b200.so"))
 SOURCES = ["riab_b200.cu"]
-HEADERS = ["riab_common.cuh", "riab_motion.cuh", "riab_place.cuh", "riab_grid.cuh", "riab_bvc.cuh",
-           os.path.join("..", "..", "include", "riab_b200.h")]
+HEADERS = None  # every csrc/*.cuh + include/riab_b200.h (see _headers)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-split-compile", "0",
 ]
+
+
+def _headers():
+    import glob
+    return sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "riab_b200.h")]
 
 
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in [os.path.join(CSRC, f) for f in SOURCES] + _headers())
 
 
 def build(force=False, verbose=False, extra=()):

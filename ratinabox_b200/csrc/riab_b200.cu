@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -68,6 +69,11 @@ struct OutK {
   long long id_offset;
   int pop, vec_ok;
   uint32_t rk7[14];         // Philox4x32-7 round keys of the spike stream (host-computed, constant bank)
+  // thinned spikes (thin_post): candidates at rate p = dt * (an upper bound of the rate), accepted with rate / bound
+  int thin;                 // 1: the population's rates are bounded and p <= 1/8
+  uint32_t thin_t[8];       // t[i] = floor(2^32 (1 - (1-p)^(i+1))): first candidate among 8 slots is slot #{i: word >= t[i]}
+  uint32_t thin_tc[7];      // conditional on "a candidate exists": floor(2^32 t[i] / t[7])
+  float thin_c1, thin_c0;   // accept <=> fma(float(word >> 8), c1, c0) < rate;  c1 = 2^-24 bound, c0 = 2^-25 bound
 };
 
 // ---------------------------------------------------------------------------
@@ -296,6 +302,7 @@ struct PlacePolicy {
   static constexpr int REC = PLACE_REC;
   static constexpr bool LIGHT = (WI == 0) && (DESC >= 0);   // few instructions per rate: HBM-bound consumers
   static constexpr bool XU_BOUND = false;
+  static constexpr bool THIN = true;                        // rates lie in [min_fr, max_fr]: thinned spikes apply
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
   static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
@@ -317,6 +324,7 @@ struct GridPolicy {
   using Regs = GridCellRegs;
   static constexpr int REC = 4;
   static constexpr bool LIGHT = false;    // 36 cell registers per thread do not fit StepCfg<8>'s 56-register consumers
+  static constexpr bool THIN = true;
   static constexpr bool XU_BOUND = false; // 3 MUFU.COS per rate, yet issue-bound: PRMT+FADD instead of I2F measured slower (95.6 vs 91.3 us, c3)
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
   static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double*, const Const&,
@@ -339,6 +347,7 @@ struct OvcPolicy {
   using Regs = OvcCellRegs;
   static constexpr int REC = OVC_REC;
   static constexpr bool LIGHT = false;
+  static constexpr bool THIN = false;     // sums over objects: no a-priori rate bound
   static constexpr bool XU_BOUND = false;
   static __device__ __forceinline__ const double* head_dir(const Const& c) { return c.head_dir; }
   static __device__ __forceinline__ void record(float* rec, double px, double py, double hdx, double hdy,
@@ -406,13 +415,14 @@ struct __align__(16) StepSlot {
   int pad[3];
 };
 
-// The consumers' hot loop: agent pairs (2p, 2p+1) of one ring slot, 4 cells per thread, no OU noise,
-// 16-byte aligned rows, even first global id.  FULL: every cell-thread owns 4 existing cells (no
-// predicate on the stores).  The line-of-sight band test is deferred: a pair whose float32 decision fell
+// The consumers' hot loop: consecutive agent pairs (2p, 2p+1) of one ring slot, 4 cells per thread, no OU noise,
+// 16-byte aligned rows, even first global id.  The line-of-sight band test is deferred: a pair whose float32 decision fell
 // inside the band only sets its bit in `redo`; the caller redoes those pairs through the general path
 // (per-agent exact float64 fall-back) after the loop -- no call and no branch in here.
-template <class P, bool SPIKES, bool FULL, int EXP>
-__device__ __forceinline__ void consume_pairs(int& a, const int na, const int G, const typename P::Regs& regs,
+// DENSE: the dense spike stream (one Philox4x32-7 call per pair, a threshold test per rate) runs in the loop;
+// thinned spikes are a post-pass over the slot (thin_post) and leave this loop spike-free.
+template <class P, bool DENSE, int EXP>
+__device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typename P::Regs& regs,
                                               const typename P::Const& pc, const OutK& out, const TailCtx& tc,
                                               const int cell0, const float*& recp, const uint32_t inner_s, RowCursor& rc,
                                               const bool act, const float q16, uint32_t& redo) {
@@ -420,38 +430,245 @@ __device__ __forceinline__ void consume_pairs(int& a, const int na, const int G,
   uint32_t bit = 1u;
   uint32_t* spk = rc.spk;
   unsigned long long pair = rc.gid >> 1;
-  const long long pair_rate = 2ll * G * out.ld, pair_spk = 2ll * G * out.spike_ld;     // elements per pair step
-  for (; a + 1 < na; a += 2 * G) {
+  const long long pair_rate = 2ll * out.ld, pair_spk = 2ll * out.spike_ld;     // elements per pair step
+  for (; a + 1 < a_end; a += 2) {
     float o[4];
     uint32_t c[4], bl[4];
     bool unsure = false;
     P::template rates4<true, EXP>(o, regs, pc, cell0, recp, inner_s, unsure);
-    if (FULL || act) st_cs_f4(dst, o[0], o[1], o[2], o[3]);
+    if (act) st_cs_f4(dst, o[0], o[1], o[2], o[3]);
     float nv = 0.f;
-    if (SPIKES) {
+    if (DENSE) {
       c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
       philox_keyed<7>(c, out.rk7);
       nv = spike_neg_dither(c);
-      spike_ballots<false, P::XU_BOUND>(bl, c[0], c[1], nv, o, q16, 0u, FULL || act);
+      spike_ballots<false, P::XU_BOUND>(bl, c[0], c[1], nv, o, q16, 0u, act);
       spike_store(bl, spk);
     }
     P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
-    if (FULL || act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
-    if (SPIKES) {
-      spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, FULL || act);
+    if (act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
+    if (DENSE) {
+      spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, act);
       spike_store(bl, spk + out.spike_ld);
     }
     redo |= unsure ? bit : 0u;
     bit <<= 1;
     dst += pair_rate;
     spk += pair_spk;
-    pair += (unsigned long long)G;
-    recp += 2 * G * P::REC;
+    pair += 1ull;
+    recp += 2 * P::REC;
   }
   rc.dst = dst; rc.spk = spk; rc.gid = pair << 1;
 }
 
-template <class P, int MODE, bool SPIKES, bool NOISE, class C>
+// ---------------------------------------------------------------------------
+// Thinned spikes (Neurons.py:681-684: spike <=> uniform < dt * rate) for populations whose rates are bounded by `bound`
+// with p = dt * bound <= 1/8 (the usual case: dt = 10 ms, max_fr = 1 Hz gives p = 0.01).  Exact Bernoulli(dt * rate) by
+// thinning: every (agent, cell) is a CANDIDATE with probability p, a candidate spikes with probability rate / bound.
+// Candidates are drawn per group of 8 slots = (agent pair P = gid >> 1, 4-cell group g; slot k = 4 (gid & 1) + (cell & 3)):
+//   level 1   R = Philox7(ctr = (P >> 2, g, step, THIN_FIRST | population)), w = R[P & 3]:
+//             the group holds a candidate  <=>  w < t[7]      (t[i] = floor(2^32 (1 - (1-p)^(i+1))), probability 1 - (1-p)^8)
+//   level 2   only for groups with a candidate: words S_0, S_1, ... of Philox7(ctr = (P, g, step, (THIN_CHAIN + n) | population)),
+//             n = 0, 1, ...:   first candidate slot K = #{i < 7: S_0 >= tc[i]}   (tc = t conditioned on a candidate existing),
+//             then alternately   accept slot K  <=>  fma(float(S >> 8), c1, c0) < rate[K]     (24-bit uniform times the bound)
+//             and                K += 1 + #{i < 8: S >= t[i]}                                 (geometric gap to the next candidate)
+//             until K >= 8.
+// The hot loop does nothing for spikes: this post-pass over a ring slot zero-fills the slot's spike words, runs level 1 for
+// its threads' groups (1 Philox call per 4 pairs), and the ~8 % of (thread, pair) groups with a candidate walk their chain,
+// read the candidate's rate back (this lane stored it moments ago: L2 hit) and set accepted bits with RED.OR.  Cost:
+// ~4 instructions per rate against ~10 for the dense stream.  NumPy mirror: tests/philox_np.py (expected_spikes_thin).
+__device__ __forceinline__ int thin_gap(const OutK& out, uint32_t w) {
+  if (w >= out.thin_t[7]) return 8;
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) n += (w >= out.thin_t[i]) ? 1 : 0;
+  return n;
+}
+__device__ __forceinline__ void thin_accept(const OutK& out, const TailCtx& tc, int K, uint32_t w, unsigned long long pair,
+                                            long long row_lo, long long row_hi, int lane) {
+  const long long row = (long long)(2ull * pair + (unsigned)(K >> 2)) - out.id_offset;
+  const int i = K & 3;
+  if (row < row_lo || row >= row_hi || !((tc.vmask >> i) & 1u)) return;      // the other shard's / tile's half, padding cell
+  float rate;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate) : "l"(out.rates + row * out.ld + tc.cell0 + i));
+  if (fmaf((float)(w >> 8), out.thin_c1, out.thin_c0) < rate)
+    atomicOr(out.spikes + row * out.spike_ld + ((tc.cell0 >> 7) << 2) + i, 1u << lane);
+}
+// rows [row_lo, row_hi) of this launch, cells of tail context `tc` (a warp covers 128 consecutive cells); whole warp calls
+__device__ __forceinline__ void thin_post(const OutK& out, const TailCtx& tc, const long long row_lo, const long long row_hi,
+                                          const bool act) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long gid_lo = (unsigned long long)(out.id_offset + row_lo), gid_hi = (unsigned long long)(out.id_offset + row_hi);
+  const unsigned long long pair_lo = gid_lo >> 1, pair_hi = (gid_hi + 1ull) >> 1;       // [lo, hi)
+  uint32_t pend = 0u;                                    // bit j: pair pair_lo + j holds a candidate (at most 16 pairs + 1)
+  const uint32_t c3 = (tc.c3_spk & 0x00ffffffu) | (RIAB_STREAM_THIN_FIRST << 24);
+  for (unsigned long long q = pair_lo >> 2; q < ((pair_hi + 3ull) >> 2); ++q) {
+    uint32_t R[4];
+    R[0] = (uint32_t)q; R[1] = tc.sub ^ ((uint32_t)(q >> 32) << 24); R[2] = tc.c2; R[3] = c3;
+    philox_keyed<7>(R, out.rk7);
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const long long j = (long long)(4ull * q + (unsigned)w) - (long long)pair_lo;
+      if (j >= 0 && 4ull * q + (unsigned)w < pair_hi && R[w] < out.thin_t[7]) pend |= 1u << j;
+    }
+  }
+  if (!act) pend = 0u;
+  while (__any_sync(0xffffffffu, pend != 0u)) {
+    if (pend != 0u) {
+      const int j = __ffs(pend) - 1;
+      pend &= pend - 1u;
+      const unsigned long long pair = pair_lo + (unsigned)j;
+      uint32_t S[4];
+      uint32_t n = 0u;
+      S[0] = (uint32_t)pair; S[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2;
+      S[3] = (tc.c3_spk & 0x00ffffffu) | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
+      philox_keyed<7>(S, out.rk7);
+      int K = 0;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) K += (S[0] >= out.thin_tc[i]) ? 1 : 0;
+      thin_accept(out, tc, K, S[1], pair, row_lo, row_hi, lane);
+      K += 1 + thin_gap(out, S[2]);
+      while (K < 8) {                                    // a second (third, ...) candidate in the same group: ~7 % of groups
+        thin_accept(out, tc, K, S[3], pair, row_lo, row_hi, lane);
+        ++n;
+        S[0] = (uint32_t)pair; S[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2;
+        S[3] = (tc.c3_spk & 0x00ffffffu) | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
+        philox_keyed<7>(S, out.rk7);
+        K += 1 + thin_gap(out, S[0]);
+        if (K >= 8) break;
+        thin_accept(out, tc, K, S[1], pair, row_lo, row_hi, lane);
+        K += 1 + thin_gap(out, S[2]);
+      }
+    }
+  }
+}
+
+// The consumers' slot loop (see k_step).  EXP: exponent form of the fast pair loop (PlacePolicy::expanded).
+template <class P, int SPK, bool NOISE, class C, int EXP>
+__device__ __forceinline__ void consumer_slots(const typename P::Const& pc, const OutK& out, StepSlot<P::REC>* s_slot,
+                                               uint64_t* s_full, uint64_t* s_empty, const double* s_walls,
+                                               const long long nq, const int ctid, const int lane) {
+  constexpr int NS = C::NS;
+  constexpr int NC = RW * 32;
+  constexpr bool DENSE = (SPK == 1);
+  const int CT = pc.n_pad >> 2;                       // cell-threads needed (multiple of 32)
+  const int chunks = (CT + NC - 1) / NC;
+  const int G = (chunks == 1) ? (NC / CT) : 1;        // agent groups when the cells need fewer threads
+  const int grp = (chunks == 1) ? (ctid / CT) : 0;
+  const bool idle = (chunks == 1) && (grp >= G);
+  // group `grp` takes the consecutive agents [2 grp PPG, 2 (grp+1) PPG) of a slot (PPG pairs)
+  const int PPG = (TA / 2 + G - 1) / G;
+  typename P::Regs regs;
+  int cell0 = (chunks == 1) ? (ctid % CT) * 4 : 0;
+  TailCtx tc;
+  if (chunks == 1 && !idle) {
+    P::load(regs, pc, cell0);
+    tail_init(tc, out, cell0, pc.n_cells);
+  }
+  const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);   // float64 inner walls (exact fall-back)
+  // Fast pair loop: rows are 16-byte aligned and every thread owns 4 existing cells or none, the
+  // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
+  const bool fast = !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
+  const float q16 = out.dt * 65536.0f;
+  for (long long q = 0; q < nq; ++q) {
+    const int s = (int)(q % NS);
+    mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
+    const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * TA;
+    const int na = s_slot[s].na;
+    const int a_lo = 2 * grp * PPG;
+    const int a_hi = (a_lo + 2 * PPG < na) ? a_lo + 2 * PPG : na;       // this group's agents of the slot: [a_lo, a_hi)
+    // chunks == 1: the cell registers loaded above serve every slot; more than 2048 cells: the 16 warps walk
+    // the cells in chunks of 2048 and reload their registers per chunk (G = 1, all warps on the same agents)
+    for (int ch = 0; ch < chunks; ++ch) {
+      if (chunks > 1) {
+        cell0 = (ch * NC + ctid) * 4;
+        if (cell0 >= pc.n_pad) continue;              // warp-uniform (n_pad is a multiple of 128)
+        P::load(regs, pc, cell0);
+        tail_init(tc, out, cell0, pc.n_cells);
+      } else if (idle) {
+        continue;
+      }
+      if (a_lo >= a_hi) continue;                     // warp-uniform
+      const bool act = cell0 < pc.n_cells;
+      {
+        // agents are taken in pairs (2p, 2p+1) so that one Philox call feeds the (dense) spikes of both
+        RowCursor rc;
+        cursor_init(rc, out, tc, a0 + a_lo);
+        if (SPK == 2) {
+          // thinned spikes: clear this warp's 16 bytes of every row of the group, accepted bits are OR-ed in by thin_post
+          if (lane < a_hi - a_lo) {
+            uint32_t* z = rc.spk + (long long)lane * out.spike_ld;
+            asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(z), "r"(0u) : "memory");
+          }
+        }
+        const float* recp = s_slot[s].rec[a_lo];
+        int a = a_lo;
+        uint32_t only = 0xffffffffu;       // pairs (by iteration index) the general loop below evaluates
+        if (fast) {
+          uint32_t redo = 0u;
+          consume_pairs<P, DENSE, EXP>(a, a_hi, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
+          redo = __reduce_or_sync(0xffffffffu, redo);
+          if (redo != 0u) {
+            // some float32 line-of-sight decision was inside the band: redo those pairs through the
+            // general path (the stores are idempotent); complete pairs not in `redo` are skipped
+            only = redo;
+            a = a_lo;
+            cursor_init(rc, out, tc, a0 + a_lo);
+            recp = s_slot[s].rec[a_lo];
+          }
+        }
+        // general path: the last agent of an odd tile, odd shard offsets, OU noise, ragged cell counts
+        const RowStride stride = make_stride(out, 2);
+        const bool even = ((rc.gid & 1ull) == 0ull);      // uniform: a0 and a_lo are even
+        for (uint32_t it = (uint32_t)((a - a_lo) >> 1); a < a_hi; a += 2, ++it) {
+          float oa[4], ob[4];
+          const bool has_b = (a + 1 < a_hi);
+          if (has_b && !((only >> (it & 31u)) & 1u)) {      // warp-uniform
+            cursor_advance(rc, stride);
+            recp += 2 * P::REC;
+            continue;
+          }
+          bool dummy = false;
+          P::template rates4<false>(oa, regs, pc, cell0, recp, inner_s, dummy);
+          store4<NOISE>(oa, out, tc, rc, 0);
+          if (has_b) {
+            P::template rates4<false>(ob, regs, pc, cell0, recp + P::REC, inner_s, dummy);
+            store4<NOISE>(ob, out, tc, rc, out.ld);
+          }
+          if (DENSE && (!NOISE || rc.spk != nullptr)) {
+            if (has_b && even) {
+              uint32_t c[4], bl[4];
+              spike_words(c, out, tc, rc.gid);
+              const float nv = spike_neg_dither(c);
+              spike_ballots<true>(bl, c[0], c[1], nv, oa, q16, tc.vmask, true);
+              spike_store(bl, rc.spk);
+              spike_ballots<true>(bl, c[2], c[3], nv, ob, q16, tc.vmask, true);
+              spike_store(bl, rc.spk + out.spike_ld);
+            } else {
+              spikes1(oa, out, tc, rc);
+              if (has_b) {
+                RowCursor rb = rc;
+                rb.gid += 1; rb.spk += out.spike_ld;
+                spikes1(ob, out, tc, rb);
+              }
+            }
+          }
+          cursor_advance(rc, stride);
+          recp += 2 * P::REC;
+        }
+        if (SPK == 2) {
+          __syncwarp();      // orders the zero-fill and this warp's rate stores before the chain's loads / RED.ORs
+          thin_post(out, tc, a0 + a_lo, a0 + a_hi, act || (tc.vmask != 0u));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+}
+
+// SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_post per ring slot)
+template <class P, int MODE, int SPK, bool NOISE, class C>
 __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
                                                           const riab_step_io io, const typename P::Const pc, const OutK out,
@@ -528,116 +745,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
     // ------------------------------------------------------------- consumers
     reg_set<C::REGS_CONSUMER, C::REGS_LAUNCH>();
     const int ctid = threadIdx.x - ctid0;
-    constexpr int NC = RW * 32;
-    const int CT = pc.n_pad >> 2;                       // cell-threads needed (multiple of 32)
-    const int chunks = (CT + NC - 1) / NC;
-    const int G = (chunks == 1) ? (NC / CT) : 1;        // agent groups when the cells need fewer threads
-    const int grp = (chunks == 1) ? (ctid / CT) : 0;
-    const bool idle = (chunks == 1) && (grp >= G);
-    typename P::Regs regs;
-    int cell0 = (chunks == 1) ? (ctid % CT) * 4 : 0;
-    TailCtx tc;
-    if (chunks == 1 && !idle) {
-      P::load(regs, pc, cell0);
-      tail_init(tc, out, cell0, pc.n_cells);
-    }
-    const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);   // float64 inner walls (exact fall-back)
-    // Fast pair loop: rows are 16-byte aligned and every thread owns 4 existing cells or none, the
-    // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
-    const bool fast = !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
-    const bool full = (pc.n_cells == pc.n_pad);          // no padding cells at all
-    const float q16 = out.dt * 65536.0f;
-    for (long long q = 0; q < nq; ++q) {
-      const int s = (int)(q % NS);
-      mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
-      const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * TA;
-      const int na = s_slot[s].na;
-      // chunks == 1: the cell registers loaded above serve every slot; more than 2048 cells: the 16 warps walk
-      // the cells in chunks of 2048 and reload their registers per chunk (G = 1, all warps on the same agents)
-      for (int ch = 0; ch < chunks; ++ch) {
-        if (chunks > 1) {
-          cell0 = (ch * NC + ctid) * 4;
-          if (cell0 >= pc.n_pad) continue;              // warp-uniform (n_pad is a multiple of 128)
-          P::load(regs, pc, cell0);
-          tail_init(tc, out, cell0, pc.n_cells);
-        } else if (idle) {
-          continue;
-        }
-        const bool act = cell0 < pc.n_cells;
-        {
-          // agents are taken in pairs (2p, 2p+1) so that one Philox call feeds the spikes of both
-          RowCursor rc;
-          cursor_init(rc, out, tc, a0 + 2 * grp);
-          const float* recp = s_slot[s].rec[2 * grp];
-          int a = 2 * grp;
-          uint32_t only = 0xffffffffu;       // pairs (by iteration index) the general loop below evaluates
-          if (fast) {
-            uint32_t redo = 0u;
-            const int ex = P::expanded(pc);
-            if (ex == 2) {
-              if (full) consume_pairs<P, SPIKES, true, 2>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
-              else consume_pairs<P, SPIKES, false, 2>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
-            } else if (ex == 1) {
-              if (full) consume_pairs<P, SPIKES, true, 1>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
-              else consume_pairs<P, SPIKES, false, 1>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
-            } else {
-              if (full) consume_pairs<P, SPIKES, true, 0>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
-              else consume_pairs<P, SPIKES, false, 0>(a, na, G, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
-            }
-            redo = __reduce_or_sync(0xffffffffu, redo);
-            if (redo != 0u) {
-              // some float32 line-of-sight decision was inside the band: redo those pairs through the
-              // general path (the stores are idempotent); complete pairs not in `redo` are skipped
-              only = redo;
-              a = 2 * grp;
-              cursor_init(rc, out, tc, a0 + 2 * grp);
-              recp = s_slot[s].rec[2 * grp];
-            }
-          }
-          // general path: the last agent of an odd tile, odd shard offsets, OU noise, ragged cell counts
-          const RowStride stride = make_stride(out, 2 * G);
-          const bool even = ((rc.gid & 1ull) == 0ull);      // uniform: a0 and 2*grp are even
-          for (uint32_t it = 0; a < na; a += 2 * G, ++it) {
-            float oa[4], ob[4];
-            const bool has_b = (a + 1 < na);
-            if (has_b && !((only >> (it & 31u)) & 1u)) {      // warp-uniform
-              cursor_advance(rc, stride);
-              recp += 2 * G * P::REC;
-              continue;
-            }
-            bool dummy = false;
-            P::template rates4<false>(oa, regs, pc, cell0, recp, inner_s, dummy);
-            store4<NOISE>(oa, out, tc, rc, 0);
-            if (has_b) {
-              P::template rates4<false>(ob, regs, pc, cell0, recp + P::REC, inner_s, dummy);
-              store4<NOISE>(ob, out, tc, rc, out.ld);
-            }
-            if (SPIKES && (!NOISE || rc.spk != nullptr)) {
-              if (has_b && even) {
-                uint32_t c[4], bl[4];
-                spike_words(c, out, tc, rc.gid);
-                const float nv = spike_neg_dither(c);
-                spike_ballots<true>(bl, c[0], c[1], nv, oa, q16, tc.vmask, true);
-                spike_store(bl, rc.spk);
-                spike_ballots<true>(bl, c[2], c[3], nv, ob, q16, tc.vmask, true);
-                spike_store(bl, rc.spk + out.spike_ld);
-              } else {
-                spikes1(oa, out, tc, rc);
-                if (has_b) {
-                  RowCursor rb = rc;
-                  rb.gid += 1; rb.spk += out.spike_ld;
-                  spikes1(ob, out, tc, rb);
-                }
-              }
-            }
-            cursor_advance(rc, stride);
-            recp += 2 * G * P::REC;
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
-    }
+    // one copy of the slot loop per exponent form (0: direct, 1: expanded, 2: expanded + folded scale), chosen once:
+    // the cell registers then stay in registers across slots (a run-time switch inside the loop made ptxas park them
+    // in local memory around every slot)
+    const int ex = P::expanded(pc);
+    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane);
+    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane);
+    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane);
   }
 }
 
@@ -1037,7 +1151,9 @@ int check_motion(const riab_motion_params* p) {
   return 0;
 }
 
-int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, double dt, long long id_offset, OutK& k) {
+// fr_bound: an upper bound of the population's rates (thinned spikes), negative when there is none
+int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, double dt, long long id_offset, OutK& k,
+             double fr_bound = -1.0) {
   if (o == nullptr || o->rates_row == nullptr) return fail(RIAB_ERR_INVALID, "rates_row is NULL");
   if (o->ld < n_cells) return fail(RIAB_ERR_INVALID, "ld (%lld) < n_cells (%d)", (long long)o->ld, n_cells);
   memset(&k, 0, sizeof(k));
@@ -1063,6 +1179,24 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
   {
     uint32_t k0 = (uint32_t)k.seed, k1 = (uint32_t)(k.seed >> 32);
     for (int i = 0; i < 7; ++i) { k.rk7[2 * i] = k0; k.rk7[2 * i + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+  }
+  // thinned spikes (thin_post): p = dt * bound * (1 + 2^-10) -- the margin covers the rates' float32 rounding above `bound`
+  k.thin = 0;
+  if (k.spikes != nullptr && k.noise == nullptr && fr_bound >= 0.0 && getenv("RIAB_DENSE_SPIKES") == nullptr) {
+    const double bound = fr_bound * (1.0 + 1.0 / 1024.0), p = dt * bound;
+    if (p <= 0.125) {
+      k.thin = 1;
+      double qq = 1.0;
+      for (int i = 0; i < 8; ++i) {
+        qq *= (1.0 - p);
+        const double t = floor(4294967296.0 * (1.0 - qq));
+        k.thin_t[i] = (t >= 4294967295.0) ? 4294967295u : (uint32_t)t;
+      }
+      for (int i = 0; i < 7; ++i)
+        k.thin_tc[i] = k.thin_t[7] ? (uint32_t)((((uint64_t)k.thin_t[i]) << 32) / k.thin_t[7]) : 0u;
+      k.thin_c1 = (float)(bound * (1.0 / 16777216.0));
+      k.thin_c0 = (float)(bound * (1.0 / 33554432.0));
+    }
   }
   return 0;
 }
@@ -1120,6 +1254,8 @@ int make_grid(const riab_grid_cells* gc, const EnvK& env, GridConst& c) {
     c.A = (float)(2.0 / 9.0); c.B = (float)(1.0 / 3.0); c.rectify = 0;                                 // Neurons.py:1216-1218
   } else return fail(RIAB_ERR_INVALID, "bad grid description %d", gc->description);
   c.min_fr = gc->min_fr; c.span = gc->max_fr - gc->min_fr;
+  c.As = c.A * c.span; c.Bs = fmaf(c.B, c.span, c.min_fr);
+  c.clamp = c.rectify ? (c.span >= 0.f ? 1 : 2) : 0;
   c.packed = gc->packed_dev; c.cxm = env.cxm; c.cym = env.cym;
   return 0;
 }
@@ -1162,12 +1298,16 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (MODE != 0) derive_motion(mp, md);
-  if (noise) k_step<P, MODE, true, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-  else if (spikes) k_step<P, MODE, true, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  if (noise) k_step<P, MODE, 1, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else if (spikes && out.thin) {
+    if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+    else return fail(RIAB_ERR_INVALID, "thinned spikes requested for a population without a rate bound");
+  }
+  else if (spikes) k_step<P, MODE, 1, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   else {
     // light consumers without spikes run at the HBM write rate: twice the producer warps (only instantiated for them)
-    if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, false, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-    else k_step<P, MODE, false, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+    if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, 0, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+    else k_step<P, MODE, 0, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
@@ -1618,7 +1758,9 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
   if (cells_kind == RIAB_CELLS_PLACE) {
     const riab_place_cells* pc = (const riab_place_cells*)cells;
     PlaceConst c;
-    if ((rc = make_place(pc, ek, c)) || (rc = make_out(out, noise, pc->n_cells, dt, agents->id_offset, ok))) return rc;
+    const bool onehot = pc != nullptr && pc->description == RIAB_PC_ONE_HOT;     // post-pass spikes (k_finish_rows): dense
+    if ((rc = make_place(pc, ek, c)) ||
+        (rc = make_out(out, noise, pc->n_cells, dt, agents->id_offset, ok, onehot ? -1.0 : (double)fmaxf(pc->min_fr, pc->max_fr)))) return rc;
     if (c.desc == RIAB_PC_ONE_HOT) {             // arg-min across cells: its own kernel after the motion kernel
       if (MODE == 2) return fail(RIAB_ERR_UNSUPPORTED, "one_hot populations are stepped unskewed");
       if (MODE == 1 && (rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
@@ -1629,7 +1771,8 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
   if (cells_kind == RIAB_CELLS_GRID) {
     const riab_grid_cells* gc = (const riab_grid_cells*)cells;
     GridConst c;
-    if ((rc = make_grid(gc, ek, c)) || (rc = make_out(out, noise, gc->n_cells, dt, agents->id_offset, ok))) return rc;
+    if ((rc = make_grid(gc, ek, c)) ||
+        (rc = make_out(out, noise, gc->n_cells, dt, agents->id_offset, ok, (double)fmaxf(gc->min_fr, gc->max_fr)))) return rc;
     return launch_tile<GridPolicy, MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_BVC) {

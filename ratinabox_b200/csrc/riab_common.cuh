@@ -73,7 +73,9 @@ RIAB_DEV void philox_round_keys(uint32_t (&rk)[2 * R], unsigned long long seed) 
 }
 
 // Stream ids (third counter word, top byte)
-enum : uint32_t { RIAB_STREAM_AGENT_OU = 0, RIAB_STREAM_CELL_NOISE = 1, RIAB_STREAM_SPIKES = 2, RIAB_STREAM_MEASURE = 3 };
+enum : uint32_t { RIAB_STREAM_AGENT_OU = 0, RIAB_STREAM_CELL_NOISE = 1, RIAB_STREAM_SPIKES = 2, RIAB_STREAM_MEASURE = 3,
+                  RIAB_STREAM_THIN_FIRST = 4,      // thinned spikes: candidate word per (agent pair, 4-cell group)
+                  RIAB_STREAM_THIN_CHAIN = 8 };    // + n: n-th Philox call of a candidate group's chain (slot, accept, gap, accept)
 
 // counter = (agent id lo32, sub-index, step lo32, (step hi & 0xffff) | stream<<24 | population<<16)
 RIAB_HD void philox_ctr(uint32_t (&c)[4], uint64_t agent, uint32_t sub, uint64_t step, uint32_t stream, uint32_t pop) {
@@ -147,6 +149,19 @@ RIAB_DEV float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// Packed float32 pairs (PTX f32x2, SASS FFMA2 / FMUL2 / FADD2, sm_100): one issue slot for two FMA-pipe operations on an
+// even-aligned register pair.  `bc2(x)` is the broadcast pair (x, x): ptxas folds it into the instruction's scalar
+// `.F32` operand form, so per-agent shared-memory broadcasts need no duplicated record fields and no MOVs.
+// scripts/ubench_packed.cu: 2.0 cycles per packed instruction per sub-partition = the FMA-pipe time of two scalar
+// operations in one issue slot (the rate consumers are issue-bound, not FMA-pipe bound).
+typedef unsigned long long f32x2;
+RIAB_DEV f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+RIAB_DEV f32x2 bc2(float x) { return pk2(x, x); }
+RIAB_DEV void upk2(f32x2 r, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+RIAB_DEV f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+RIAB_DEV f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+RIAB_DEV f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5*2^23 trick,
 // degree-5 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.5e-7, ex2.approx's own is ~2e-7), exponent

@@ -15,6 +15,10 @@ struct GridConst {
   int n_cells, n_pad, rectify;
   float A, B;          // f = A * (cos1+cos2+cos3) + B   (then max(0,.) when rectify)
   float min_fr, span;
+  // scale folded into the affine map (make_grid): rate = clamp(As * sum + Bs) with As = A span, Bs = B span + min_fr;
+  // max(f, 0) span + min_fr = max(As sum + Bs, min_fr) for span >= 0 (min(.) for span < 0)   (Neurons.py:1214,1232-1234)
+  float As, Bs;
+  int clamp;           // 0: none (shifted cosines), 1: max(., min_fr), 2: min(., min_fr)
   const float* packed;
   double cxm, cym;
 };
@@ -38,17 +42,22 @@ RIAB_DEV void grid_load_cells(GridCellRegs& r, const GridConst& c, int cell0) {
 
 RIAB_DEV void grid_rates4(float (&out)[4], const GridCellRegs& r, const GridConst& c, const float* __restrict__ rec) {
   const float2 p = *reinterpret_cast<const float2*>(rec);
+  const f32x2 npx = bc2(-p.x), npy = bc2(-p.y);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float s = 0.f;
+  for (int h = 0; h < 2; ++h) {                       // cell pairs: the three phases are 2 FFMA2 each per two rates
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const float phi = fmaf(-p.y, r.ky[k][i], fmaf(-p.x, r.kx[k][i], r.ph[k][i]));
-      s += __cosf(phi);
+      f32x2 phi = ffma2(pk2(r.kx[k][2 * h], r.kx[k][2 * h + 1]), npx, pk2(r.ph[k][2 * h], r.ph[k][2 * h + 1]));
+      phi = ffma2(pk2(r.ky[k][2 * h], r.ky[k][2 * h + 1]), npy, phi);
+      float a, b;
+      upk2(phi, a, b);
+      s0 += __cosf(a); s1 += __cosf(b);
     }
-    float v = fmaf(s, c.A, c.B);
-    if (c.rectify) v = fmaxf(v, 0.f);                 // Neurons.py:1214
-    out[i] = fmaf(v, c.span, c.min_fr);               // Neurons.py:1232-1234
+    float v0 = fmaf(s0, c.As, c.Bs), v1 = fmaf(s1, c.As, c.Bs);
+    if (c.clamp == 1) { v0 = fmaxf(v0, c.min_fr); v1 = fmaxf(v1, c.min_fr); }
+    else if (c.clamp == 2) { v0 = fminf(v0, c.min_fr); v1 = fminf(v1, c.min_fr); }
+    out[2 * h] = v0; out[2 * h + 1] = v1;
   }
 }
 

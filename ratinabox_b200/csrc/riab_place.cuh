@@ -14,11 +14,11 @@
 // each inner wall with utils.vector_intercepts (utils.py:30-118): blocked iff
 // 0<l_a<1 and 0<l_b<1.  With f = signed distance to the wall's line and t = the
 // parameter along the wall, l_a = f_c/(f_c-f_p) and l_b = (f_c t_p - f_p t_c)/(f_c-f_p),
-// so per (agent, cell, wall) the float32 fast path is 9 instructions on
-// per-cell registers and per-agent shared-memory broadcasts (5 on the FMA pipe,
-// 2 three-input FMNMX3 on the half-rate ALU pipe, the select done arithmetically
-// with a saturating multiply).  Results within an absolute band of 0 or 1 are
-// re-evaluated in float64 with the reference's exact expression
+// so per (agent, cell, wall) the float32 fast path is three FMA-pipe operations on
+// per-cell registers and per-agent shared-memory broadcasts -- issued as packed
+// FFMA2 / FMUL2 over cell pairs, 1.5 issue slots -- and one three-input FMNMX3; the
+// select is arithmetic (the penalty enters the exponent).  Results within an absolute
+// band of 0 are re-evaluated in float64 with the reference's exact expression
 // (los_blocked_exact), so the decision equals the oracle's.
 #pragma once
 #include "riab_common.cuh"
@@ -26,7 +26,9 @@
 namespace riab {
 
 constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
-// Agent record (floats): [px, py, ep0, ep1] [t_p/|f_p|, (1-t_p)/|f_p|, -f_p * 2^20, band/|f_p|] x PLACE_MAX_WI [float64 px, py]
+// Agent record (floats): [px, py, ep0, ep1] [-s t_p/|f_p|, -s (1-t_p)/|f_p|, -f_p * 2^20, band/|f_p|] x PLACE_MAX_WI [float64 px, py]
+// with s = sign(f_p): multiplied by the cell's SIGNED f_c these give |f_c| t_p/|f_p| etc. exactly when centre and agent
+// lie on opposite sides of the wall's line (the only case in which X and Y matter), with no |.| on the cell side.
 constexpr int PLACE_WALL0 = 4;                               // float index of wall 0's float4
 constexpr int PLACE_POS64 = PLACE_WALL0 + 4 * PLACE_MAX_WI;  // float index of the float64 position
 constexpr int PLACE_REC = PLACE_POS64 + 4;                   // 40 floats = 160 B per agent
@@ -79,7 +81,10 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
       wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
       const double b = fabs(f);
       if (b < 1e-9) w = make_float4(0.f, 0.f, 0.f, 3.0e38f);      // agent on the wall's line: every decision -> exact path
-      else w = make_float4((float)(t / b), (float)((1.0 - t) / b), (float)(-f) * PLACE_QSCALE, (float)((double)band / b));
+      else {
+        const double ns = (f > 0.0) ? -1.0 : 1.0;                  // -sign(f_p)
+        w = make_float4((float)(ns * t / b), (float)(ns * (1.0 - t) / b), (float)(-f) * PLACE_QSCALE, (float)((double)band / b));
+      }
     }
     *reinterpret_cast<float4*>(rec + PLACE_WALL0 + 4 * j) = w;
   }
@@ -206,9 +211,11 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     // With a = |f_c|, b = |f_p| and q' = -f_c f_p 2^20 (> 0 iff the agent is on the other side of the wall's line):
     //   |D| = a + b,  M' = b t_c + a t_p  (a convex combination of t_p, t_c scaled by |D|),
     //   blocked  <=>  q' > 0 and 0 < M' < |D|.
-    // Everything is divided by b on the agent side (record: t_p/b, (1-t_p)/b, band/b), so per pair
-    //   X = M'/b = fma(a, t_p/b, t_c),  Y = (|D|-M')/b = fma(a, (1-t_p)/b, 1-t_c),  m3 = min(X, Y, q')
-    // is 2 FFMA + 1 FMUL + 1 FMNMX3, and blocked <=> m3 > 0.
+    // Everything is divided by b on the agent side and carries -sign(f_p) (record: -s t_p/b, -s (1-t_p)/b, band/b), so
+    //   X = M'/b = fma(f_c, -s t_p/b, t_c),  Y = (|D|-M')/b = fma(f_c, -s (1-t_p)/b, 1-t_c),  q' = f_c (-f_p 2^20)
+    // hold whenever q' > 0 (f_c * -s = a then); on the same side q' < 0 decides alone.  m3 = min(X, Y, q'):
+    // per CELL PAIR 2 FFMA2 + 1 FMUL2 (agent values are the instructions' broadcast operands), per cell 1 FMNMX3;
+    // blocked <=> m3 > 0.
     // |m3| below band/b => the sign of m3 is not certain in float32: re-evaluate in float64.
     // The select is arithmetic: pen = max(0, max_j m3_j) (one FMNMX3 for two walls; NaN -> 0) enters the exponent /
     // the squared distance multiplied by 2^100: any pen above the band (>= ~1e-6 / b) makes the rate exactly 0.
@@ -220,11 +227,18 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       const float4 pw = *reinterpret_cast<const float4*>(rec + PLACE_WALL0 + 4 * j);
       float m3[4];
 #pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const f32x2 fc = pk2(r.fc[j][2 * h], r.fc[j][2 * h + 1]);
+        const f32x2 X = ffma2(fc, bc2(pw.x), pk2(r.tc[j][2 * h], r.tc[j][2 * h + 1]));
+        const f32x2 Y = ffma2(fc, bc2(pw.y), pk2(r.tq[j][2 * h], r.tq[j][2 * h + 1]));
+        const f32x2 Q = fmul2(fc, bc2(pw.z));
+        float x0, x1, y0, y1, q0, q1;
+        upk2(X, x0, x1); upk2(Y, y0, y1); upk2(Q, q0, q1);
+        m3[2 * h] = fminf(fminf(x0, y0), q0);
+        m3[2 * h + 1] = fminf(fminf(x1, y1), q1);
+      }
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float fc = r.fc[j][i], a = fabsf(fc);
-        const float X = fmaf(a, pw.x, r.tc[j][i]);
-        const float Y = fmaf(a, pw.y, r.tq[j][i]);
-        m3[i] = fminf(fminf(X, Y), fc * pw.z);
         if ((j & 1) == 1) worst[i] = fmaxf(fmaxf(worst[i], m3[i]), m3_prev[i]);   // pairs of walls: one FMNMX3
         else if (j == WI - 1) worst[i] = fmaxf(worst[i], m3[i]);                                    // odd wall count: the last one
         m3_prev[i] = m3[i];
@@ -246,14 +260,18 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
   // 1 FADD + 2 FFMA per rate on per-cell registers (2k cx, 2k cy, -k|c|^2); only used when k * r2_max <= 10,
   // where the cancellation costs < 4e-6 relative (make_place).  Blocked pairs: exponent - 1e5 -> rate 0 (d = 1000).
   if (DESC == RIAB_PC_GAUSSIAN && (EXP >= 1 || (EXP < 0 && c.expanded))) {
+    const f32x2 zz = bc2(r0.z), px2 = bc2(r0.x), py2 = bc2(r0.y);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float t = r.k[i] + r0.z;
-      t = fmaf(r.cx[i], r0.x, t);
-      t = fmaf(r.cy[i], r0.y, t);
-      if (WI > 0) t = fmaf(pen[i], -PLACE_PEN, t);
+    for (int h = 0; h < 2; ++h) {                         // cell pairs: FADD2 + 2 (3) FFMA2 per two rates
+      f32x2 t = fadd2(pk2(r.k[2 * h], r.k[2 * h + 1]), zz);
+      t = ffma2(pk2(r.cx[2 * h], r.cx[2 * h + 1]), px2, t);
+      t = ffma2(pk2(r.cy[2 * h], r.cy[2 * h + 1]), py2, t);
+      if (WI > 0) t = ffma2(pk2(pen[2 * h], pen[2 * h + 1]), bc2(-PLACE_PEN), t);
+      float t0, t1;
+      upk2(t, t0, t1);
       // Neurons.py:978-980; EXP == 2: min_fr == 0 and log2(span) already sits in the agent's -k|p|^2 term
-      out[i] = (EXP == 2 || (EXP < 0 && c.fold)) ? ex2f(t) : fmaf(ex2f(t), c.span, c.min_fr);
+      if (EXP == 2 || (EXP < 0 && c.fold)) { out[2 * h] = ex2f(t0); out[2 * h + 1] = ex2f(t1); }
+      else { out[2 * h] = fmaf(ex2f(t0), c.span, c.min_fr); out[2 * h + 1] = fmaf(ex2f(t1), c.span, c.min_fr); }
     }
     return;
   }

@@ -1,0 +1,33 @@
+"""Tiny driver for ncu: python scripts/prof_driver.py <workload> <spikes 0|1> <mode rates|run> [steps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import ratinabox_b200 as rb  # noqa: E402
+
+name, spikes, mode = sys.argv[1], sys.argv[2] == "1", sys.argv[3]
+steps = int(sys.argv[4]) if len(sys.argv) > 4 else 6
+wl = bench.WORKLOADS[name]
+A = wl["agents"]
+np.random.seed(0)
+Env = rb.Environment()
+for w in wl["walls"]:
+    Env.add_wall(w)
+Ag = rb.Agent(Env, {"dt": 0.01, "n_agents": A, "seed": 7})
+pos, vel = bench.synthetic_agents(A, wl["walls"], 100)
+Ag.pos, Ag.velocity = pos, vel
+pops = bench.build_populations(rb, Ag, wl)
+for ns in pops:
+    ns.save_spikes = spikes
+if mode == "rates":
+    for _ in range(steps):
+        for ns in pops:
+            ns.update()
+else:
+    Ag.run(steps)
+torch.cuda.synchronize()

@@ -56,12 +56,16 @@ def agent_normals(seed, step, agents):
                      (rad * np.sin(ang).astype(f32)).astype(np.float64)), axis=-1)
 
 
-def expected_spikes(seed, step, agents, fr, dt, pop=0):
-    """(A, n_cells) bool spikes of one step given the float32 rates `fr` (A, n_cells):
+def expected_spikes(seed, step, agents, fr, dt, pop=0, fr_bound=None):
+    """(A, n_cells) bool spikes of one step given the float32 rates `fr` (A, n_cells).
+    fr_bound = max(min_fr, max_fr) of a PlaceCells / GridCells population without OU noise: the library uses the thinned
+    stream when dt * fr_bound * (1 + 2^-10) <= 1/8 (expected_spikes_thin), else -- and for every other population -- the dense one:
         spike <=> m < fma(rate, dt*65536, -v)      (riab_b200.cu: spike_ballots)
     One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words 2h, 2h+1 as four
     16-bit integers m; all eight share the dither v = ((r0^r2)>>8) * 2^-24.  The float32 fma is mirrored
     in float64: the 48-bit product and the 24-bit dither add exactly, so the sum rounds to float32 once."""
+    if fr_bound is not None and thin_tables(dt, fr_bound) is not None:
+        return expected_spikes_thin(seed, step, agents, fr, dt, fr_bound, pop)
     agents = np.asarray(agents, dtype=np.uint64)
     fr = np.asarray(fr, dtype=np.float32)
     n_cells = fr.shape[1]
@@ -79,3 +83,72 @@ def expected_spikes(seed, step, agents, fr, dt, pop=0):
     q = np.float64(np.float32(np.float32(dt) * np.float32(65536.0)))
     thr = (fr.astype(np.float64) * q - vv).astype(np.float32)
     return m < thr
+
+
+STREAM_THIN_FIRST, STREAM_THIN_CHAIN = 4, 8
+
+
+def thin_tables(dt, fr_bound):
+    """Thresholds of the thinned spike stream (riab_b200.cu: make_out).  None when the dense stream is used."""
+    bound = float(fr_bound) * (1.0 + 1.0 / 1024.0)
+    p = float(dt) * bound
+    if not (fr_bound >= 0.0 and p <= 0.125):
+        return None
+    t, qq = [], 1.0
+    for _ in range(8):
+        qq *= (1.0 - p)
+        v = np.floor(4294967296.0 * (1.0 - qq))
+        t.append(4294967295 if v >= 4294967295.0 else int(v))
+    tc = [((t[i] << 32) // t[7]) if t[7] else 0 for i in range(7)]
+    c1, c0 = np.float32(bound / 16777216.0), np.float32(bound / 33554432.0)
+    return np.array(t, dtype=np.uint64), np.array(tc, dtype=np.uint64), c1, c0
+
+
+def expected_spikes_thin(seed, step, agents, fr, dt, fr_bound, pop=0):
+    """Mirror of thin_post (riab_b200.cu): candidates per (agent pair, 4-cell group) of 8 slots, slot = 4*(gid&1) + cell&3.
+    Level 1: word (gid>>1)&3 of Philox7((gid>>3, group), THIN_FIRST) < t[7]  <=>  the group holds a candidate.
+    Level 2: words of Philox7((gid>>1, group), THIN_CHAIN + n), n = 0, 1, ...: first slot from the conditional table,
+    then alternately accept (24-bit uniform * bound < rate) and geometric gap to the next candidate."""
+    agents = np.asarray(agents, dtype=np.uint64)
+    fr = np.asarray(fr, dtype=np.float32)
+    A, n_cells = fr.shape
+    t, tc, c1, c0 = thin_tables(dt, fr_bound)
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    groups = (n_cells + 3) // 4
+    out = np.zeros((A, n_cells), dtype=bool)
+    row_of = {int(g): i for i, g in enumerate(agents)}
+    pairs = np.unique(agents >> np.uint64(1))
+    g = np.arange(groups, dtype=np.uint64)[None, :]
+    first = philox4x32(counter((pairs >> np.uint64(2))[:, None], g, step, STREAM_THIN_FIRST, pop), key, rounds=7)   # (P,G,4)
+    w = np.take_along_axis(first, (pairs & np.uint64(3)).astype(np.int64)[:, None, None].repeat(groups, 1), axis=2)[..., 0]
+    cand_p, cand_g = np.nonzero(w.astype(np.uint64) < t[7])
+
+    def gap(x):
+        x = np.uint64(x)
+        return 8 if x >= t[7] else int((x >= t[:7]).sum())
+
+    def accept(pair, grp, K, word):
+        gid = 2 * int(pair) + (K >> 2)
+        cell = 4 * int(grp) + (K & 3)
+        if gid not in row_of or cell >= n_cells:
+            return
+        thr = np.float32(np.float64(int(word) >> 8) * np.float64(c1) + np.float64(c0))
+        if thr < fr[row_of[gid], cell]:
+            out[row_of[gid], cell] = True
+
+    for pi, gi in zip(cand_p, cand_g):
+        pair, n = pairs[pi], 0
+        S = philox4x32(counter(np.uint64(pair), np.uint64(gi), step, STREAM_THIN_CHAIN + n, pop), key, rounds=7)
+        K = int((np.uint64(S[0]) >= tc).sum())
+        accept(pair, gi, K, S[1])
+        K += 1 + gap(S[2])
+        while K < 8:
+            accept(pair, gi, K, S[3])
+            n += 1
+            S = philox4x32(counter(np.uint64(pair), np.uint64(gi), step, STREAM_THIN_CHAIN + n, pop), key, rounds=7)
+            K += 1 + gap(S[0])
+            if K >= 8:
+                break
+            accept(pair, gi, K, S[1])
+            K += 1 + gap(S[2])
+    return out

@@ -112,9 +112,35 @@ def test_spikes_match_numpy_philox():
     h = PCs.get_history_arrays()
     assert h["firingrate"].shape == (3, A, N) and h["spikes"].shape == (3, A, N) and h["spikes"].dtype == bool
     for s in range(3):
-        want = expected_spikes(11, s, np.arange(A), h["firingrate"][s], 0.05, pop=0)
+        want = expected_spikes(11, s, np.arange(A), h["firingrate"][s], 0.05, pop=0, fr_bound=15.0)
         assert np.array_equal(h["spikes"][s], want), s
     assert 0.02 < h["spikes"].mean() < 0.6
+
+
+@pytest.mark.parametrize("A,N,stepped", [(131, 300, False), (64, 1024, False), (70, 128, True), (33, 2304, False)])
+def test_thinned_spikes_match_numpy_mirror(A, N, stepped):
+    """dt * max_fr <= 1/8 (here 0.01 * 1 Hz): PlaceCells / GridCells without OU noise use the thinned spike stream
+    (candidates at rate dt*max_fr per group of 8 slots, accepted with rate/max_fr; riab_b200.cu: thin_post).  Bit-equal to
+    the NumPy mirror for odd agent counts, ragged cell counts, several cell chunks (N > 2048), riab_run and the stepped API;
+    still Bernoulli(dt * rate) (Neurons.py:682-684)."""
+    import ratinabox_b200 as rb
+    E, Ag = make(rb, A)
+    PCs = rb.PlaceCells(Ag, {"n": N, "wall_geometry": "line_of_sight"})
+    GCs = rb.GridCells(Ag, {"n": 64, "max_fr": 3.0})
+    steps = 3
+    if stepped:
+        for _ in range(steps):
+            Ag.update(); PCs.update(); GCs.update()
+    else:
+        Ag.run(steps)
+    for pop, (Ns, bound) in enumerate(((PCs, 1.0), (GCs, 3.0))):
+        h = Ns.get_history_arrays()
+        for s in range(steps):
+            want = expected_spikes(11, s, np.arange(A), h["firingrate"][s].reshape(A, Ns.n), 0.01, pop=pop, fr_bound=bound)
+            assert np.array_equal(h["spikes"][s].reshape(A, Ns.n), want), (pop, s)
+        p = 0.01 * h["firingrate"].astype(np.float64)
+        n_sp, mu, var = h["spikes"].sum(), p.sum(), (p * (1 - p)).sum()
+        assert abs(n_sp - mu) < 6 * np.sqrt(var) + 1, (n_sp, mu)
 
 
 def test_multistep_tracking_config1():
