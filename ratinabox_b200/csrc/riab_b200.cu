@@ -484,62 +484,100 @@ __device__ __forceinline__ int thin_gap(const OutK& out, uint32_t w) {
   for (int i = 0; i < 7; ++i) n += (w >= out.thin_t[i]) ? 1 : 0;
   return n;
 }
-__device__ __forceinline__ void thin_accept(const OutK& out, const TailCtx& tc, int K, uint32_t w, unsigned long long pair,
-                                            long long row_lo, long long row_hi, int lane) {
-  const long long row = (long long)(2ull * pair + (unsigned)(K >> 2)) - out.id_offset;
-  const int i = K & 3;
-  if (row < row_lo || row >= row_hi || !((tc.vmask >> i) & 1u)) return;      // the other shard's / tile's half, padding cell
+// Rows / words of one warp's (ring slot, 128-cell block): 32-bit offsets from two base pointers.
+struct ThinBlock {
+  const float* rates;       // out.rates + row_lo * ld + (first cell of the warp's block)
+  uint32_t* spikes;         // out.spikes + row_lo * spike_ld + 4 * (block index)
+  unsigned long long gid_lo;
+  int n_rows, ld, spike_ld;
+  int cells_left;           // n_cells - (first cell of the block): cells of the block that exist
+};
+// slot K of group (pair, source lane L): accept <=> 24-bit uniform * bound < rate
+__device__ __forceinline__ void thin_accept(const OutK& out, const ThinBlock& b, int K, uint32_t w, unsigned long long pair,
+                                            int L) {
+  const int r = (int)(2ull * pair - b.gid_lo) + (K >> 2);           // row within the block's rows
+  const int c = 4 * L + (K & 3);                                   // cell within the block
+  if ((unsigned)r >= (unsigned)b.n_rows || c >= b.cells_left) return;   // the other shard's / tile's half, padding cell
   float rate;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate) : "l"(out.rates + row * out.ld + tc.cell0 + i));
-  if (fmaf((float)(w >> 8), out.thin_c1, out.thin_c0) < rate)
-    atomicOr(out.spikes + row * out.spike_ld + ((tc.cell0 >> 7) << 2) + i, 1u << lane);
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate) : "l"(b.rates + (r * b.ld + c)));
+  if (fmaf((float)(w >> 8), out.thin_c1, out.thin_c0) < rate) atomicOr(b.spikes + (r * b.spike_ld + (K & 3)), 1u << L);
 }
-// rows [row_lo, row_hi) of this launch, cells of tail context `tc` (a warp covers 128 consecutive cells); whole warp calls
+// rows [row_lo, row_hi) of this launch, cells of tail context `tc` (a warp covers 128 consecutive cells); whole warp calls.
+// queue: this warp's 64 x uint16 scratch in shared memory.
 __device__ __forceinline__ void thin_post(const OutK& out, const TailCtx& tc, const long long row_lo, const long long row_hi,
-                                          const bool act) {
+                                          uint16_t* __restrict__ queue) {
   const int lane = threadIdx.x & 31;
-  const unsigned long long gid_lo = (unsigned long long)(out.id_offset + row_lo), gid_hi = (unsigned long long)(out.id_offset + row_hi);
-  const unsigned long long pair_lo = gid_lo >> 1, pair_hi = (gid_hi + 1ull) >> 1;       // [lo, hi)
-  uint32_t pend = 0u;                                    // bit j: pair pair_lo + j holds a candidate (at most 16 pairs + 1)
-  const uint32_t c3 = (tc.c3_spk & 0x00ffffffu) | (RIAB_STREAM_THIN_FIRST << 24);
+  ThinBlock b;
+  const int cell_blk = tc.cell0 - 4 * lane;                        // first cell of the warp's 128-cell block
+  b.rates = out.rates + row_lo * out.ld + cell_blk;
+  b.spikes = out.spikes + row_lo * out.spike_ld + ((cell_blk >> 7) << 2);
+  b.gid_lo = (unsigned long long)(out.id_offset + row_lo);
+  b.n_rows = (int)(row_hi - row_lo); b.ld = (int)out.ld; b.spike_ld = (int)out.spike_ld;
+  b.cells_left = tc.n_cells - cell_blk;
+  const unsigned long long pair_lo = b.gid_lo >> 1, pair_hi = (b.gid_lo + (unsigned)b.n_rows + 1ull) >> 1;       // [lo, hi)
+  const uint32_t sub_blk = tc.sub - (uint32_t)lane;                // cell-group index of lane 0
+  const uint32_t c3 = tc.c3_spk & 0x00ffffffu;
+  // ---- level 1: which of this lane's (pair, cell group) octets hold a candidate
+  uint32_t pend = 0u;                                    // bit j: pair pair_lo + j (at most 17 pairs)
   for (unsigned long long q = pair_lo >> 2; q < ((pair_hi + 3ull) >> 2); ++q) {
     uint32_t R[4];
-    R[0] = (uint32_t)q; R[1] = tc.sub ^ ((uint32_t)(q >> 32) << 24); R[2] = tc.c2; R[3] = c3;
+    R[0] = (uint32_t)q; R[1] = tc.sub ^ ((uint32_t)(q >> 32) << 24); R[2] = tc.c2; R[3] = c3 | (RIAB_STREAM_THIN_FIRST << 24);
     philox_keyed<7>(R, out.rk7);
+    const int j0 = (int)(4ull * q - pair_lo);            // may be negative for the first quad
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-      const long long j = (long long)(4ull * q + (unsigned)w) - (long long)pair_lo;
-      if (j >= 0 && 4ull * q + (unsigned)w < pair_hi && R[w] < out.thin_t[7]) pend |= 1u << j;
+      const int j = j0 + w;
+      if (j >= 0 && j < (int)(pair_hi - pair_lo) && R[w] < out.thin_t[7]) pend |= 1u << j;
     }
   }
-  if (!act) pend = 0u;
+  if (4 * lane >= b.cells_left) pend = 0u;               // lanes whose cells do not exist
+  // ---- level 2, compacted over the warp: ~8 % of the octets hold a candidate, so the (lane, pair) items of the whole warp
+  // are queued in shared memory and every lane walks the chain of ONE item per pass (one pass for <= 32 items).
   while (__any_sync(0xffffffffu, pend != 0u)) {
-    if (pend != 0u) {
-      const int j = __ffs(pend) - 1;
-      pend &= pend - 1u;
-      const unsigned long long pair = pair_lo + (unsigned)j;
-      uint32_t S[4];
-      uint32_t n = 0u;
-      S[0] = (uint32_t)pair; S[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2;
-      S[3] = (tc.c3_spk & 0x00ffffffu) | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
-      philox_keyed<7>(S, out.rk7);
-      int K = 0;
+    // each lane contributes up to 2 items per round (the queue holds 64)
+    const uint32_t first = pend & (0u - pend), rest = pend ^ first;
+    const uint32_t second = rest & (0u - rest);
+    const int cnt = (first != 0u) + (second != 0u);
+    int incl = cnt;
 #pragma unroll
-      for (int i = 0; i < 7; ++i) K += (S[0] >= out.thin_tc[i]) ? 1 : 0;
-      thin_accept(out, tc, K, S[1], pair, row_lo, row_hi, lane);
-      K += 1 + thin_gap(out, S[2]);
-      while (K < 8) {                                    // a second (third, ...) candidate in the same group: ~7 % of groups
-        thin_accept(out, tc, K, S[3], pair, row_lo, row_hi, lane);
-        ++n;
-        S[0] = (uint32_t)pair; S[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2;
-        S[3] = (tc.c3_spk & 0x00ffffffu) | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
+    for (int d = 1; d < 32; d <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += n;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int at = incl - cnt;
+    if (first) queue[at++] = (uint16_t)((lane << 5) | (31 - __clz(first)));
+    if (second) queue[at] = (uint16_t)((lane << 5) | (31 - __clz(second)));
+    pend = rest ^ second;
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+      if (base + lane < total) {
+        const uint32_t item = queue[base + lane];
+        const int L = (int)(item >> 5), j = (int)(item & 31u);
+        const unsigned long long pair = pair_lo + (unsigned)j;
+        const uint32_t sub = sub_blk + (uint32_t)L;
+        uint32_t S[4];
+        uint32_t n = 0u;
+        S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2; S[3] = c3 | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
         philox_keyed<7>(S, out.rk7);
-        K += 1 + thin_gap(out, S[0]);
-        if (K >= 8) break;
-        thin_accept(out, tc, K, S[1], pair, row_lo, row_hi, lane);
+        int K = 0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) K += (S[0] >= out.thin_tc[i]) ? 1 : 0;
+        thin_accept(out, b, K, S[1], pair, L);
         K += 1 + thin_gap(out, S[2]);
+        while (K < 8) {                                  // a second (third, ...) candidate in the same octet: ~7 % of them
+          thin_accept(out, b, K, S[3], pair, L);
+          ++n;
+          S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2; S[3] = c3 | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
+          philox_keyed<7>(S, out.rk7);
+          K += 1 + thin_gap(out, S[0]);
+          if (K >= 8) break;
+          thin_accept(out, b, K, S[1], pair, L);
+          K += 1 + thin_gap(out, S[2]);
+        }
       }
     }
+    __syncwarp();                                        // the queue is rewritten by the next round
   }
 }
 
@@ -547,7 +585,7 @@ __device__ __forceinline__ void thin_post(const OutK& out, const TailCtx& tc, co
 template <class P, int SPK, bool NOISE, class C, int EXP>
 __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, const OutK& out, StepSlot<P::REC>* s_slot,
                                                uint64_t* s_full, uint64_t* s_empty, const double* s_walls,
-                                               const long long nq, const int ctid, const int lane) {
+                                               const long long nq, const int ctid, const int lane, uint16_t* thin_queue) {
   constexpr int NS = C::NS;
   constexpr int NC = RW * 32;
   constexpr bool DENSE = (SPK == 1);
@@ -658,7 +696,7 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
         }
         if (SPK == 2) {
           __syncwarp();      // orders the zero-fill and this warp's rate stores before the chain's loads / RED.ORs
-          thin_post(out, tc, a0 + a_lo, a0 + a_hi, act || (tc.vmask != 0u));
+          thin_post(out, tc, a0 + a_lo, a0 + a_hi, thin_queue);
         }
       }
     }
@@ -677,6 +715,7 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
   constexpr int MW = C::MW, NS = C::NS;
   __shared__ StepSlot<P::REC> s_slot[NS];
   __shared__ uint64_t s_bar, s_full[NS], s_empty[NS];
+  __shared__ uint16_t s_thinq[(SPK == 2) ? RW : 1][64];       // per consumer warp: candidate items of thin_post
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RW); }
@@ -749,9 +788,9 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
     // the cell registers then stay in registers across slots (a run-time switch inside the loop made ptxas park them
     // in local memory around every slot)
     const int ex = P::expanded(pc);
-    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane);
-    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane);
-    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane);
+    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, s_thinq[(SPK == 2) ? (ctid >> 5) : 0]);
+    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, s_thinq[(SPK == 2) ? (ctid >> 5) : 0]);
+    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, s_thinq[(SPK == 2) ? (ctid >> 5) : 0]);
   }
 }
 

@@ -52,7 +52,8 @@ RIAB_DEV void grid_rates4(float (&out)[4], const GridCellRegs& r, const GridCons
       phi = ffma2(pk2(r.ky[k][2 * h], r.ky[k][2 * h + 1]), npy, phi);
       float a, b;
       upk2(phi, a, b);
-      s0 += __cosf(a); s1 += __cosf(b);
+      if (k == 0) { s0 = __cosf(a); s1 = __cosf(b); }
+      else { s0 += __cosf(a); s1 += __cosf(b); }
     }
     float v0 = fmaf(s0, c.As, c.Bs), v1 = fmaf(s1, c.As, c.Bs);
     if (c.clamp == 1) { v0 = fmaxf(v0, c.min_fr); v1 = fmaxf(v1, c.min_fr); }
