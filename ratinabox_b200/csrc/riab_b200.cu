@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "riab_bvc.cuh"
@@ -71,8 +72,9 @@ struct OutK {
   uint32_t rk7[14];         // Philox4x32-7 round keys of the spike stream (host-computed, constant bank)
   // thinned spikes (thin_post): candidates at rate p = dt * (an upper bound of the rate), accepted with rate / bound
   int thin;                 // 1: the population's rates are bounded and p <= 1/8
-  uint32_t thin_t[8];       // t[i] = floor(2^32 (1 - (1-p)^(i+1))): first candidate among 8 slots is slot #{i: word >= t[i]}
-  uint32_t thin_tc[7];      // conditional on "a candidate exists": floor(2^32 t[i] / t[7])
+  uint32_t thin_t16;        // an octet of 8 slots holds a candidate  <=>  its 16-bit word < t16  (= ceil(2^16 (1 - (1-p)^8)))
+  uint32_t thin_t[8];       // t[i] = floor(2^32 (1 - (1-p')^(i+1))), p' the per-slot probability t16 implies: gap to the next candidate
+  uint32_t thin_tc[7];      // first candidate slot of an octet that holds one: floor(2^32 (1 - (1-p')^(i+1)) / (1 - (1-p')^8))
   float thin_c1, thin_c0;   // accept <=> fma(float(word >> 8), c1, c0) < rate;  c1 = 2^-24 bound, c0 = 2^-25 bound
 };
 
@@ -154,11 +156,13 @@ struct RowCursor {
   unsigned long long gid;  // global agent id
 };
 
+template <int CPT = 4>
 __device__ __forceinline__ void tail_init(TailCtx& t, const OutK& out, int cell0, int n_cells) {
   t.cell0 = cell0; t.n_cells = n_cells;
-  t.vmask = (cell0 < n_cells ? 1u : 0u) | (cell0 + 1 < n_cells ? 2u : 0u) | (cell0 + 2 < n_cells ? 4u : 0u) |
-            (cell0 + 3 < n_cells ? 8u : 0u);
-  t.full4 = out.vec_ok && (t.vmask == 0xFu);
+  t.vmask = 0u;
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) t.vmask |= (cell0 + i < n_cells) ? (1u << i) : 0u;
+  t.full4 = out.vec_ok && (t.vmask == ((1u << CPT) - 1u));
   t.sub = (uint32_t)(cell0 >> 2);
   t.c2 = (uint32_t)out.step;
   const uint32_t hi = ((uint32_t)(out.step >> 32) & 0xffffu) | (((uint32_t)out.pop & 0xffu) << 16);
@@ -295,33 +299,36 @@ __device__ __forceinline__ void finish4(float (&o)[4], const OutK& out, const Ta
 
 // ---------------------------------------------------------------------------
 // Cell-type policies for the step kernel.
-template <int WI, int DESC>
+template <int WI, int DESC, int CPT_ = 4>
 struct PlacePolicy {
   using Const = PlaceConst;
-  using Regs = PlaceCellRegs<WI>;
-  static constexpr int REC = PLACE_REC;
+  using Regs = PlaceCellRegs<WI, CPT_>;
+  static constexpr int CPT = CPT_;                          // cells per consumer thread
+  static constexpr int REC = place_rec(WI);
   static constexpr bool LIGHT = (WI == 0) && (DESC >= 0);   // few instructions per rate: HBM-bound consumers
   static constexpr bool XU_BOUND = false;
   static constexpr bool THIN = true;                        // rates lie in [min_fr, max_fr]: thinned spikes apply
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
   static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double* s_walls,
                                                 const Const& c, const EnvK& env) {
-    place_agent_record(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx, c.fold ? c.lspan : 0.f);
+    place_agent_record<WI>(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx, c.fold ? c.lspan : 0.f);
   }
-  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI>(r, c, cell0); }
+  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI, CPT_>(r, c, cell0); }
   template <bool DEFER, int EXP = -1>
-  static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int cell0,
+  static __device__ __forceinline__ void rates4(float (&o)[CPT_], const Regs& r, const Const& c, int cell0,
                                                 const float* rec, uint32_t inner_s, bool& unsure) {
-    place_rates4<WI, DESC, DEFER, EXP>(o, r, c, cell0, rec, inner_s, unsure);
+    place_rates4<WI, DESC, DEFER, EXP, CPT_>(o, r, c, cell0, rec, inner_s, unsure);
   }
   // 0: direct form, 1: expanded exponent, 2: expanded with the [0, max_fr] scale folded into the exponent
   static __device__ __forceinline__ int expanded(const Const& c) { return (DESC == RIAB_PC_GAUSSIAN && c.expanded) ? 1 + c.fold : 0; }
   static __device__ __forceinline__ int wall0(const Const& c) { return c.wall0; }
 };
 
+template <int CPT_ = 4>
 struct GridPolicy {
   using Const = GridConst;
-  using Regs = GridCellRegs;
+  using Regs = GridCellRegs<CPT_>;
+  static constexpr int CPT = CPT_;
   static constexpr int REC = 4;
   static constexpr bool LIGHT = false;    // 36 cell registers per thread do not fit StepCfg<8>'s 56-register consumers
   static constexpr bool THIN = true;
@@ -332,11 +339,11 @@ struct GridPolicy {
     rec[0] = (float)(px - env.cxm);
     rec[1] = (float)(py - env.cym);
   }
-  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { grid_load_cells(r, c, cell0); }
+  static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { grid_load_cells<CPT_>(r, c, cell0); }
   template <bool DEFER, int EXP = -1>
-  static __device__ __forceinline__ void rates4(float (&o)[4], const Regs& r, const Const& c, int, const float* rec,
+  static __device__ __forceinline__ void rates4(float (&o)[CPT_], const Regs& r, const Const& c, int, const float* rec,
                                                 uint32_t, bool&) {
-    grid_rates4(o, r, c, rec);
+    grid_rates4<CPT_>(o, r, c, rec);
   }
   static __device__ __forceinline__ int expanded(const Const&) { return 0; }
   static __device__ __forceinline__ int wall0(const Const&) { return 0; }
@@ -345,6 +352,7 @@ struct GridPolicy {
 struct OvcPolicy {
   using Const = OvcConst;
   using Regs = OvcCellRegs;
+  static constexpr int CPT = 4;
   static constexpr int REC = OVC_REC;
   static constexpr bool LIGHT = false;
   static constexpr bool THIN = false;     // sums over objects: no a-priori rate bound
@@ -381,8 +389,7 @@ struct OvcPolicy {
 //   StepCfg<4>: 4 producer + 16 consumer warps (640 threads x 96 regs): heavy consumers
 //               (line-of-sight / spikes / noise) set the pace, so they get 104 registers and the 4
 //               producers run (spilling) in 64 -- their latency stays hidden (measured: r104 > r96 > r88).
-//               Do NOT raise the consumers to 112 (producers 56): the setmaxnreg.inc of the 16 consumer warps
-//               never completes (the kernel hangs) although 16*32*112 + 4*32*56 <= 65536 on paper.
+//               112 / 56 does not fit the CTA's own allocation (see step_cfg_fits below) and hangs.
 //   StepCfg<8>: 8 producer + 16 consumer warps (768 threads x 80 regs): light consumers (Euclidean
 //               Gaussian / grid cells without spikes) run at the HBM write rate, so the float64
 //               motion chain (~14 us per 32-agent tile) needs twice the producer warps to keep up.
@@ -390,6 +397,7 @@ constexpr int RW = 16;    // consumer warps
 template <int MW_>
 struct StepCfg {
   static constexpr int MW = MW_;
+  static constexpr int CTAS = 1;                                  // CTAs per SM
   static constexpr int NS = (MW_ >= 8) ? MW_ : 2 * MW_;      // ring slots (multiple of MW; static smem <= 48 KB)
   static constexpr int THREADS = (MW_ + RW) * 32;
   static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;   // what __launch_bounds__(THREADS, 1) allocates
@@ -402,11 +410,39 @@ struct StepCfg {
   static constexpr int REGS_PRODUCER = (MW_ >= 8) ? 128 : RIAB_RP4;
   static constexpr int REGS_CONSUMER = (MW_ >= 8) ? 56 : RIAB_RC4;
 };
+// StepCfg2: TWO CTAs per SM of 2 producer + 16 consumer warps (576 threads x 56 registers each, no re-balancing: the
+// pool setmaxnreg moves registers in is the CTA's own launch allocation).  For policies with CPT = 2 cells per consumer thread (18
+// cell registers with two inner walls instead of 36): the rate consumers are latency-bound -- ncu: one instruction per 7.8
+// cycles per warp, 4.2 warps per scheduler, 54 % of the issue slots used -- so twice the resident consumer warps buy
+// more than the ~14 % extra instructions of the narrower threads cost.
+struct StepCfg2 {
+  static constexpr int MW = 2;
+  static constexpr int CTAS = 2;
+  static constexpr int NS = 4;
+  static constexpr int THREADS = (MW + RW) * 32;
+  static constexpr int REGS_LAUNCH = 56;
+  static constexpr int REGS_PRODUCER = 56;
+  static constexpr int REGS_CONSUMER = 56;
+};
+// setmaxnreg only moves registers WITHIN the CTA's launch allocation (THREADS x REGS_LAUNCH): an .inc blocks until enough
+// warps of the same CTA have released theirs with .dec.  A split whose total exceeds the allocation therefore never
+// completes -- the hang of round 1's 112 / 56 experiment: 16*32*112 + 4*32*56 = 64512 > 640*96 = 61440.
+template <class C>
+constexpr bool step_cfg_fits() {
+  return RW * 32 * C::REGS_CONSUMER + C::MW * 32 * C::REGS_PRODUCER <= C::THREADS * C::REGS_LAUNCH;
+}
+static_assert(step_cfg_fits<StepCfg<4>>() && step_cfg_fits<StepCfg<8>>() && step_cfg_fits<StepCfg2>(),
+              "setmaxnreg split exceeds the CTA's register allocation: the kernel would hang");
 // setmaxnreg towards N registers from the launch allocation L (inc when N > L, dec when N < L)
 template <int N, int L> __device__ __forceinline__ void reg_set() {
   if (N > L) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
   else if (N < L) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
+
+// ring slots of a (policy, configuration): the configuration's count, halved for the fat records (8 inner walls, object
+// vector cells: 160 B per agent) so that the static shared memory stays under 48 KB next to the thinned-spike queues
+template <class P, class C>
+constexpr int ring_slots() { return (P::REC > 24 && C::NS >= 2 * C::MW) ? C::NS / 2 : C::NS; }
 
 template <int REC>
 struct __align__(16) StepSlot {
@@ -432,13 +468,13 @@ __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typ
   unsigned long long pair = rc.gid >> 1;
   const long long pair_rate = 2ll * out.ld, pair_spk = 2ll * out.spike_ld;     // elements per pair step
   for (; a + 1 < a_end; a += 2) {
-    float o[4];
+    float o[P::CPT];
     uint32_t c[4], bl[4];
     bool unsure = false;
     P::template rates4<true, EXP>(o, regs, pc, cell0, recp, inner_s, unsure);
-    if (act) st_cs_f4(dst, o[0], o[1], o[2], o[3]);
+    if (act) st_cs_fv<P::CPT>(dst, o);
     float nv = 0.f;
-    if (DENSE) {
+    if constexpr (DENSE && P::CPT == 4) {
       c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
       philox_keyed<7>(c, out.rk7);
       nv = spike_neg_dither(c);
@@ -446,8 +482,8 @@ __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typ
       spike_store(bl, spk);
     }
     P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
-    if (act) st_cs_f4(dst + out.ld, o[0], o[1], o[2], o[3]);
-    if (DENSE) {
+    if (act) st_cs_fv<P::CPT>(dst + out.ld, o);
+    if constexpr (DENSE && P::CPT == 4) {
       spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, act);
       spike_store(bl, spk + out.spike_ld);
     }
@@ -464,19 +500,20 @@ __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typ
 // ---------------------------------------------------------------------------
 // Thinned spikes (Neurons.py:681-684: spike <=> uniform < dt * rate) for populations whose rates are bounded by `bound`
 // with p = dt * bound <= 1/8 (the usual case: dt = 10 ms, max_fr = 1 Hz gives p = 0.01).  Exact Bernoulli(dt * rate) by
-// thinning: every (agent, cell) is a CANDIDATE with probability p, a candidate spikes with probability rate / bound.
-// Candidates are drawn per group of 8 slots = (agent pair P = gid >> 1, 4-cell group g; slot k = 4 (gid & 1) + (cell & 3)):
-//   level 1   R = Philox7(ctr = (P >> 2, g, step, THIN_FIRST | population)), w = R[P & 3]:
-//             the group holds a candidate  <=>  w < t[7]      (t[i] = floor(2^32 (1 - (1-p)^(i+1))), probability 1 - (1-p)^8)
-//   level 2   only for groups with a candidate: words S_0, S_1, ... of Philox7(ctr = (P, g, step, (THIN_CHAIN + n) | population)),
-//             n = 0, 1, ...:   first candidate slot K = #{i < 7: S_0 >= tc[i]}   (tc = t conditioned on a candidate existing),
-//             then alternately   accept slot K  <=>  fma(float(S >> 8), c1, c0) < rate[K]     (24-bit uniform times the bound)
-//             and                K += 1 + #{i < 8: S >= t[i]}                                 (geometric gap to the next candidate)
+// thinning: every (agent, cell) is a CANDIDATE with probability p' >= p, a candidate spikes with probability rate dt / p'.
+// Candidates are drawn per OCTET of 8 slots = (agent pair P = gid >> 1, 4-cell group g; slot k = 4 (gid & 1) + (cell & 3)):
+//   level 1   R = Philox7(ctr = (P >> 3, g, step, THIN_FIRST | population)): the octet holds a candidate  <=>  half-word
+//             (P & 7) of R (low half of word (P & 7) >> 1 first) < T16.  T16 = ceil(2^16 (1 - (1-p)^8)) fixes the octet
+//             probability exactly, and p' = 1 - (1 - T16 2^-16)^(1/8) is the per-slot candidate probability it implies.
+//   level 2   only for octets with a candidate: words S_0, S_1, ... of Philox7(ctr = (P, g, step, (THIN_CHAIN + n) | population)),
+//             n = 0, 1, ...:   first candidate slot K = #{i < 7: S_0 >= tc[i]}   (tc[i] = 2^32 P(first slot <= i | a candidate exists)),
+//             then alternately   accept slot K  <=>  fma(float(S >> 8), c1, c0) < rate[K]     (24-bit uniform times p'/dt)
+//             and                K += 1 + #{i < 8: S >= t[i]}      (t[i] = 2^32 (1 - (1-p')^(i+1)): geometric gap to the next candidate)
 //             until K >= 8.
-// The hot loop does nothing for spikes: this post-pass over a ring slot zero-fills the slot's spike words, runs level 1 for
-// its threads' groups (1 Philox call per 4 pairs), and the ~8 % of (thread, pair) groups with a candidate walk their chain,
-// read the candidate's rate back (this lane stored it moments ago: L2 hit) and set accepted bits with RED.OR.  Cost:
-// ~4 instructions per rate against ~10 for the dense stream.  NumPy mirror: tests/philox_np.py (expected_spikes_thin).
+// The hot loop does nothing for spikes.  Per ring slot a consumer warp runs level 1 for its lanes' octets (one Philox call per
+// 8 pairs) and pushes the ~8 % that hold a candidate into a per-warp shared-memory queue that persists across slots; whenever
+// 32 are queued every lane walks one chain: it reads the candidate's rate back (this warp stored it: an L2 hit) and sets
+// accepted bits with RED.OR in the spike rows the producer cleared.  NumPy mirror: tests/philox_np.py (expected_spikes_thin).
 __device__ __forceinline__ int thin_gap(const OutK& out, uint32_t w) {
   if (w >= out.thin_t[7]) return 8;
   int n = 0;
@@ -484,112 +521,136 @@ __device__ __forceinline__ int thin_gap(const OutK& out, uint32_t w) {
   for (int i = 0; i < 7; ++i) n += (w >= out.thin_t[i]) ? 1 : 0;
   return n;
 }
-// Rows / words of one warp's (ring slot, 128-cell block): 32-bit offsets from two base pointers.
-struct ThinBlock {
-  const float* rates;       // out.rates + row_lo * ld + (first cell of the warp's block)
-  uint32_t* spikes;         // out.spikes + row_lo * spike_ld + 4 * (block index)
-  unsigned long long gid_lo;
-  int n_rows, ld, spike_ld;
-  int cells_left;           // n_cells - (first cell of the block): cells of the block that exist
+constexpr int THINQ_CAP = 256;                 // items per warp (power of two) >= the 32 x 8 pushes one Philox call per lane can cause
+struct ThinWarp {
+  uint32_t* q;                                 // shared memory: THINQ_CAP items ((pair - pair0) << 5 | group) + the tail counter
+  uint32_t head, tail;                         // items popped / pushed so far (warp-uniform); q[THINQ_CAP] hands out push positions
+  uint32_t rel0;                               // id_offset & 1: pair of launch row r = (r + rel0) >> 1, relative to pair0
+  unsigned long long pair0;                    // id_offset >> 1
+  long long n_rows;                            // rows of this launch
+  const float* rates;                          // out.rates + first cell of the block
+  uint32_t* spikes;                            // out.spikes + 4 * (128-cell block index)
+  int cells_left;                              // n_cells - first cell of the block
+  int bit0;                                    // bit of the block's group 0 in its spike words
+  uint32_t sub_blk, c2, c3;                    // Philox counter words: cell-group index of group 0, step, step hi | population
 };
-// slot K of group (pair, source lane L): accept <=> 24-bit uniform * bound < rate
-__device__ __forceinline__ void thin_accept(const OutK& out, const ThinBlock& b, int K, uint32_t w, unsigned long long pair,
-                                            int L) {
-  const int r = (int)(2ull * pair - b.gid_lo) + (K >> 2);           // row within the block's rows
-  const int c = 4 * L + (K & 3);                                   // cell within the block
-  if ((unsigned)r >= (unsigned)b.n_rows || c >= b.cells_left) return;   // the other shard's / tile's half, padding cell
-  float rate;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate) : "l"(b.rates + (r * b.ld + c)));
-  if (fmaf((float)(w >> 8), out.thin_c1, out.thin_c0) < rate) atomicOr(b.spikes + (r * b.spike_ld + (K & 3)), 1u << L);
-}
-// rows [row_lo, row_hi) of this launch, cells of tail context `tc` (a warp covers 128 consecutive cells); whole warp calls.
-// queue: this warp's 64 x uint16 scratch in shared memory.
-__device__ __forceinline__ void thin_post(const OutK& out, const TailCtx& tc, const long long row_lo, const long long row_hi,
-                                          uint16_t* __restrict__ queue) {
+template <int CPT>
+__device__ __forceinline__ void thin_init(ThinWarp& t, const OutK& out, const TailCtx& tc, long long n_rows, uint32_t* queue) {
   const int lane = threadIdx.x & 31;
-  ThinBlock b;
-  const int cell_blk = tc.cell0 - 4 * lane;                        // first cell of the warp's 128-cell block
-  b.rates = out.rates + row_lo * out.ld + cell_blk;
-  b.spikes = out.spikes + row_lo * out.spike_ld + ((cell_blk >> 7) << 2);
-  b.gid_lo = (unsigned long long)(out.id_offset + row_lo);
-  b.n_rows = (int)(row_hi - row_lo); b.ld = (int)out.ld; b.spike_ld = (int)out.spike_ld;
-  b.cells_left = tc.n_cells - cell_blk;
-  const unsigned long long pair_lo = b.gid_lo >> 1, pair_hi = (b.gid_lo + (unsigned)b.n_rows + 1ull) >> 1;       // [lo, hi)
-  const uint32_t sub_blk = tc.sub - (uint32_t)lane;                // cell-group index of lane 0
-  const uint32_t c3 = tc.c3_spk & 0x00ffffffu;
-  // ---- level 1: which of this lane's (pair, cell group) octets hold a candidate
-  uint32_t pend = 0u;                                    // bit j: pair pair_lo + j (at most 17 pairs)
-  for (unsigned long long q = pair_lo >> 2; q < ((pair_hi + 3ull) >> 2); ++q) {
-    uint32_t R[4];
-    R[0] = (uint32_t)q; R[1] = tc.sub ^ ((uint32_t)(q >> 32) << 24); R[2] = tc.c2; R[3] = c3 | (RIAB_STREAM_THIN_FIRST << 24);
-    philox_keyed<7>(R, out.rk7);
-    const int j0 = (int)(4ull * q - pair_lo);            // may be negative for the first quad
+  const int cell_blk = tc.cell0 - CPT * lane;
+  t.q = queue; t.head = 0u; t.tail = 0u;
+  if (lane == 0) queue[THINQ_CAP] = 0u;
+  __syncwarp();
+  t.rel0 = (uint32_t)(out.id_offset & 1ll);
+  t.pair0 = (unsigned long long)out.id_offset >> 1;
+  t.n_rows = n_rows;
+  t.rates = out.rates + cell_blk;
+  t.spikes = out.spikes + ((cell_blk >> 7) << 2);
+  t.cells_left = tc.n_cells - cell_blk;
+  t.bit0 = (cell_blk & 127) >> 2;
+  t.sub_blk = (uint32_t)(cell_blk >> 2); t.c2 = tc.c2; t.c3 = tc.c3_spk & 0x00ffffffu;
+}
+// slot K of octet (pair, group g): accept <=> 24-bit uniform * bound < rate (read back: this warp stored it)
+__device__ __forceinline__ void thin_accept(const OutK& out, const ThinWarp& t, int K, uint32_t w, uint32_t rel, int g) {
+  const long long r = (long long)(2u * rel) - (long long)t.rel0 + (K >> 2);   // row of this launch
+  const int c = 4 * g + (K & 3);                                              // cell within the block
+  if (r < 0 || r >= t.n_rows || c >= t.cells_left) return;                   // another shard's half, padding cell
+  float rate;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate) : "l"(t.rates + r * out.ld + c));
+  if (fmaf((float)(w >> 8), out.thin_c1, out.thin_c0) < rate) atomicOr(t.spikes + r * out.spike_ld + (K & 3), 1u << (t.bit0 + g));
+}
+// one pass: lane l walks the chain of queue item head + l (n <= 32 items)
+__device__ __forceinline__ void thin_pass(ThinWarp& t, const OutK& out, int n) {
+  const int lane = threadIdx.x & 31;
+  if (lane < n) {
+    const uint32_t item = t.q[(t.head + (uint32_t)lane) & (THINQ_CAP - 1)];
+    const int g = (int)(item & 31u);
+    const uint32_t rel = item >> 5;
+    const unsigned long long pair = t.pair0 + rel;
+    const uint32_t sub = t.sub_blk + (uint32_t)g;
+    uint32_t S[4];
+    uint32_t n_call = 0u;
+    S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = t.c2; S[3] = t.c3 | ((RIAB_STREAM_THIN_CHAIN + n_call) << 24);
+    philox_keyed<7>(S, out.rk7);
+    int K = 0;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int j = j0 + w;
-      if (j >= 0 && j < (int)(pair_hi - pair_lo) && R[w] < out.thin_t[7]) pend |= 1u << j;
+    for (int i = 0; i < 7; ++i) K += (S[0] >= out.thin_tc[i]) ? 1 : 0;
+    thin_accept(out, t, K, S[1], rel, g);
+    K += 1 + thin_gap(out, S[2]);
+    while (K < 8) {                                    // a second (third, ...) candidate in the same octet: ~7 % of them
+      thin_accept(out, t, K, S[3], rel, g);
+      ++n_call;
+      S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = t.c2; S[3] = t.c3 | ((RIAB_STREAM_THIN_CHAIN + n_call) << 24);
+      philox_keyed<7>(S, out.rk7);
+      K += 1 + thin_gap(out, S[0]);
+      if (K >= 8) break;
+      thin_accept(out, t, K, S[1], rel, g);
+      K += 1 + thin_gap(out, S[2]);
     }
   }
-  if (4 * lane >= b.cells_left) pend = 0u;               // lanes whose cells do not exist
-  // ---- level 2, compacted over the warp: ~8 % of the octets hold a candidate, so the (lane, pair) items of the whole warp
-  // are queued in shared memory and every lane walks the chain of ONE item per pass (one pass for <= 32 items).
-  while (__any_sync(0xffffffffu, pend != 0u)) {
-    // each lane contributes up to 2 items per round (the queue holds 64)
-    const uint32_t first = pend & (0u - pend), rest = pend ^ first;
-    const uint32_t second = rest & (0u - rest);
-    const int cnt = (first != 0u) + (second != 0u);
-    int incl = cnt;
+  __syncwarp();
+  t.head += (uint32_t)n;
+}
+// Level 1 for the rows [row_lo, row_hi) of this launch (at most 32: one ring slot's share of this warp) + queueing;
+// full passes run as soon as 32 items wait.  The rows' rates must have been stored (and __syncwarp'ed) by this warp.
+template <int CPT>
+__device__ __forceinline__ void thin_rows(ThinWarp& t, const OutK& out, const long long row_lo, const long long row_hi) {
+  const int lane = threadIdx.x & 31;
+  constexpr int NG = 8 * CPT;                                      // 4-cell groups of the block: 32 (CPT 4) or 16 (CPT 2)
+  const uint32_t rel_lo = ((uint32_t)row_lo + t.rel0) >> 1, rel_hi = ((uint32_t)row_hi + t.rel0 + 1u) >> 1;   // pairs [lo, hi) - pair0
+  const int g1 = lane % NG;                                        // lane l: group l % NG, every (32/NG)-th block of 8 pairs
+  const unsigned long long o_lo = (t.pair0 + rel_lo) >> 3, o_hi = (t.pair0 + rel_hi - 1u) >> 3;     // blocks of 8 pairs
+  for (unsigned long long ob = o_lo; ob <= o_hi; ob += 32 / NG) {  // warp-uniform rounds: one Philox call per lane each
+    const unsigned long long o = ob + (unsigned)(lane / NG);
+    uint32_t mine = 0u, mine_rel8 = 0u;                            // this lane's candidate pairs of the round
+    if (4 * g1 < t.cells_left && o <= o_hi) {                      // (groups whose cells do not exist: nothing to draw)
+      uint32_t R[4];
+      R[0] = (uint32_t)o; R[1] = (t.sub_blk + (uint32_t)g1) ^ ((uint32_t)(o >> 32) << 24); R[2] = t.c2; R[3] = t.c3 | (RIAB_STREAM_THIN_FIRST << 24);
+      philox_keyed<7>(R, out.rk7);
+      uint32_t hits = 0u;                                          // bit h: pair 8 o + h holds a candidate
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int n = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += n;
-    }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int at = incl - cnt;
-    if (first) queue[at++] = (uint16_t)((lane << 5) | (31 - __clz(first)));
-    if (second) queue[at] = (uint16_t)((lane << 5) | (31 - __clz(second)));
-    pend = rest ^ second;
-    __syncwarp();
-    for (int base = 0; base < total; base += 32) {
-      if (base + lane < total) {
-        const uint32_t item = queue[base + lane];
-        const int L = (int)(item >> 5), j = (int)(item & 31u);
-        const unsigned long long pair = pair_lo + (unsigned)j;
-        const uint32_t sub = sub_blk + (uint32_t)L;
-        uint32_t S[4];
-        uint32_t n = 0u;
-        S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2; S[3] = c3 | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
-        philox_keyed<7>(S, out.rk7);
-        int K = 0;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) K += (S[0] >= out.thin_tc[i]) ? 1 : 0;
-        thin_accept(out, b, K, S[1], pair, L);
-        K += 1 + thin_gap(out, S[2]);
-        while (K < 8) {                                  // a second (third, ...) candidate in the same octet: ~7 % of them
-          thin_accept(out, b, K, S[3], pair, L);
-          ++n;
-          S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = tc.c2; S[3] = c3 | ((RIAB_STREAM_THIN_CHAIN + n) << 24);
-          philox_keyed<7>(S, out.rk7);
-          K += 1 + thin_gap(out, S[0]);
-          if (K >= 8) break;
-          thin_accept(out, b, K, S[1], pair, L);
-          K += 1 + thin_gap(out, S[2]);
-        }
+      for (int w = 0; w < 4; ++w) {
+        hits |= ((R[w] & 0xffffu) < out.thin_t16 ? 1u : 0u) << (2 * w);
+        hits |= ((R[w] >> 16) < out.thin_t16 ? 1u : 0u) << (2 * w + 1);
       }
+      const long long rel8 = (long long)(8ull * o - t.pair0);      // relative pair of half-word 0 (may lie before rel_lo)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {                                // pairs outside [rel_lo, rel_hi) belong to other slots
+        const long long rel = rel8 + h;
+        if (rel < (long long)rel_lo || rel >= (long long)rel_hi) hits &= ~(1u << h);
+      }
+      mine = hits; mine_rel8 = (uint32_t)rel8;
     }
-    __syncwarp();                                        // the queue is rewritten by the next round
+    // the queue never overflows: make room for this round's pushes (<= 256 = THINQ_CAP) before they happen
+    const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mine));
+    while (t.tail - t.head + cnt > (uint32_t)THINQ_CAP) thin_pass(t, out, (t.tail - t.head) < 32u ? (int)(t.tail - t.head) : 32);
+    while (mine) {                                                 // ~8 % of the octets: push (pair, group)
+      const int h = __ffs(mine) - 1;
+      mine &= mine - 1u;
+      const uint32_t pos = atomicAdd(&t.q[THINQ_CAP], 1u);
+      t.q[pos & (THINQ_CAP - 1)] = ((mine_rel8 + (uint32_t)h) << 5) | (uint32_t)g1;
+    }
+    __syncwarp();
+    t.tail += cnt;
+    while (t.tail - t.head >= 32u) thin_pass(t, out, 32);
   }
+}
+__device__ __forceinline__ void thin_flush(ThinWarp& t, const OutK& out) {
+  while (t.tail != t.head) thin_pass(t, out, (t.tail - t.head) < 32u ? (int)(t.tail - t.head) : 32);
 }
 
 // The consumers' slot loop (see k_step).  EXP: exponent form of the fast pair loop (PlacePolicy::expanded).
 template <class P, int SPK, bool NOISE, class C, int EXP>
 __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, const OutK& out, StepSlot<P::REC>* s_slot,
                                                uint64_t* s_full, uint64_t* s_empty, const double* s_walls,
-                                               const long long nq, const int ctid, const int lane, uint16_t* thin_queue) {
-  constexpr int NS = C::NS;
+                                               const long long nq, const int ctid, const int lane, uint32_t* thin_queue,
+                                               const long long n_rows) {
+  constexpr int NS = ring_slots<P, C>();
   constexpr int NC = RW * 32;
   constexpr bool DENSE = (SPK == 1);
-  const int CT = pc.n_pad >> 2;                       // cell-threads needed (multiple of 32)
+  constexpr int CPT = P::CPT;
+  static_assert(CPT == 4 || (SPK != 1 && !NOISE), "2 cells per thread: no dense spikes / OU noise (ballot layout)");
+  const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32)
   const int chunks = (CT + NC - 1) / NC;
   const int G = (chunks == 1) ? (NC / CT) : 1;        // agent groups when the cells need fewer threads
   const int grp = (chunks == 1) ? (ctid / CT) : 0;
@@ -597,16 +658,16 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
   // group `grp` takes the consecutive agents [2 grp PPG, 2 (grp+1) PPG) of a slot (PPG pairs)
   const int PPG = (TA / 2 + G - 1) / G;
   typename P::Regs regs;
-  int cell0 = (chunks == 1) ? (ctid % CT) * 4 : 0;
+  int cell0 = (chunks == 1) ? (ctid % CT) * CPT : 0;
   TailCtx tc;
   if (chunks == 1 && !idle) {
     P::load(regs, pc, cell0);
-    tail_init(tc, out, cell0, pc.n_cells);
+    tail_init<CPT>(tc, out, cell0, pc.n_cells);
   }
   const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);   // float64 inner walls (exact fall-back)
   // Fast pair loop: rows are 16-byte aligned and every thread owns 4 existing cells or none, the
   // tile starts on an even global id (one Philox call per agent pair) and there is no OU noise.
-  const bool fast = !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0);
+  const bool fast = !NOISE && out.vec_ok && ((pc.n_cells & 3) == 0) && ((out.id_offset & 1ll) == 0 || SPK != 1);
   const float q16 = out.dt * 65536.0f;
   for (long long q = 0; q < nq; ++q) {
     const int s = (int)(q % NS);
@@ -619,10 +680,10 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
     // the cells in chunks of 2048 and reload their registers per chunk (G = 1, all warps on the same agents)
     for (int ch = 0; ch < chunks; ++ch) {
       if (chunks > 1) {
-        cell0 = (ch * NC + ctid) * 4;
+        cell0 = (ch * NC + ctid) * CPT;
         if (cell0 >= pc.n_pad) continue;              // warp-uniform (n_pad is a multiple of 128)
         P::load(regs, pc, cell0);
-        tail_init(tc, out, cell0, pc.n_cells);
+        tail_init<CPT>(tc, out, cell0, pc.n_cells);
       } else if (idle) {
         continue;
       }
@@ -632,13 +693,6 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
         // agents are taken in pairs (2p, 2p+1) so that one Philox call feeds the (dense) spikes of both
         RowCursor rc;
         cursor_init(rc, out, tc, a0 + a_lo);
-        if (SPK == 2) {
-          // thinned spikes: clear this warp's 16 bytes of every row of the group, accepted bits are OR-ed in by thin_post
-          if (lane < a_hi - a_lo) {
-            uint32_t* z = rc.spk + (long long)lane * out.spike_ld;
-            asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(z), "r"(0u) : "memory");
-          }
-        }
         const float* recp = s_slot[s].rec[a_lo];
         int a = a_lo;
         uint32_t only = 0xffffffffu;       // pairs (by iteration index) the general loop below evaluates
@@ -659,7 +713,7 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
         const RowStride stride = make_stride(out, 2);
         const bool even = ((rc.gid & 1ull) == 0ull);      // uniform: a0 and a_lo are even
         for (uint32_t it = (uint32_t)((a - a_lo) >> 1); a < a_hi; a += 2, ++it) {
-          float oa[4], ob[4];
+          float oa[CPT], ob[CPT];
           const bool has_b = (a + 1 < a_hi);
           if (has_b && !((only >> (it & 31u)) & 1u)) {      // warp-uniform
             cursor_advance(rc, stride);
@@ -668,35 +722,48 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
           }
           bool dummy = false;
           P::template rates4<false>(oa, regs, pc, cell0, recp, inner_s, dummy);
-          store4<NOISE>(oa, out, tc, rc, 0);
-          if (has_b) {
-            P::template rates4<false>(ob, regs, pc, cell0, recp + P::REC, inner_s, dummy);
-            store4<NOISE>(ob, out, tc, rc, out.ld);
-          }
-          if (DENSE && (!NOISE || rc.spk != nullptr)) {
-            if (has_b && even) {
-              uint32_t c[4], bl[4];
-              spike_words(c, out, tc, rc.gid);
-              const float nv = spike_neg_dither(c);
-              spike_ballots<true>(bl, c[0], c[1], nv, oa, q16, tc.vmask, true);
-              spike_store(bl, rc.spk);
-              spike_ballots<true>(bl, c[2], c[3], nv, ob, q16, tc.vmask, true);
-              spike_store(bl, rc.spk + out.spike_ld);
-            } else {
-              spikes1(oa, out, tc, rc);
-              if (has_b) {
-                RowCursor rb = rc;
-                rb.gid += 1; rb.spk += out.spike_ld;
-                spikes1(ob, out, tc, rb);
+          if (has_b) P::template rates4<false>(ob, regs, pc, cell0, recp + P::REC, inner_s, dummy);
+          if constexpr (CPT == 4) {
+            store4<NOISE>(oa, out, tc, rc, 0);
+            if (has_b) store4<NOISE>(ob, out, tc, rc, out.ld);
+            if (DENSE && (!NOISE || rc.spk != nullptr)) {
+              if (has_b && even) {
+                uint32_t c[4], bl[4];
+                spike_words(c, out, tc, rc.gid);
+                const float nv = spike_neg_dither(c);
+                spike_ballots<true>(bl, c[0], c[1], nv, oa, q16, tc.vmask, true);
+                spike_store(bl, rc.spk);
+                spike_ballots<true>(bl, c[2], c[3], nv, ob, q16, tc.vmask, true);
+                spike_store(bl, rc.spk + out.spike_ld);
+              } else {
+                spikes1(oa, out, tc, rc);
+                if (has_b) {
+                  RowCursor rb = rc;
+                  rb.gid += 1; rb.spk += out.spike_ld;
+                  spikes1(ob, out, tc, rb);
+                }
               }
+            }
+          } else {
+            // 2 cells per thread (launched only for 8-byte aligned rows and even cell counts, no noise, no dense spikes)
+            if (tc.full4) {
+              st_cs_fv<CPT>(rc.dst, oa);
+              if (has_b) st_cs_fv<CPT>(rc.dst + out.ld, ob);
+            } else {
+#pragma unroll
+              for (int i = 0; i < CPT; ++i)
+                if ((tc.vmask >> i) & 1u) { st_cs_f1(rc.dst + i, oa[i]); if (has_b) st_cs_f1(rc.dst + out.ld + i, ob[i]); }
             }
           }
           cursor_advance(rc, stride);
           recp += 2 * P::REC;
         }
         if (SPK == 2) {
-          __syncwarp();      // orders the zero-fill and this warp's rate stores before the chain's loads / RED.ORs
-          thin_post(out, tc, a0 + a_lo, a0 + a_hi, thin_queue);
+          __syncwarp();      // orders this warp's rate stores before the chains' loads
+          ThinWarp tw;       // (per chunk: the block changes with the chunk, so nothing is carried over)
+          thin_init<CPT>(tw, out, tc, n_rows, thin_queue);
+          thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
+          thin_flush(tw, out);
         }
       }
     }
@@ -705,17 +772,109 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
   }
 }
 
+// Out-of-line repairs of one ring slot for consumer_fast (rare): pairs whose float32 line-of-sight decision fell inside the
+// band (bit `it` of redo) are re-evaluated with the exact float64 fall-back, and an odd last agent gets its row.  A real
+// call: its register needs must not shape the allocation of the hot loop (the arguments travel through the stack).
+template <class P>
+__device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const typename P::Const& pc, const int cell0, const unsigned vmask,
+                                         const float* rec, const uint32_t inner_s, float* d, const long long ld,
+                                         const int n_agents, const uint32_t redo) {
+  constexpr int CPT = P::CPT;
+  for (int a = 0; a < n_agents; ++a, d += ld, rec += P::REC) {
+    const bool last_odd = (a == n_agents - 1) && ((n_agents & 1) != 0);
+    if (!last_odd && !((redo >> (a >> 1)) & 1u)) continue;          // warp-uniform
+    float o[CPT];
+    bool dummy = false;
+    P::template rates4<false>(o, regs, pc, cell0, rec, inner_s, dummy);
+    if (vmask == ((1u << CPT) - 1u)) st_cs_fv<CPT>(d, o);
+  }
+}
+
+// The consumers' slot loop for the common case: no OU noise, no dense spike stream, vector-aligned rows, whole 4-cell
+// groups, all cells resident in one set of registers (n_pad <= 512 * CPT).  Pointers advance incrementally, the rare
+// repairs are a real call (slot_fixups), thinned spikes are queued across slots (ThinWarp).
+template <class P, int SPK, class C, int EXP>
+__device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const OutK& out, StepSlot<P::REC>* s_slot,
+                                              uint64_t* s_full, uint64_t* s_empty, const double* s_walls, const long long nq,
+                                              const int ctid, const int lane, uint32_t* thin_queue, const long long n_rows) {
+  constexpr int NS = ring_slots<P, C>(), NC = RW * 32, CPT = P::CPT;
+  const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32, <= NC)
+  const int G = NC / CT, grp = ctid / CT;             // agent groups
+  if (grp >= G) {                                     // spare warps only hand the slots back
+    for (long long q = 0; q < nq; ++q) {
+      const int s = (int)(q % NS);
+      mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+    return;
+  }
+  const int PPG = (TA / 2 + G - 1) / G;               // group `grp`: agents [2 grp PPG, 2 (grp+1) PPG) of a slot
+  const int a_lo = 2 * grp * PPG;
+  typename P::Regs regs;
+  const int cell0 = (ctid % CT) * CPT;
+  TailCtx tc;
+  P::load(regs, pc, cell0);
+  tail_init<CPT>(tc, out, cell0, pc.n_cells);
+  const bool act = cell0 < pc.n_cells;                // all CPT cells exist or none (n_cells % 4 == 0)
+  const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);
+  ThinWarp tw;
+  if (SPK == 2) thin_init<CPT>(tw, out, tc, n_rows, thin_queue);
+  const long long ld = out.ld;
+  float* dst0 = out.rates + ((long long)blockIdx.x * TA + a_lo) * ld + cell0;     // this group's first row of the slot
+  const long long slot_step = (long long)gridDim.x * TA * ld;
+  long long a0 = (long long)blockIdx.x * TA;
+  for (long long q = 0; q < nq; ++q, dst0 += slot_step, a0 += (long long)gridDim.x * TA) {
+    const int s = (int)(q % NS);
+    mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
+    const int na = s_slot[s].na;
+    const int a_hi = (a_lo + 2 * PPG < na) ? a_lo + 2 * PPG : na;
+    if (a_lo < a_hi) {
+      const float* recp = s_slot[s].rec[a_lo];
+      float* d = dst0;
+      uint32_t redo = 0u;
+      const int n2 = (a_hi - a_lo) >> 1;
+      for (int it = 0; it < n2; ++it) {
+        float o[CPT];
+        bool unsure = false;
+        P::template rates4<true, EXP>(o, regs, pc, cell0, recp, inner_s, unsure);
+        if (act) st_cs_fv<CPT>(d, o);
+        P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
+        if (act) st_cs_fv<CPT>(d + ld, o);
+        redo |= (unsure ? 1u : 0u) << it;
+        d += 2 * ld;
+        recp += 2 * P::REC;
+      }
+      redo = __reduce_or_sync(0xffffffffu, redo);
+      if (redo != 0u || ((a_hi - a_lo) & 1)) {
+        if (act) {
+          const typename P::Regs rcopy = regs;          // stack copies, made on this path only
+          const typename P::Const pcopy = pc;
+          slot_fixups<P>(rcopy, pcopy, cell0, tc.vmask, s_slot[s].rec[a_lo], inner_s, dst0, ld, a_hi - a_lo, redo);
+        }
+      }
+      if (SPK == 2) {
+        __syncwarp();                                  // this warp's rate stores before the chains read them back
+        thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[s]);
+  }
+  if (SPK == 2) thin_flush(tw, out);
+}
+
 // SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_post per ring slot)
 template <class P, int MODE, int SPK, bool NOISE, class C>
-__global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const riab_agents ag,
+__global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
                                                           const riab_step_io io, const typename P::Const pc, const OutK out,
                                                           const double* __restrict__ pos_in, const long long n_rows) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
-  constexpr int MW = C::MW, NS = C::NS;
+  constexpr int MW = C::MW, NS = ring_slots<P, C>();
   __shared__ StepSlot<P::REC> s_slot[NS];
   __shared__ uint64_t s_bar, s_full[NS], s_empty[NS];
-  __shared__ uint16_t s_thinq[(SPK == 2) ? RW : 1][64];       // per consumer warp: candidate items of thin_post
+  __shared__ uint32_t s_thinq[(SPK == 2) ? RW : 1][(SPK == 2) ? THINQ_CAP + 4 : 1];   // per consumer warp: queued candidate octets + push counter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RW); }
@@ -745,6 +904,13 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
       const long long tile = (long long)blockIdx.x + q * gridDim.x;
       const long long a0 = tile * TA;
       const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
+      if (SPK == 2 && lane < na) {
+        // thinned spikes: clear the tile's spike rows; the consumers OR accepted bits in after the slot is published
+        // (mbarrier release / acquire orders these stores before their RED.ORs)
+        uint32_t* z = out.spikes + (a0 + lane) * out.spike_ld;
+        for (long long w = 0; w < out.spike_ld; w += 4)
+          asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(z + w), "r"(0u) : "memory");
+      }
       if (MODE == 2) {
         // skewed: publish the records of the CURRENT positions first, then advance the agents
         // (the next launch's rates) -- consumers never wait for the float64 motion chain.
@@ -788,9 +954,21 @@ __global__ void __launch_bounds__(C::THREADS, 1) k_step(const EnvK env, const ri
     // the cell registers then stay in registers across slots (a run-time switch inside the loop made ptxas park them
     // in local memory around every slot)
     const int ex = P::expanded(pc);
-    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, s_thinq[(SPK == 2) ? (ctid >> 5) : 0]);
-    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, s_thinq[(SPK == 2) ? (ctid >> 5) : 0]);
-    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, s_thinq[(SPK == 2) ? (ctid >> 5) : 0]);
+    uint32_t* const tq = s_thinq[(SPK == 2) ? (ctid >> 5) : 0];
+    bool lean = false;
+    if constexpr (!NOISE && SPK != 1)
+      lean = out.vec_ok && ((pc.n_cells & 3) == 0) && (pc.n_pad <= RW * 32 * P::CPT) && (out.spikes == nullptr || ((out.id_offset & 1ll) == 0));
+    if constexpr (!NOISE && SPK != 1) {
+      if (lean) {
+        if (ex == 2) consumer_fast<P, SPK, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        else if (ex == 1) consumer_fast<P, SPK, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        else consumer_fast<P, SPK, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        return;
+      }
+    }
+    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
   }
 }
 
@@ -1225,16 +1403,27 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
     const double bound = fr_bound * (1.0 + 1.0 / 1024.0), p = dt * bound;
     if (p <= 0.125) {
       k.thin = 1;
-      double qq = 1.0;
+      double q8 = 1.0 - p;
+      q8 *= q8; q8 *= q8; q8 *= q8;                                      // (1-p)^8
+      double t16 = ceil(65536.0 * (1.0 - q8));
+      if (t16 > 65535.0) t16 = 65535.0;
+      k.thin_t16 = (uint32_t)t16;
+      // the per-slot candidate probability the 16-bit threshold implies (three correctly rounded square roots)
+      const double q1 = sqrt(sqrt(sqrt(1.0 - t16 / 65536.0))), pp = 1.0 - q1;
+      double qq = 1.0, cum[8];
       for (int i = 0; i < 8; ++i) {
-        qq *= (1.0 - p);
-        const double t = floor(4294967296.0 * (1.0 - qq));
+        qq *= q1;
+        cum[i] = 1.0 - qq;
+        const double t = floor(4294967296.0 * cum[i]);
         k.thin_t[i] = (t >= 4294967295.0) ? 4294967295u : (uint32_t)t;
       }
-      for (int i = 0; i < 7; ++i)
-        k.thin_tc[i] = k.thin_t[7] ? (uint32_t)((((uint64_t)k.thin_t[i]) << 32) / k.thin_t[7]) : 0u;
-      k.thin_c1 = (float)(bound * (1.0 / 16777216.0));
-      k.thin_c0 = (float)(bound * (1.0 / 33554432.0));
+      for (int i = 0; i < 7; ++i) {
+        const double t = (cum[7] > 0.0) ? floor(4294967296.0 * (cum[i] / cum[7])) : 0.0;
+        k.thin_tc[i] = (t >= 4294967295.0) ? 4294967295u : (uint32_t)t;
+      }
+      const double bnd = (dt > 0.0) ? pp / dt : 0.0;                     // accept with rate / bnd
+      k.thin_c1 = (float)(bnd * (1.0 / 16777216.0));
+      k.thin_c0 = (float)(bnd * (1.0 / 33554432.0));
     }
   }
   return 0;
@@ -1322,7 +1511,11 @@ int g_num_sms = 0;
 
 // MODE 0: rates for given positions; 1: motion -> rates (one step); 2: skewed (rates of the current
 // positions, then motion for the NEXT step -- used inside riab_run).
-template <class P, int MODE>
+struct NoNarrow {};     // "no 2-cells-per-thread variant of this policy"
+// P: the policy with 4 cells per consumer thread (every feature); P2: its 2-cells-per-thread variant for StepCfg2 (two CTAs
+// per SM, twice the resident consumer warps) or NoNarrow.  The narrow variant serves the common case -- no OU noise, no
+// dense spike stream, vector-aligned rows, whole cell groups -- and everything else takes the wide one.
+template <class P, int MODE, class P2 = NoNarrow>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                 const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   if (n_rows == 0) return 0;
@@ -1337,6 +1530,18 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (MODE != 0) derive_motion(mp, md);
+  if constexpr (!std::is_same<P2, NoNarrow>::value) {
+    static const bool wide_only = getenv("RIAB_WIDE_ONLY") != nullptr;
+    if (!wide_only && !noise && (!spikes || out.thin) && out.vec_ok && (pc.n_cells & 3) == 0 && !(P::LIGHT && !spikes && MODE != 0)) {
+      const long long cap = 2ll * g_num_sms;
+      const unsigned grid2 = (unsigned)(n_tiles < cap ? n_tiles : cap);
+      if (spikes) k_step<P2, MODE, 2, false, StepCfg2><<<grid2, StepCfg2::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+      else k_step<P2, MODE, 0, false, StepCfg2><<<grid2, StepCfg2::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+      g_launches++;
+      RIAB_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
   if (noise) k_step<P, MODE, 1, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   else if (spikes && out.thin) {
     if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
@@ -1357,6 +1562,12 @@ template <int MODE, int DESC>
 int launch_place_d(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                    const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   const int wi = pc.n_inner;
+  // the Gaussian profile with up to two inner walls also exists with 2 cells per consumer thread (StepCfg2)
+  if constexpr (DESC == RIAB_PC_GAUSSIAN) {
+    if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE, PlacePolicy<0, DESC, 2>>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+    if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE, PlacePolicy<1, DESC, 2>>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+    if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE, PlacePolicy<2, DESC, 2>>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  }
   if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
   if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
   if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
@@ -1659,7 +1870,7 @@ int riab_grid_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, c
   riab_agents ag; memset(&ag, 0, sizeof(ag));
   riab_motion_params mp; memset(&mp, 0, sizeof(mp));
   riab_step_io io; memset(&io, 0, sizeof(io));
-  return launch_tile<GridPolicy, 0>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+  return launch_tile<GridPolicy<4>, 0, GridPolicy<2>>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------ BVC
@@ -1812,7 +2023,7 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
     GridConst c;
     if ((rc = make_grid(gc, ek, c)) ||
         (rc = make_out(out, noise, gc->n_cells, dt, agents->id_offset, ok, (double)fmaxf(gc->min_fr, gc->max_fr)))) return rc;
-    return launch_tile<GridPolicy, MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
+    return launch_tile<GridPolicy<4>, MODE, GridPolicy<2>>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_BVC) {
     if (MODE == 2) return fail(RIAB_ERR_UNSUPPORTED, "BVC populations are stepped unskewed");

@@ -138,9 +138,22 @@ RIAB_DEV void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
                : "memory");
 }
 
+// CPT consecutive floats of a packed array (16- / 8-byte vector load)
+template <int CPT>
+RIAB_DEV void ldv(float (&d)[CPT], const float* __restrict__ p) {
+  if constexpr (CPT == 4) { const float4 v = *reinterpret_cast<const float4*>(p); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+  else { const float2 v = *reinterpret_cast<const float2*>(p); d[0] = v.x; d[1] = v.y; }
+}
+
 // Streaming (evict-first) vector stores for the write-once rate rows.
 RIAB_DEV void st_cs_f4(float* p, float a, float b, float c, float d) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+RIAB_DEV void st_cs_f2(float* p, float a, float b) { asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory"); }
+template <int CPT>
+RIAB_DEV void st_cs_fv(float* p, const float (&o)[CPT]) {
+  if constexpr (CPT == 4) st_cs_f4(p, o[0], o[1], o[2], o[3]);
+  else st_cs_f2(p, o[0], o[1]);
 }
 RIAB_DEV void st_cs_f1(float* p, float a) { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory"); }
 
@@ -159,9 +172,15 @@ typedef unsigned long long f32x2;
 RIAB_DEV f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 RIAB_DEV f32x2 bc2(float x) { return pk2(x, x); }
 RIAB_DEV void upk2(f32x2 r, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+#ifndef RIAB_SCALAR_PAIRS
 RIAB_DEV f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 RIAB_DEV f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 RIAB_DEV f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#else   // experiment: the same arithmetic as two scalar FMA-pipe instructions per pair
+RIAB_DEV f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { float a0, a1, b0, b1, c0, c1; upk2(a, a0, a1); upk2(b, b0, b1); upk2(c, c0, c1); return pk2(fmaf(a0, b0, c0), fmaf(a1, b1, c1)); }
+RIAB_DEV f32x2 fmul2(f32x2 a, f32x2 b) { float a0, a1, b0, b1; upk2(a, a0, a1); upk2(b, b0, b1); return pk2(a0 * b0, a1 * b1); }
+RIAB_DEV f32x2 fadd2(f32x2 a, f32x2 b) { float a0, a1, b0, b1; upk2(a, a0, a1); upk2(b, b0, b1); return pk2(a0 + b0, a1 + b1); }
+#endif
 
 // 2^x for x <= 0 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5*2^23 trick,
 // degree-5 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.5e-7, ex2.approx's own is ~2e-7), exponent

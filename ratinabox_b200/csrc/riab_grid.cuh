@@ -23,28 +23,28 @@ struct GridConst {
   double cxm, cym;
 };
 
+template <int CPT = 4>
 struct GridCellRegs {
-  float kx[3][4], ky[3][4], ph[3][4];
+  float kx[3][CPT], ky[3][CPT], ph[3][CPT];
 };
 
-RIAB_DEV void grid_load_cells(GridCellRegs& r, const GridConst& c, int cell0) {
+template <int CPT>
+RIAB_DEV void grid_load_cells(GridCellRegs<CPT>& r, const GridConst& c, int cell0) {
   const int np = c.n_pad;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float4 a = *reinterpret_cast<const float4*>(c.packed + (3 * k + 0) * np + cell0);
-    const float4 b = *reinterpret_cast<const float4*>(c.packed + (3 * k + 1) * np + cell0);
-    const float4 d = *reinterpret_cast<const float4*>(c.packed + (3 * k + 2) * np + cell0);
-    r.kx[k][0] = a.x; r.kx[k][1] = a.y; r.kx[k][2] = a.z; r.kx[k][3] = a.w;
-    r.ky[k][0] = b.x; r.ky[k][1] = b.y; r.ky[k][2] = b.z; r.ky[k][3] = b.w;
-    r.ph[k][0] = d.x; r.ph[k][1] = d.y; r.ph[k][2] = d.z; r.ph[k][3] = d.w;
+    ldv<CPT>(r.kx[k], c.packed + (3 * k + 0) * np + cell0);
+    ldv<CPT>(r.ky[k], c.packed + (3 * k + 1) * np + cell0);
+    ldv<CPT>(r.ph[k], c.packed + (3 * k + 2) * np + cell0);
   }
 }
 
-RIAB_DEV void grid_rates4(float (&out)[4], const GridCellRegs& r, const GridConst& c, const float* __restrict__ rec) {
+template <int CPT>
+RIAB_DEV void grid_rates4(float (&out)[CPT], const GridCellRegs<CPT>& r, const GridConst& c, const float* __restrict__ rec) {
   const float2 p = *reinterpret_cast<const float2*>(rec);
   const f32x2 npx = bc2(-p.x), npy = bc2(-p.y);
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {                       // cell pairs: the three phases are 2 FFMA2 each per two rates
+  for (int h = 0; h < CPT / 2; ++h) {                 // cell pairs: the three phases are 2 FFMA2 each per two rates
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

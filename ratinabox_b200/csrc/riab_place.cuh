@@ -30,8 +30,9 @@ constexpr int PLACE_MAX_WI = 8;      // inner walls held in registers
 // with s = sign(f_p): multiplied by the cell's SIGNED f_c these give |f_c| t_p/|f_p| etc. exactly when centre and agent
 // lie on opposite sides of the wall's line (the only case in which X and Y matter), with no |.| on the cell side.
 constexpr int PLACE_WALL0 = 4;                               // float index of wall 0's float4
-constexpr int PLACE_POS64 = PLACE_WALL0 + 4 * PLACE_MAX_WI;  // float index of the float64 position
-constexpr int PLACE_REC = PLACE_POS64 + 4;                   // 40 floats = 160 B per agent
+// record of a policy with WI inner-wall slots: [px, py, ep0, ep1] [wall float4] x WI [float64 px, py]
+constexpr int place_pos64(int wi) { return PLACE_WALL0 + 4 * wi; }   // float index of the float64 position
+constexpr int place_rec(int wi) { return place_pos64(wi) + 4; }      // 16 floats = 64 B per agent with two inner walls
 constexpr float PLACE_PEN = 1.2676506002282294e30f;          // 2^100: pen * PLACE_PEN is >= 1e24 for every certain blocked pair
 constexpr float PLACE_QSCALE = 1048576.0f;                   // 2^20: q' = f_c * (-f_p * 2^20) never enters the band by magnitude
 
@@ -61,6 +62,7 @@ RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, cons
 
 // Per-agent record for the rate phase, from the float64 position.
 // inner = walls + 4*n_boundary (float64 endpoints), cxm/cym = box centre.
+template <int WI>
 RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, const double* __restrict__ inner,
                                  int n_inner, int geometry, double cxm, double cym, float band, int expanded, float kx,
                                  float lfold /* log2(span) when the scale is folded into the exponent, else 0 */) {
@@ -74,7 +76,7 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
   const float pxf = (float)(px - cxm), pyf = (float)(py - cym);
   if (expanded) ep0 = (float)((double)kx * ((double)pxf * pxf + (double)pyf * pyf) + (double)lfold);   // -k |p|^2 [+ log2 span]
   *reinterpret_cast<float4*>(rec) = make_float4(pxf, pyf, ep0, ep1);
-  for (int j = 0; j < PLACE_MAX_WI; ++j) {
+  for (int j = 0; j < WI; ++j) {
     float4 w = make_float4(-1.f, 2.f, -PLACE_QSCALE, 1.0e-6f);    // dummy wall: same side (q' < 0), X = -2, Y = 4
     if (j < n_inner) {
       double f, t;
@@ -88,7 +90,7 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
     }
     *reinterpret_cast<float4*>(rec + PLACE_WALL0 + 4 * j) = w;
   }
-  *reinterpret_cast<double2*>(rec + PLACE_POS64) = make_double2(px, py);      // exact fall-back only
+  *reinterpret_cast<double2*>(rec + place_pos64(WI)) = make_double2(px, py);  // exact fall-back only
 }
 
 struct PlaceConst {                  // uniform per launch
@@ -110,47 +112,42 @@ struct PlaceConst {                  // uniform per launch
   double cxm, cym;
 };
 
-// Per-thread cell registers: 4 consecutive cells.
-template <int WI>
+// Per-thread cell registers: CPT consecutive cells (4, or 2 for the high-occupancy consumers of StepCfg2).
+template <int WI, int CPT = 4>
 struct PlaceCellRegs {
-  float cx[4], cy[4], k[4];
-  float fc[WI > 0 ? WI : 1][4], tc[WI > 0 ? WI : 1][4], tq[WI > 0 ? WI : 1][4];   // tq = 1 - tc
-  float ce0[4], ce1[4];
+  float cx[CPT], cy[CPT], k[CPT];
+  float fc[WI > 0 ? WI : 1][CPT], tc[WI > 0 ? WI : 1][CPT], tq[WI > 0 ? WI : 1][CPT];   // tq = 1 - tc
+  float ce0[CPT], ce1[CPT];
 };
 
-template <int WI>
-RIAB_DEV void place_load_cells(PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0) {
+template <int WI, int CPT>
+RIAB_DEV void place_load_cells(PlaceCellRegs<WI, CPT>& r, const PlaceConst& c, int cell0) {
   const float* base = c.packed;
   const int np = c.n_pad;
-  const float4 x = *reinterpret_cast<const float4*>(base + cell0);
-  const float4 y = *reinterpret_cast<const float4*>(base + np + cell0);
-  const float4 k = *reinterpret_cast<const float4*>(base + 2 * np + cell0);
-  r.cx[0] = x.x; r.cx[1] = x.y; r.cx[2] = x.z; r.cx[3] = x.w;
-  r.cy[0] = y.x; r.cy[1] = y.y; r.cy[2] = y.z; r.cy[3] = y.w;
-  r.k[0] = k.x; r.k[1] = k.y; r.k[2] = k.z; r.k[3] = k.w;
+  ldv<CPT>(r.cx, base + cell0);
+  ldv<CPT>(r.cy, base + np + cell0);
+  ldv<CPT>(r.k, base + 2 * np + cell0);
   if (c.expanded) {                                      // registers hold (2k cx, 2k cy, -k|c|^2) instead of (cx, cy, k)
-    const float4 a = *reinterpret_cast<const float4*>(base + 3 * np + cell0);
     const float k2 = -2.f * c.kx;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { r.cx[i] *= k2; r.cy[i] *= k2; }
-    r.k[0] = a.x; r.k[1] = a.y; r.k[2] = a.z; r.k[3] = a.w;
+    for (int i = 0; i < CPT; ++i) { r.cx[i] *= k2; r.cy[i] *= k2; }
+    ldv<CPT>(r.k, base + 3 * np + cell0);
   }
 #pragma unroll
   for (int j = 0; j < WI; ++j) {
-    float4 f = make_float4(1.f, 1.f, 1.f, 1.f), t = make_float4(-1.f, -1.f, -1.f, -1.f);   // dummy wall (see place_agent_record)
     if (j < c.n_inner) {
-      f = *reinterpret_cast<const float4*>(base + (4 + 2 * j) * np + cell0);
-      t = *reinterpret_cast<const float4*>(base + (5 + 2 * j) * np + cell0);
+      ldv<CPT>(r.fc[j], base + (4 + 2 * j) * np + cell0);
+      ldv<CPT>(r.tc[j], base + (5 + 2 * j) * np + cell0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < CPT; ++i) { r.fc[j][i] = 1.f; r.tc[j][i] = -1.f; }   // dummy wall (see place_agent_record)
     }
-    r.fc[j][0] = f.x; r.fc[j][1] = f.y; r.fc[j][2] = f.z; r.fc[j][3] = f.w;
-    r.tc[j][0] = t.x; r.tc[j][1] = t.y; r.tc[j][2] = t.z; r.tc[j][3] = t.w;
-    r.tq[j][0] = 1.f - t.x; r.tq[j][1] = 1.f - t.y; r.tq[j][2] = 1.f - t.z; r.tq[j][3] = 1.f - t.w;
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) r.tq[j][i] = 1.f - r.tc[j][i];
   }
   if (WI > 0 && c.geometry == RIAB_GEOM_GEODESIC) {
-    const float4 a = *reinterpret_cast<const float4*>(base + (4 + 2 * c.n_inner) * np + cell0);
-    const float4 b = *reinterpret_cast<const float4*>(base + (5 + 2 * c.n_inner) * np + cell0);
-    r.ce0[0] = a.x; r.ce0[1] = a.y; r.ce0[2] = a.z; r.ce0[3] = a.w;
-    r.ce1[0] = b.x; r.ce1[1] = b.y; r.ce1[2] = b.z; r.ce1[3] = b.w;
+    ldv<CPT>(r.ce0, base + (4 + 2 * c.n_inner) * np + cell0);
+    ldv<CPT>(r.ce1, base + (5 + 2 * c.n_inner) * np + cell0);
   }
 }
 
@@ -178,10 +175,10 @@ RIAB_DEV double lds_f64(uint32_t saddr) {
 }
 template <int WI>
 __device__ __noinline__ unsigned place_blocked_exact4(const double* __restrict__ centres64, int n_cells, int n_inner,
-                                                      int cell0, uint32_t rec_s, uint32_t inner_s) {
-  const double px = lds_f64(rec_s + 4u * PLACE_POS64), py = lds_f64(rec_s + 4u * PLACE_POS64 + 8u);
+                                                      int cell0, uint32_t rec_s, uint32_t inner_s, int cpt = 4) {
+  const double px = lds_f64(rec_s + 4u * place_pos64(WI)), py = lds_f64(rec_s + 4u * place_pos64(WI) + 8u);
   unsigned m = 0;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < cpt; ++i) {
     const int cell = cell0 + i;
     if (cell >= n_cells) continue;
     const double cx = centres64[2 * cell], cy = centres64[2 * cell + 1];
@@ -201,12 +198,14 @@ __device__ __noinline__ unsigned place_blocked_exact4(const double* __restrict__
 //   unsure  : DEFER = true only ORs the band test into it -- the caller redoes the agents it covers
 //             later with DEFER = false, which tests per agent and takes the exact float64 path at once.
 //   EXP     : 1 = the expanded Gaussian form is known to be on (no branch), 0 = known off, -1 = test c.expanded
-template <int WI, int DESC, bool DEFER, int EXP = -1>
-RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const PlaceConst& c, int cell0,
+template <int WI, int DESC, bool DEFER, int EXP = -1, int CPT = 4>
+RIAB_DEV void place_rates4(float (&out)[CPT], const PlaceCellRegs<WI, CPT>& r, const PlaceConst& c, int cell0,
                            const float* __restrict__ rec, uint32_t inner_s, bool& unsure_io) {
   const float4 r0 = *reinterpret_cast<const float4*>(rec);          // px, py, ep0 | -k|p|^2, ep1
   // ---- line of sight: pen[i] = 1 if the segment centre_i -> agent crosses an inner wall, else 0
-  float pen[4] = {0.f, 0.f, 0.f, 0.f};
+  float pen[CPT];
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) pen[i] = 0.f;
   if (WI > 0) {
     // With a = |f_c|, b = |f_p| and q' = -f_c f_p 2^20 (> 0 iff the agent is on the other side of the wall's line):
     //   |D| = a + b,  M' = b t_c + a t_p  (a convex combination of t_p, t_c scaled by |D|),
@@ -219,41 +218,41 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     // |m3| below band/b => the sign of m3 is not certain in float32: re-evaluate in float64.
     // The select is arithmetic: pen = max(0, max_j m3_j) (one FMNMX3 for two walls; NaN -> 0) enters the exponent /
     // the squared distance multiplied by 2^100: any pen above the band (>= ~1e-6 / b) makes the rate exactly 0.
-    float worst[4] = {0.f, 0.f, 0.f, 0.f};                // max(0, max over walls of m3)
+    float worst[CPT], m3_prev[CPT];                       // worst = max(0, max over walls of m3)
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) { worst[i] = 0.f; m3_prev[i] = 0.f; }
     bool unsure = DEFER ? unsure_io : false;
-    float m3_prev[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < WI; ++j) {
       const float4 pw = *reinterpret_cast<const float4*>(rec + PLACE_WALL0 + 4 * j);
-      float m3[4];
+      float m3[CPT];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const f32x2 fc = pk2(r.fc[j][2 * h], r.fc[j][2 * h + 1]);
-        const f32x2 X = ffma2(fc, bc2(pw.x), pk2(r.tc[j][2 * h], r.tc[j][2 * h + 1]));
-        const f32x2 Y = ffma2(fc, bc2(pw.y), pk2(r.tq[j][2 * h], r.tq[j][2 * h + 1]));
-        const f32x2 Q = fmul2(fc, bc2(pw.z));
-        float x0, x1, y0, y1, q0, q1;
-        upk2(X, x0, x1); upk2(Y, y0, y1); upk2(Q, q0, q1);
-        m3[2 * h] = fminf(fminf(x0, y0), q0);
-        m3[2 * h + 1] = fminf(fminf(x1, y1), q1);
+      for (int i = 0; i < CPT; ++i) {
+        // scalar FMA-pipe operations: packed FFMA2 / FMUL2 here measured SLOWER in this mix with FMNMX3 (16.2 vs 13.1 cycles
+        // per cell pair and wall, scripts/ubench_packed.cu: a packed instruction holds the math dispatch port two cycles)
+        const float fc = r.fc[j][i];
+        const float X = fmaf(fc, pw.x, r.tc[j][i]);
+        const float Y = fmaf(fc, pw.y, r.tq[j][i]);
+        m3[i] = fminf(fminf(X, Y), fc * pw.z);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < CPT; ++i) {
         if ((j & 1) == 1) worst[i] = fmaxf(fmaxf(worst[i], m3[i]), m3_prev[i]);   // pairs of walls: one FMNMX3
         else if (j == WI - 1) worst[i] = fmaxf(worst[i], m3[i]);                                    // odd wall count: the last one
         m3_prev[i] = m3[i];
       }
-      const float am = fminf(fminf(fminf(fabsf(m3[0]), fabsf(m3[1])), fabsf(m3[2])), fabsf(m3[3]));
+      float am = fminf(fabsf(m3[0]), fabsf(m3[1]));
+      if constexpr (CPT == 4) am = fminf(fminf(am, fabsf(m3[2])), fabsf(m3[3]));
       unsure = unsure || (am < pw.w);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pen[i] = worst[i];
+    for (int i = 0; i < CPT; ++i) pen[i] = worst[i];
     if (DEFER) unsure_io = unsure;
     else if (unsure) {                                   // rare: redo the group's flags with the reference's float64 test
       const unsigned m = place_blocked_exact4<WI>(c.centres64, c.n_cells, c.n_inner, cell0,
-                                                  (uint32_t)__cvta_generic_to_shared(rec), inner_s);
+                                                  (uint32_t)__cvta_generic_to_shared(rec), inner_s, CPT);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) pen[i] = ((m >> i) & 1u) ? 1.f : 0.f;
+      for (int i = 0; i < CPT; ++i) pen[i] = ((m >> i) & 1u) ? 1.f : 0.f;
     }
   }
   // ---- Gaussian with one common width, expanded:  -k|c-p|^2 = (-k|c|^2 - k|p|^2) + (2k cx) px + (2k cy) py.
@@ -262,7 +261,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
   if (DESC == RIAB_PC_GAUSSIAN && (EXP >= 1 || (EXP < 0 && c.expanded))) {
     const f32x2 zz = bc2(r0.z), px2 = bc2(r0.x), py2 = bc2(r0.y);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {                         // cell pairs: FADD2 + 2 (3) FFMA2 per two rates
+    for (int h = 0; h < CPT / 2; ++h) {                   // cell pairs: FADD2 + 2 (3) FFMA2 per two rates
       f32x2 t = fadd2(pk2(r.k[2 * h], r.k[2 * h + 1]), zz);
       t = ffma2(pk2(r.cx[2 * h], r.cx[2 * h + 1]), px2, t);
       t = ffma2(pk2(r.cy[2 * h], r.cy[2 * h + 1]), py2, t);
@@ -275,10 +274,10 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     }
     return;
   }
-  float d2[4];
+  float d2[CPT];
   if (WI == 0 && c.periodic) {                           // warp-uniform
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CPT; ++i) {
       float dx = fabsf(r0.x - r.cx[i]), dy = fabsf(r0.y - r.cy[i]);
       dx = (dx > c.half_f) ? c.scale_f - dx : dx;        // the short way round
       dy = (dy > c.half_f) ? c.scale_f - dy : dy;
@@ -286,26 +285,26 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < CPT; ++i) {
       const float dx = r0.x - r.cx[i], dy = r0.y - r.cy[i];
       d2[i] = fmaf(dy, dy, dx * dx);
     }
   }
   // final squared distances (blocked pairs get a distance >= 1000, Environment.py:730)
-  float dd[4];
+  float dd[CPT];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) dd[i] = (WI > 0) ? fmaf(pen[i], PLACE_PEN, d2[i]) : d2[i];
+  for (int i = 0; i < CPT; ++i) dd[i] = (WI > 0) ? fmaf(pen[i], PLACE_PEN, d2[i]) : d2[i];
   const bool geodesic = (DESC < 0) && (WI > 0) && (c.geometry == RIAB_GEOM_GEODESIC);
   const int desc = (DESC >= 0) ? DESC : c.desc;
   if (desc != RIAB_PC_TOP_HAT && !geodesic) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < CPT; ++i)
       out[i] = fmaf(place_profile<DESC>(dd[i], r.k[i], c.desc), c.span, c.min_fr);   // Neurons.py:978-980
     return;
   }
   const float2 ep = make_float2(r0.z, r0.w);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < CPT; ++i) {
     const bool blocked = (WI > 0) && (dd[i] != d2[i]);
     float dv = dd[i];
     if (geodesic && blocked) {
@@ -322,7 +321,7 @@ RIAB_DEV void place_rates4(float (&out)[4], const PlaceCellRegs<WI>& r, const Pl
       if (fabsf(dv - c.top_hat_w2) < 4e-6f * (c.top_hat_w2 + 1e-3f) && !blocked) {
         const int cell = cell0 + i;
         if (cell < c.n_cells) {
-          const double2 p64 = *reinterpret_cast<const double2*>(rec + PLACE_POS64);
+          const double2 p64 = *reinterpret_cast<const double2*>(rec + place_pos64(WI));
           D ex = D(c.centres64[2 * cell]) - D(p64.x), ey = D(c.centres64[2 * cell + 1]) - D(p64.y);
           if (c.periodic) {
             if (fabs(ex.v) > c.scale / 2) ex = D(-copysign(1.0, ex.v)) * (D(c.scale) - D(fabs(ex.v)));

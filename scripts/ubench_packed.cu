@@ -33,6 +33,18 @@ __global__ void k(float* out, const float* in, long long* cycles) {
       if (KIND == 5) { r[i] = ffma2(r[i], bb, cc); s8[i] = fmaf(s8[i], a, b); }                          // FFMA2 + FFMA (2 ops)
       if (KIND == 6) { r[i] = ffma2(r[i], bb, cc); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(s8[i])); }   // FFMA2 + MUFU (2 ops)
       if (KIND == 7) { r[i] = ffma2(r[i], bb, cc); r[i] = fmul2(r[i], ab); s8[i] = fminf(fminf(s8[i], a), b); }  // 2 packed + FMNMX3 (3 ops)
+      if (KIND == 9) {   // packed LoS mix per cell pair and wall: 2 FFMA2 + FMUL2 + 2 FMNMX3 (5 ops)
+        const u64 X = ffma2(r[i], bb, cc), Y = ffma2(r[i], ab, cc), Q = fmul2(r[i], bb);
+        float x0, x1, y0, y1, q0, q1; upk(X, x0, x1); upk(Y, y0, y1); upk(Q, q0, q1);
+        s8[i] = fmaxf(s8[i], fminf(fminf(x0, y0), q0)); s8[i] = fmaxf(s8[i], fminf(fminf(x1, y1), q1));
+        r[i] = fadd2(r[i], ab);
+      }
+      if (KIND == 10) {  // the same in scalar form: 4 FFMA + 2 FMUL + 2 FMNMX3 (+ the chain FADDs)
+        float r0, r1; upk(r[i], r0, r1);
+        const float x0 = fmaf(r0, b, c), x1 = fmaf(r1, b, a), y0 = fmaf(r0, a, c), y1 = fmaf(r1, b, a), q0 = r0 * b, q1 = r1 * b;
+        s8[i] = fmaxf(s8[i], fminf(fminf(x0, y0), q0)); s8[i] = fmaxf(s8[i], fminf(fminf(x1, y1), q1));
+        r[i] = pk(r0 + a, r1 + b);
+      }
       if (KIND == 8) { float x, y; upk(r[i], x, y); s8[i] = fminf(fminf(x, y), s8[i]); r[i] = ffma2(r[i], bb, cc); } // dependent unpack
     }
   }
@@ -88,6 +100,8 @@ int main() {
     run<6>("FFMA2 + MUFU.EX2 (2 ops)", w, 2);
     run<7>("FFMA2 + FMUL2 + FMNMX3 (3 ops)", w, 3);
     run<8>("FMNMX3(unpack) + FFMA2 (2 ops)", w, 2);
+    run<9>("LoS mix packed (per cell pair+wall)", w, 1);
+    run<10>("LoS mix scalar (per cell pair+wall)", w, 1);
   }
   unsigned* words; long long* cyc;
   const int n_words = 2 * 1024 * 1024;    // 8 MB of spike words

@@ -94,34 +94,44 @@ def thin_tables(dt, fr_bound):
     p = float(dt) * bound
     if not (fr_bound >= 0.0 and p <= 0.125):
         return None
-    t, qq = [], 1.0
+    q8 = 1.0 - p
+    q8 *= q8; q8 *= q8; q8 *= q8
+    t16 = min(np.ceil(65536.0 * (1.0 - q8)), 65535.0)
+    q1 = np.sqrt(np.sqrt(np.sqrt(1.0 - t16 / 65536.0)))
+    pp = 1.0 - q1
+    cum, qq = [], 1.0
     for _ in range(8):
-        qq *= (1.0 - p)
-        v = np.floor(4294967296.0 * (1.0 - qq))
-        t.append(4294967295 if v >= 4294967295.0 else int(v))
-    tc = [((t[i] << 32) // t[7]) if t[7] else 0 for i in range(7)]
-    c1, c0 = np.float32(bound / 16777216.0), np.float32(bound / 33554432.0)
-    return np.array(t, dtype=np.uint64), np.array(tc, dtype=np.uint64), c1, c0
+        qq *= q1
+        cum.append(1.0 - qq)
+    clamp = lambda v: 4294967295 if v >= 4294967295.0 else int(v)
+    t = [clamp(np.floor(4294967296.0 * c)) for c in cum]
+    tc = [clamp(np.floor(4294967296.0 * (cum[i] / cum[7]))) if cum[7] > 0.0 else 0 for i in range(7)]
+    bnd = pp / float(dt) if dt > 0 else 0.0
+    c1, c0 = np.float32(bnd / 16777216.0), np.float32(bnd / 33554432.0)
+    return int(t16), np.array(t, dtype=np.uint64), np.array(tc, dtype=np.uint64), c1, c0
 
 
 def expected_spikes_thin(seed, step, agents, fr, dt, fr_bound, pop=0):
-    """Mirror of thin_post (riab_b200.cu): candidates per (agent pair, 4-cell group) of 8 slots, slot = 4*(gid&1) + cell&3.
-    Level 1: word (gid>>1)&3 of Philox7((gid>>3, group), THIN_FIRST) < t[7]  <=>  the group holds a candidate.
+    """Mirror of the thinned spike stream (riab_b200.cu: thin_rows / thin_pass): candidates per octet = (agent pair, 4-cell group)
+    of 8 slots, slot = 4*(gid&1) + cell&3.
+    Level 1: half-word (gid>>1)&7 of Philox7((gid>>4, group), THIN_FIRST) < t16  <=>  the octet holds a candidate.
     Level 2: words of Philox7((gid>>1, group), THIN_CHAIN + n), n = 0, 1, ...: first slot from the conditional table,
     then alternately accept (24-bit uniform * bound < rate) and geometric gap to the next candidate."""
     agents = np.asarray(agents, dtype=np.uint64)
     fr = np.asarray(fr, dtype=np.float32)
     A, n_cells = fr.shape
-    t, tc, c1, c0 = thin_tables(dt, fr_bound)
+    t16, t, tc, c1, c0 = thin_tables(dt, fr_bound)
     key = (seed & 0xFFFFFFFF, seed >> 32)
     groups = (n_cells + 3) // 4
     out = np.zeros((A, n_cells), dtype=bool)
     row_of = {int(g): i for i, g in enumerate(agents)}
     pairs = np.unique(agents >> np.uint64(1))
     g = np.arange(groups, dtype=np.uint64)[None, :]
-    first = philox4x32(counter((pairs >> np.uint64(2))[:, None], g, step, STREAM_THIN_FIRST, pop), key, rounds=7)   # (P,G,4)
-    w = np.take_along_axis(first, (pairs & np.uint64(3)).astype(np.int64)[:, None, None].repeat(groups, 1), axis=2)[..., 0]
-    cand_p, cand_g = np.nonzero(w.astype(np.uint64) < t[7])
+    first = philox4x32(counter((pairs >> np.uint64(3))[:, None], g, step, STREAM_THIN_FIRST, pop), key, rounds=7)   # (P,G,4)
+    h = (pairs & np.uint64(7)).astype(np.int64)
+    word = np.take_along_axis(first, (h >> 1)[:, None, None].repeat(groups, 1), axis=2)[..., 0]
+    half = np.where((h & 1)[:, None] == 1, word >> np.uint32(16), word & np.uint32(0xFFFF))
+    cand_p, cand_g = np.nonzero(half < np.uint32(t16))
 
     def gap(x):
         x = np.uint64(x)
