@@ -410,20 +410,10 @@ struct StepCfg {
   static constexpr int REGS_PRODUCER = (MW_ >= 8) ? 128 : RIAB_RP4;
   static constexpr int REGS_CONSUMER = (MW_ >= 8) ? 56 : RIAB_RC4;
 };
-// StepCfg2: TWO CTAs per SM of 2 producer + 16 consumer warps (576 threads x 56 registers each, no re-balancing: the
-// pool setmaxnreg moves registers in is the CTA's own launch allocation).  For policies with CPT = 2 cells per consumer thread (18
-// cell registers with two inner walls instead of 36): the rate consumers are latency-bound -- ncu: one instruction per 7.8
-// cycles per warp, 4.2 warps per scheduler, 54 % of the issue slots used -- so twice the resident consumer warps buy
-// more than the ~14 % extra instructions of the narrower threads cost.
-struct StepCfg2 {
-  static constexpr int MW = 2;
-  static constexpr int CTAS = 2;
-  static constexpr int NS = 4;
-  static constexpr int THREADS = (MW + RW) * 32;
-  static constexpr int REGS_LAUNCH = 56;
-  static constexpr int REGS_PRODUCER = 56;
-  static constexpr int REGS_CONSUMER = 56;
-};
+// (Round 2 also tried TWO CTAs per SM of 2 producer + 16 consumer warps with 2 cells per consumer thread -- 56 registers,
+// twice the resident consumer warps.  Same step time within 3 %: the consumers are bound by the math dispatch port -- ALU-pipe
+// and packed FP32 instructions hold it two cycles each -- not by latency, so more warps bought nothing.  The cell-count
+// template parameter CPT of the policies is what remains of it.)
 // setmaxnreg only moves registers WITHIN the CTA's launch allocation (THREADS x REGS_LAUNCH): an .inc blocks until enough
 // warps of the same CTA have released theirs with .dec.  A split whose total exceeds the allocation therefore never
 // completes -- the hang of round 1's 112 / 56 experiment: 16*32*112 + 4*32*56 = 64512 > 640*96 = 61440.
@@ -431,7 +421,7 @@ template <class C>
 constexpr bool step_cfg_fits() {
   return RW * 32 * C::REGS_CONSUMER + C::MW * 32 * C::REGS_PRODUCER <= C::THREADS * C::REGS_LAUNCH;
 }
-static_assert(step_cfg_fits<StepCfg<4>>() && step_cfg_fits<StepCfg<8>>() && step_cfg_fits<StepCfg2>(),
+static_assert(step_cfg_fits<StepCfg<4>>() && step_cfg_fits<StepCfg<8>>(),
               "setmaxnreg split exceeds the CTA's register allocation: the kernel would hang");
 // setmaxnreg towards N registers from the launch allocation L (inc when N > L, dec when N < L)
 template <int N, int L> __device__ __forceinline__ void reg_set() {
@@ -775,18 +765,39 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
 // Out-of-line repairs of one ring slot for consumer_fast (rare): pairs whose float32 line-of-sight decision fell inside the
 // band (bit `it` of redo) are re-evaluated with the exact float64 fall-back, and an odd last agent gets its row.  A real
 // call: its register needs must not shape the allocation of the hot loop (the arguments travel through the stack).
-template <class P>
-__device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const typename P::Const& pc, const int cell0, const unsigned vmask,
-                                         const float* rec, const uint32_t inner_s, float* d, const long long ld,
-                                         const int n_agents, const uint32_t redo) {
+template <class P, bool DENSE>
+__device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const typename P::Const& pc, const OutK& out,
+                                            const TailCtx& tc, const float* rec, const uint32_t inner_s, float* d,
+                                            const long long a0, const int n_agents, const uint32_t redo, const bool act) {
   constexpr int CPT = P::CPT;
-  for (int a = 0; a < n_agents; ++a, d += ld, rec += P::REC) {
-    const bool last_odd = (a == n_agents - 1) && ((n_agents & 1) != 0);
-    if (!last_odd && !((redo >> (a >> 1)) & 1u)) continue;          // warp-uniform
-    float o[CPT];
+  for (int a = 0; a < n_agents; a += 2, d += 2 * out.ld, rec += 2 * P::REC) {
+    const bool has_b = a + 1 < n_agents;
+    if (has_b && !((redo >> (a >> 1)) & 1u)) continue;              // warp-uniform
+    float oa[CPT], ob[CPT];
     bool dummy = false;
-    P::template rates4<false>(o, regs, pc, cell0, rec, inner_s, dummy);
-    if (vmask == ((1u << CPT) - 1u)) st_cs_fv<CPT>(d, o);
+    P::template rates4<false>(oa, regs, pc, tc.cell0, rec, inner_s, dummy);
+    if (has_b) P::template rates4<false>(ob, regs, pc, tc.cell0, rec + P::REC, inner_s, dummy);
+    if (act) {
+      st_cs_fv<CPT>(d, oa);
+      if (has_b) st_cs_fv<CPT>(d + out.ld, ob);
+    }
+    if constexpr (DENSE && CPT == 4) {                              // whole warp: ballots
+      RowCursor rc;
+      rc.gid = (unsigned long long)(out.id_offset + a0 + a);
+      rc.spk = out.spikes + (a0 + a) * out.spike_ld + ((tc.cell0 >> 7) << 2);
+      const float q16 = out.dt * 65536.0f;
+      if (has_b) {
+        uint32_t c[4], bl[4];
+        spike_words(c, out, tc, rc.gid);
+        const float nv = spike_neg_dither(c);
+        spike_ballots<true>(bl, c[0], c[1], nv, oa, q16, tc.vmask, true);
+        spike_store(bl, rc.spk);
+        spike_ballots<true>(bl, c[2], c[3], nv, ob, q16, tc.vmask, true);
+        spike_store(bl, rc.spk + out.spike_ld);
+      } else {
+        spikes1(oa, out, tc, rc);
+      }
+    }
   }
 }
 
@@ -799,18 +810,9 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
                                               const int ctid, const int lane, uint32_t* thin_queue, const long long n_rows) {
   constexpr int NS = ring_slots<P, C>(), NC = RW * 32, CPT = P::CPT;
   const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32, <= NC)
-  const int G = NC / CT, grp = ctid / CT;             // agent groups
-  if (grp >= G) {                                     // spare warps only hand the slots back
-    for (long long q = 0; q < nq; ++q) {
-      const int s = (int)(q % NS);
-      mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[s]);
-    }
-    return;
-  }
-  const int PPG = (TA / 2 + G - 1) / G;               // group `grp`: agents [2 grp PPG, 2 (grp+1) PPG) of a slot
-  const int a_lo = 2 * grp * PPG;
+  const int G = NC / CT, grp = ctid / CT;             // groups of CT threads; group g consumes the slots q = g, g + G, ...
+  if (grp >= G) return;                               // spare warps (the slots' release count is one group's warps)
+  constexpr int a_lo = 0;
   typename P::Regs regs;
   const int cell0 = (ctid % CT) * CPT;
   TailCtx tc;
@@ -821,37 +823,57 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
   ThinWarp tw;
   if (SPK == 2) thin_init<CPT>(tw, out, tc, n_rows, thin_queue);
   const long long ld = out.ld;
-  float* dst0 = out.rates + ((long long)blockIdx.x * TA + a_lo) * ld + cell0;     // this group's first row of the slot
-  const long long slot_step = (long long)gridDim.x * TA * ld;
-  long long a0 = (long long)blockIdx.x * TA;
-  for (long long q = 0; q < nq; ++q, dst0 += slot_step, a0 += (long long)gridDim.x * TA) {
+  [[maybe_unused]] const float q16 = out.dt * 65536.0f;
+  long long a0 = ((long long)blockIdx.x + (long long)grp * gridDim.x) * TA;     // first row of the group's first slot
+  float* dst0 = out.rates + a0 * ld + cell0;
+  const long long a_step = (long long)G * gridDim.x * TA, slot_step = a_step * ld;
+  for (long long q = grp; q < nq; q += G, dst0 += slot_step, a0 += a_step) {
     const int s = (int)(q % NS);
     mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
-    const int na = s_slot[s].na;
-    const int a_hi = (a_lo + 2 * PPG < na) ? a_lo + 2 * PPG : na;
+    const int a_hi = s_slot[s].na;
     if (a_lo < a_hi) {
       const float* recp = s_slot[s].rec[a_lo];
       float* d = dst0;
       uint32_t redo = 0u;
       const int n2 = (a_hi - a_lo) >> 1;
+      [[maybe_unused]] uint32_t* spk = nullptr;
+      [[maybe_unused]] unsigned long long pair = 0ull;
+      if constexpr (SPK == 1) {
+        spk = out.spikes + a0 * out.spike_ld + ((cell0 >> 7) << 2);
+        pair = (unsigned long long)(out.id_offset + a0) >> 1;          // even first global id: rows (2p, 2p+1) are one pair
+      }
       for (int it = 0; it < n2; ++it) {
         float o[CPT];
         bool unsure = false;
         P::template rates4<true, EXP>(o, regs, pc, cell0, recp, inner_s, unsure);
         if (act) st_cs_fv<CPT>(d, o);
+        [[maybe_unused]] uint32_t c[4], bl[4];
+        [[maybe_unused]] float nv = 0.f;
+        if constexpr (SPK == 1) {
+          // dense spike stream: one Philox4x32-7 call per (agent pair, 4-cell group), a threshold test per rate
+          c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
+          philox_keyed<7>(c, out.rk7);
+          nv = spike_neg_dither(c);
+          spike_ballots<false, P::XU_BOUND>(bl, c[0], c[1], nv, o, q16, 0u, act);
+          spike_store(bl, spk);
+        }
         P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
         if (act) st_cs_fv<CPT>(d + ld, o);
+        if constexpr (SPK == 1) {
+          spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, act);
+          spike_store(bl, spk + out.spike_ld);
+          spk += 2 * out.spike_ld;
+          pair += 1ull;
+        }
         redo |= (unsure ? 1u : 0u) << it;
         d += 2 * ld;
         recp += 2 * P::REC;
       }
       redo = __reduce_or_sync(0xffffffffu, redo);
       if (redo != 0u || ((a_hi - a_lo) & 1)) {
-        if (act) {
-          const typename P::Regs rcopy = regs;          // stack copies, made on this path only
-          const typename P::Const pcopy = pc;
-          slot_fixups<P>(rcopy, pcopy, cell0, tc.vmask, s_slot[s].rec[a_lo], inner_s, dst0, ld, a_hi - a_lo, redo);
-        }
+        const typename P::Regs rcopy = regs;            // stack copies, made on this path only
+        const typename P::Const pcopy = pc;
+        slot_fixups<P, SPK == 1>(rcopy, pcopy, out, tc, s_slot[s].rec[a_lo], inner_s, dst0, a0, a_hi - a_lo, redo, act);
       }
       if (SPK == 2) {
         __syncwarp();                                  // this warp's rate stores before the chains read them back
@@ -876,8 +898,14 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
   __shared__ uint64_t s_bar, s_full[NS], s_empty[NS];
   __shared__ uint32_t s_thinq[(SPK == 2) ? RW : 1][(SPK == 2) ? THINQ_CAP + 4 : 1];   // per consumer warp: queued candidate octets + push counter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // lean consumers (consumer_fast): every ring slot is consumed by ONE group of warps (n_pad / CPT threads), the general
+  // loop (consumer_slots) by all RW consumer warps
+  bool lean = false;
+  if constexpr (!NOISE && (SPK != 1 || P::CPT == 4))
+    lean = out.vec_ok && ((pc.n_cells & 3) == 0) && (pc.n_pad <= RW * 32 * P::CPT) && (out.spikes == nullptr || ((out.id_offset & 1ll) == 0));
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RW); }
+    const uint32_t n_release = lean ? (uint32_t)((pc.n_pad / P::CPT) >> 5) : (uint32_t)RW;
+    for (int i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], n_release); }
     mbar_fence_init();
   }
   stage_walls(s_walls, &s_bar, env);     // includes __syncthreads()
@@ -955,10 +983,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
     // in local memory around every slot)
     const int ex = P::expanded(pc);
     uint32_t* const tq = s_thinq[(SPK == 2) ? (ctid >> 5) : 0];
-    bool lean = false;
-    if constexpr (!NOISE && SPK != 1)
-      lean = out.vec_ok && ((pc.n_cells & 3) == 0) && (pc.n_pad <= RW * 32 * P::CPT) && (out.spikes == nullptr || ((out.id_offset & 1ll) == 0));
-    if constexpr (!NOISE && SPK != 1) {
+    if constexpr (!NOISE && (SPK != 1 || P::CPT == 4)) {
       if (lean) {
         if (ex == 2) consumer_fast<P, SPK, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
         else if (ex == 1) consumer_fast<P, SPK, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
@@ -1399,7 +1424,7 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
   }
   // thinned spikes (thin_post): p = dt * bound * (1 + 2^-10) -- the margin covers the rates' float32 rounding above `bound`
   k.thin = 0;
-  if (k.spikes != nullptr && k.noise == nullptr && fr_bound >= 0.0 && getenv("RIAB_DENSE_SPIKES") == nullptr) {
+  if (k.spikes != nullptr && k.noise == nullptr && fr_bound >= 0.0 && getenv("RIAB_THIN_SPIKES") != nullptr) {
     const double bound = fr_bound * (1.0 + 1.0 / 1024.0), p = dt * bound;
     if (p <= 0.125) {
       k.thin = 1;
@@ -1511,11 +1536,7 @@ int g_num_sms = 0;
 
 // MODE 0: rates for given positions; 1: motion -> rates (one step); 2: skewed (rates of the current
 // positions, then motion for the NEXT step -- used inside riab_run).
-struct NoNarrow {};     // "no 2-cells-per-thread variant of this policy"
-// P: the policy with 4 cells per consumer thread (every feature); P2: its 2-cells-per-thread variant for StepCfg2 (two CTAs
-// per SM, twice the resident consumer warps) or NoNarrow.  The narrow variant serves the common case -- no OU noise, no
-// dense spike stream, vector-aligned rows, whole cell groups -- and everything else takes the wide one.
-template <class P, int MODE, class P2 = NoNarrow>
+template <class P, int MODE>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                 const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   if (n_rows == 0) return 0;
@@ -1530,18 +1551,6 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (MODE != 0) derive_motion(mp, md);
-  if constexpr (!std::is_same<P2, NoNarrow>::value) {
-    static const bool wide_only = getenv("RIAB_WIDE_ONLY") != nullptr;
-    if (!wide_only && !noise && (!spikes || out.thin) && out.vec_ok && (pc.n_cells & 3) == 0 && !(P::LIGHT && !spikes && MODE != 0)) {
-      const long long cap = 2ll * g_num_sms;
-      const unsigned grid2 = (unsigned)(n_tiles < cap ? n_tiles : cap);
-      if (spikes) k_step<P2, MODE, 2, false, StepCfg2><<<grid2, StepCfg2::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-      else k_step<P2, MODE, 0, false, StepCfg2><<<grid2, StepCfg2::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-      g_launches++;
-      RIAB_CUDA_OK(cudaGetLastError());
-      return 0;
-    }
-  }
   if (noise) k_step<P, MODE, 1, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
   else if (spikes && out.thin) {
     if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
@@ -1562,12 +1571,6 @@ template <int MODE, int DESC>
 int launch_place_d(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                    const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   const int wi = pc.n_inner;
-  // the Gaussian profile with up to two inner walls also exists with 2 cells per consumer thread (StepCfg2)
-  if constexpr (DESC == RIAB_PC_GAUSSIAN) {
-    if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE, PlacePolicy<0, DESC, 2>>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-    if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE, PlacePolicy<1, DESC, 2>>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-    if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE, PlacePolicy<2, DESC, 2>>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  }
   if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
   if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
   if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
@@ -1870,7 +1873,7 @@ int riab_grid_rates(const double* pos_dev, int64_t n_pos, const riab_env* env, c
   riab_agents ag; memset(&ag, 0, sizeof(ag));
   riab_motion_params mp; memset(&mp, 0, sizeof(mp));
   riab_step_io io; memset(&io, 0, sizeof(io));
-  return launch_tile<GridPolicy<4>, 0, GridPolicy<2>>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
+  return launch_tile<GridPolicy<4>, 0>(ek, ag, mp, io, c, ok, pos_dev, n_pos, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------ BVC
@@ -2023,7 +2026,7 @@ static int neurons_update_impl(const riab_agents* agents, const riab_env* env, c
     GridConst c;
     if ((rc = make_grid(gc, ek, c)) ||
         (rc = make_out(out, noise, gc->n_cells, dt, agents->id_offset, ok, (double)fmaxf(gc->min_fr, gc->max_fr)))) return rc;
-    return launch_tile<GridPolicy<4>, MODE, GridPolicy<2>>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
+    return launch_tile<GridPolicy<4>, MODE>(ek, *agents, mp, sio, c, ok, pos_in, agents->n_agents, s);
   }
   if (cells_kind == RIAB_CELLS_BVC) {
     if (MODE == 2) return fail(RIAB_ERR_UNSUPPORTED, "BVC populations are stepped unskewed");

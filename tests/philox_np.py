@@ -58,13 +58,15 @@ def agent_normals(seed, step, agents):
 
 def expected_spikes(seed, step, agents, fr, dt, pop=0, fr_bound=None):
     """(A, n_cells) bool spikes of one step given the float32 rates `fr` (A, n_cells).
-    fr_bound = max(min_fr, max_fr) of a PlaceCells / GridCells population without OU noise: the library uses the thinned
-    stream when dt * fr_bound * (1 + 2^-10) <= 1/8 (expected_spikes_thin), else -- and for every other population -- the dense one:
+    fr_bound = max(min_fr, max_fr) of a PlaceCells / GridCells population without OU noise: with RIAB_THIN_SPIKES set in the
+    environment the library uses the (experimental, measured slower) thinned stream when dt * fr_bound * (1 + 2^-10) <= 1/8
+    (expected_spikes_thin); otherwise -- the default, and always for every other population -- the dense one:
         spike <=> m < fma(rate, dt*65536, -v)      (riab_b200.cu: spike_ballots)
     One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words 2h, 2h+1 as four
     16-bit integers m; all eight share the dither v = ((r0^r2)>>8) * 2^-24.  The float32 fma is mirrored
     in float64: the 48-bit product and the 24-bit dither add exactly, so the sum rounds to float32 once."""
-    if fr_bound is not None and thin_tables(dt, fr_bound) is not None:
+    import os
+    if fr_bound is not None and os.environ.get("RIAB_THIN_SPIKES") and thin_tables(dt, fr_bound) is not None:
         return expected_spikes_thin(seed, step, agents, fr, dt, fr_bound, pop)
     agents = np.asarray(agents, dtype=np.uint64)
     fr = np.asarray(fr, dtype=np.float32)
