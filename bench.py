@@ -209,8 +209,14 @@ def build_population(rb, Ag, kind, n, geom, k=0):
     if kind == "grid":
         return rb.GridCells(Ag, {"gridscale": cp["gridscales"], "orientation": cp["orientations"],
                                  "phase_offset": cp["phase_offsets"]})
-    return rb.BoundaryVectorCells(Ag, {"tuning_distance": cp["mu_d"], "tuning_angle": cp["mu_t"],
-                                       "sigma_distance": cp["sg_d"], "sigma_angle": cp["sg_t"]})
+    # The reference's VectorCells declare `angular_spread` in default_params but hand **params to
+    # utils.create_random_assembly, which reads `sigma_angle` (ratinabox/Neurons.py:1315 vs utils.py:1124-1131): a
+    # `sigma_angle` key works but warns, an `angular_spread` key is silently ignored.  The tuning is therefore set the way
+    # the reference tells its users to (Neurons.py:1612): by assigning the arrays after construction.
+    B = rb.BoundaryVectorCells(Ag, {"n": n})
+    B.tuning_distances, B.tuning_angles = np.asarray(cp["mu_d"], float), np.radians(cp["mu_t"])
+    B.sigma_distances, B.sigma_angles = np.asarray(cp["sg_d"], float), np.radians(cp["sg_t"])
+    return B
 
 
 def algorithmic_bytes_per_agent_step(n_cells, spikes):

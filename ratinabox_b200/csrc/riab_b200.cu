@@ -438,7 +438,8 @@ template <int REC>
 struct __align__(16) StepSlot {
   float rec[TA][REC];
   int na;
-  int pad[3];
+  unsigned nanmask;         // bit a: agent a's position is NaN -> its rates are zero (Neurons.py:163-164)
+  int pad[2];
 };
 
 // The consumers' hot loop: consecutive agent pairs (2p, 2p+1) of one ring slot, 4 cells per thread, no OU noise,
@@ -690,6 +691,9 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
           uint32_t redo = 0u;
           consume_pairs<P, DENSE, EXP>(a, a_hi, regs, pc, out, tc, cell0, recp, inner_s, rc, act, q16, redo);
           redo = __reduce_or_sync(0xffffffffu, redo);
+          if (const unsigned nm = s_slot[s].nanmask; nm != 0u)          // pairs with a NaN position: zero rates below
+            for (int it = 0; a_lo + 2 * it < a_hi; ++it)
+              if ((nm >> (a_lo + 2 * it)) & 3u) redo |= 1u << it;
           if (redo != 0u) {
             // some float32 line-of-sight decision was inside the band: redo those pairs through the
             // general path (the stores are idempotent); complete pairs not in `redo` are skipped
@@ -713,6 +717,13 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
           bool dummy = false;
           P::template rates4<false>(oa, regs, pc, cell0, recp, inner_s, dummy);
           if (has_b) P::template rates4<false>(ob, regs, pc, cell0, recp + P::REC, inner_s, dummy);
+          if (const unsigned nm = s_slot[s].nanmask; nm != 0u) {        // NaN position -> zero rates (Neurons.py:163-164)
+#pragma unroll
+            for (int i = 0; i < CPT; ++i) {
+              if ((nm >> a) & 1u) oa[i] = 0.f;
+              if (has_b && ((nm >> (a + 1)) & 1u)) ob[i] = 0.f;
+            }
+          }
           if constexpr (CPT == 4) {
             store4<NOISE>(oa, out, tc, rc, 0);
             if (has_b) store4<NOISE>(ob, out, tc, rc, out.ld);
@@ -875,6 +886,13 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
         const typename P::Const pcopy = pc;
         slot_fixups<P, SPK == 1>(rcopy, pcopy, out, tc, s_slot[s].rec[a_lo], inner_s, dst0, a0, a_hi - a_lo, redo, act);
       }
+      if (const unsigned nm = s_slot[s].nanmask; nm != 0u && act) {     // NaN position -> zero rates (Neurons.py:163-164)
+        float z[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) z[i] = 0.f;
+        for (int a = a_lo; a < a_hi; ++a)
+          if ((nm >> a) & 1u) st_cs_fv<CPT>(dst0 + (long long)(a - a_lo) * ld, z);
+      }
       if (SPK == 2) {
         __syncwarp();                                  // this warp's rate stores before the chains read them back
         thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
@@ -942,12 +960,15 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
       if (MODE == 2) {
         // skewed: publish the records of the CURRENT positions first, then advance the agents
         // (the next launch's rates) -- consumers never wait for the float64 motion chain.
+        bool nanpos = false;
         if (lane < na) {
           const long long i = a0 + lane;
           const double px = ag.pos[2 * i], py = ag.pos[2 * i + 1];
+          nanpos = (px != px);
           P::record(s_slot[s].rec[lane], px, py, ag.head_direction[2 * i], ag.head_direction[2 * i + 1], s_walls, pc, env);
         }
-        if (lane == 0) s_slot[s].na = na;
+        const unsigned nanmask = __ballot_sync(0xffffffffu, nanpos);
+        if (lane == 0) { s_slot[s].na = na; s_slot[s].nanmask = nanmask; }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_full[s]);
         if (lane < na) {
@@ -956,6 +977,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
         }
         continue;
       }
+      bool nanpos = false;
       if (lane < na) {
         const long long i = a0 + lane;
         double px, py, hdx = 1.0, hdy = 0.0;
@@ -968,9 +990,11 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
           const double* hd = P::head_dir(pc);                 // egocentric cells evaluated at given positions
           if (hd != nullptr) { hdx = hd[2 * i]; hdy = hd[2 * i + 1]; }
         }
+        nanpos = (px != px);
         P::record(s_slot[s].rec[lane], px, py, hdx, hdy, s_walls, pc, env);
       }
-      if (lane == 0) s_slot[s].na = na;
+      const unsigned nanmask = __ballot_sync(0xffffffffu, nanpos);
+      if (lane == 0) { s_slot[s].na = na; s_slot[s].nanmask = nanmask; }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_full[s]);
     }
@@ -1123,7 +1147,8 @@ template <bool FUSED, bool REC>
 __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agents ag, const riab_motion_params mp,
                                                  const MotionDerived md, const riab_step_io io, const BvcConst bc,
                                                  const double* __restrict__ pos_in, const long long n_rows,
-                                                 float* __restrict__ scratch, int32_t* __restrict__ first_wall) {
+                                                 float* __restrict__ scratch, int32_t* __restrict__ first_wall,
+                                                 uint32_t* __restrict__ spikes_zero, const long long spike_ld) {
   extern __shared__ __align__(128) unsigned char dyn[];
   double* s_dirs = reinterpret_cast<double*>(dyn);                 // T*2
   __shared__ __align__(16) double s_walls[MAXW * 4];
@@ -1154,6 +1179,11 @@ __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agen
     s_pos[threadIdx.x][1] = py;
   }
   __syncthreads();
+  if (spikes_zero != nullptr) {
+    // the integration kernel ORs this step's spikes into the tile's (contiguous) spike rows: clear them here
+    uint4* z = reinterpret_cast<uint4*>(spikes_zero + a0 * spike_ld);
+    for (long long w = threadIdx.x; w < (long long)na * spike_ld / 4; w += blockDim.x) z[w] = make_uint4(0u, 0u, 0u, 0u);
+  }
   float* tile = scratch + (size_t)blockIdx.x * bc.T * BVC_AT;
   for (int idx = threadIdx.x; idx < bc.T * BVC_AT; idx += blockDim.x) {
     const int th = idx >> 5, a = idx & 31;
@@ -1167,9 +1197,37 @@ __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agen
 
 // BVC phase B: grid.x = cell tiles, grid.y = agent-tile lanes; 256 threads:
 // cell = tid & 63, agent group g = tid >> 6 handles agents 8g..8g+7 of the tile.
+// Neurons.save_to_history spikes (Neurons.py:681-684) of one cell for 8 consecutive agents (rows r0 .. r0+7, r0 even, even
+// shard offset), the dense stream of spike_words / spike_ballots: one Philox4x32-7 call per (agent pair, 4-cell group) --
+// every thread of a group repeats it for its own cell, 4 calls per 180 x 8 integrand terms -- and RED.OR into the rows
+// k_bvc_rays cleared.
+__device__ __forceinline__ void bvc_spikes8(const OutK& out, const float (&v)[8], const long long r0, const long long n_rows,
+                                            const int cell) {
+  const int i = cell & 3;
+  const uint32_t sub = (uint32_t)(cell >> 2);
+  const uint32_t hi = ((uint32_t)(out.step >> 32) & 0xffffu) | (((uint32_t)out.pop & 0xffu) << 16) | (RIAB_STREAM_SPIKES << 24);
+  const float q16 = out.dt * 65536.0f;
+  const uint32_t bit = 1u << ((cell >> 2) & 31);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long row = r0 + 2 * k;
+    if (row >= n_rows) break;
+    const unsigned long long pair = (unsigned long long)(out.id_offset + row) >> 1;
+    uint32_t c[4];
+    c[0] = (uint32_t)pair; c[1] = sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = (uint32_t)out.step; c[3] = hi;
+    philox_keyed<7>(c, out.rk7);
+    const float nv = spike_neg_dither(c);
+    const uint32_t wa = (i < 2) ? c[0] : c[1], wb = (i < 2) ? c[2] : c[3];
+    const float ma = (float)((wa >> (16 * (i & 1))) & 0xffffu), mb = (float)((wb >> (16 * (i & 1))) & 0xffffu);
+    uint32_t* w = out.spikes + row * out.spike_ld + ((cell >> 7) << 2) + i;
+    if (ma < fmaf(v[2 * k], q16, nv)) atomicOr(w, bit);
+    if (row + 1 < n_rows && mb < fmaf(v[2 * k + 1], q16, nv)) atomicOr(w + out.spike_ld, bit);
+  }
+}
+
 __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const float* __restrict__ scratch,
                                                       const long long n_rows, const long long n_tiles,
-                                                      const OutK out) {
+                                                      const OutK out, const int fold_spikes) {
   extern __shared__ __align__(128) unsigned char dyn[];
   const int T = bc.T;
   float* s_vm = reinterpret_cast<float*>(dyn);                     // [T][64]
@@ -1224,11 +1282,15 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
       }
     }
     if (cell < bc.n_cells) {
+      float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long row = t * BVC_AT + 8 * g + i;
-        if (row < n_rows) st_cs_f1(out.rates + row * out.ld + cell, fmaf(acc[i] * scale, bc.span, bc.min_fr));
+        // a NaN position makes every distance NaN: the reference returns zero rates for it (Neurons.py:163-164)
+        v[i] = (acc[i] != acc[i]) ? 0.f : fmaf(acc[i] * scale, bc.span, bc.min_fr);
+        if (row < n_rows) st_cs_f1(out.rates + row * out.ld + cell, v[i]);
       }
+      if (fold_spikes) bvc_spikes8(out, v, t * BVC_AT + 8 * g, n_rows, cell);
     }
     __syncthreads();   // everyone done with this buffer before it is refilled two iterations later
   }
@@ -1237,7 +1299,7 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
 // BVC phase B, egocentric frame: same tiling as k_bvc_integrate, no von Mises table.
 __global__ void __launch_bounds__(NT) k_bvc_integrate_ego(const BvcConst bc, const float* __restrict__ scratch,
                                                           const long long n_rows, const long long n_tiles,
-                                                          const OutK out) {
+                                                          const OutK out, const int fold_spikes) {
   extern __shared__ __align__(128) unsigned char dyn[];
   const int T = bc.T;
   float2* s_th = reinterpret_cast<float2*>(dyn);                    // [T] (cos, sin) of the test angles
@@ -1304,11 +1366,15 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate_ego(const BvcConst bc, con
       }
     }
     if (cell < bc.n_cells) {
+      float v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const long long row = t * BVC_AT + 8 * g + i;
-        if (row < n_rows) st_cs_f1(out.rates + row * out.ld + cell, fmaf(acc[i] * scale, bc.span, bc.min_fr));
+        // a NaN position makes every distance NaN: the reference returns zero rates for it (Neurons.py:163-164)
+        v[i] = (acc[i] != acc[i]) ? 0.f : fmaf(acc[i] * scale, bc.span, bc.min_fr);
+        if (row < n_rows) st_cs_f1(out.rates + row * out.ld + cell, v[i]);
       }
+      if (fold_spikes) bvc_spikes8(out, v, t * BVC_AT + 8 * g, n_rows, cell);
     }
     __syncthreads();
   }
@@ -1540,10 +1606,13 @@ template <class P, int MODE>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                 const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
   if (n_rows == 0) return 0;
-  if (g_num_sms == 0) {
+  {
+    static int sms_of[64] = {0};                      // SM count per device ordinal (a process may drive several GPUs)
     int dev = 0;
     RIAB_CUDA_OK(cudaGetDevice(&dev));
-    RIAB_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 0 || dev >= 64) return fail(RIAB_ERR_UNSUPPORTED, "device ordinal %d", dev);
+    if (sms_of[dev] == 0) RIAB_CUDA_OK(cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = sms_of[dev];
   }
   const long long n_tiles = (n_rows + TA - 1) / TA;
   const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
@@ -1630,33 +1699,33 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (FUSED) derive_motion(mp, md);
-  if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall);
-  else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall);
+  // spikes without OU noise are drawn in the integration kernel's epilogue (the ray kernel clears the rows first);
+  // OU noise (a read-modify-write of the noise state per rate) and odd shard offsets keep the k_finish_rows post-pass
+  const int fold = (out.spikes != nullptr && out.noise == nullptr && (out.id_offset & 1ll) == 0) ? 1 : 0;
+  uint32_t* const zsp = fold ? out.spikes : nullptr;
+  if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
+  else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
-  static bool attr_set = false;
-  if (!attr_set) {
-    RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  // (the attribute belongs to the current device's function image: set per call, a single process may drive several GPUs)
+  RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  int dev = 0, sms = 148;
+  RIAB_CUDA_OK(cudaGetDevice(&dev));
+  RIAB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned cts = (unsigned)(bc.n_pad / BVC_CT);
-  unsigned gy = (unsigned)((2 * 148 + cts - 1) / cts);           // ~2 CTAs per SM in total
+  unsigned gy = (unsigned)((2 * sms + cts - 1) / cts);           // ~2 CTAs per SM in total
   if (gy > n_tiles) gy = (unsigned)n_tiles;
   if (gy < 1) gy = 1;
   if (bc.ego) {
-    static bool attr_ego = false;
-    if (!attr_ego) {
-      RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate_ego, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_ego = true;
-    }
+    RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate_ego, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     const size_t smemE = ((size_t)((bc.T + 1) / 2 * 2) * 2 + (size_t)bc.T * 2 * BVC_AT) * sizeof(float);
-    k_bvc_integrate_ego<<<dim3(cts, gy), NT, smemE, s>>>(bc, scratch, n_rows, n_tiles, out);
+    k_bvc_integrate_ego<<<dim3(cts, gy), NT, smemE, s>>>(bc, scratch, n_rows, n_tiles, out, fold);
   } else {
-    k_bvc_integrate<<<dim3(cts, gy), NT, smemB, s>>>(bc, scratch, n_rows, n_tiles, out);
+    k_bvc_integrate<<<dim3(cts, gy), NT, smemB, s>>>(bc, scratch, n_rows, n_tiles, out, fold);
   }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
-  if (out.noise != nullptr || out.spikes != nullptr) {
+  if (out.noise != nullptr || (out.spikes != nullptr && !fold)) {
     const int np128 = (bc.n_cells + CELL_PAD - 1) / CELL_PAD * CELL_PAD;
     k_finish_rows<<<dim3((unsigned)n_rows, (unsigned)((np128 / 4 + NT - 1) / NT)), NT, 0, s>>>(out, bc.n_cells, np128, n_rows);
     g_launches++;

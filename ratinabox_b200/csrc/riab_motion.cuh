@@ -163,7 +163,11 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
     for (int w = 0; w < W; ++w) {
       const D ax(walls[4 * w]), ay(walls[4 * w + 1]), bx(walls[4 * w + 2]), by(walls[4 * w + 3]);
       const D ddx = px - ax, ddy = py - ay, sx = bx - ax, sy = by - ay;
-      D l = (ddx * sx + ddy * sy) / (sx * sx + sy * sy);
+      const D s2 = sx * sx + sy * sy;
+      D l = (ddx * sx + ddy * sy) / s2;
+      // a zero-length wall (the reference's own tests/test_environment.py:20-23 adds one) is a point: the reference's 1e-6
+      // jitter (utils.py:143-144) turns it into a ~1e-6 m segment; with zero jitter its 0/0 would poison the state with NaN
+      if (s2.v == 0.0) l = D(0.0);
       if (l.v > 1.0) l = D(1.0);
       if (l.v < 0.0) l = D(0.0);
       const D qx = px - (ax + l * sx), qy = py - (ay + l * sy);
@@ -172,7 +176,9 @@ RIAB_DEV void motion_step(AgentState& s, const double* __restrict__ walls, int W
       if (x2.v <= near2 || x2.v != x2.v) {
         // only walls within wall_repel_distance contribute (the others add exact zeros, Agent.py:390-393)
         const D x = dsqrt(x2);
-        if (x <= d) {
+        // x == 0: the agent sits exactly on the wall (e.g. Ag.pos = [0.5, 0.5] with a wall at x = 0.5).  The reference's jitter
+        // gives that case a random 1e-6 m offset; without it the unit normal is 0/0, so the wall is skipped for this step
+        if (x <= d && x.v > 0.0) {
           const D ux = qx / x, uy = qy / x;
           const D acc = k * (d - x);
           const D dx2 = (d - x) * (d - x);

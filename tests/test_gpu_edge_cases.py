@@ -207,3 +207,76 @@ def test_population_parameters_beyond_the_defaults():
                                       1.0, 5.0, scalar_width=0.25)
         err = np.abs(P.get_state(evaluate_at=None, pos=pos) - ref)
         assert err.max() <= 4e-5, (desc, err.max())
+
+
+def test_nan_position_gives_zero_rates_like_the_reference():
+    """Neurons.update: `if np.isnan(self.Agent.pos[0]): firingrate = zeros` (ratinabox/Neurons.py:163-164) -- per agent here,
+    for every cell type, in the stepped API and in get_state-free updates; the other agents are unaffected."""
+    import ratinabox_b200 as rb
+    A = 70
+    E, Ag = _make(rb, A, _walls(2))
+    PCs = rb.PlaceCells(Ag, {"n": 96, "min_fr": 0.2, "max_fr": 3.0})
+    GCs = rb.GridCells(Ag, {"n": 40})
+    BVCs = rb.BoundaryVectorCells(Ag, {"n": 24})
+    NZ = rb.PlaceCells(Ag, {"n": 32, "noise_std": 0.1})
+    pos = Ag.pos.copy()
+    bad = [0, 33, 69]
+    pos[bad, 0] = np.nan
+    Ag.pos = pos
+    for ns in (PCs, GCs, BVCs, NZ):
+        ns.update()                                   # rates at the current positions (no motion step queued)
+    for ns in (PCs, GCs, BVCs):
+        fr = ns.firingrate
+        assert np.array_equal(fr[bad], np.zeros((len(bad), ns.n))), type(ns).__name__
+        good = np.setdiff1d(np.arange(A), bad)
+        assert np.isfinite(fr[good]).all() and np.abs(fr[good]).max() > 0
+        assert not ns.get_history_arrays()["spikes"][-1][bad].any()
+    frz = NZ.firingrate                               # zeros + OU noise (Neurons.py:167-168)
+    assert np.isfinite(frz[bad]).all() and 0 < np.abs(frz[bad]).max() < 1.0
+
+
+def test_zero_length_wall_is_a_point_obstacle():
+    """The reference's own test adds a zero-length wall (tests/test_environment.py:20-23).  Its jittered arithmetic treats it
+    as a ~1e-6 m segment; the engine's zero-jitter arithmetic treats it as the point itself instead of dividing 0 / 0
+    (utils.py:121-184): positions stay finite and equal the oracle's for the same box with a 1e-9 m wall at that point."""
+    import ratinabox_b200 as rb
+    A = 300
+    pt = [0.4, 0.4]
+    E, Ag = _make(rb, A, [[pt, pt]])
+    assert len(E.walls) == 5
+    rs = np.random.RandomState(3)
+    pos0 = np.clip(np.array(pt) + rs.normal(0, 0.06, (A, 2)), 0.02, 0.98)      # many agents inside the repulsion radius
+    Ag.pos = pos0
+    vel0 = Ag.velocity.copy()
+    xi = rs.normal(size=(A, 2))
+    PCs = rb.PlaceCells(Ag, {"n": 64, "wall_geometry": "line_of_sight"})
+    BVCs = rb.BoundaryVectorCells(Ag, {"n": 16})
+    Ag.update(_xi=xi)
+    PCs.update(); BVCs.update()
+    pos1 = Ag.pos
+    assert np.isfinite(pos1).all() and np.isfinite(PCs.firingrate).all() and np.isfinite(BVCs.firingrate).all()
+    env = O.OracleEnvironment(walls=[[pt, [pt[0] + 1e-9, pt[1]]]])
+    near = 0
+    for a in range(A):
+        oa = O.OracleAgent(env, pos0[a], vel0[a], {"dt": 0.01})
+        oa.update(O.TapeRNG(agent_xi=xi[a]))
+        assert np.abs(oa.pos - pos1[a]).max() <= 1e-6, a
+        near += np.linalg.norm(pos0[a] - pt) < 0.1
+    assert near > 50
+    for _ in range(200):
+        Ag.update()
+    assert np.isfinite(Ag.pos).all()
+
+
+def test_agent_exactly_on_a_wall_stays_finite():
+    """`Ag.pos = [0.5, 0.5]` with a wall through x = 0.5: the reference's 1e-6 jitter hides the 0 / 0 of the unit normal
+    (Agent.py:370, utils.py:143-144); the engine skips that wall's repulsion for the step instead of poisoning the state."""
+    import ratinabox_b200 as rb
+    E, Ag = _make(rb, 8, [[[0.5, 0.2], [0.5, 0.8]]])
+    pos = Ag.pos.copy()
+    pos[:4] = [0.5, 0.5]
+    Ag.pos = pos
+    PCs = rb.PlaceCells(Ag, {"n": 32})
+    for _ in range(50):
+        Ag.update(); PCs.update()
+    assert np.isfinite(Ag.pos).all() and np.isfinite(Ag.velocity).all() and np.isfinite(PCs.firingrate).all()
