@@ -1,10 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* RatInABox reference.
 
-Used only in the build container (where /root/reference exists) by
-``oracle/gen_golden.py`` and ``tests/test_oracle_vs_reference.py`` to pin the
-oracle restatement against the live reference.  Nothing in the product path
-imports this file, and it is never used on the GPU box (/root/reference does
-not exist there).
+Used by ``oracle/gen_golden.py`` (build container, /root/reference) to pin the
+oracle restatement against the live reference, and -- through the copy that
+``oracle/make_ref.py`` stages into the git-ignored ``oracle/_ref/`` -- by
+``bench.py``'s CPU legs and ``tests/test_gpu_vs_reference.py`` on the GPU box.
+Nothing in the product path imports this file.
 
 The reference imports matplotlib and shapely at module top
 (ratinabox/Environment.py:6-8, Agent.py:7-8, Neurons.py:7-12, utils.py:2-3).
@@ -23,7 +23,10 @@ import sys
 import types
 import importlib
 
+import os
+
 REFERENCE_ROOT = "/root/reference"
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # oracle/make_ref.py (travels to the GPU box)
 
 
 def _polygon_contains_strict(verts, p):
@@ -116,15 +119,23 @@ def install():
         sys.modules["shapely.geometry"] = geom
 
 
+def reference_root():
+    """Where the unmodified reference lives: /root/reference (build container) or the copy staged by oracle/make_ref.py."""
+    for root in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isdir(os.path.join(root, "ratinabox")):
+            return root
+    return None
+
+
 def import_reference():
-    """Return the unmodified reference package (``ratinabox``), or None when
-    /root/reference is not present (i.e. on the GPU box)."""
-    import os
-    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "ratinabox")):
+    """Return the unmodified reference package (``ratinabox``), or None when neither /root/reference nor the staged copy
+    (oracle/_ref, git-ignored, shipped by gpurun) is present."""
+    root = reference_root()
+    if root is None:
         return None
     install()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

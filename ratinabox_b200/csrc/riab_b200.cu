@@ -1675,6 +1675,21 @@ int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_param
   return launch_place_d<MODE, -1>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
 }
 
+// riab_run pipelines BoundaryVectorCells across steps: the float64 ray kernel of step s+1 (latency-bound, FP64 pipe) runs
+// on the caller's stream while the angular integral of step s (MUFU-bound) still runs on a side stream -- different pipes,
+// so the two overlap almost completely.  Needs a second ray-distance buffer (steps alternate) and, per buffer, an event
+// that the integral which read it has finished.  Allocentric cells only (egocentric ones read the head directions the next
+// motion step overwrites).
+constexpr int PIPE_POPS = 8;
+struct BvcPipe {
+  cudaStream_t side = nullptr;
+  cudaEvent_t rays_done = nullptr, int_done[2][PIPE_POPS] = {};
+  bool used[2][PIPE_POPS] = {};
+  float* scratch2[PIPE_POPS] = {};
+  long long step = 0;
+};
+thread_local BvcPipe* g_pipe = nullptr;
+
 template <bool FUSED>
 int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
                const riab_bvc_cells* bvc, const OutK& out, const double* pos_in, long long n_rows, float* scratch,
@@ -1703,10 +1718,22 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
   // OU noise (a read-modify-write of the noise state per rate) and odd shard offsets keep the k_finish_rows post-pass
   const int fold = (out.spikes != nullptr && out.noise == nullptr && (out.id_offset & 1ll) == 0) ? 1 : 0;
   uint32_t* const zsp = fold ? out.spikes : nullptr;
+  BvcPipe* const pipe = (g_pipe != nullptr && !bc.ego && out.pop >= 0 && out.pop < PIPE_POPS && g_pipe->scratch2[out.pop] != nullptr) ? g_pipe : nullptr;
+  const int pb = pipe ? (int)(pipe->step & 1) : 0;
+  if (pipe) {
+    if (pb) scratch = pipe->scratch2[out.pop];
+    // the integral of two steps ago read this buffer (and wrote the ring slot a short ring re-uses now)
+    if (pipe->used[pb][out.pop]) RIAB_CUDA_OK(cudaStreamWaitEvent(s, pipe->int_done[pb][out.pop], 0));
+  }
   if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
   else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
+  if (pipe) {                                         // the integral (and its post-pass) go to the side stream
+    RIAB_CUDA_OK(cudaEventRecord(pipe->rays_done, s));
+    RIAB_CUDA_OK(cudaStreamWaitEvent(pipe->side, pipe->rays_done, 0));
+    s = pipe->side;
+  }
   // (the attribute belongs to the current device's function image: set per call, a single process may drive several GPUs)
   RIAB_CUDA_OK(cudaFuncSetAttribute(k_bvc_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
   int dev = 0, sms = 148;
@@ -1730,6 +1757,10 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
     k_finish_rows<<<dim3((unsigned)n_rows, (unsigned)((np128 / 4 + NT - 1) / NT)), NT, 0, s>>>(out, bc.n_cells, np128, n_rows);
     g_launches++;
     RIAB_CUDA_OK(cudaGetLastError());
+  }
+  if (pipe) {
+    RIAB_CUDA_OK(cudaEventRecord(pipe->int_done[pb][out.pop], s));
+    pipe->used[pb][out.pop] = true;
   }
   return 0;
 }
@@ -2156,7 +2187,52 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
     const riab_step_io s0 = step_io(0);
     if ((rc = riab_agent_update(agents, env, prm, &s0, stream))) return rc;
   }
+  // ---- BoundaryVectorCells: pipeline rays(s+1) against the integral of step s (see BvcPipe)
+  static thread_local BvcPipe pipes[16];
+  BvcPipe* pipe = nullptr;
+  {
+    int dev = 0;
+    bool want = false;
+    for (int p = 0; p < n_pops && p < PIPE_POPS; ++p)
+      want = want || (pops[p].kind == RIAB_CELLS_BVC && pops[p].cells != nullptr && !((const riab_bvc_cells*)pops[p].cells)->egocentric &&
+                      pops[p].ring_rows >= 2 && pops[p].out.bvc_scratch != nullptr);
+    if (want && n_steps >= 2 && getenv("RIAB_NO_BVC_PIPELINE") == nullptr && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16) {
+      pipe = &pipes[dev];
+      if (pipe->side == nullptr) {
+        RIAB_CUDA_OK(cudaStreamCreateWithFlags(&pipe->side, cudaStreamNonBlocking));
+        RIAB_CUDA_OK(cudaEventCreateWithFlags(&pipe->rays_done, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b)
+          for (int p = 0; p < PIPE_POPS; ++p) RIAB_CUDA_OK(cudaEventCreateWithFlags(&pipe->int_done[b][p], cudaEventDisableTiming));
+      }
+      for (int b = 0; b < 2; ++b)
+        for (int p = 0; p < PIPE_POPS; ++p) pipe->used[b][p] = false;
+      for (int p = 0; p < PIPE_POPS; ++p) pipe->scratch2[p] = nullptr;
+      for (int p = 0; p < n_pops && p < PIPE_POPS; ++p) {
+        if (pops[p].kind != RIAB_CELLS_BVC || pops[p].cells == nullptr || pops[p].ring_rows < 2 || pops[p].out.bvc_scratch == nullptr) continue;
+        const riab_bvc_cells* bc = (const riab_bvc_cells*)pops[p].cells;
+        if (bc->egocentric) continue;
+        const int pid = pops[p].noise.population_id;
+        if (pid < 0 || pid >= PIPE_POPS) continue;
+        RIAB_CUDA_OK(cudaMallocAsync((void**)&pipe->scratch2[pid], (size_t)riab_bvc_scratch_floats(A, bc->n_test_angles) * sizeof(float),
+                                     (cudaStream_t)stream));
+      }
+    }
+  }
+  struct PipeGuard {                                      // leaves riab_run: join the side stream, free the second buffers
+    BvcPipe* p; cudaStream_t s;
+    ~PipeGuard() {
+      g_pipe = nullptr;
+      if (p == nullptr) return;
+      for (int b = 0; b < 2; ++b)
+        for (int q = 0; q < PIPE_POPS; ++q)
+          if (p->used[b][q]) cudaStreamWaitEvent(s, p->int_done[b][q], 0);
+      for (int q = 0; q < PIPE_POPS; ++q)
+        if (p->scratch2[q] != nullptr) { cudaFreeAsync(p->scratch2[q], s); p->scratch2[q] = nullptr; }
+    }
+  } guard{pipe, (cudaStream_t)stream};
+  g_pipe = pipe;
   for (int64_t st = 0; st < n_steps; ++st) {
+    if (pipe) pipe->step = st;
     const riab_step_io sio = step_io(st);
     if (n_pops == 0) {
       if ((rc = riab_agent_update(agents, env, prm, &sio, stream))) return rc;
