@@ -282,7 +282,8 @@ def measure(rb, lib, torch, dist, name, steps, warmup, rank, world, local_rank, 
     Env = rb.Environment()
     for w in wl["walls"]:
         Env.add_wall(w)
-    Ag = rb.Agent(Env, {"dt": 0.01, "n_agents": A, "seed": 7, "id_offset": rank * A})
+    Ag = rb.Agent(Env, {"dt": 0.01, "n_agents": A, "seed": 7, "id_offset": rank * A,
+                        "fused_step": os.environ.get("RIAB_BENCH_FUSED_STEP") == "1"})
     pos, vel = synthetic_agents(A, wl["walls"], 100 + rank)
     Ag.pos, Ag.velocity = pos, vel
     Ag.measured_velocity = vel

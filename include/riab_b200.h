@@ -334,6 +334,24 @@ int riab_step_fused_host(const riab_agents* agents, const riab_env* env, const r
                          const double* drift_host, double* drift_staging_dev,
                          double* pos_out_host, void* stream);
 
+/* Agent.update with HOST buffers, for per-step control loops (the policy-control caller of
+ * ratinabox/contribs/TaskEnvironment.py:399-408 passes one drift velocity per agent and reads the positions back):
+ *   1. drift_host (A,2 f64, page-locked; may be NULL) is uploaded to drift_staging_dev by a copy engine on the
+ *      library's side stream -- at once, i.e. while kernels queued earlier on `stream` (the previous step's rate
+ *      kernels) still run;
+ *   2. the motion kernel (riab_agent_update semantics; io->drift_velocity is set to the staging buffer) runs on
+ *      `stream` after that copy;
+ *   3. the new positions are copied to pos_out_host (page-locked; may be NULL) on the side stream, concurrently with
+ *      whatever the caller queues on `stream` next (the rate kernels).
+ * riab_positions_wait() blocks until step 3 of the LAST call on this device has finished (not the stream).  The next
+ * kernel that overwrites agents->pos must be ordered after that copy: riab_positions_fence(stream) inserts the
+ * dependency (riab_agent_update_host does it itself). */
+int riab_agent_update_host(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                           riab_step_io* io, const double* drift_host, double* drift_staging_dev,
+                           double* pos_out_host, void* stream);
+int riab_positions_wait(void);
+int riab_positions_fence(void* stream);
+
 #ifdef __cplusplus
 }
 #endif

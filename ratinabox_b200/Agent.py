@@ -85,6 +85,13 @@ class Agent:
         "seed": 0,
         "id_offset": 0,
         "history_bytes_limit": 2 << 30,
+        # stepped API: True  = update() queues the motion step and the first Neurons.update() runs it fused with its rates
+        #                      (riab_step_fused, one kernel per (motion, cell type));
+        #              False = update() launches the motion kernel at once and Neurons.update() the rate kernel: the float64
+        #                      motion chain then overlaps the host side of Neurons.update() instead of gating the rate warps
+        #                      inside one kernel (measured faster end to end, profiles/r02_summary.md), and reading
+        #                      positions only waits for the motion kernel.
+        "fused_step": False,
     }
 
     def __init__(self, Environment, params={}):
@@ -121,6 +128,10 @@ class Agent:
         self._pos_mirror_current = False
         self._drift_keep = None
         self._env_key = None
+        self._staging_only = False          # run(): update() only fills the structs
+        self._drift_host_ptr = None         # pinned drift commands of the queued step (eager stepped API)
+        self._pos_copy_inflight = False
+        self._motion_event_valid = False
 
         # ---- initial state (Agent.py:523-535, :136-141), sampled on the host like the reference
         pos = Environment.sample_positions(n=A, method="random")
@@ -211,11 +222,15 @@ class Agent:
             buf = self._pinned.get(name)
             if buf is None:
                 buf = self._pinned[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            if not (name == "pos" and self._pos_mirror_current):
-                # (the motion kernels post the new positions straight into the pinned `pos` buffer:
-                # riab_step_io.pos_mirror -- no copy needed while that mirror is current)
-                buf.copy_(t, non_blocking=True)
-            self._sync_stream()
+            if name == "pos" and self._pos_mirror_current and self._motion_event_valid:
+                # the copy engine is bringing the positions into this buffer: wait for that copy only
+                _lib.check(self._lib.riab_positions_wait())
+            else:
+                if not (name == "pos" and self._pos_mirror_current):
+                    # (the motion kernels post the new positions straight into the pinned `pos` buffer:
+                    # riab_step_io.pos_mirror -- no copy needed while that mirror is current)
+                    buf.copy_(t, non_blocking=True)
+                self._sync_stream()
             arr = buf.numpy()
             if view:
                 arr = arr.view()
@@ -243,6 +258,8 @@ class Agent:
         self._shadow.pop(name, None)
         if name == "pos":
             self._pos_mirror_current = False
+        if name == "pos":
+            self._wait_pos_copy()
         arr = np.asarray(value, dtype=np.float64)
         if name in _VEC:
             arr = np.broadcast_to(arr.reshape(-1, 2) if arr.size == 2 * self.n_agents else arr, (self.n_agents, 2))
@@ -292,6 +309,7 @@ class Agent:
 
         io = self._io
         io.drift_velocity = None
+        self._drift_host_ptr = None
         if drift_velocity is not None:
             if self._drift_dev is None:
                 self._drift_dev = torch.empty((self.n_agents, 2), dtype=torch.float64, device=self.device)
@@ -304,10 +322,17 @@ class Agent:
             if d.dtype != torch.float64:
                 d = d.to(torch.float64)
             if (not d.is_cuda) and d.is_pinned() and d.is_contiguous() and tuple(d.shape) == (self.n_agents, 2):
-                # page-locked host commands: the motion kernel reads them over the bus itself (unified addressing),
-                # no staging copy.  Like a non_blocking copy, the buffer must not change before the step has run.
                 self._drift_keep = d
-                io.drift_velocity = d.data_ptr()
+                if self.fused_step or self._staging_only:
+                    # page-locked host commands: the fused kernel reads them over the bus itself (unified addressing),
+                    # no staging copy.  Like a non_blocking copy, the buffer must not change before the step has run.
+                    io.drift_velocity = d.data_ptr()
+                else:
+                    # page-locked host commands: riab_agent_update_host uploads them with a copy engine on the library's side
+                    # stream at once -- while the previous step's rate kernel still occupies the compute stream -- and the
+                    # motion kernel waits for that copy only.  (Zero-copy loads inside the float64 motion chain would stall
+                    # it on PCIe latency instead.)
+                    self._drift_host_ptr = d.data_ptr()
             else:
                 # host -> device on the current stream (asynchronous when the host buffer is pinned)
                 self._drift_dev.copy_(d.expand(self.n_agents, 2), non_blocking=True)
@@ -337,7 +362,7 @@ class Agent:
             io.history_row = self._history_row_ptr()
             self._t_hist.append(self.t)
         io.pos_mirror = None
-        if self.n_agents > self._SHADOW_MAX:
+        if self.n_agents > self._SHADOW_MAX and (self.fused_step or self._staging_only):
             # large batches: the motion step also posts the new positions into the pinned host buffer that
             # `Ag.pos` hands out, so reading them back after the step costs a stream sync and no copy
             buf = self._pinned.get("pos")
@@ -347,18 +372,48 @@ class Agent:
             self._pos_mirror_current = True
         self._pending = True
         self._step += 1
+        if not self.fused_step and not self._staging_only:
+            self._flush_pending()                      # launch the motion kernel now (asynchronous)
+
+    def _wait_pos_copy(self):
+        """Order the compute stream behind an in-flight D2H copy of the positions (it reads what comes next overwrites)."""
+        if self._pos_copy_inflight:
+            _lib.check(self._lib.riab_positions_fence(self._stream()))
+            self._pos_copy_inflight = False
 
     def _flush_pending(self):
         """Run a queued motion step that no Neurons.update() fused with."""
         if self._pending:
             self._pending = None
-            _lib.check(self._lib.riab_agent_update(C.byref(self._agents_c), C.byref(self._env_struct()),
-                                                   C.byref(self._mp), C.byref(self._io), self._stream()))
+            if self.fused_step:
+                self._wait_pos_copy()
+                _lib.check(self._lib.riab_agent_update(C.byref(self._agents_c), C.byref(self._env_struct()),
+                                                       C.byref(self._mp), C.byref(self._io), self._stream()))
+                return
+            # eager stepped API: one C call = [copy-engine upload of pinned drift commands on the side stream] -> motion
+            # kernel -> [copy-engine download of the new positions on the side stream, large batches]; readers of `pos`
+            # then wait for that download only, not for the rate kernels queued behind the motion kernel
+            pos_out = None
+            if self.n_agents > self._SHADOW_MAX:
+                import torch
+                buf = self._pinned.get("pos")
+                if buf is None:
+                    buf = self._pinned["pos"] = torch.empty((self.n_agents, 2), dtype=torch.float64).pin_memory()
+                pos_out = buf.data_ptr()
+            stage = self._drift_dev.data_ptr() if self._drift_host_ptr is not None else None
+            _lib.check(self._lib.riab_agent_update_host(C.byref(self._agents_c), C.byref(self._env_struct()), C.byref(self._mp),
+                                                        C.byref(self._io), self._drift_host_ptr, stage, pos_out, self._stream()))
+            if pos_out is not None:
+                self._pos_copy_inflight = True
+                self._motion_event_valid = True
+                self._pos_mirror_current = True
 
     def _take_pending(self):
         """Called by Neurons.update(): hands over the queued step for fusion."""
         if self._pending:
             self._pending = None
+            self._wait_pos_copy()
+            self._motion_event_valid = False            # the fused kernel posts the positions: wait for the stream
             return True
         return False
 
@@ -374,12 +429,18 @@ class Agent:
         if "drift_velocity" in kwargs and kwargs["drift_velocity"] is not None:
             raise NotImplementedError("run() is the free-exploration loop; step with update(drift_velocity=...) for control")
         # stage everything exactly like one update() would, then hand the loop to C
-        self.update(**kwargs)
+        self._staging_only = True
+        try:
+            self.update(**kwargs)
+        finally:
+            self._staging_only = False
         self._pending = None
         # a device-resident loop needs no per-step host mirror of the positions (1 MB of bus writes per step at
         # 65 536 agents); reads after the run copy once
         self._io.pos_mirror = None
         self._pos_mirror_current = False
+        self._motion_event_valid = False
+        self._wait_pos_copy()
         dt = self.dt
         first_step = self._step - 1
         A = self.n_agents

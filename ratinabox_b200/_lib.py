@@ -138,6 +138,10 @@ SYMBOLS = {
                                       C.POINTER(RatesOut), C.c_void_p]),
     "riab_run": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
                            C.POINTER(Population), C.c_int32, C.POINTER(AgentHistory), C.c_int64, C.c_void_p]),
+    "riab_agent_update_host": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "riab_positions_wait": (C.c_int, []),
+    "riab_positions_fence": (C.c_int, [C.c_void_p]),
     "riab_step_fused_host": (C.c_int, [C.POINTER(Agents), C.POINTER(Env), C.POINTER(MotionParams), C.POINTER(StepIO),
                                        C.c_int32, C.c_void_p, C.POINTER(NeuronNoise), C.POINTER(RatesOut),
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

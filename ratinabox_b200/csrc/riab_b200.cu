@@ -2284,4 +2284,74 @@ int riab_step_fused_host(const riab_agents* agents, const riab_env* env, const r
   return 0;
 }
 
+
+// ---- host-buffer motion step on two streams (see include/riab_b200.h)
+namespace {
+struct HostIo {
+  cudaStream_t side = nullptr;
+  cudaEvent_t up_done = nullptr, motion_done = nullptr, pos_done = nullptr;
+  bool pos_inflight = false;
+};
+thread_local HostIo g_hostio[16];
+int hostio(HostIo*& h) {
+  int dev = 0;
+  RIAB_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return fail(RIAB_ERR_UNSUPPORTED, "device ordinal %d", dev);
+  h = &g_hostio[dev];
+  if (h->side == nullptr) {
+    RIAB_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    RIAB_CUDA_OK(cudaEventCreateWithFlags(&h->up_done, cudaEventDisableTiming));
+    RIAB_CUDA_OK(cudaEventCreateWithFlags(&h->motion_done, cudaEventDisableTiming));
+    RIAB_CUDA_OK(cudaEventCreateWithFlags(&h->pos_done, cudaEventDisableTiming));
+  }
+  return 0;
+}
+}  // namespace
+
+int riab_positions_fence(void* stream) {
+  HostIo* h = nullptr;
+  int rc;
+  if ((rc = hostio(h))) return rc;
+  if (h->pos_inflight) RIAB_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, h->pos_done, 0));
+  return 0;
+}
+
+int riab_positions_wait(void) {
+  HostIo* h = nullptr;
+  int rc;
+  if ((rc = hostio(h))) return rc;
+  if (h->pos_inflight) RIAB_CUDA_OK(cudaEventSynchronize(h->pos_done));
+  return 0;
+}
+
+int riab_agent_update_host(const riab_agents* agents, const riab_env* env, const riab_motion_params* prm,
+                           riab_step_io* io, const double* drift_host, double* drift_staging_dev,
+                           double* pos_out_host, void* stream) {
+  if (agents == nullptr || io == nullptr) return fail(RIAB_ERR_INVALID, "agents / io NULL");
+  HostIo* h = nullptr;
+  int rc;
+  if ((rc = hostio(h))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)agents->n_agents * 2 * sizeof(double);
+  if (drift_host != nullptr) {
+    if (drift_staging_dev == nullptr) return fail(RIAB_ERR_INVALID, "drift_staging_dev NULL");
+    // the previous motion kernel (the last reader of the staging buffer) finished before the side stream's last copy
+    // started (that copy waited for motion_done), so the upload may start at once
+    RIAB_CUDA_OK(cudaMemcpyAsync(drift_staging_dev, drift_host, bytes, cudaMemcpyHostToDevice, h->side));
+    RIAB_CUDA_OK(cudaEventRecord(h->up_done, h->side));
+    RIAB_CUDA_OK(cudaStreamWaitEvent(s, h->up_done, 0));
+    io->drift_velocity = drift_staging_dev;
+  }
+  if (h->pos_inflight) RIAB_CUDA_OK(cudaStreamWaitEvent(s, h->pos_done, 0));   // the copy that still reads agents->pos
+  if ((rc = riab_agent_update(agents, env, prm, io, stream))) return rc;
+  RIAB_CUDA_OK(cudaEventRecord(h->motion_done, s));
+  RIAB_CUDA_OK(cudaStreamWaitEvent(h->side, h->motion_done, 0));
+  if (pos_out_host != nullptr) {
+    RIAB_CUDA_OK(cudaMemcpyAsync(pos_out_host, agents->pos, bytes, cudaMemcpyDeviceToHost, h->side));
+    RIAB_CUDA_OK(cudaEventRecord(h->pos_done, h->side));
+    h->pos_inflight = true;
+  }
+  return 0;
+}
+
 }  // extern "C"

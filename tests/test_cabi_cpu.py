@@ -252,7 +252,7 @@ def test_mirror_default_params_match_the_reference():
              "FieldOfViewBVCs": (rb.FieldOfViewBVCs, ["Neurons", "VectorCells", "BoundaryVectorCells", "FieldOfViewBVCs"]),
              "ObjectVectorCells": (rb.ObjectVectorCells, ["Neurons", "VectorCells", "ObjectVectorCells"]),
              "FieldOfViewOVCs": (rb.FieldOfViewOVCs, ["Neurons", "VectorCells", "ObjectVectorCells", "FieldOfViewOVCs"])}
-    added = {"Agent": {"n_agents", "seed", "id_offset", "history_bytes_limit"}, "Neurons": {"save_spikes", "history_bytes_limit"}}
+    added = {"Agent": {"n_agents", "seed", "id_offset", "history_bytes_limit", "fused_step"}, "Neurons": {"save_spikes", "history_bytes_limit"}}
     for name, (cls, chain) in pairs.items():
         want = {}
         for c in chain:
@@ -346,8 +346,9 @@ def test_ctypes_structs_have_the_headers_layout(tmp_path):
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the CPU arm: the NumPy port on the host cores) prints ONE JSON line with the keys
-    the driver reads; it needs no GPU, so it is checked here."""
+    """`bench.py --impl reference` (the CPU arm: the live reference staged in oracle/_ref -- or the NumPy port when it is
+    absent -- on the host cores) prints ONE JSON line with the keys the driver reads, and its `steps x ms_per_step` is the
+    time it really measured; it needs no GPU, so it is checked here."""
     import json
     import subprocess
     env = dict(os.environ, OMP_NUM_THREADS="1")
@@ -361,6 +362,10 @@ def test_bench_reference_arm_prints_the_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "agent-steps/sec" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    want_kind = "reference" if ref_shim.reference_root() is not None else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1
+    assert d["steps"] * d["ms_per_step"] * 1e-3 <= d["wall_s"]          # the timed region fits inside the run
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "c2" in d["config"]["workload"]

@@ -29,12 +29,14 @@ def oracle_step(env, pos, vel, xi, dt=0.01, **state):
     return oa, info
 
 
-def test_fused_step_all_cell_types():
-    """Ag.update(); Ns.update() -> one fused kernel per (motion, cell type); every population
-    of the same Agent sees the same new positions."""
+@pytest.mark.parametrize("fused", [True, False])
+def test_fused_step_all_cell_types(fused):
+    """Ag.update(); Ns.update() -> fused_step=True: one fused kernel per (motion, cell type) (riab_step_fused);
+    False (default): the motion kernel is launched by update() and the populations' rate kernels follow.  Either way
+    every population of the same Agent sees the same new positions."""
     import ratinabox_b200 as rb
     A = 200
-    E, Ag = make(rb, A)
+    E, Ag = make(rb, A, fused_step=fused)
     pos0, vel0 = Ag.pos.copy(), Ag.velocity.copy()
     PCs = rb.PlaceCells(Ag, {"n": 150, "wall_geometry": "line_of_sight"})
     GCs = rb.GridCells(Ag, {"n": 60})
@@ -366,7 +368,7 @@ def test_step_fused_host_entry_point():
     A = 200
     res = []
     for use_host_entry in (False, True):
-        E, Ag = make(rb, A)
+        E, Ag = make(rb, A, fused_step=True)          # (the host entry wraps the FUSED step: keep update() queueing)
         PCs = rb.PlaceCells(Ag, {"n": 48})
         rs = np.random.RandomState(5)
         for s in range(3):
