@@ -351,6 +351,9 @@ def measure(rb, lib, torch, dist, name, steps, warmup, rank, world, local_rank, 
         res["_objects"] = (Env, Ag, pops)
     else:
         del pops, Ag, Env
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         torch.cuda.empty_cache()
     return res
 
@@ -364,6 +367,7 @@ def gather_check(torch, dist, Ag, pops, rank, world):
     A = Ag.n_agents
     row = ns._hist[ns._last_slot]                               # (A, ld) float32, the step's rates
     pos = Ag._s["pos"]
+    gather_agent_axis(row[:64], 64 * world, axis=0, dst=0)      # untimed: NCCL sets its channels up on the first collective
     torch.cuda.synchronize(); dist.barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

@@ -71,6 +71,9 @@ struct OutK {
   int pop, vec_ok;
   uint32_t rk7[14];         // Philox4x32-7 round keys of the spike stream (host-computed, constant bank)
   // thinned spikes (thin_post): candidates at rate p = dt * (an upper bound of the rate), accepted with rate / bound
+  int tile_agents;          // agents per ring slot of k_step (<= TA, even): launch_tile shrinks the tiles of small batches so
+                            // that every (CTA, consumer group) gets an equal share (strong scaling: 8 192 agents per GPU
+                            // are 256 tiles of 32 on 148 x 2 groups -- 1.7 waves -- but 293 tiles of 28)
   int thin;                 // 1: the population's rates are bounded and p <= 1/8
   uint32_t thin_t16;        // an octet of 8 slots holds a candidate  <=>  its 16-bit word < t16  (= ceil(2^16 (1 - (1-p)^8)))
   uint32_t thin_t[8];       // t[i] = floor(2^32 (1 - (1-p')^(i+1))), p' the per-slot probability t16 implies: gap to the next candidate
@@ -434,6 +437,16 @@ template <int N, int L> __device__ __forceinline__ void reg_set() {
 template <class P, class C>
 constexpr int ring_slots() { return (P::REC > 24 && C::NS >= 2 * C::MW) ? C::NS / 2 : C::NS; }
 
+// Consumer groups of the lean slot loop: each ring slot is consumed by ONE group, slot q by group q % G.  A group must see
+// every phase of the slots it waits on (an mbarrier parity wait cannot skip a phase), so G has to divide the ring size.
+__host__ __device__ constexpr int lean_groups(int cell_threads, int ring) {
+  int g = (RW * 32) / (cell_threads > 0 ? cell_threads : 1);
+  if (g < 1) g = 1;
+  if (g > ring) g = ring;
+  while (ring % g != 0) --g;
+  return g;
+}
+
 template <int REC>
 struct __align__(16) StepSlot {
   float rec[TA][REC];
@@ -663,7 +676,7 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
   for (long long q = 0; q < nq; ++q) {
     const int s = (int)(q % NS);
     mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
-    const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * TA;
+    const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * out.tile_agents;
     const int na = s_slot[s].na;
     const int a_lo = 2 * grp * PPG;
     const int a_hi = (a_lo + 2 * PPG < na) ? a_lo + 2 * PPG : na;       // this group's agents of the slot: [a_lo, a_hi)
@@ -821,7 +834,7 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
                                               const int ctid, const int lane, uint32_t* thin_queue, const long long n_rows) {
   constexpr int NS = ring_slots<P, C>(), NC = RW * 32, CPT = P::CPT;
   const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32, <= NC)
-  const int G = NC / CT, grp = ctid / CT;             // groups of CT threads; group g consumes the slots q = g, g + G, ...
+  const int G = lean_groups(CT, NS), grp = ctid / CT; // groups of CT threads; group g consumes the slots q = g, g + G, ...
   if (grp >= G) return;                               // spare warps (the slots' release count is one group's warps)
   constexpr int a_lo = 0;
   typename P::Regs regs;
@@ -835,9 +848,9 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
   if (SPK == 2) thin_init<CPT>(tw, out, tc, n_rows, thin_queue);
   const long long ld = out.ld;
   [[maybe_unused]] const float q16 = out.dt * 65536.0f;
-  long long a0 = ((long long)blockIdx.x + (long long)grp * gridDim.x) * TA;     // first row of the group's first slot
+  long long a0 = ((long long)blockIdx.x + (long long)grp * gridDim.x) * out.tile_agents;     // first row of the group's first slot
   float* dst0 = out.rates + a0 * ld + cell0;
-  const long long a_step = (long long)G * gridDim.x * TA, slot_step = a_step * ld;
+  const long long a_step = (long long)G * gridDim.x * out.tile_agents, slot_step = a_step * ld;
   for (long long q = grp; q < nq; q += G, dst0 += slot_step, a0 += a_step) {
     const int s = (int)(q % NS);
     mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
@@ -928,7 +941,8 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
   }
   stage_walls(s_walls, &s_bar, env);     // includes __syncthreads()
 
-  const long long n_tiles = (n_rows + TA - 1) / TA;
+  const int ta = out.tile_agents;
+  const long long n_tiles = (n_rows + ta - 1) / ta;
   const long long nq = (n_tiles > (long long)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
 #ifdef RIAB_PRODUCERS_FIRST
@@ -948,8 +962,8 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
       const uint32_t k = (uint32_t)(q / NS);
       mbar_wait(&s_empty[s], (k & 1u) ^ 1u);
       const long long tile = (long long)blockIdx.x + q * gridDim.x;
-      const long long a0 = tile * TA;
-      const int na = (int)((n_rows - a0) < TA ? (n_rows - a0) : TA);
+      const long long a0 = tile * ta;
+      const int na = (int)((n_rows - a0) < ta ? (n_rows - a0) : ta);
       if (SPK == 2 && lane < na) {
         // thinned spikes: clear the tile's spike rows; the consumers OR accepted bits in after the slot is published
         // (mbarrier release / acquire orders these stores before their RED.ORs)
@@ -1604,7 +1618,7 @@ int g_num_sms = 0;
 // positions, then motion for the NEXT step -- used inside riab_run).
 template <class P, int MODE>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
-                const typename P::Const& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+                const typename P::Const& pc, const OutK& out_in, const double* pos_in, long long n_rows, cudaStream_t s) {
   if (n_rows == 0) return 0;
   {
     static int sms_of[64] = {0};                      // SM count per device ordinal (a process may drive several GPUs)
@@ -1614,7 +1628,25 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
     if (sms_of[dev] == 0) RIAB_CUDA_OK(cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
     g_num_sms = sms_of[dev];
   }
-  const long long n_tiles = (n_rows + TA - 1) / TA;
+  // agents per ring slot: 32 for large batches; small ones get equal shares per (CTA, consumer group)
+  OutK outk = out_in;
+  {
+    const int ct = pc.n_pad / P::CPT;                                 // cell-threads of one consumer group
+    const long long groups = (ct > 0 && ct <= RW * 32) ? (long long)g_num_sms * lean_groups(ct, ring_slots<P, StepCfg<4>>())
+                                                         : (long long)g_num_sms;
+    int ta = TA;
+    if (n_rows < 4ll * TA * groups) {
+      const long long per = (n_rows + groups - 1) / groups;          // agents per group if every group gets one slot
+      const long long rounds = (per + TA - 1) / TA;                   // slots per group
+      ta = (int)((n_rows + groups * rounds - 1) / (groups * rounds));
+      ta = (ta + 1) & ~1;
+      if (ta < 2) ta = 2;
+      if (ta > TA) ta = TA;
+    }
+    outk.tile_agents = ta;
+  }
+  const OutK& out = outk;
+  const long long n_tiles = (n_rows + out.tile_agents - 1) / out.tile_agents;
   const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
   const bool spikes = out.spikes != nullptr, noise = out.noise != nullptr;
   MotionDerived md;
@@ -2192,10 +2224,12 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
   BvcPipe* pipe = nullptr;
   {
     int dev = 0;
-    bool want = false;
-    for (int p = 0; p < n_pops && p < PIPE_POPS; ++p)
-      want = want || (pops[p].kind == RIAB_CELLS_BVC && pops[p].cells != nullptr && !((const riab_bvc_cells*)pops[p].cells)->egocentric &&
-                      pops[p].ring_rows >= 2 && pops[p].out.bvc_scratch != nullptr);
+    // only when every population is a BoundaryVectorCells one: next to Place / Grid rate kernels (HBM- and dispatch-bound) the
+    // overlapped integral just competes for the same SMs (measured: configs[4] 2.22 ms without, 2.37 ms with the pipeline)
+    bool want = n_pops >= 1;
+    for (int p = 0; p < n_pops; ++p)
+      want = want && p < PIPE_POPS && (pops[p].kind == RIAB_CELLS_BVC && pops[p].cells != nullptr && !((const riab_bvc_cells*)pops[p].cells)->egocentric &&
+                                       pops[p].ring_rows >= 2 && pops[p].out.bvc_scratch != nullptr);
     if (want && n_steps >= 2 && getenv("RIAB_NO_BVC_PIPELINE") == nullptr && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16) {
       pipe = &pipes[dev];
       if (pipe->side == nullptr) {

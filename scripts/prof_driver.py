@@ -28,6 +28,18 @@ if mode == "rates":
     for _ in range(steps):
         for ns in pops:
             ns.update()
+elif mode == "range":
+    # DRAM traffic of `steps` CONSECUTIVE steps as one profiled range (ncu --replay-mode range): a single-launch capture
+    # misses the dirty tail the 126 MB L2 still holds when the kernel ends; over a range of steps every step's rows are
+    # evicted by the next ones (and the range ends with an L2-sized flush write so the last step's tail is counted too)
+    Ag.run(8)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    Ag.run(steps)
+    flush.fill_(1)
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
 else:
     Ag.run(steps)
 torch.cuda.synchronize()
