@@ -81,6 +81,19 @@ struct OutK {
   float thin_c1, thin_c0;   // accept <=> fma(float(word >> 8), c1, c0) < rate;  c1 = 2^-24 bound, c0 = 2^-25 bound
 };
 
+// MODE 3 of k_step: the whole riab_run loop of a single Place / Grid population in ONE launch.  Agents are independent and
+// the tile -> CTA assignment is static, so a CTA can run all n_steps for its own agents with no grid-wide synchronisation:
+// the producers keep advancing their tiles into the next step while the consumers still write the rates of this one, and
+// the per-launch ramp (wall staging, cell registers, first records) and tail are paid once per run instead of once per step.
+struct RunK {
+  long long n_steps;
+  float* rates_ring;            // (ring_rows, A, ld): step s writes row (ring_next + s) % ring_rows
+  uint32_t* spikes_ring;        // (ring_rows, A, spike_ld) or NULL
+  long long ring_rows, ring_next;
+  float* hist_ring;             // (hist_rows, A, 8) agent history rows or NULL
+  long long hist_rows, hist_next;
+};
+
 // ---------------------------------------------------------------------------
 // walls -> shared memory through a 1-D TMA bulk copy when 16-byte aligned.
 __device__ __forceinline__ void stage_walls(double* s_walls, uint64_t* bar, const EnvK& env) {
@@ -160,15 +173,21 @@ struct RowCursor {
 };
 
 template <int CPT = 4>
+__device__ __forceinline__ void tail_init(TailCtx& t, const OutK& out, int cell0, int n_cells, unsigned long long step);
+template <int CPT = 4>
 __device__ __forceinline__ void tail_init(TailCtx& t, const OutK& out, int cell0, int n_cells) {
+  tail_init<CPT>(t, out, cell0, n_cells, out.step);
+}
+template <int CPT>
+__device__ __forceinline__ void tail_init(TailCtx& t, const OutK& out, int cell0, int n_cells, unsigned long long step) {
   t.cell0 = cell0; t.n_cells = n_cells;
   t.vmask = 0u;
 #pragma unroll
   for (int i = 0; i < CPT; ++i) t.vmask |= (cell0 + i < n_cells) ? (1u << i) : 0u;
   t.full4 = out.vec_ok && (t.vmask == ((1u << CPT) - 1u));
   t.sub = (uint32_t)(cell0 >> 2);
-  t.c2 = (uint32_t)out.step;
-  const uint32_t hi = ((uint32_t)(out.step >> 32) & 0xffffu) | (((uint32_t)out.pop & 0xffu) << 16);
+  t.c2 = (uint32_t)step;
+  const uint32_t hi = ((uint32_t)(step >> 32) & 0xffffu) | (((uint32_t)out.pop & 0xffu) << 16);
   t.c3_spk = hi | (RIAB_STREAM_SPIKES << 24);
 }
 
@@ -312,9 +331,12 @@ struct PlacePolicy {
   static constexpr bool XU_BOUND = false;
   static constexpr bool THIN = true;                        // rates lie in [min_fr, max_fr]: thinned spikes apply
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
+  static __device__ __forceinline__ void prepare(double* aux, const double* s_walls, const Const& c) {
+    place_wall_invariants(aux, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0);
+  }
   static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double* s_walls,
-                                                const Const& c, const EnvK& env) {
-    place_agent_record<WI>(rec, px, py, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx, c.fold ? c.lspan : 0.f);
+                                                const double* aux, const Const& c, const EnvK& env) {
+    place_agent_record<WI>(rec, px, py, s_walls + 4 * c.wall0, aux, WI > 0 ? c.n_inner : 0, c.geometry, env.cxm, env.cym, c.band, c.expanded, c.kx, c.fold ? c.lspan : 0.f);
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { place_load_cells<WI, CPT_>(r, c, cell0); }
   template <bool DEFER, int EXP = -1>
@@ -337,8 +359,9 @@ struct GridPolicy {
   static constexpr bool THIN = true;
   static constexpr bool XU_BOUND = false; // 3 MUFU.COS per rate, yet issue-bound: PRMT+FADD instead of I2F measured slower (95.6 vs 91.3 us, c3)
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
-  static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double*, const Const&,
-                                                const EnvK& env) {
+  static __device__ __forceinline__ void prepare(double*, const double*, const Const&) {}
+  static __device__ __forceinline__ void record(float* rec, double px, double py, double, double, const double*, const double*,
+                                                const Const&, const EnvK& env) {
     rec[0] = (float)(px - env.cxm);
     rec[1] = (float)(py - env.cym);
   }
@@ -361,8 +384,9 @@ struct OvcPolicy {
   static constexpr bool THIN = false;     // sums over objects: no a-priori rate bound
   static constexpr bool XU_BOUND = false;
   static __device__ __forceinline__ const double* head_dir(const Const& c) { return c.head_dir; }
+  static __device__ __forceinline__ void prepare(double*, const double*, const Const&) {}
   static __device__ __forceinline__ void record(float* rec, double px, double py, double hdx, double hdy,
-                                                const double* s_walls, const Const& c, const EnvK&) {
+                                                const double* s_walls, const double*, const Const& c, const EnvK&) {
     ovc_agent_record(rec, px, py, hdx, hdy, s_walls, c);
   }
   static __device__ __forceinline__ void load(Regs& r, const Const& c, int cell0) { ovc_load_cells(r, c, cell0); }
@@ -792,7 +816,8 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
 template <class P, bool DENSE>
 __device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const typename P::Const& pc, const OutK& out,
                                             const TailCtx& tc, const float* rec, const uint32_t inner_s, float* d,
-                                            const long long a0, const int n_agents, const uint32_t redo, const bool act) {
+                                            uint32_t* spikes, const long long a0, const int n_agents, const uint32_t redo,
+                                            const bool act) {
   constexpr int CPT = P::CPT;
   for (int a = 0; a < n_agents; a += 2, d += 2 * out.ld, rec += 2 * P::REC) {
     const bool has_b = a + 1 < n_agents;
@@ -808,7 +833,7 @@ __device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const 
     if constexpr (DENSE && CPT == 4) {                              // whole warp: ballots
       RowCursor rc;
       rc.gid = (unsigned long long)(out.id_offset + a0 + a);
-      rc.spk = out.spikes + (a0 + a) * out.spike_ld + ((tc.cell0 >> 7) << 2);
+      rc.spk = spikes + (a0 + a) * out.spike_ld + ((tc.cell0 >> 7) << 2);
       const float q16 = out.dt * 65536.0f;
       if (has_b) {
         uint32_t c[4], bl[4];
@@ -828,13 +853,13 @@ __device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const 
 // The consumers' slot loop for the common case: no OU noise, no dense spike stream, vector-aligned rows, whole 4-cell
 // groups, all cells resident in one set of registers (n_pad <= 512 * CPT).  Pointers advance incrementally, the rare
 // repairs are a real call (slot_fixups), thinned spikes are queued across slots (ThinWarp).
-template <class P, int SPK, class C, int EXP>
-__device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const OutK& out, StepSlot<P::REC>* s_slot,
+template <class P, int SPK, class C, int EXP, bool MULTI>
+__device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const OutK& out, const RunK& run, StepSlot<P::REC>* s_slot,
                                               uint64_t* s_full, uint64_t* s_empty, const double* s_walls, const long long nq,
                                               const int ctid, const int lane, uint32_t* thin_queue, const long long n_rows) {
-  constexpr int NS = ring_slots<P, C>(), NC = RW * 32, CPT = P::CPT;
-  const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32, <= NC)
-  const int G = lean_groups(CT, NS), grp = ctid / CT; // groups of CT threads; group g consumes the slots q = g, g + G, ...
+  constexpr int NS = ring_slots<P, C>(), MW = C::MW, NSP = NS / MW, CPT = P::CPT;
+  const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32, <= RW * 32)
+  const int G = lean_groups(CT, NS), grp = ctid / CT; // groups of CT threads; group g consumes the tiles q = g, g + G, ...
   if (grp >= G) return;                               // spare warps (the slots' release count is one group's warps)
   constexpr int a_lo = 0;
   typename P::Regs regs;
@@ -844,77 +869,98 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
   tail_init<CPT>(tc, out, cell0, pc.n_cells);
   const bool act = cell0 < pc.n_cells;                // all CPT cells exist or none (n_cells % 4 == 0)
   const uint32_t inner_s = smem_u32(s_walls) + 32u * (uint32_t)P::wall0(pc);
-  ThinWarp tw;
-  if (SPK == 2) thin_init<CPT>(tw, out, tc, n_rows, thin_queue);
   const long long ld = out.ld;
   [[maybe_unused]] const float q16 = out.dt * 65536.0f;
-  long long a0 = ((long long)blockIdx.x + (long long)grp * gridDim.x) * out.tile_agents;     // first row of the group's first slot
-  float* dst0 = out.rates + a0 * ld + cell0;
+  const long long a_first = ((long long)blockIdx.x + (long long)grp * gridDim.x) * out.tile_agents;   // first row of the group's first tile
   const long long a_step = (long long)G * gridDim.x * out.tile_agents, slot_step = a_step * ld;
-  for (long long q = grp; q < nq; q += G, dst0 += slot_step, a0 += a_step) {
-    const int s = (int)(q % NS);
-    mbar_wait(&s_full[s], (uint32_t)((q / NS) & 1));
-    const int a_hi = s_slot[s].na;
-    if (a_lo < a_hi) {
-      const float* recp = s_slot[s].rec[a_lo];
-      float* d = dst0;
-      uint32_t redo = 0u;
-      const int n2 = (a_hi - a_lo) >> 1;
-      [[maybe_unused]] uint32_t* spk = nullptr;
-      [[maybe_unused]] unsigned long long pair = 0ull;
-      if constexpr (SPK == 1) {
-        spk = out.spikes + a0 * out.spike_ld + ((cell0 >> 7) << 2);
-        pair = (unsigned long long)(out.id_offset + a0) >> 1;          // even first global id: rows (2p, 2p+1) are one pair
-      }
-      for (int it = 0; it < n2; ++it) {
-        float o[CPT];
-        bool unsure = false;
-        P::template rates4<true, EXP>(o, regs, pc, cell0, recp, inner_s, unsure);
-        if (act) st_cs_fv<CPT>(d, o);
-        [[maybe_unused]] uint32_t c[4], bl[4];
-        [[maybe_unused]] float nv = 0.f;
-        if constexpr (SPK == 1) {
-          // dense spike stream: one Philox4x32-7 call per (agent pair, 4-cell group), a threshold test per rate
-          c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
-          philox_keyed<7>(c, out.rk7);
-          nv = spike_neg_dither(c);
-          spike_ballots<false, P::XU_BOUND>(bl, c[0], c[1], nv, o, q16, 0u, act);
-          spike_store(bl, spk);
-        }
-        P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
-        if (act) st_cs_fv<CPT>(d + ld, o);
-        if constexpr (SPK == 1) {
-          spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, act);
-          spike_store(bl, spk + out.spike_ld);
-          spk += 2 * out.spike_ld;
-          pair += 1ull;
-        }
-        redo |= (unsure ? 1u : 0u) << it;
-        d += 2 * ld;
-        recp += 2 * P::REC;
-      }
-      redo = __reduce_or_sync(0xffffffffu, redo);
-      if (redo != 0u || ((a_hi - a_lo) & 1)) {
-        const typename P::Regs rcopy = regs;            // stack copies, made on this path only
-        const typename P::Const pcopy = pc;
-        slot_fixups<P, SPK == 1>(rcopy, pcopy, out, tc, s_slot[s].rec[a_lo], inner_s, dst0, a0, a_hi - a_lo, redo, act);
-      }
-      if (const unsigned nm = s_slot[s].nanmask; nm != 0u && act) {     // NaN position -> zero rates (Neurons.py:163-164)
-        float z[CPT];
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) z[i] = 0.f;
-        for (int a = a_lo; a < a_hi; ++a)
-          if ((nm >> a) & 1u) st_cs_fv<CPT>(dst0 + (long long)(a - a_lo) * ld, z);
-      }
-      if (SPK == 2) {
-        __syncwarp();                                  // this warp's rate stores before the chains read them back
-        thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
-      }
+  const long long n_steps = MULTI ? run.n_steps : 1;
+  for (long long st = 0; st < n_steps; ++st) {
+    // this step's rows: the caller's (single step) or the rings' row (ring_next + st) % ring_rows
+    float* rates = out.rates;
+    uint32_t* spikes = out.spikes;
+    if (MULTI) {
+      const long long slot = (run.ring_next + st) % run.ring_rows;
+      rates = run.rates_ring + slot * n_rows * ld;
+      spikes = run.spikes_ring ? run.spikes_ring + slot * n_rows * out.spike_ld : nullptr;
+      tail_init<CPT>(tc, out, cell0, pc.n_cells, out.step + (unsigned long long)st);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s_empty[s]);
+    [[maybe_unused]] ThinWarp tw;
+    if constexpr (SPK == 2) {
+      OutK o = out;                                     // (the thinned stream keeps the row pointers / step in its own state)
+      o.rates = rates; o.spikes = spikes; o.step = out.step + (unsigned long long)st;
+      thin_init<CPT>(tw, o, tc, n_rows, thin_queue);
+    }
+    long long a0 = a_first;
+    float* dst0 = rates + a0 * ld + cell0;
+    for (long long q = grp; q < nq; q += G, dst0 += slot_step, a0 += a_step) {
+      // tile q is produced by warp q % MW as its n-th tile overall: slot and phase of that producer's private ring
+      const int pw = (int)(q % MW);
+      const long long npw = (nq - pw + MW - 1) / MW;    // tiles of that producer per step
+      const long long n = st * npw + q / MW;
+      const int s = pw + MW * (int)(n % NSP);
+      mbar_wait(&s_full[s], (uint32_t)((n / NSP) & 1));
+      const int a_hi = s_slot[s].na;
+      if (a_lo < a_hi) {
+        const float* recp = s_slot[s].rec[a_lo];
+        float* d = dst0;
+        uint32_t redo = 0u;
+        const int n2 = (a_hi - a_lo) >> 1;
+        [[maybe_unused]] uint32_t* spk = nullptr;
+        [[maybe_unused]] unsigned long long pair = 0ull;
+        if constexpr (SPK == 1) {
+          spk = spikes + a0 * out.spike_ld + ((cell0 >> 7) << 2);
+          pair = (unsigned long long)(out.id_offset + a0) >> 1;          // even first global id: rows (2p, 2p+1) are one pair
+        }
+        for (int it = 0; it < n2; ++it) {
+          float o[CPT];
+          bool unsure = false;
+          P::template rates4<true, EXP>(o, regs, pc, cell0, recp, inner_s, unsure);
+          if (act) st_cs_fv<CPT>(d, o);
+          [[maybe_unused]] uint32_t c[4], bl[4];
+          [[maybe_unused]] float nv = 0.f;
+          if constexpr (SPK == 1) {
+            // dense spike stream: one Philox4x32-7 call per (agent pair, 4-cell group), a threshold test per rate
+            c[0] = (uint32_t)pair; c[1] = tc.sub ^ ((uint32_t)(pair >> 32) << 24); c[2] = tc.c2; c[3] = tc.c3_spk;
+            philox_keyed<7>(c, out.rk7);
+            nv = spike_neg_dither(c);
+            spike_ballots<false, P::XU_BOUND>(bl, c[0], c[1], nv, o, q16, 0u, act);
+            spike_store(bl, spk);
+          }
+          P::template rates4<true, EXP>(o, regs, pc, cell0, recp + P::REC, inner_s, unsure);
+          if (act) st_cs_fv<CPT>(d + ld, o);
+          if constexpr (SPK == 1) {
+            spike_ballots<false, P::XU_BOUND>(bl, c[2], c[3], nv, o, q16, 0u, act);
+            spike_store(bl, spk + out.spike_ld);
+            spk += 2 * out.spike_ld;
+            pair += 1ull;
+          }
+          redo |= (unsure ? 1u : 0u) << it;
+          d += 2 * ld;
+          recp += 2 * P::REC;
+        }
+        redo = __reduce_or_sync(0xffffffffu, redo);
+        if (redo != 0u || ((a_hi - a_lo) & 1)) {
+          const typename P::Regs rcopy = regs;            // stack copies, made on this path only
+          const typename P::Const pcopy = pc;
+          slot_fixups<P, SPK == 1>(rcopy, pcopy, out, tc, s_slot[s].rec[a_lo], inner_s, dst0, spikes, a0, a_hi - a_lo, redo, act);
+        }
+        if (const unsigned nm = s_slot[s].nanmask; nm != 0u && act) {     // NaN position -> zero rates (Neurons.py:163-164)
+          float z[CPT];
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) z[i] = 0.f;
+          for (int a = a_lo; a < a_hi; ++a)
+            if ((nm >> a) & 1u) st_cs_fv<CPT>(dst0 + (long long)(a - a_lo) * ld, z);
+        }
+        if constexpr (SPK == 2) {
+          __syncwarp();                                  // this warp's rate stores before the chains read them back
+          thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[s]);
+    }
+    if constexpr (SPK == 2) thin_flush(tw, out);
   }
-  if (SPK == 2) thin_flush(tw, out);
 }
 
 // SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_post per ring slot)
@@ -922,7 +968,8 @@ template <class P, int MODE, int SPK, bool NOISE, class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
                                                           const riab_step_io io, const typename P::Const pc, const OutK out,
-                                                          const double* __restrict__ pos_in, const long long n_rows) {
+                                                          const double* __restrict__ pos_in, const long long n_rows,
+                                                          const RunK run) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
   constexpr int MW = C::MW, NS = ring_slots<P, C>();
   __shared__ StepSlot<P::REC> s_slot[NS];
@@ -940,6 +987,9 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
     mbar_fence_init();
   }
   stage_walls(s_walls, &s_bar, env);     // includes __syncthreads()
+  __shared__ double s_aux[2 * PLACE_MAX_WI];             // per-wall invariants of the agent records (policy-specific)
+  P::prepare(s_aux, s_walls, pc);
+  __syncthreads();
 
   const int ta = out.tile_agents;
   const long long n_tiles = (n_rows + ta - 1) / ta;
@@ -957,6 +1007,43 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
   if (producer) {
     // ------------------------------------------------------------- producers
     reg_set<C::REGS_PRODUCER, C::REGS_LAUNCH>();
+    if constexpr (MODE == 3) {
+      // whole run: this warp advances ITS tiles (q = pw, pw + MW, ...) step after step -- the same warp for every step of a
+      // tile, so a tile's steps are ordered -- and publishes each (step, tile) record into its private ring (slots
+      // pw + MW * i): the n-th record it produces goes to slot i = n % NSP in phase n / NSP
+      constexpr int NSP = NS / MW;
+      const long long npw = (nq > pw) ? (nq - pw + MW - 1) / MW : 0;
+      long long n = 0;
+      for (long long st = 0; st < run.n_steps; ++st) {
+        riab_step_io io_st = io;
+        io_st.step = io.step + (unsigned long long)st;
+        io_st.history_row = run.hist_ring ? run.hist_ring + ((run.hist_next + st) % run.hist_rows) * n_rows * 8 : nullptr;
+        uint32_t* const spikes_st = run.spikes_ring ? run.spikes_ring + ((run.ring_next + st) % run.ring_rows) * n_rows * out.spike_ld : nullptr;
+        for (long long q = pw; q < nq; q += MW, ++n) {
+          const int s = pw + MW * (int)(n % NSP);
+          mbar_wait(&s_empty[s], (uint32_t)(((n / NSP) & 1) ^ 1));
+          const long long a0 = ((long long)blockIdx.x + q * gridDim.x) * ta;
+          const int na = (int)((n_rows - a0) < ta ? (n_rows - a0) : ta);
+          if (SPK == 2 && lane < na && spikes_st != nullptr) {
+            uint32_t* z = spikes_st + (a0 + lane) * out.spike_ld;
+            for (long long w = 0; w < out.spike_ld; w += 4)
+              asm volatile("st.global.cs.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(z + w), "r"(0u) : "memory");
+          }
+          bool nanpos = false;
+          if (lane < na) {
+            AgentState as;
+            agent_update_one<false>(ag, mp, md, io_st, env, s_walls, a0 + lane, as);
+            nanpos = (as.px != as.px);
+            P::record(s_slot[s].rec[lane], as.px, as.py, as.hdx, as.hdy, s_walls, s_aux, pc, env);
+          }
+          const unsigned nanmask = __ballot_sync(0xffffffffu, nanpos);
+          if (lane == 0) { s_slot[s].na = na; s_slot[s].nanmask = nanmask; }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_full[s]);
+        }
+      }
+      return;
+    }
     for (long long q = pw; q < nq; q += MW) {
       const int s = (int)(q % NS);
       const uint32_t k = (uint32_t)(q / NS);
@@ -979,7 +1066,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
           const long long i = a0 + lane;
           const double px = ag.pos[2 * i], py = ag.pos[2 * i + 1];
           nanpos = (px != px);
-          P::record(s_slot[s].rec[lane], px, py, ag.head_direction[2 * i], ag.head_direction[2 * i + 1], s_walls, pc, env);
+          P::record(s_slot[s].rec[lane], px, py, ag.head_direction[2 * i], ag.head_direction[2 * i + 1], s_walls, s_aux, pc, env);
         }
         const unsigned nanmask = __ballot_sync(0xffffffffu, nanpos);
         if (lane == 0) { s_slot[s].na = na; s_slot[s].nanmask = nanmask; }
@@ -1005,7 +1092,7 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
           if (hd != nullptr) { hdx = hd[2 * i]; hdy = hd[2 * i + 1]; }
         }
         nanpos = (px != px);
-        P::record(s_slot[s].rec[lane], px, py, hdx, hdy, s_walls, pc, env);
+        P::record(s_slot[s].rec[lane], px, py, hdx, hdy, s_walls, s_aux, pc, env);
       }
       const unsigned nanmask = __ballot_sync(0xffffffffu, nanpos);
       if (lane == 0) { s_slot[s].na = na; s_slot[s].nanmask = nanmask; }
@@ -1023,12 +1110,13 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
     uint32_t* const tq = s_thinq[(SPK == 2) ? (ctid >> 5) : 0];
     if constexpr (!NOISE && (SPK != 1 || P::CPT == 4)) {
       if (lean) {
-        if (ex == 2) consumer_fast<P, SPK, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
-        else if (ex == 1) consumer_fast<P, SPK, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
-        else consumer_fast<P, SPK, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        if (ex == 2) consumer_fast<P, SPK, C, 2, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        else if (ex == 1) consumer_fast<P, SPK, C, 1, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        else consumer_fast<P, SPK, C, 0, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
         return;
       }
     }
+    if constexpr (MODE == 3) return;                    // (the host launches whole runs only where the lean loop applies)
     if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
     else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
     else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
@@ -1618,7 +1706,8 @@ int g_num_sms = 0;
 // positions, then motion for the NEXT step -- used inside riab_run).
 template <class P, int MODE>
 int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
-                const typename P::Const& pc, const OutK& out_in, const double* pos_in, long long n_rows, cudaStream_t s) {
+                const typename P::Const& pc, const OutK& out_in, const double* pos_in, long long n_rows, cudaStream_t s,
+                const RunK* run_in = nullptr) {
   if (n_rows == 0) return 0;
   {
     static int sms_of[64] = {0};                      // SM count per device ordinal (a process may drive several GPUs)
@@ -1646,22 +1735,25 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
     outk.tile_agents = ta;
   }
   const OutK& out = outk;
+  RunK run;
+  memset(&run, 0, sizeof(run));
+  if (run_in != nullptr) run = *run_in;
   const long long n_tiles = (n_rows + out.tile_agents - 1) / out.tile_agents;
   const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
   const bool spikes = out.spikes != nullptr, noise = out.noise != nullptr;
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (MODE != 0) derive_motion(mp, md);
-  if (noise) k_step<P, MODE, 1, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  if (noise) k_step<P, MODE, 1, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
   else if (spikes && out.thin) {
-    if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+    if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
     else return fail(RIAB_ERR_INVALID, "thinned spikes requested for a population without a rate bound");
   }
-  else if (spikes) k_step<P, MODE, 1, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+  else if (spikes) k_step<P, MODE, 1, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
   else {
     // light consumers without spikes run at the HBM write rate: twice the producer warps (only instantiated for them)
-    if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, 0, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
-    else k_step<P, MODE, 0, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows);
+    if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, 0, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
+    else k_step<P, MODE, 0, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
   }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
@@ -1670,13 +1762,14 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
 
 template <int MODE, int DESC>
 int launch_place_d(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
-                   const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+                   const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s,
+                   const RunK* run = nullptr) {
   const int wi = pc.n_inner;
-  if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  if (wi <= 4) return launch_tile<PlacePolicy<4, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  return launch_tile<PlacePolicy<8, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+  if (wi == 0) return launch_tile<PlacePolicy<0, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
+  if (wi == 1) return launch_tile<PlacePolicy<1, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
+  if (wi == 2) return launch_tile<PlacePolicy<2, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
+  if (wi <= 4) return launch_tile<PlacePolicy<4, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
+  return launch_tile<PlacePolicy<8, DESC>, MODE>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
 }
 
 int launch_onehot(const EnvK& env, const PlaceConst& pc, const OutK& out, const double* pos, long long n_rows,
@@ -1696,15 +1789,16 @@ int launch_onehot(const EnvK& env, const PlaceConst& pc, const OutK& out, const 
 
 template <int MODE>
 int launch_place(const EnvK& env, const riab_agents& ag, const riab_motion_params& mp, const riab_step_io& io,
-                 const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s) {
+                 const PlaceConst& pc, const OutK& out, const double* pos_in, long long n_rows, cudaStream_t s,
+                 const RunK* run = nullptr) {
   if (pc.desc == RIAB_PC_ONE_HOT) {
     if (MODE != 0) return fail(RIAB_ERR_INVALID, "one_hot is launched unfused");
     return launch_onehot(env, pc, out, pos_in, n_rows, s);
   }
   // the common Gaussian profile without geodesic detours gets a compile-time specialisation
   if (pc.desc == RIAB_PC_GAUSSIAN && pc.geometry != RIAB_GEOM_GEODESIC)
-    return launch_place_d<MODE, RIAB_PC_GAUSSIAN>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
-  return launch_place_d<MODE, -1>(env, ag, mp, io, pc, out, pos_in, n_rows, s);
+    return launch_place_d<MODE, RIAB_PC_GAUSSIAN>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
+  return launch_place_d<MODE, -1>(env, ag, mp, io, pc, out, pos_in, n_rows, s, run);
 }
 
 // riab_run pipelines BoundaryVectorCells across steps: the float64 ray kernel of step s+1 (latency-bound, FP64 pipe) runs
@@ -2215,6 +2309,60 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
     return sio;
   };
   int rc;
+  // ---- a single Place / Grid population: the whole run as ONE launch (k_step MODE 3, see RunK) where the lean consumer
+  // loop applies: vector-aligned rows, whole 4-cell groups, all cells in one register set, consumer groups that divide the
+  // producers, no OU noise, no parity taps, and rings that hold the run without wrapping onto rows still being written
+  if (n_pops == 1 && skew && getenv("RIAB_NO_WHOLE_RUN") == nullptr && io->drift_velocity == nullptr && io->pos_mirror == nullptr) {
+    const riab_population& pp = pops[0];
+    EnvK ek;
+    OutK ok;
+    if ((rc = check_agents(agents)) || (rc = make_env(env, ek)) || (rc = check_motion(prm))) return rc;
+    const bool place = pp.kind == RIAB_CELLS_PLACE, grid = pp.kind == RIAB_CELLS_GRID;
+    if ((place || grid) && pp.rates_ring != nullptr && pp.ring_rows > 0 && pp.noise.noise_std == 0.f) {
+      PlaceConst pcst;
+      GridConst gcst;
+      int n_cells = 0, n_pad = 0;
+      double bound = -1.0;
+      bool ok_cells = true;
+      if (place) {
+        const riab_place_cells* pc = (const riab_place_cells*)pp.cells;
+        if ((rc = make_place(pc, ek, pcst))) return rc;
+        n_cells = pc->n_cells; n_pad = pc->n_pad; bound = (double)fmaxf(pc->min_fr, pc->max_fr);
+        ok_cells = pc->description != RIAB_PC_ONE_HOT;
+      } else {
+        const riab_grid_cells* gc = (const riab_grid_cells*)pp.cells;
+        if ((rc = make_grid(gc, ek, gcst))) return rc;
+        n_cells = gc->n_cells; n_pad = gc->n_pad; bound = (double)fmaxf(gc->min_fr, gc->max_fr);
+      }
+      riab_rates_out ro = pp.out;
+      ro.rates_row = pp.rates_ring;                                    // (alignment / vector checks of make_out)
+      ro.spikes_row = pp.spikes_ring;
+      riab_neuron_noise nz = pp.noise;
+      nz.dt = (float)prm->dt;
+      if ((rc = make_out(&ro, &nz, n_cells, prm->dt, agents->id_offset, ok, bound))) return rc;
+      const int ct = n_pad / 4;
+      const bool rows_ok = ((A * ok.ld) % 4 == 0) && ((A * ok.spike_ld) % 4 == 0);        // every ring row stays 16-byte aligned
+      const bool lean = ok_cells && ok.vec_ok && rows_ok && (n_cells % 4 == 0) && ct <= RW * 32 &&
+                        (ok.spikes == nullptr || (agents->id_offset & 1) == 0) &&
+                        (4 % lean_groups(ct, 8) == 0) && (4 % lean_groups(ct, 4) == 0);      // groups divide the 4 producers
+      const bool hist_ok = hist == nullptr || hist->ring == nullptr || hist->ring_rows > 0;
+      if (lean && hist_ok) {
+        RunK run;
+        memset(&run, 0, sizeof(run));
+        run.n_steps = n_steps;
+        run.rates_ring = pp.rates_ring; run.spikes_ring = pp.spikes_ring;
+        run.ring_rows = pp.ring_rows; run.ring_next = pp.ring_next;
+        if (hist != nullptr && hist->ring != nullptr && hist->ring_rows > 0) {
+          run.hist_ring = hist->ring; run.hist_rows = hist->ring_rows; run.hist_next = hist->ring_next;
+        }
+        riab_step_io io0 = *io;
+        io0.history_row = nullptr;
+        cudaStream_t s = (cudaStream_t)stream;
+        if (place) return launch_place<3>(ek, *agents, *prm, io0, pcst, ok, nullptr, A, s, &run);
+        return launch_tile<GridPolicy<4>, 3>(ek, *agents, *prm, io0, gcst, ok, nullptr, A, s, &run);
+      }
+    }
+  }
   if (skew) {
     const riab_step_io s0 = step_io(0);
     if ((rc = riab_agent_update(agents, env, prm, &s0, stream))) return rc;

@@ -62,8 +62,21 @@ RIAB_DEV bool los_blocked_exact(double cx, double cy, double px, double py, cons
 
 // Per-agent record for the rate phase, from the float64 position.
 // inner = walls + 4*n_boundary (float64 endpoints), cxm/cym = box centre.
+// Per-CTA wall invariants of the agent records (shared memory, 2 doubles per inner wall): 1 / |s| and 1 / |s|^2, so that a
+// record costs one float64 division per wall (1 / |f_p|) instead of a square root and five divisions -- the records are
+// built by the float64 producer warps, whose chain bounds the step once the consumers are fast.
+RIAB_DEV void place_wall_invariants(double* __restrict__ aux, const double* __restrict__ inner, int n_inner) {
+  for (int j = threadIdx.x; j < n_inner && j < PLACE_MAX_WI; j += blockDim.x) {
+    const double sx = inner[4 * j + 2] - inner[4 * j], sy = inner[4 * j + 3] - inner[4 * j + 1];
+    const double n2 = sx * sx + sy * sy;
+    aux[2 * j] = 1.0 / sqrt(n2);
+    aux[2 * j + 1] = 1.0 / n2;
+  }
+}
+
 template <int WI>
 RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, const double* __restrict__ inner,
+                                 const double* __restrict__ aux,
                                  int n_inner, int geometry, double cxm, double cym, float band, int expanded, float kx,
                                  float lfold /* log2(span) when the scale is folded into the exponent, else 0 */) {
   float ep0 = 0.f, ep1 = 0.f;
@@ -79,13 +92,15 @@ RIAB_DEV void place_agent_record(float* __restrict__ rec, double px, double py, 
   for (int j = 0; j < WI; ++j) {
     float4 w = make_float4(-1.f, 2.f, -PLACE_QSCALE, 1.0e-6f);    // dummy wall: same side (q' < 0), X = -2, Y = 4
     if (j < n_inner) {
-      double f, t;
-      wall_coords(px, py, inner[4 * j], inner[4 * j + 1], inner[4 * j + 2], inner[4 * j + 3], f, t);
+      // wall_coords with the wall's invariants (float32 screen quantities: the last float64 ulp is irrelevant)
+      const double ax = inner[4 * j], ay = inner[4 * j + 1], sx = inner[4 * j + 2] - ax, sy = inner[4 * j + 3] - ay;
+      const double qx = px - ax, qy = py - ay;
+      const double f = (sx * qy - sy * qx) * aux[2 * j], t = (qx * sx + qy * sy) * aux[2 * j + 1];
       const double b = fabs(f);
-      if (b < 1e-9) w = make_float4(0.f, 0.f, 0.f, 3.0e38f);      // agent on the wall's line: every decision -> exact path
+      if (!(b >= 1e-9)) w = make_float4(0.f, 0.f, 0.f, 3.0e38f);  // agent on the wall's line (or a degenerate wall): exact path
       else {
-        const double ns = (f > 0.0) ? -1.0 : 1.0;                  // -sign(f_p)
-        w = make_float4((float)(ns * t / b), (float)(ns * (1.0 - t) / b), (float)(-f) * PLACE_QSCALE, (float)((double)band / b));
+        const double rb = ((f > 0.0) ? -1.0 : 1.0) / b;            // -sign(f_p) / |f_p|
+        w = make_float4((float)(t * rb), (float)((1.0 - t) * rb), (float)(-f) * PLACE_QSCALE, (float)((double)band / b));
       }
     }
     *reinterpret_cast<float4*>(rec + PLACE_WALL0 + 4 * j) = w;
