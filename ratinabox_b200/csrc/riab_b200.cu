@@ -2381,6 +2381,13 @@ int riab_run(const riab_agents* agents, const riab_env* env, const riab_motion_p
     if (want && n_steps >= 2 && getenv("RIAB_NO_BVC_PIPELINE") == nullptr && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 16) {
       pipe = &pipes[dev];
       if (pipe->side == nullptr) {
+        // keep the stream-ordered pool's memory across runs (by default it goes back to the driver at every synchronisation
+        // and each run would pay a ~1 ms cudaMalloc for its second ray buffer again)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         RIAB_CUDA_OK(cudaStreamCreateWithFlags(&pipe->side, cudaStreamNonBlocking));
         RIAB_CUDA_OK(cudaEventCreateWithFlags(&pipe->rays_done, cudaEventDisableTiming));
         for (int b = 0; b < 2; ++b)

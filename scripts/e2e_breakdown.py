@@ -15,7 +15,7 @@ Ag = rb.Agent(Env, {"dt": 0.01, "n_agents": A, "seed": 7})
 pops = bench.build_populations(rb, Ag, wl)
 drift = (0.05 * torch.randn((A, 2), dtype=torch.float64)).pin_memory()
 for _ in range(20):
-    Ag.update(drift_velocity=drift); pops[0].update(); _ = Ag.pos
+    Ag.update(drift_velocity=drift); pops[0].update(); _ = Ag.state_view('pos')
 torch.cuda.synchronize()
 N = 300
 t_upd = t_ns = t_pos = 0.0
@@ -29,10 +29,10 @@ for i in range(N):
     pops[0].update()
     ev[i][1].record()
     c = time.perf_counter()
-    p = Ag.pos
+    p = Ag.state_view('pos')
     d = time.perf_counter()
     t_upd += b - a; t_ns += c - b; t_pos += d - c
 torch.cuda.synchronize()
 tot = time.perf_counter() - t0
 dev = sum(e0.elapsed_time(e1) for e0, e1 in ev) / N * 1e3
-print(f"per step: total {tot/N*1e6:.1f} us | Agent.update {t_upd/N*1e6:.1f} | Neurons.update (launch) {t_ns/N*1e6:.1f} | Ag.pos (sync) {t_pos/N*1e6:.1f} | device (events around Neurons.update) {dev:.1f} us")
+print(f"per step: total {tot/N*1e6:.1f} us | Agent.update {t_upd/N*1e6:.1f} | Neurons.update (launch) {t_ns/N*1e6:.1f} | Ag.state_view('pos') (wait) {t_pos/N*1e6:.1f} | device (events around Neurons.update) {dev:.1f} us")

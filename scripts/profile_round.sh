@@ -1,30 +1,27 @@
 #!/bin/bash
-# Round profile pass, run on the GPU box:   gpurun --timeout 1500 -- 'bash scripts/profile_round.sh r01'
-# Writes into gpurun_out/: launch lists (ncu, per-launch device time), one `--set full` capture of the headline
-# kernel, and the bench lines of every workload.  Numbers printed under ncu are never bench values.
+# Round-2 measurement pass on one B200 (gpurun): bench lines, launch lists, full ncu captures, range-replay DRAM traffic.
+# Everything lands in gpurun_out/ (CSV / JSON only: an .ncu-rep with sources is ~75 MB).
 set -u
-TAG=${1:-r01}
-OUT=gpurun_out
-mkdir -p $OUT
-NCU="ncu --clock-control none"
-# 1. launch lists
-timeout 300 $NCU --metrics gpu__time_duration.sum -c 60 --csv --log-file $OUT/${TAG}_launches_c2.csv \
-    python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches_c2.log 2>&1
-timeout 300 $NCU --metrics gpu__time_duration.sum -c 140 --csv --log-file $OUT/${TAG}_launches_c4.csv \
-    python bench.py --workload c4 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches_c4.log 2>&1
-# 2. the headline kernel, full set, one launch well inside the timed region
-timeout 600 $NCU --set full --import-source on -k regex:k_step -s 12 -c 1 -f -o $OUT/${TAG}_k_step_c2 \
-    python bench.py --steps 12 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-# the report can exceed what gpurun_out/ carries back (64 MiB): keep its raw and source pages as gzipped CSV
-ncu -i $OUT/${TAG}_k_step_c2.ncu-rep --page raw --csv 2>/dev/null | gzip > $OUT/${TAG}_k_step_c2.raw.csv.gz
-ncu -i $OUT/${TAG}_k_step_c2.ncu-rep --page source --csv --print-source sass 2>/dev/null | gzip > $OUT/${TAG}_k_step_c2.source.csv.gz
-if [ $(stat -c %s $OUT/${TAG}_k_step_c2.ncu-rep) -gt 40000000 ]; then rm -f $OUT/${TAG}_k_step_c2.ncu-rep; fi
-# 3. bench lines (not under ncu)
-for W in c2 c2e c3; do
-  python bench.py --workload $W --steps 600 --warmup 50 2> $OUT/${TAG}_bench_${W}.err | tail -1 > $OUT/${TAG}_bench_${W}.json
-  python bench.py --workload $W --steps 600 --warmup 50 --no-spikes --no-cpu-baseline 2> /dev/null | tail -1 > $OUT/${TAG}_bench_${W}_nospikes.json
+mkdir -p gpurun_out
+python bench.py --steps 200 --warmup 20 > gpurun_out/r02_bench_c2.json 2> gpurun_out/r02_bench_c2.err
+python bench.py --steps 200 --warmup 20 --no-spikes --no-extra --no-cpu-baseline > gpurun_out/r02_bench_c2_nospikes.json 2>/dev/null
+for w in c2e c3; do
+  python bench.py --workload $w --steps 200 --warmup 20 --no-extra --no-cpu-baseline > gpurun_out/r02_bench_$w.json 2>/dev/null
+  python bench.py --workload $w --steps 200 --warmup 20 --no-extra --no-cpu-baseline --no-spikes > gpurun_out/r02_bench_${w}_nospikes.json 2>/dev/null
 done
-python bench.py --workload c4 --steps 300 --warmup 20 2> $OUT/${TAG}_bench_c4.err | tail -1 > $OUT/${TAG}_bench_c4.json
-python bench.py --workload c5 --steps 60 --warmup 5 --no-cpu-baseline 2> $OUT/${TAG}_bench_c5.err | tail -1 > $OUT/${TAG}_bench_c5.json
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2> /dev/null | tail -1 > $OUT/${TAG}_bench_reference.json
-ls -la $OUT | tail -30
+python bench.py --workload c4 --steps 100 --warmup 10 --no-extra --no-cpu-baseline > gpurun_out/r02_bench_c4.json 2>/dev/null
+python bench.py --workload c5 --steps 40 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r02_bench_c5.json 2>/dev/null
+python scripts/rates_only.py c2 c2e c3 c4 2>/dev/null | grep -v Warn > gpurun_out/r02_rates_only.txt
+python scripts/e2e_breakdown.py > gpurun_out/r02_e2e_breakdown.txt 2>&1
+# launch lists (every launch with its device time; cold-cache, serialised: compare shares)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 4 -c 40 --csv --log-file gpurun_out/r02_launches_c2.csv python bench.py --steps 8 --warmup 2 --no-extra --no-cpu-baseline > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 8 -c 60 --csv --log-file gpurun_out/r02_launches_c4.csv python bench.py --workload c4 --steps 8 --warmup 2 --no-extra --no-cpu-baseline > /dev/null 2>&1
+RIAB_NO_WHOLE_RUN=1 ncu --metrics gpu__time_duration.sum --clock-control none -s 4 -c 40 --csv --log-file gpurun_out/r02_launches_c2_perstep.csv python bench.py --steps 8 --warmup 2 --no-extra --no-cpu-baseline > /dev/null 2>&1
+# full captures: the whole-run kernel (8 steps in one launch), the per-step skewed kernel, the BVC kernels
+scripts/ncu_export.sh r02_c2_wholerun k_step 1 c2 1 run 8 > /dev/null
+RIAB_NO_WHOLE_RUN=1 scripts/ncu_export.sh r02_c2_perstep k_step 4 c2 1 run 8 > /dev/null
+scripts/ncu_export.sh r02_c4_integrate k_bvc_integrate 2 c4 1 run 4 > /dev/null
+scripts/ncu_export.sh r02_c4_rays k_bvc_rays 2 c4 1 run 4 > /dev/null
+rm -f gpurun_out/*.source.csv.gz.tmp
+scripts/traffic_round.sh 6 > gpurun_out/r02_traffic.log 2>&1
+ls -la gpurun_out | tail -40
