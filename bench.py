@@ -78,7 +78,10 @@ def synthetic_cells(kind, n, seed):
                     phase_offsets=rng.uniform(0, 2 * np.pi, (n, 2)))
     if kind == "bvc":
         mu_d = rng.uniform(0.05, 0.3, n)
-        return dict(mu_d=mu_d, sg_d=0.08 + mu_d / 12, mu_t=rng.uniform(0, 360, n), sg_t=rng.uniform(10, 30, n))
+        sg_t = rng.uniform(10, 30, n)                    # the reference's default angular spread (utils.py:1129-1131)
+        if os.environ.get("RIAB_BENCH_BVC_SIGMA_DEG"):   # experiment: one narrow angular tuning for all cells
+            sg_t = np.full(n, float(os.environ["RIAB_BENCH_BVC_SIGMA_DEG"]))
+        return dict(mu_d=mu_d, sg_d=0.08 + mu_d / 12, mu_t=rng.uniform(0, 360, n), sg_t=sg_t)
     raise ValueError(kind)
 
 

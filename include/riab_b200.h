@@ -199,6 +199,10 @@ int64_t riab_bvc_pack_floats(int32_t n_cells, int32_t n_test_angles);
 int riab_bvc_pack(const double* tuning_distances, const double* tuning_angles, const double* sigma_distances,
                   const double* sigma_angles, int32_t n_cells, const double* test_angles, int32_t n_test_angles,
                   riab_bvc_cells* meta_out, float* out_host);
+/* Packed block (float32 unless noted), Np = n_cells rounded up to 64:  s[Np] | m[Np] | 1/norm[Np] (cell order) |
+ * von Mises weights, peak 1, [Np/64][T][64] in SLOT order | egocentric extras 3 Np + 2 T | int32 perm[Np] (slot -> cell:
+ * the cells sorted by tuning angle) | int32 (th0, len)[Np/32]: the angular window of each 32 slots outside which every
+ * weight is < 2^-30 and the integrand terms are skipped (their sum is < T 2^-30 / norm of the peak rate). */
 /* BoundaryVectorCells.get_state (allocentric), Neurons.py:1617-1778.
  * scratch_dev: riab_bvc_scratch_floats(n_pos, T) float32 workspace holding dist_to_first_wall in
  * [agent tile of 32][T][32] order; first_wall_dev optional (n_pos,T) int32 (argmax wall id, Neurons.py:1677-1679). */

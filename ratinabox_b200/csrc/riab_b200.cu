@@ -8,7 +8,9 @@
 //                       in registers and stream float4 rate rows (+ OU noise, + bit-packed spikes)
 //   k_bvc_rays<FUSED>   BVC phase A (float64 rays) [+ Agent.update]
 //   k_bvc_integrate     BVC phase B (float32 angular integral, TMA-staged tables)
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1245,7 +1247,7 @@ __global__ void __launch_bounds__(NT) k_finish_rows(const OutK out, const int n_
 
 // ---------------------------------------------------------------------------
 // BVC phase A (+ optional fused Agent.update): one CTA per tile of 32 agents.
-template <bool FUSED, bool REC>
+template <bool FUSED, bool REC, bool TABLE>
 __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agents ag, const riab_motion_params mp,
                                                  const MotionDerived md, const riab_step_io io, const BvcConst bc,
                                                  const double* __restrict__ pos_in, const long long n_rows,
@@ -1287,11 +1289,54 @@ __global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agen
     for (long long w = threadIdx.x; w < (long long)na * spike_ld / 4; w += blockDim.x) z[w] = make_uint4(0u, 0u, 0u, 0u);
   }
   float* tile = scratch + (size_t)blockIdx.x * bc.T * BVC_AT;
+  float cmax = 1.f, lmax = 0.f;                         // error floors of the float32 screens (riab_bvc.cuh)
+  for (int w = 0; w < env.W; ++w) {
+    const float4 wl = s_wf[w];
+    cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(wl.x), fabsf(wl.y)), fmaxf(fabsf(wl.x + wl.z), fabsf(wl.y + wl.w))));
+    lmax = fmaxf(lmax, fabsf(wl.z) + fabsf(wl.w));
+  }
+  if (TABLE) {
+    // (angle, wall) table + float32 directions, then one agent per thread for all its angles (idx & 31 is constant)
+    float2* s_dirf = reinterpret_cast<float2*>(s_dirs + 2 * bc.T);
+    BvcTab* s_tab = reinterpret_cast<BvcTab*>(s_dirf + bc.T);
+    const int W = env.W;
+    for (int e = threadIdx.x; e < bc.T * W; e += blockDim.x) {
+      const int th = e / W, w = e - th * W;
+      s_tab[e] = bvc_table_entry(s_dirs[2 * th], s_dirs[2 * th + 1], s_walls + 4 * w, cmax);
+    }
+    for (int th = threadIdx.x; th < bc.T; th += blockDim.x) s_dirf[th] = make_float2((float)s_dirs[2 * th], (float)s_dirs[2 * th + 1]);
+    __syncthreads();
+    const int a = threadIdx.x & 31;
+    const double px = s_pos[a][0], py = s_pos[a][1];
+    const float pxf = (float)px, pyf = (float)py;
+    const float ka = 1e-9f * cmax * lmax;
+    float numA[BVC_NW];
+#pragma unroll
+    for (int w = 0; w < BVC_NW; ++w) {
+      numA[w] = 0.f;
+      if (w < W) {
+        const double ax = s_walls[4 * w], ay = s_walls[4 * w + 1];
+        numA[w] = (float)((ax - px) * (s_walls[4 * w + 3] - ay) - (ay - py) * (s_walls[4 * w + 2] - ax));   // (a - p) x sb
+      }
+    }
+    for (int th = threadIdx.x >> 5; th < bc.T; th += NT / 32) {
+      const float2 u = s_dirf[th];
+      uint32_t mask = bvc_table_mask<BVC_NW>(s_tab + th * W, numA, W, pxf * u.y - pyf * u.x, ka);
+      if (!(fabsf(pxf) + fabsf(pyf) <= 4.f * cmax)) mask = 0xffffffffu >> (32 - W);   // far outside (or NaN): no screen
+      double d;
+      int wid;
+      bvc_walk<uint32_t>(mask, px, py, s_dirs[2 * th], s_dirs[2 * th + 1], s_walls, d, wid);
+      tile[th * BVC_AT + a] = (float)d;
+      if (first_wall != nullptr && a < na) first_wall[(a0 + a) * bc.T + th] = wid;
+    }
+    return;
+  }
+  const float flo_env = 1e-6f * cmax * lmax;
   for (int idx = threadIdx.x; idx < bc.T * BVC_AT; idx += blockDim.x) {
     const int th = idx >> 5, a = idx & 31;
     double d;
     int wid;
-    bvc_first_wall(s_pos[a][0], s_pos[a][1], s_dirs[2 * th], s_dirs[2 * th + 1], s_walls, s_wf, env.W, d, wid);
+    bvc_first_wall(s_pos[a][0], s_pos[a][1], s_dirs[2 * th], s_dirs[2 * th + 1], s_walls, s_wf, env.W, flo_env, d, wid);
     tile[idx] = (float)d;
     if (first_wall != nullptr && a < na) first_wall[(a0 + a) * bc.T + th] = wid;
   }
@@ -1338,7 +1383,12 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
   __shared__ uint64_t bar_vm, bar_d[2];
   const int ct = blockIdx.x;
   const int tid = threadIdx.x, cl = tid & 63, g = tid >> 6;
-  const int cell = ct * BVC_CT + cl;
+  const int slot = ct * BVC_CT + cl;
+  // slot -> cell and this warp's angular window (riab_bvc_pack): outside [th0, th0 + tlen) mod T all 32 von Mises weights
+  // are < 2^-30 of their peak
+  const int32_t* perm = reinterpret_cast<const int32_t*>(bc.packed + 6 * (size_t)bc.n_pad + (size_t)bc.n_pad * T + 2 * (size_t)T);
+  const int cell = perm[slot];
+  const int th0 = perm[bc.n_pad + 2 * (slot >> 5)], tlen = perm[bc.n_pad + 2 * (slot >> 5) + 1];
   const uint32_t vm_bytes = (uint32_t)T * BVC_CT * 4u, d_bytes = (uint32_t)T * BVC_AT * 4u;
   const float* vm_src = bc.packed + 3 * (size_t)bc.n_pad + (size_t)ct * T * BVC_CT;
   if (tid == 0) {
@@ -1366,8 +1416,9 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    int th = th0;
 #pragma unroll 2
-    for (int th = 0; th < T; ++th) {
+    for (int j = 0; j < tlen; ++j, th = (th + 1 == T) ? 0 : th + 1) {
       const float vm = s_vm[th * BVC_CT + cl];
       const float4 da = *reinterpret_cast<const float4*>(sd + th * BVC_AT);
       const float4 db = *reinterpret_cast<const float4*>(sd + th * BVC_AT + 4);
@@ -1851,8 +1902,17 @@ int launch_bvc(const EnvK& env, const riab_agents& ag, const riab_motion_params&
     // the integral of two steps ago read this buffer (and wrote the ring slot a short ring re-uses now)
     if (pipe->used[pb][out.pop]) RIAB_CUDA_OK(cudaStreamWaitEvent(s, pipe->int_done[pb][out.pop], 0));
   }
-  if (rec) k_bvc_rays<FUSED, FUSED><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
-  else k_bvc_rays<FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
+  // (angle, wall) table of the float32 screen in shared memory: up to BVC_NW walls and 40 KB (one ray CTA still fits next to
+  // two integration CTAs of the previous step, 2 x 92 KB at T = 180)
+  const size_t smemT = smemA + (size_t)bc.T * (sizeof(float2) + (size_t)env.W * sizeof(BvcTab));
+  const bool table = env.W <= BVC_NW && smemT <= 40 * 1024;
+  if (table) {
+    if (rec) k_bvc_rays<FUSED, FUSED, true><<<(unsigned)n_tiles, NT, smemT, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
+    else k_bvc_rays<FUSED, false, true><<<(unsigned)n_tiles, NT, smemT, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
+  } else {
+    if (rec) k_bvc_rays<FUSED, FUSED, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
+    else k_bvc_rays<FUSED, false, false><<<(unsigned)n_tiles, NT, smemA, s>>>(env, ag, mp, md, io, bc, pos_in, n_rows, scratch, first_wall, zsp, out.spike_ld);
+  }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());
   if (pipe) {                                         // the integral (and its post-pass) go to the side stream
@@ -2107,8 +2167,11 @@ static int bvc_n_pad(int n) { return (n + BVC_CT - 1) / BVC_CT * BVC_CT; }
 
 int64_t riab_bvc_pack_floats(int32_t n_cells, int32_t T) {
   const int64_t np = bvc_n_pad(n_cells);
-  return 3 * np + np * (int64_t)T + 3 * np + 2 * (int64_t)T;
+  return 3 * np + np * (int64_t)T + 3 * np + 2 * (int64_t)T + np + 2 * (np / 32);
 }
+// Cut-off of the angular windows: a von Mises weight (peak 1) below 2^-30 is dropped.  The dropped part of a rate is at
+// most T 2^-30 / norm of the population's peak rate (norm = sum of the peak-1 weights >= 1), below float32 resolution of the sum.
+static const double BVC_VM_CUT = 9.313225746154785e-10;
 int64_t riab_bvc_scratch_floats(int64_t n_pos, int32_t T) {
   return ((n_pos + BVC_AT - 1) / BVC_AT) * (int64_t)T * BVC_AT;
 }
@@ -2121,6 +2184,14 @@ int riab_bvc_pack(const double* mu_d, const double* mu_t, const double* sg_d, co
   const int64_t total = riab_bvc_pack_floats(n, T);
   for (int64_t i = 0; i < total; ++i) out[i] = 0.f;
   float* s = out; float* m = out + np; float* sc = out + 2 * np; float* vm = out + 3 * (size_t)np;
+  // Slots: the cells sorted by preferred angle, so that the 32 cells of a warp of k_bvc_integrate share a narrow angular
+  // window outside which every von Mises weight is < BVC_VM_CUT and the terms are skipped.  s | m | sc stay in cell order;
+  // the von Mises table is in slot order; perm[slot] = cell (padding slots map to themselves).
+  std::vector<int> order(n);
+  std::vector<double> key(n);
+  const double two_pi = 6.283185307179586;
+  for (int i = 0; i < n; ++i) { order[i] = i; double a = fmod(mu_t[i], two_pi); key[i] = a < 0 ? a + two_pi : a; }
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
   for (int i = 0; i < n; ++i) {
     const double sv = sqrt(1.4426950408889634 / 2.0) / sg_d[i];       // exp(-(d-mu)^2/(2 sg^2)) = 2^-((d-mu) s)^2
     s[i] = (float)sv; m[i] = (float)(mu_d[i] * sv);
@@ -2128,9 +2199,38 @@ int riab_bvc_pack(const double* mu_d, const double* mu_t, const double* sg_d, co
     double norm = 0.0;
     for (int t = 0; t < T; ++t) norm += exp(kappa * cos(test_angles[t] - 0.0)) * (1.0 / exp(kappa));   // Neurons.py:1599-1604
     sc[i] = (float)(1.0 / norm);
-    const int tile = i / BVC_CT, cl = i % BVC_CT;
-    for (int t = 0; t < T; ++t)
-      vm[((size_t)tile * T + t) * BVC_CT + cl] = (float)(exp(kappa * cos(test_angles[t] - mu_t[i])) * (1.0 / exp(kappa)));
+  }
+  int32_t* perm = reinterpret_cast<int32_t*>(out + 3 * (size_t)np + (size_t)np * T + 3 * (size_t)np + 2 * (size_t)T);
+  int32_t* win = perm + np;
+  std::vector<char> keep(T);
+  for (int slot = 0; slot < np; ++slot) {
+    const int i = slot < n ? order[slot] : slot;
+    perm[slot] = i;
+    if (slot < n) {
+      const double kappa = 1.0 / (sg_t[i] * sg_t[i]);
+      const int tile = slot / BVC_CT, cl = slot % BVC_CT;
+      for (int t = 0; t < T; ++t)
+        vm[((size_t)tile * T + t) * BVC_CT + cl] = (float)(exp(kappa * cos(test_angles[t] - mu_t[i])) * (1.0 / exp(kappa)));
+    }
+    if (slot % 32 == 31) {                                            // window of this warp's 32 slots: [th0, th0 + len) mod T
+      const int s0 = slot - 31, tile = s0 / BVC_CT;
+      for (int t = 0; t < T; ++t) {
+        keep[t] = 0;
+        for (int q = s0; q <= slot; ++q)
+          if (!(vm[((size_t)tile * T + t) * BVC_CT + q % BVC_CT] < (float)BVC_VM_CUT)) { keep[t] = 1; break; }   // NaN keeps
+      }
+      int best_len = 0, best_end = 0;                                 // longest circular run of skippable angles
+      for (int t0 = 0; t0 < T; ++t0) {
+        if (keep[t0] || !keep[(t0 + T - 1) % T]) continue;            // runs start after a kept angle
+        int len = 0;
+        while (len < T && !keep[(t0 + len) % T]) ++len;
+        if (len > best_len) { best_len = len; best_end = (t0 + len) % T; }
+      }
+      bool any = false;
+      for (int t = 0; t < T; ++t) any = any || keep[t];
+      win[2 * (s0 / 32)] = any ? (best_len ? best_end : 0) : 0;
+      win[2 * (s0 / 32) + 1] = any ? T - best_len : 0;
+    }
   }
   float* ext = vm + (size_t)np * T;                                  // egocentric: kap | cmu | smu | cth | sth
   for (int i = 0; i < n; ++i) {

@@ -101,9 +101,24 @@ def test_grid_and_bvc_pack():
     np_ = bmeta.n_pad
     assert np_ == 64
     assert np.allclose(bout[2 * np_:2 * np_ + n], 1 / O.bvc_cell_fr_norm(angs, sg_t), rtol=1e-6)
+    # von Mises table in SLOT order (cells sorted by preferred angle), perm[slot] = cell, one angular window per 32 slots
+    tail = bout[6 * np_ + np_ * T + 2 * T:].view(np.int32)
+    perm, win = tail[:np_], tail[np_:].reshape(-1, 2)
+    assert len(tail) == np_ + 2 * (np_ // 32) and sorted(perm[:n]) == list(range(n)) and list(perm[n:]) == list(range(n, np_))
+    assert np.all(np.diff(mu_t[perm[:n]]) >= 0)
     vm = bout[3 * np_:3 * np_ + np_ * T].reshape(1, T, 64)[0, :, :n].T
-    assert np.allclose(vm, O.von_mises_peak1(angs[None, :], mu_t[:, None], sg_t[:, None]), rtol=1e-6, atol=1e-30)
-    ext = bout[3 * np_ + np_ * T:]                      # egocentric extras: kap | cos mu | sin mu | cos theta | sin theta
+    full = O.von_mises_peak1(angs[None, :], mu_t[:, None], sg_t[:, None])
+    assert np.allclose(vm, full[perm[:n]], rtol=1e-6, atol=1e-30)
+    for w, (th0, tlen) in enumerate(win):                   # outside the window every weight of the warp is < 2^-30
+        cells = perm[32 * w:32 * w + 32]
+        cells = cells[cells < n]
+        inside = np.zeros(T, bool)
+        inside[(th0 + np.arange(tlen)) % T] = True
+        assert 0 <= th0 < T and 0 <= tlen <= T
+        if len(cells):
+            assert full[cells][:, ~inside].max(initial=0.0) < 2.0 ** -30 * (1 + 1e-6)
+            assert tlen == T or (full[cells][:, th0].max() >= 2.0 ** -30 * (1 - 1e-6) and full[cells][:, (th0 + tlen - 1) % T].max() >= 2.0 ** -30 * (1 - 1e-6))
+    ext = bout[3 * np_ + np_ * T:6 * np_ + np_ * T + 2 * T]  # egocentric extras: kap | cos mu | sin mu | cos theta | sin theta
     assert np.allclose(ext[:n], np.log2(np.e) / sg_t ** 2, rtol=1e-6)
     assert np.allclose(ext[np_:np_ + n], np.cos(mu_t), atol=1e-7) and np.allclose(ext[2 * np_:2 * np_ + n], np.sin(mu_t), atol=1e-7)
     assert np.allclose(ext[3 * np_:3 * np_ + T], np.cos(angs), atol=1e-7) and len(ext) == 3 * np_ + 2 * T

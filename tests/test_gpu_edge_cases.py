@@ -280,3 +280,44 @@ def test_agent_exactly_on_a_wall_stays_finite():
     for _ in range(50):
         Ag.update(); PCs.update()
     assert np.isfinite(Ag.pos).all() and np.isfinite(Ag.velocity).all() and np.isfinite(PCs.firingrate).all()
+
+
+@pytest.mark.parametrize("scale", [1.0, 10.0])
+def test_bvc_first_wall_exact_under_the_float32_screen(scale):
+    """k_bvc_rays drops walls with a float32 screen (l_b margin, l_a certainly negative / certainly behind another wall)
+    before the float64 walk: distance to the first wall (as float32) and the wall index equal the oracle's argmax
+    (Neurons.py:1651-1684) for positions on wall lines, at wall ends and corners, 1e-9 next to walls, and random ones."""
+    import ctypes as C
+    import torch
+    import ratinabox_b200 as rb
+    from ratinabox_b200 import _lib
+    walls = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]], [[0.3, 0.5], [0.5, 0.7]], [[0.1, 0.8], [0.45, 0.8]],
+             [[0.6, 0.2], [0.9, 0.2]], [[0.9, 0.2], [0.9, 0.45]]]
+    walls = (np.array(walls) * scale).tolist()
+    E = rb.Environment({"scale": scale})
+    for w in walls:
+        E.add_wall(w)
+    Ag = rb.Agent(E, {"dt": 0.01})
+    bvc = rb.BoundaryVectorCells(Ag, {"n": 8})
+    rs = np.random.RandomState(3)
+    P = [rs.uniform(0, scale, (300, 2))]
+    aw = np.array(E.walls, dtype=float)
+    for w in aw:                                        # on the wall line, at its ends, just off it, on its extension
+        t = rs.uniform(-0.3, 1.3, 12)[:, None]
+        on = w[0] + t * (w[1] - w[0])
+        nrm = np.array([-(w[1] - w[0])[1], (w[1] - w[0])[0]]) / np.linalg.norm(w[1] - w[0])
+        P += [on, on + 1e-9 * scale * nrm, on - 1e-7 * scale * nrm, w[0][None], w[1][None], w[0][None] + 1e-12]
+    P = np.clip(np.concatenate(P), 0.0, scale)
+    n, T = len(P), bvc.n_test_angles
+    pos = torch.as_tensor(P, device=bvc.device)
+    out = torch.empty((n, 8), dtype=torch.float32, device=bvc.device)
+    first = torch.full((n, T), -7, dtype=torch.int32, device=bvc.device)
+    bvc._rates_from_positions(pos, n, out, first_wall=first)
+    torch.cuda.synchronize()
+    nt = (n + 31) // 32
+    d_gpu = bvc._scratch_for(n)[:nt * T * 32].reshape(nt, T, 32).permute(0, 2, 1).reshape(nt * 32, T)[:n].cpu().numpy()
+    env = O.OracleEnvironment(scale=scale, walls=walls)
+    d, fw = O.bvc_first_wall_distances(env, P, np.asarray(bvc.test_directions), O.TapeRNG())
+    assert np.array_equal(first.cpu().numpy(), fw.astype(np.int32))
+    with np.errstate(over="ignore"):
+        assert np.array_equal(d_gpu, d.astype(np.float32), equal_nan=True)
