@@ -438,7 +438,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spikes", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the `workloads` / `strong` / `gather` objects")
+    ap.add_argument("--agents", type=int, default=None,
+                    help="experiments only: agents per GPU instead of the workload's (the line's config says so)")
     args = ap.parse_args()
+    if args.agents is not None:                          # experiment: same workload at another batch size
+        w0 = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = dict(w0, agents=args.agents, desc=w0["desc"] + f" [--agents {args.agents}: NOT the configuration]")
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
