@@ -513,21 +513,22 @@ def main():
 
     extra = {}
     if not args.no_extra:
-        # every other BASELINE.json config (20 steps each) so that the driver's one line carries them
+        # every other BASELINE.json config so that the driver's one line carries them (100 steps for the whole-run
+        # single-population workloads, whose one launch per run pays ~50 us of ramp; 20 for the millisecond steps)
         wls = {}
         for name in ("c2e", "c3", "c4", "c5"):
             if name == args.workload:
                 continue
-            r = measure(rb, lib, torch, dist, name, 20, 3, rank, world, local_rank, spikes=spikes)
+            r = measure(rb, lib, torch, dist, name, 100 if name in ("c2e", "c3") else 20, 5, rank, world, local_rank, spikes=spikes)
             wls[name] = {"workload": WORKLOADS[name]["desc"], "agents_per_gpu": r["agents_per_gpu"], "scaling": r["scaling"],
                          "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": "agent-steps/s", "steps": r["steps"],
                          "gpu_launches": r["gpu_launches"], "roofline": roofline_of(name, r), "e2e": r["e2e"]}
         extra["workloads"] = wls
         if world > 1:
             # strong scaling of the headline workload: configs[1]'s 65 536 agents IN TOTAL (north_star's 8-GPU target)
-            r = measure(rb, lib, torch, dist, "c2", 20, 3, rank, world, local_rank, spikes=spikes, total_agents=65536)
+            r = measure(rb, lib, torch, dist, "c2", 200, 10, rank, world, local_rank, spikes=spikes, total_agents=65536)
             extra["strong"] = {"c2": {"agents_total": 65536, "agents_per_gpu": r["agents_per_gpu"], "ms_per_step": r["ms_per_step"],
-                                      "value": r["value"], "unit": "agent-steps/s", "e2e": r["e2e"],
+                                      "value": r["value"], "unit": "agent-steps/s", "steps": r["steps"], "e2e": r["e2e"],
                                       "note": "efficiency = value(N) / (N * value(1) of the same 65 536-agent job): divide by the "
                                               "N=1 headline value"},
                                "c5": {"agents_total": 262144, "see": "workloads.c5 (configs[4] is a strong-scaling job)"}}
