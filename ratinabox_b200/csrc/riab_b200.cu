@@ -72,7 +72,7 @@ struct OutK {
   long long id_offset;
   int pop, vec_ok;
   uint32_t rk7[14];         // Philox4x32-7 round keys of the spike stream (host-computed, constant bank)
-  // thinned spikes (thin_post): candidates at rate p = dt * (an upper bound of the rate), accepted with rate / bound
+  // thinned spikes (thin_pass): candidates at rate p = dt * (an upper bound of the rate), accepted with rate / bound
   int tile_agents;          // agents per ring slot of k_step (<= TA, even): launch_tile shrinks the tiles of small batches so
                             // that every (CTA, consumer group) gets an equal share (strong scaling: 8 192 agents per GPU
                             // are 256 tiles of 32 on 148 x 2 groups -- 1.7 waves -- but 293 tiles of 28)
@@ -486,7 +486,7 @@ struct __align__(16) StepSlot {
 // inside the band only sets its bit in `redo`; the caller redoes those pairs through the general path
 // (per-agent exact float64 fall-back) after the loop -- no call and no branch in here.
 // DENSE: the dense spike stream (one Philox4x32-7 call per pair, a threshold test per rate) runs in the loop;
-// thinned spikes are a post-pass over the slot (thin_post) and leave this loop spike-free.
+// thinned spikes are a post-pass over the slot (thin_pass) and leave this loop spike-free.
 template <class P, bool DENSE, int EXP>
 __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typename P::Regs& regs,
                                               const typename P::Const& pc, const OutK& out, const TailCtx& tc,
@@ -965,7 +965,7 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
   }
 }
 
-// SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_post per ring slot)
+// SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_pass per ring slot)
 template <class P, int MODE, int SPK, bool NOISE, class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
@@ -1641,7 +1641,7 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
     uint32_t k0 = (uint32_t)k.seed, k1 = (uint32_t)(k.seed >> 32);
     for (int i = 0; i < 7; ++i) { k.rk7[2 * i] = k0; k.rk7[2 * i + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
   }
-  // thinned spikes (thin_post): p = dt * bound * (1 + 2^-10) -- the margin covers the rates' float32 rounding above `bound`
+  // thinned spikes (thin_pass): p = dt * bound * (1 + 2^-10) -- the margin covers the rates' float32 rounding above `bound`
   k.thin = 0;
   if (k.spikes != nullptr && k.noise == nullptr && fr_bound >= 0.0 && getenv("RIAB_THIN_SPIKES") != nullptr) {
     const double bound = fr_bound * (1.0 + 1.0 / 1024.0), p = dt * bound;

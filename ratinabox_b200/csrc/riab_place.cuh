@@ -14,9 +14,8 @@
 // each inner wall with utils.vector_intercepts (utils.py:30-118): blocked iff
 // 0<l_a<1 and 0<l_b<1.  With f = signed distance to the wall's line and t = the
 // parameter along the wall, l_a = f_c/(f_c-f_p) and l_b = (f_c t_p - f_p t_c)/(f_c-f_p),
-// so per (agent, cell, wall) the float32 fast path is three FMA-pipe operations on
-// per-cell registers and per-agent shared-memory broadcasts -- issued as packed
-// FFMA2 / FMUL2 over cell pairs, 1.5 issue slots -- and one three-input FMNMX3; the
+// so per (agent, cell, wall) the float32 fast path is three scalar FMA-pipe operations on
+// per-cell registers and per-agent shared-memory broadcasts and one three-input FMNMX3; the
 // select is arithmetic (the penalty enters the exponent).  Results within an absolute
 // band of 0 are re-evaluated in float64 with the reference's exact expression
 // (los_blocked_exact), so the decision equals the oracle's.
@@ -228,7 +227,7 @@ RIAB_DEV void place_rates4(float (&out)[CPT], const PlaceCellRegs<WI, CPT>& r, c
     // Everything is divided by b on the agent side and carries -sign(f_p) (record: -s t_p/b, -s (1-t_p)/b, band/b), so
     //   X = M'/b = fma(f_c, -s t_p/b, t_c),  Y = (|D|-M')/b = fma(f_c, -s (1-t_p)/b, 1-t_c),  q' = f_c (-f_p 2^20)
     // hold whenever q' > 0 (f_c * -s = a then); on the same side q' < 0 decides alone.  m3 = min(X, Y, q'):
-    // per CELL PAIR 2 FFMA2 + 1 FMUL2 (agent values are the instructions' broadcast operands), per cell 1 FMNMX3;
+    // per cell 2 FFMA + 1 FMUL (agent values from the record) + 1 FMNMX3;
     // blocked <=> m3 > 0.
     // |m3| below band/b => the sign of m3 is not certain in float32: re-evaluate in float64.
     // The select is arithmetic: pen = max(0, max_j m3_j) (one FMNMX3 for two walls; NaN -> 0) enters the exponent /

@@ -321,3 +321,28 @@ def test_bvc_first_wall_exact_under_the_float32_screen(scale):
     assert np.array_equal(first.cpu().numpy(), fw.astype(np.int32))
     with np.errstate(over="ignore"):
         assert np.array_equal(d_gpu, d.astype(np.float32), equal_nan=True)
+
+
+@pytest.mark.parametrize("n,lo,hi", [(100, 4.0, 9.0), (64, 11.25, 11.25), (200, 6.0, 30.0), (31, 3.0, 4.0)])
+def test_bvc_angular_windows_skip_only_negligible_terms(n, lo, hi):
+    """riab_bvc_pack sorts the cells by tuning angle and k_bvc_integrate skips, per warp of 32 slots, the test angles where
+    every von Mises weight is < 2^-30 of its peak: rates of narrowly tuned populations (windows much shorter than the
+    circle) equal the oracle's full sums (Neurons.py:1710-1744) to 1e-5 of the rate scale, in the cells' own order."""
+    import ratinabox_b200 as rb
+    walls = _walls(3)
+    E, Ag = _make(rb, 1, walls)
+    rs = np.random.RandomState(n)
+    bvc = rb.BoundaryVectorCells(Ag, {"n": n, "min_fr": 0.0, "max_fr": 3.0})
+    bvc.tuning_angles = rs.uniform(0, 2 * np.pi, n)
+    bvc.sigma_angles = np.radians(rs.uniform(lo, hi, n))
+    bvc.tuning_distances = rs.uniform(0.05, 0.5, n)
+    bvc.sigma_distances = bvc.tuning_distances / 12 + 0.08
+    P = rs.uniform(0.02, 0.98, (150, 2))
+    got = bvc.get_state(evaluate_at=None, pos=P)
+    env = O.OracleEnvironment(walls=walls)
+    ref = O.bvc_get_state(env, bvc.tuning_distances, bvc.tuning_angles, bvc.sigma_distances, bvc.sigma_angles, P, O.TapeRNG(),
+                          min_fr=0.0, max_fr=3.0)
+    assert got.shape == ref.shape == (n, 150)
+    assert np.abs(got - ref).max() <= 3e-5, np.abs(got - ref).max()
+    big = ref > 3e-3
+    assert (np.abs(got - ref)[big] / ref[big]).max() <= 2e-5
