@@ -544,7 +544,7 @@ def main():
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:          # a reported baseline, timed at N=1 only
         kind_cpu = cpu_kind()
-        per = 12 * CPU_STEPS_PER_PASS[args.workload]
+        per = 36 * CPU_STEPS_PER_PASS[args.workload]         # ~12 s of CPU work on the GPU box's host (bounded sample)
         _cpu_worker_init(args.workload, kind_cpu)
         n, secs = _cpu_worker_run(per)
         cpu_baseline = {"value": n / secs, "unit": "agent-steps/s", "cores": 1, "kind": kind_cpu,

@@ -282,8 +282,8 @@ def test_agent_exactly_on_a_wall_stays_finite():
     assert np.isfinite(Ag.pos).all() and np.isfinite(Ag.velocity).all() and np.isfinite(PCs.firingrate).all()
 
 
-@pytest.mark.parametrize("scale", [1.0, 10.0])
-def test_bvc_first_wall_exact_under_the_float32_screen(scale):
+@pytest.mark.parametrize("scale,n_extra", [(1.0, 0), (10.0, 0), (1.0, -6), (1.0, 10), (1.0, 34)])
+def test_bvc_first_wall_exact_under_the_float32_screen(scale, n_extra):
     """k_bvc_rays drops walls with a float32 screen (l_b margin, l_a certainly negative / certainly behind another wall)
     before the float64 walk: distance to the first wall (as float32) and the wall index equal the oracle's argmax
     (Neurons.py:1651-1684) for positions on wall lines, at wall ends and corners, 1e-9 next to walls, and random ones."""
@@ -293,7 +293,17 @@ def test_bvc_first_wall_exact_under_the_float32_screen(scale):
     from ratinabox_b200 import _lib
     walls = [[[0.3, 0.0], [0.3, 0.5]], [[0.7, 1.0], [0.7, 0.5]], [[0.3, 0.5], [0.5, 0.7]], [[0.1, 0.8], [0.45, 0.8]],
              [[0.6, 0.2], [0.9, 0.2]], [[0.9, 0.2], [0.9, 0.45]]]
-    walls = (np.array(walls) * scale).tolist()
+    # n_extra: -6 = the empty box (4 walls); > 0 = short random extra walls: 20 walls take the generic screen with a 32-bit
+    # mask (the table screen holds 16), 44 walls the 64-bit one
+    rsw = np.random.RandomState(17)
+    if n_extra < 0:
+        walls = []
+    for _ in range(max(n_extra, 0)):
+        a = rsw.uniform(0.05, 0.95, 2)
+        th = rsw.uniform(0, np.pi)
+        b = np.clip(a + rsw.uniform(0.03, 0.15) * np.array([np.cos(th), np.sin(th)]), 0.02, 0.98)
+        walls.append([a.tolist(), b.tolist()])
+    walls = (np.array(walls).reshape(-1, 2, 2) * scale).tolist()
     E = rb.Environment({"scale": scale})
     for w in walls:
         E.add_wall(w)
