@@ -1248,7 +1248,7 @@ __global__ void __launch_bounds__(NT) k_finish_rows(const OutK out, const int n_
 // ---------------------------------------------------------------------------
 // BVC phase A (+ optional fused Agent.update): one CTA per tile of 32 agents.
 template <bool FUSED, bool REC, bool TABLE>
-__global__ void __launch_bounds__(NT) k_bvc_rays(const EnvK env, const riab_agents ag, const riab_motion_params mp,
+__global__ void __launch_bounds__(NT, (TABLE && !FUSED) ? 4 : 1) k_bvc_rays(const EnvK env, const riab_agents ag, const riab_motion_params mp,
                                                  const MotionDerived md, const riab_step_io io, const BvcConst bc,
                                                  const double* __restrict__ pos_in, const long long n_rows,
                                                  float* __restrict__ scratch, int32_t* __restrict__ first_wall,
@@ -1416,22 +1416,30 @@ __global__ void __launch_bounds__(NT) k_bvc_integrate(const BvcConst bc, const f
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    int th = th0;
-#pragma unroll 2
-    for (int j = 0; j < tlen; ++j, th = (th + 1 == T) ? 0 : th + 1) {
-      const float vm = s_vm[th * BVC_CT + cl];
-      const float4 da = *reinterpret_cast<const float4*>(sd + th * BVC_AT);
-      const float4 db = *reinterpret_cast<const float4*>(sd + th * BVC_AT + 4);
-      const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+    // the window [th0, th0 + tlen) mod T as two plain segments (no wrap test in the loop); 4 angles in flight per thread:
+    // the loop is bound by MUFU.EX2 (one warp instruction per 8 cycles), whose queue has to be kept fed across the
+    // LDS -> FFMA -> FMUL head of every angle
+    const int n0 = min(tlen, T - th0);
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {
+      const int tb = seg ? 0 : th0, tn = seg ? tlen - n0 : n0;
+      const float* pv = s_vm + tb * BVC_CT + cl;
+      const float* pd = sd + tb * BVC_AT;
+#pragma unroll 4
+      for (int j = 0; j < tn; ++j, pv += BVC_CT, pd += BVC_AT) {
+        const float vm = *pv;
+        const float4 da = *reinterpret_cast<const float4*>(pd);
+        const float4 db = *reinterpret_cast<const float4*>(pd + 4);
+        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float u = fmaf(dv[i], sc, -mc);                    // (d - mu_d) * s
-        // gaussian * von Mises.  The loop is bound by MUFU.EX2 (one warp instruction per 8 cycles against 4 issue
-        // slots per term).  Moving some of the eight exponentials to the 11-instruction FMA-pipe form (ex2_fma,
-        // -DRIAB_BVC_MUFU_TERMS=7) measured 545 vs 558 us/step on c4 in a --split-compile build but 572 vs 559 in the
-        // default build (register allocation of the unrolled loop decides): all eight stay on MUFU.
-        const float e = (i < BVC_MUFU_TERMS) ? ex2f(-u * u) : ex2_fma(-u * u);
-        acc[i] = fmaf(e, vm, acc[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float u = fmaf(dv[i], sc, -mc);                    // (d - mu_d) * s
+          // gaussian * von Mises.  Moving some of the eight exponentials to the 11-instruction FMA-pipe form (ex2_fma,
+          // -DRIAB_BVC_MUFU_TERMS=7) measured 545 vs 558 us/step on c4 in a --split-compile build but 572 vs 559 in the
+          // default build (register allocation of the unrolled loop decides): all eight stay on MUFU.
+          const float e = (i < BVC_MUFU_TERMS) ? ex2f(-u * u) : ex2_fma(-u * u);
+          acc[i] = fmaf(e, vm, acc[i]);
+        }
       }
     }
     if (cell < bc.n_cells) {
