@@ -72,15 +72,13 @@ struct OutK {
   long long id_offset;
   int pop, vec_ok;
   uint32_t rk7[14];         // Philox4x32-7 round keys of the spike stream (host-computed, constant bank)
-  // thinned spikes (thin_pass): candidates at rate p = dt * (an upper bound of the rate), accepted with rate / bound
+  // thinned spikes (thin_block): candidates at rate p' = dt * (an upper bound of the rate), accepted with rate / bound
   int tile_agents;          // agents per ring slot of k_step (<= TA, even): launch_tile shrinks the tiles of small batches so
                             // that every (CTA, consumer group) gets an equal share (strong scaling: 8 192 agents per GPU
                             // are 256 tiles of 32 on 148 x 2 groups -- 1.7 waves -- but 293 tiles of 28)
-  int thin;                 // 1: the population's rates are bounded and p <= 1/8
-  uint32_t thin_t16;        // an octet of 8 slots holds a candidate  <=>  its 16-bit word < t16  (= ceil(2^16 (1 - (1-p)^8)))
-  uint32_t thin_t[8];       // t[i] = floor(2^32 (1 - (1-p')^(i+1))), p' the per-slot probability t16 implies: gap to the next candidate
-  uint32_t thin_tc[7];      // first candidate slot of an octet that holds one: floor(2^32 (1 - (1-p')^(i+1)) / (1 - (1-p')^8))
-  float thin_c1, thin_c0;   // accept <=> fma(float(word >> 8), c1, c0) < rate;  c1 = 2^-24 bound, c0 = 2^-25 bound
+  int thin;                 // 1: the population's rates are bounded and p' = dt * bound <= 1/16 (thin_block)
+  uint32_t thin_cdf[32];    // cdf[k] = floor(2^32 P(Binomial(128, p') <= k)): candidates of a (row, 128-cell block) = #{k: word >= cdf[k]}
+  float thin_c1, thin_c0;   // accept <=> fma(float(20-bit uniform), c1, c0) < rate;  c1 = 2^-20 bound, c0 = 2^-21 bound
 };
 
 // MODE 3 of k_step: the whole riab_run loop of a single Place / Grid population in ONE launch.  Agents are independent and
@@ -486,7 +484,7 @@ struct __align__(16) StepSlot {
 // inside the band only sets its bit in `redo`; the caller redoes those pairs through the general path
 // (per-agent exact float64 fall-back) after the loop -- no call and no branch in here.
 // DENSE: the dense spike stream (one Philox4x32-7 call per pair, a threshold test per rate) runs in the loop;
-// thinned spikes are a post-pass over the slot (thin_pass) and leave this loop spike-free.
+// thinned spikes are a post-pass over the slot (thin_block) and leave this loop spike-free.
 template <class P, bool DENSE, int EXP>
 __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typename P::Regs& regs,
                                               const typename P::Const& pc, const OutK& out, const TailCtx& tc,
@@ -529,151 +527,81 @@ __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typ
 
 // ---------------------------------------------------------------------------
 // Thinned spikes (Neurons.py:681-684: spike <=> uniform < dt * rate) for populations whose rates are bounded by `bound`
-// with p = dt * bound <= 1/8 (the usual case: dt = 10 ms, max_fr = 1 Hz gives p = 0.01).  Exact Bernoulli(dt * rate) by
-// thinning: every (agent, cell) is a CANDIDATE with probability p' >= p, a candidate spikes with probability rate dt / p'.
-// Candidates are drawn per OCTET of 8 slots = (agent pair P = gid >> 1, 4-cell group g; slot k = 4 (gid & 1) + (cell & 3)):
-//   level 1   R = Philox7(ctr = (P >> 3, g, step, THIN_FIRST | population)): the octet holds a candidate  <=>  half-word
-//             (P & 7) of R (low half of word (P & 7) >> 1 first) < T16.  T16 = ceil(2^16 (1 - (1-p)^8)) fixes the octet
-//             probability exactly, and p' = 1 - (1 - T16 2^-16)^(1/8) is the per-slot candidate probability it implies.
-//   level 2   only for octets with a candidate: words S_0, S_1, ... of Philox7(ctr = (P, g, step, (THIN_CHAIN + n) | population)),
-//             n = 0, 1, ...:   first candidate slot K = #{i < 7: S_0 >= tc[i]}   (tc[i] = 2^32 P(first slot <= i | a candidate exists)),
-//             then alternately   accept slot K  <=>  fma(float(S >> 8), c1, c0) < rate[K]     (24-bit uniform times p'/dt)
-//             and                K += 1 + #{i < 8: S >= t[i]}      (t[i] = 2^32 (1 - (1-p')^(i+1)): geometric gap to the next candidate)
-//             until K >= 8.
-// The hot loop does nothing for spikes.  Per ring slot a consumer warp runs level 1 for its lanes' octets (one Philox call per
-// 8 pairs) and pushes the ~8 % that hold a candidate into a per-warp shared-memory queue that persists across slots; whenever
-// 32 are queued every lane walks one chain: it reads the candidate's rate back (this warp stored it: an L2 hit) and sets
-// accepted bits with RED.OR in the spike rows the producer cleared.  NumPy mirror: tests/philox_np.py (expected_spikes_thin).
-__device__ __forceinline__ int thin_gap(const OutK& out, uint32_t w) {
-  if (w >= out.thin_t[7]) return 8;
-  int n = 0;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) n += (w >= out.thin_t[i]) ? 1 : 0;
-  return n;
-}
-constexpr int THINQ_CAP = 256;                 // items per warp (power of two) >= the 32 x 8 pushes one Philox call per lane can cause
-struct ThinWarp {
-  uint32_t* q;                                 // shared memory: THINQ_CAP items ((pair - pair0) << 5 | group) + the tail counter
-  uint32_t head, tail;                         // items popped / pushed so far (warp-uniform); q[THINQ_CAP] hands out push positions
-  uint32_t rel0;                               // id_offset & 1: pair of launch row r = (r + rel0) >> 1, relative to pair0
-  unsigned long long pair0;                    // id_offset >> 1
-  long long n_rows;                            // rows of this launch
-  const float* rates;                          // out.rates + first cell of the block
-  uint32_t* spikes;                            // out.spikes + 4 * (128-cell block index)
-  int cells_left;                              // n_cells - first cell of the block
-  int bit0;                                    // bit of the block's group 0 in its spike words
-  uint32_t sub_blk, c2, c3;                    // Philox counter words: cell-group index of group 0, step, step hi | population
-};
+// with p' = dt * bound <= 1/16 (the usual case: dt = 10 ms, max_fr = 1 Hz gives p' = 0.01).  Exact Bernoulli(dt * rate) by
+// thinning: every (agent, cell) is a CANDIDATE with probability p', a candidate spikes with probability rate / bound.
+// Candidates are drawn per (agent row gid, 128-cell block B) -- the 32 x 128 rates one consumer warp has just stored for a
+// ring slot, lane = row -- so that the result does not depend on tiles, shards or the launch path:
+//   call n = 0, 1, ...:  R = Philox7(ctr = (gid, B | n << 16, step, THIN | population))
+//   K       = #{k < 32 : R_0[0] >= cdf[k]},  cdf[k] = floor(2^32 P(Binomial(128, p') <= k))        (call 0 only)
+//   draws   d = 4 n + j, j = 0..3:  position pos_d = (R_n[1] >> 7 j) & 127,
+//                                   20-bit uniform x_d = (half-word j of (R_n[2], R_n[3])) << 4 | R_n[1] >> 28
+//   the candidates are the first K DISTINCT positions of the draw sequence (a draw that repeats an earlier position is
+//   skipped: sampling without replacement, i.e. a uniform K-subset, i.e. 128 independent Bernoulli(p') cells);
+//   candidate at pos_d spikes  <=>  fma(float(x_d), c1, c0) < rate[gid, 128 B + pos_d]      (c1 = 2^-20 bound, c0 = 2^-21 bound).
+// The pair loop does nothing for spikes.  After a slot's rates are stored the warp runs this once: ~1.3 candidates per
+// lane at p' = 0.01, one Philox call per lane serves four of them; the rates are read back from L2 (this warp stored them),
+// accepted bits go into the spike rows the producer cleared with RED.OR.  NumPy mirror: tests/philox_np.py (expected_spikes_thin).
 template <int CPT>
-__device__ __forceinline__ void thin_init(ThinWarp& t, const OutK& out, const TailCtx& tc, long long n_rows, uint32_t* queue) {
+__device__ __forceinline__ void thin_block(const OutK& out, const TailCtx& tc, const float* __restrict__ rates,
+                                           uint32_t* __restrict__ spikes, const long long row_lo, const int rows) {
+  static_assert(CPT == 4, "a warp covers one 128-cell block");
   const int lane = threadIdx.x & 31;
-  const int cell_blk = tc.cell0 - CPT * lane;
-  t.q = queue; t.head = 0u; t.tail = 0u;
-  if (lane == 0) queue[THINQ_CAP] = 0u;
-  __syncwarp();
-  t.rel0 = (uint32_t)(out.id_offset & 1ll);
-  t.pair0 = (unsigned long long)out.id_offset >> 1;
-  t.n_rows = n_rows;
-  t.rates = out.rates + cell_blk;
-  t.spikes = out.spikes + ((cell_blk >> 7) << 2);
-  t.cells_left = tc.n_cells - cell_blk;
-  t.bit0 = (cell_blk & 127) >> 2;
-  t.sub_blk = (uint32_t)(cell_blk >> 2); t.c2 = tc.c2; t.c3 = tc.c3_spk & 0x00ffffffu;
-}
-// slot K of octet (pair, group g): accept <=> 24-bit uniform * bound < rate (read back: this warp stored it)
-__device__ __forceinline__ void thin_accept(const OutK& out, const ThinWarp& t, int K, uint32_t w, uint32_t rel, int g) {
-  const long long r = (long long)(2u * rel) - (long long)t.rel0 + (K >> 2);   // row of this launch
-  const int c = 4 * g + (K & 3);                                              // cell within the block
-  if (r < 0 || r >= t.n_rows || c >= t.cells_left) return;                   // another shard's half, padding cell
-  float rate;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate) : "l"(t.rates + r * out.ld + c));
-  if (fmaf((float)(w >> 8), out.thin_c1, out.thin_c0) < rate) atomicOr(t.spikes + r * out.spike_ld + (K & 3), 1u << (t.bit0 + g));
-}
-// one pass: lane l walks the chain of queue item head + l (n <= 32 items)
-__device__ __forceinline__ void thin_pass(ThinWarp& t, const OutK& out, int n) {
-  const int lane = threadIdx.x & 31;
-  if (lane < n) {
-    const uint32_t item = t.q[(t.head + (uint32_t)lane) & (THINQ_CAP - 1)];
-    const int g = (int)(item & 31u);
-    const uint32_t rel = item >> 5;
-    const unsigned long long pair = t.pair0 + rel;
-    const uint32_t sub = t.sub_blk + (uint32_t)g;
-    uint32_t S[4];
-    uint32_t n_call = 0u;
-    S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = t.c2; S[3] = t.c3 | ((RIAB_STREAM_THIN_CHAIN + n_call) << 24);
-    philox_keyed<7>(S, out.rk7);
-    int K = 0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) K += (S[0] >= out.thin_tc[i]) ? 1 : 0;
-    thin_accept(out, t, K, S[1], rel, g);
-    K += 1 + thin_gap(out, S[2]);
-    while (K < 8) {                                    // a second (third, ...) candidate in the same octet: ~7 % of them
-      thin_accept(out, t, K, S[3], rel, g);
-      ++n_call;
-      S[0] = (uint32_t)pair; S[1] = sub ^ ((uint32_t)(pair >> 32) << 24); S[2] = t.c2; S[3] = t.c3 | ((RIAB_STREAM_THIN_CHAIN + n_call) << 24);
-      philox_keyed<7>(S, out.rk7);
-      K += 1 + thin_gap(out, S[0]);
-      if (K >= 8) break;
-      thin_accept(out, t, K, S[1], rel, g);
-      K += 1 + thin_gap(out, S[2]);
-    }
+  const int blk0 = tc.cell0 - CPT * lane;                 // first cell of the warp's block (warp-uniform)
+  const int cells_left = tc.n_cells - blk0;
+  if (cells_left <= 0 || spikes == nullptr) return;      // padding block
+  const uint32_t B = (uint32_t)(blk0 >> 7);
+  const long long row = row_lo + lane;
+  const unsigned long long gid = (unsigned long long)(out.id_offset + row);
+  const uint32_t c1w = B ^ ((uint32_t)(gid >> 32) << 24);
+  const uint32_t c3w = (tc.c3_spk & 0x00ffffffu) | (RIAB_STREAM_THIN << 24);
+  uint32_t R[4];
+  int K = 0;
+  if (lane < rows) {
+    R[0] = (uint32_t)gid; R[1] = c1w; R[2] = tc.c2; R[3] = c3w;
+    philox_keyed<7>(R, out.rk7);
+    while (K < 32 && R[0] >= out.thin_cdf[K]) ++K;
   }
-  __syncwarp();
-  t.head += (uint32_t)n;
-}
-// Level 1 for the rows [row_lo, row_hi) of this launch (at most 32: one ring slot's share of this warp) + queueing;
-// full passes run as soon as 32 items wait.  The rows' rates must have been stored (and __syncwarp'ed) by this warp.
-template <int CPT>
-__device__ __forceinline__ void thin_rows(ThinWarp& t, const OutK& out, const long long row_lo, const long long row_hi) {
-  const int lane = threadIdx.x & 31;
-  constexpr int NG = 8 * CPT;                                      // 4-cell groups of the block: 32 (CPT 4) or 16 (CPT 2)
-  const uint32_t rel_lo = ((uint32_t)row_lo + t.rel0) >> 1, rel_hi = ((uint32_t)row_hi + t.rel0 + 1u) >> 1;   // pairs [lo, hi) - pair0
-  const int g1 = lane % NG;                                        // lane l: group l % NG, every (32/NG)-th block of 8 pairs
-  const unsigned long long o_lo = (t.pair0 + rel_lo) >> 3, o_hi = (t.pair0 + rel_hi - 1u) >> 3;     // blocks of 8 pairs
-  for (unsigned long long ob = o_lo; ob <= o_hi; ob += 32 / NG) {  // warp-uniform rounds: one Philox call per lane each
-    const unsigned long long o = ob + (unsigned)(lane / NG);
-    uint32_t mine = 0u, mine_rel8 = 0u;                            // this lane's candidate pairs of the round
-    if (4 * g1 < t.cells_left && o <= o_hi) {                      // (groups whose cells do not exist: nothing to draw)
-      uint32_t R[4];
-      R[0] = (uint32_t)o; R[1] = (t.sub_blk + (uint32_t)g1) ^ ((uint32_t)(o >> 32) << 24); R[2] = t.c2; R[3] = t.c3 | (RIAB_STREAM_THIN_FIRST << 24);
-      philox_keyed<7>(R, out.rk7);
-      uint32_t hits = 0u;                                          // bit h: pair 8 o + h holds a candidate
+  if (K == 0) return;                                      // (lanes leave independently: no warp-wide operation in here)
+  const float* rrow = rates + row * out.ld + blk0;
+  uint32_t* srow = spikes + row * out.spike_ld + 4u * B;
+  unsigned long long occ_lo = 0ull, occ_hi = 0ull;
+  int cnt = 0;
+  for (uint32_t n = 0u;;) {
+    bool take[4];
+    int pos[4];
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        hits |= ((R[w] & 0xffffu) < out.thin_t16 ? 1u : 0u) << (2 * w);
-        hits |= ((R[w] >> 16) < out.thin_t16 ? 1u : 0u) << (2 * w + 1);
-      }
-      const long long rel8 = (long long)(8ull * o - t.pair0);      // relative pair of half-word 0 (may lie before rel_lo)
+    for (int j = 0; j < 4; ++j) {
+      pos[j] = (int)((R[1] >> (7 * j)) & 127u);
+      const unsigned long long oh_lo = (pos[j] < 64) ? (1ull << pos[j]) : 0ull;
+      const unsigned long long oh_hi = (pos[j] < 64) ? 0ull : (1ull << (pos[j] - 64));
+      take[j] = (cnt < K) && (((occ_lo & oh_lo) | (occ_hi & oh_hi)) == 0ull);
+      if (take[j]) { occ_lo |= oh_lo; occ_hi |= oh_hi; ++cnt; }
+      take[j] = take[j] && (pos[j] < cells_left);       // candidates on padding cells count, but have no rate
+    }
+    float rate[4];
 #pragma unroll
-      for (int h = 0; h < 8; ++h) {                                // pairs outside [rel_lo, rel_hi) belong to other slots
-        const long long rel = rel8 + h;
-        if (rel < (long long)rel_lo || rel >= (long long)rel_hi) hits &= ~(1u << h);
-      }
-      mine = hits; mine_rel8 = (uint32_t)rel8;
+    for (int j = 0; j < 4; ++j) {
+      rate[j] = 0.f;
+      if (take[j]) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate[j]) : "l"(rrow + pos[j]));
     }
-    // the queue never overflows: make room for this round's pushes (<= 256 = THINQ_CAP) before they happen
-    const uint32_t cnt = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mine));
-    while (t.tail - t.head + cnt > (uint32_t)THINQ_CAP) thin_pass(t, out, (t.tail - t.head) < 32u ? (int)(t.tail - t.head) : 32);
-    while (mine) {                                                 // ~8 % of the octets: push (pair, group)
-      const int h = __ffs(mine) - 1;
-      mine &= mine - 1u;
-      const uint32_t pos = atomicAdd(&t.q[THINQ_CAP], 1u);
-      t.q[pos & (THINQ_CAP - 1)] = ((mine_rel8 + (uint32_t)h) << 5) | (uint32_t)g1;
+    const uint32_t dith = R[1] >> 28;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t m = ((j < 2 ? R[2] : R[3]) >> (16 * (j & 1))) & 0xffffu;
+      const float x = (float)((m << 4) | dith);
+      if (take[j] && fmaf(x, out.thin_c1, out.thin_c0) < rate[j]) atomicOr(srow + (pos[j] & 3), 1u << (pos[j] >> 2));
     }
-    __syncwarp();
-    t.tail += cnt;
-    while (t.tail - t.head >= 32u) thin_pass(t, out, 32);
+    if (cnt >= K || ++n >= 256u) break;
+    R[0] = (uint32_t)gid; R[1] = c1w ^ (n << 16); R[2] = tc.c2; R[3] = c3w;
+    philox_keyed<7>(R, out.rk7);
   }
-}
-__device__ __forceinline__ void thin_flush(ThinWarp& t, const OutK& out) {
-  while (t.tail != t.head) thin_pass(t, out, (t.tail - t.head) < 32u ? (int)(t.tail - t.head) : 32);
 }
 
 // The consumers' slot loop (see k_step).  EXP: exponent form of the fast pair loop (PlacePolicy::expanded).
 template <class P, int SPK, bool NOISE, class C, int EXP>
 __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, const OutK& out, StepSlot<P::REC>* s_slot,
                                                uint64_t* s_full, uint64_t* s_empty, const double* s_walls,
-                                               const long long nq, const int ctid, const int lane, uint32_t* thin_queue,
+                                               const long long nq, const int ctid, const int lane,
                                                const long long n_rows) {
   constexpr int NS = ring_slots<P, C>();
   constexpr int NC = RW * 32;
@@ -799,11 +727,8 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
           recp += 2 * P::REC;
         }
         if (SPK == 2) {
-          __syncwarp();      // orders this warp's rate stores before the chains' loads
-          ThinWarp tw;       // (per chunk: the block changes with the chunk, so nothing is carried over)
-          thin_init<CPT>(tw, out, tc, n_rows, thin_queue);
-          thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
-          thin_flush(tw, out);
+          __syncwarp();      // orders this warp's rate stores before the read-back
+          if constexpr (CPT == 4) thin_block<CPT>(out, tc, out.rates, out.spikes, a0 + a_lo, a_hi - a_lo);
         }
       }
     }
@@ -854,11 +779,11 @@ __device__ __forceinline__ void slot_fixups(const typename P::Regs& regs, const 
 
 // The consumers' slot loop for the common case: no OU noise, no dense spike stream, vector-aligned rows, whole 4-cell
 // groups, all cells resident in one set of registers (n_pad <= 512 * CPT).  Pointers advance incrementally, the rare
-// repairs are a real call (slot_fixups), thinned spikes are queued across slots (ThinWarp).
+// repairs are a real call (slot_fixups), thinned spikes are a post-pass per slot (thin_block).
 template <class P, int SPK, class C, int EXP, bool MULTI>
 __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const OutK& out, const RunK& run, StepSlot<P::REC>* s_slot,
                                               uint64_t* s_full, uint64_t* s_empty, const double* s_walls, const long long nq,
-                                              const int ctid, const int lane, uint32_t* thin_queue, const long long n_rows) {
+                                              const int ctid, const int lane, const long long n_rows) {
   constexpr int NS = ring_slots<P, C>(), MW = C::MW, NSP = NS / MW, CPT = P::CPT;
   const int CT = pc.n_pad / CPT;                      // cell-threads needed (multiple of 32, <= RW * 32)
   const int G = lean_groups(CT, NS), grp = ctid / CT; // groups of CT threads; group g consumes the tiles q = g, g + G, ...
@@ -885,12 +810,6 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
       rates = run.rates_ring + slot * n_rows * ld;
       spikes = run.spikes_ring ? run.spikes_ring + slot * n_rows * out.spike_ld : nullptr;
       tail_init<CPT>(tc, out, cell0, pc.n_cells, out.step + (unsigned long long)st);
-    }
-    [[maybe_unused]] ThinWarp tw;
-    if constexpr (SPK == 2) {
-      OutK o = out;                                     // (the thinned stream keeps the row pointers / step in its own state)
-      o.rates = rates; o.spikes = spikes; o.step = out.step + (unsigned long long)st;
-      thin_init<CPT>(tw, o, tc, n_rows, thin_queue);
     }
     long long a0 = a_first;
     float* dst0 = rates + a0 * ld + cell0;
@@ -954,18 +873,17 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
             if ((nm >> a) & 1u) st_cs_fv<CPT>(dst0 + (long long)(a - a_lo) * ld, z);
         }
         if constexpr (SPK == 2) {
-          __syncwarp();                                  // this warp's rate stores before the chains read them back
-          thin_rows<CPT>(tw, out, a0 + a_lo, a0 + a_hi);
+          __syncwarp();                                  // this warp's rate stores before the read-back
+          thin_block<CPT>(out, tc, rates, spikes, a0 + a_lo, a_hi - a_lo);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[s]);
     }
-    if constexpr (SPK == 2) thin_flush(tw, out);
   }
 }
 
-// SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_pass per ring slot)
+// SPK: 0 no spikes, 1 dense spike stream (in the loops), 2 thinned spikes (thin_block per ring slot)
 template <class P, int MODE, int SPK, bool NOISE, class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
@@ -976,7 +894,6 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
   constexpr int MW = C::MW, NS = ring_slots<P, C>();
   __shared__ StepSlot<P::REC> s_slot[NS];
   __shared__ uint64_t s_bar, s_full[NS], s_empty[NS];
-  __shared__ uint32_t s_thinq[(SPK == 2) ? RW : 1][(SPK == 2) ? THINQ_CAP + 4 : 1];   // per consumer warp: queued candidate octets + push counter
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // lean consumers (consumer_fast): every ring slot is consumed by ONE group of warps (n_pad / CPT threads), the general
   // loop (consumer_slots) by all RW consumer warps
@@ -1109,19 +1026,18 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, co
     // the cell registers then stay in registers across slots (a run-time switch inside the loop made ptxas park them
     // in local memory around every slot)
     const int ex = P::expanded(pc);
-    uint32_t* const tq = s_thinq[(SPK == 2) ? (ctid >> 5) : 0];
     if constexpr (!NOISE && (SPK != 1 || P::CPT == 4)) {
       if (lean) {
-        if (ex == 2) consumer_fast<P, SPK, C, 2, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
-        else if (ex == 1) consumer_fast<P, SPK, C, 1, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
-        else consumer_fast<P, SPK, C, 0, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+        if (ex == 2) consumer_fast<P, SPK, C, 2, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, n_rows);
+        else if (ex == 1) consumer_fast<P, SPK, C, 1, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, n_rows);
+        else consumer_fast<P, SPK, C, 0, MODE == 3>(pc, out, run, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, n_rows);
         return;
       }
     }
     if constexpr (MODE == 3) return;                    // (the host launches whole runs only where the lean loop applies)
-    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
-    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
-    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, tq, n_rows);
+    if (ex == 2) consumer_slots<P, SPK, NOISE, C, 2>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, n_rows);
+    else if (ex == 1) consumer_slots<P, SPK, NOISE, C, 1>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, n_rows);
+    else consumer_slots<P, SPK, NOISE, C, 0>(pc, out, s_slot, s_full, s_empty, s_walls, nq, ctid, lane, n_rows);
   }
 }
 
@@ -1649,33 +1565,27 @@ int make_out(const riab_rates_out* o, const riab_neuron_noise* nz, int n_cells, 
     uint32_t k0 = (uint32_t)k.seed, k1 = (uint32_t)(k.seed >> 32);
     for (int i = 0; i < 7; ++i) { k.rk7[2 * i] = k0; k.rk7[2 * i + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
   }
-  // thinned spikes (thin_pass): p = dt * bound * (1 + 2^-10) -- the margin covers the rates' float32 rounding above `bound`
+  // thinned spikes (thin_block): p' = dt * bound * (1 + 2^-10) -- the margin covers the rates' float32 rounding above `bound`.
+  // The default for bounded populations without OU noise when p' <= 1/16 (beyond that the candidates are no rarer than the
+  // dense stream's work); RIAB_DENSE_SPIKES=1 in the environment keeps the dense stream everywhere.
   k.thin = 0;
-  if (k.spikes != nullptr && k.noise == nullptr && fr_bound >= 0.0 && getenv("RIAB_THIN_SPIKES") != nullptr) {
+  if (k.spikes != nullptr && k.noise == nullptr && fr_bound >= 0.0 && getenv("RIAB_DENSE_SPIKES") == nullptr) {
     const double bound = fr_bound * (1.0 + 1.0 / 1024.0), p = dt * bound;
-    if (p <= 0.125) {
+    if (p > 0.0 && p <= 0.0625) {
       k.thin = 1;
-      double q8 = 1.0 - p;
-      q8 *= q8; q8 *= q8; q8 *= q8;                                      // (1-p)^8
-      double t16 = ceil(65536.0 * (1.0 - q8));
-      if (t16 > 65535.0) t16 = 65535.0;
-      k.thin_t16 = (uint32_t)t16;
-      // the per-slot candidate probability the 16-bit threshold implies (three correctly rounded square roots)
-      const double q1 = sqrt(sqrt(sqrt(1.0 - t16 / 65536.0))), pp = 1.0 - q1;
-      double qq = 1.0, cum[8];
-      for (int i = 0; i < 8; ++i) {
-        qq *= q1;
-        cum[i] = 1.0 - qq;
-        const double t = floor(4294967296.0 * cum[i]);
-        k.thin_t[i] = (t >= 4294967295.0) ? 4294967295u : (uint32_t)t;
+      // Binomial(128, p) by the pmf recurrence, IEEE operations in this order (tests/philox_np.py: thin_tables repeats them)
+      const double q = 1.0 - p, r = p / q;
+      double pmf = q;
+      for (int i = 0; i < 7; ++i) pmf = pmf * pmf;                       // q^128
+      double cdf = 0.0;
+      for (int i = 0; i < 32; ++i) {
+        cdf = cdf + pmf;
+        const double t = floor(4294967296.0 * cdf);
+        k.thin_cdf[i] = (t >= 4294967295.0) ? 4294967295u : (uint32_t)t;
+        pmf = pmf * ((double)(128 - i) * r) / (double)(i + 1);
       }
-      for (int i = 0; i < 7; ++i) {
-        const double t = (cum[7] > 0.0) ? floor(4294967296.0 * (cum[i] / cum[7])) : 0.0;
-        k.thin_tc[i] = (t >= 4294967295.0) ? 4294967295u : (uint32_t)t;
-      }
-      const double bnd = (dt > 0.0) ? pp / dt : 0.0;                     // accept with rate / bnd
-      k.thin_c1 = (float)(bnd * (1.0 / 16777216.0));
-      k.thin_c0 = (float)(bnd * (1.0 / 33554432.0));
+      k.thin_c1 = (float)(bound * (1.0 / 1048576.0));
+      k.thin_c0 = (float)(bound * (1.0 / 2097152.0));
     }
   }
   return 0;

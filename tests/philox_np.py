@@ -58,15 +58,15 @@ def agent_normals(seed, step, agents):
 
 def expected_spikes(seed, step, agents, fr, dt, pop=0, fr_bound=None):
     """(A, n_cells) bool spikes of one step given the float32 rates `fr` (A, n_cells).
-    fr_bound = max(min_fr, max_fr) of a PlaceCells / GridCells population without OU noise: with RIAB_THIN_SPIKES set in the
-    environment the library uses the (experimental, measured slower) thinned stream when dt * fr_bound * (1 + 2^-10) <= 1/8
-    (expected_spikes_thin); otherwise -- the default, and always for every other population -- the dense one:
+    fr_bound = max(min_fr, max_fr) of a PlaceCells / GridCells population without OU noise: the library uses the thinned
+    stream when dt * fr_bound * (1 + 2^-10) <= 1/16 (expected_spikes_thin; RIAB_DENSE_SPIKES=1 in the environment turns it
+    off); otherwise -- and always for every other population -- the dense one:
         spike <=> m < fma(rate, dt*65536, -v)      (riab_b200.cu: spike_ballots)
     One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words 2h, 2h+1 as four
     16-bit integers m; all eight share the dither v = ((r0^r2)>>8) * 2^-24.  The float32 fma is mirrored
     in float64: the 48-bit product and the 24-bit dither add exactly, so the sum rounds to float32 once."""
     import os
-    if fr_bound is not None and os.environ.get("RIAB_THIN_SPIKES") and thin_tables(dt, fr_bound) is not None:
+    if fr_bound is not None and not os.environ.get("RIAB_DENSE_SPIKES") and thin_tables(dt, fr_bound) is not None:
         return expected_spikes_thin(seed, step, agents, fr, dt, fr_bound, pop)
     agents = np.asarray(agents, dtype=np.uint64)
     fr = np.asarray(fr, dtype=np.float32)
@@ -87,80 +87,69 @@ def expected_spikes(seed, step, agents, fr, dt, pop=0, fr_bound=None):
     return m < thr
 
 
-STREAM_THIN_FIRST, STREAM_THIN_CHAIN = 4, 8
+STREAM_THIN = 4
 
 
 def thin_tables(dt, fr_bound):
-    """Thresholds of the thinned spike stream (riab_b200.cu: make_out).  None when the dense stream is used."""
+    """Tables of the thinned spike stream (riab_b200.cu: make_out; the same IEEE operations in the same order).
+    None when the dense stream is used.  cdf[k] = floor(2^32 P(Binomial(128, p') <= k)), k < 32."""
     bound = float(fr_bound) * (1.0 + 1.0 / 1024.0)
     p = float(dt) * bound
-    if not (fr_bound >= 0.0 and p <= 0.125):
+    if not (fr_bound >= 0.0 and 0.0 < p <= 0.0625):
         return None
-    q8 = 1.0 - p
-    q8 *= q8; q8 *= q8; q8 *= q8
-    t16 = min(np.ceil(65536.0 * (1.0 - q8)), 65535.0)
-    q1 = np.sqrt(np.sqrt(np.sqrt(1.0 - t16 / 65536.0)))
-    pp = 1.0 - q1
-    cum, qq = [], 1.0
-    for _ in range(8):
-        qq *= q1
-        cum.append(1.0 - qq)
-    clamp = lambda v: 4294967295 if v >= 4294967295.0 else int(v)
-    t = [clamp(np.floor(4294967296.0 * c)) for c in cum]
-    tc = [clamp(np.floor(4294967296.0 * (cum[i] / cum[7]))) if cum[7] > 0.0 else 0 for i in range(7)]
-    bnd = pp / float(dt) if dt > 0 else 0.0
-    c1, c0 = np.float32(bnd / 16777216.0), np.float32(bnd / 33554432.0)
-    return int(t16), np.array(t, dtype=np.uint64), np.array(tc, dtype=np.uint64), c1, c0
+    q = 1.0 - p
+    r = p / q
+    pmf = q
+    for _ in range(7):
+        pmf = pmf * pmf
+    cdf, tab = 0.0, []
+    for i in range(32):
+        cdf = cdf + pmf
+        t = np.floor(4294967296.0 * cdf)
+        tab.append(4294967295 if t >= 4294967295.0 else int(t))
+        pmf = pmf * (float(128 - i) * r) / float(i + 1)
+    return np.array(tab, dtype=np.uint64), np.float32(bound / 1048576.0), np.float32(bound / 2097152.0)
 
 
 def expected_spikes_thin(seed, step, agents, fr, dt, fr_bound, pop=0):
-    """Mirror of the thinned spike stream (riab_b200.cu: thin_rows / thin_pass): candidates per octet = (agent pair, 4-cell group)
-    of 8 slots, slot = 4*(gid&1) + cell&3.
-    Level 1: half-word (gid>>1)&7 of Philox7((gid>>4, group), THIN_FIRST) < t16  <=>  the octet holds a candidate.
-    Level 2: words of Philox7((gid>>1, group), THIN_CHAIN + n), n = 0, 1, ...: first slot from the conditional table,
-    then alternately accept (24-bit uniform * bound < rate) and geometric gap to the next candidate."""
+    """Mirror of the thinned spike stream (riab_b200.cu: thin_block).  Per (row gid, 128-cell block B), calls n = 0, 1, ...
+    R_n = Philox7(ctr(gid, B | n << 16, step, THIN, pop)):  K = #{k: R_0[0] >= cdf[k]} candidates; draw d = 4n + j has the
+    position (R_n[1] >> 7j) & 127 and the 20-bit uniform x = half-word j of (R_n[2], R_n[3]) << 4 | R_n[1] >> 28; the
+    candidates are the first K distinct positions of the draw sequence; a candidate spikes iff fma(x, c1, c0) < rate."""
     agents = np.asarray(agents, dtype=np.uint64)
     fr = np.asarray(fr, dtype=np.float32)
     A, n_cells = fr.shape
-    t16, t, tc, c1, c0 = thin_tables(dt, fr_bound)
+    cdf, c1, c0 = thin_tables(dt, fr_bound)
     key = (seed & 0xFFFFFFFF, seed >> 32)
-    groups = (n_cells + 3) // 4
-    out = np.zeros((A, n_cells), dtype=bool)
-    row_of = {int(g): i for i, g in enumerate(agents)}
-    pairs = np.unique(agents >> np.uint64(1))
-    g = np.arange(groups, dtype=np.uint64)[None, :]
-    first = philox4x32(counter((pairs >> np.uint64(3))[:, None], g, step, STREAM_THIN_FIRST, pop), key, rounds=7)   # (P,G,4)
-    h = (pairs & np.uint64(7)).astype(np.int64)
-    word = np.take_along_axis(first, (h >> 1)[:, None, None].repeat(groups, 1), axis=2)[..., 0]
-    half = np.where((h & 1)[:, None] == 1, word >> np.uint32(16), word & np.uint32(0xFFFF))
-    cand_p, cand_g = np.nonzero(half < np.uint32(t16))
-
-    def gap(x):
-        x = np.uint64(x)
-        return 8 if x >= t[7] else int((x >= t[:7]).sum())
-
-    def accept(pair, grp, K, word):
-        gid = 2 * int(pair) + (K >> 2)
-        cell = 4 * int(grp) + (K & 3)
-        if gid not in row_of or cell >= n_cells:
-            return
-        thr = np.float32(np.float64(int(word) >> 8) * np.float64(c1) + np.float64(c0))
-        if thr < fr[row_of[gid], cell]:
-            out[row_of[gid], cell] = True
-
-    for pi, gi in zip(cand_p, cand_g):
-        pair, n = pairs[pi], 0
-        S = philox4x32(counter(np.uint64(pair), np.uint64(gi), step, STREAM_THIN_CHAIN + n, pop), key, rounds=7)
-        K = int((np.uint64(S[0]) >= tc).sum())
-        accept(pair, gi, K, S[1])
-        K += 1 + gap(S[2])
-        while K < 8:
-            accept(pair, gi, K, S[3])
-            n += 1
-            S = philox4x32(counter(np.uint64(pair), np.uint64(gi), step, STREAM_THIN_CHAIN + n, pop), key, rounds=7)
-            K += 1 + gap(S[0])
-            if K >= 8:
-                break
-            accept(pair, gi, K, S[1])
-            K += 1 + gap(S[2])
-    return out
+    nb = (n_cells + 127) // 128
+    frp = np.zeros((A, nb * 128), dtype=np.float32)
+    frp[:, :n_cells] = fr
+    frp = frp.reshape(A, nb, 128)
+    exists = (np.arange(nb * 128) < n_cells).reshape(1, nb, 128)
+    gid = agents[:, None]
+    blk = np.arange(nb, dtype=np.uint64)[None, :]
+    R = philox4x32(counter(gid, blk, step, STREAM_THIN, pop), key, rounds=7)                       # (A, nb, 4)
+    K = (R[..., 0].astype(np.uint64)[..., None] >= cdf[None, None, :]).sum(-1)                     # (A, nb)
+    occ = np.zeros((A, nb, 128), dtype=bool)
+    out = np.zeros((A, nb, 128), dtype=bool)
+    cnt = np.zeros((A, nb), dtype=np.int64)
+    ai, bi = np.meshgrid(np.arange(A), np.arange(nb), indexing="ij")
+    n = 0
+    while True:
+        dith = R[..., 1] >> np.uint32(28)
+        for j in range(4):
+            pos = ((R[..., 1] >> np.uint32(7 * j)) & np.uint32(127)).astype(np.int64)
+            take = (cnt < K) & ~occ[ai, bi, pos]
+            occ[ai, bi, pos] |= take
+            cnt += take
+            w = R[..., 2] if j < 2 else R[..., 3]
+            m = (w >> np.uint32(16 * (j & 1))) & np.uint32(0xFFFF)
+            x = ((m << np.uint32(4)) | dith).astype(np.float64)
+            thr = (x * np.float64(c1) + np.float64(c0)).astype(np.float32)      # the fused multiply-add rounds once
+            hit = take & exists[0, bi, pos] & (thr < frp[ai, bi, pos])
+            out[ai, bi, pos] |= hit
+        n += 1
+        if not (cnt < K).any() or n >= 256:
+            break
+        R = philox4x32(counter(gid, blk | np.uint64(n << 16), step, STREAM_THIN, pop), key, rounds=7)
+    return out.reshape(A, nb * 128)[:, :n_cells]

@@ -120,13 +120,12 @@ def test_spikes_match_numpy_philox():
 
 
 @pytest.mark.parametrize("A,N,stepped", [(131, 300, False), (64, 1024, False), (70, 128, True), (33, 2304, False)])
-def test_thinned_spikes_match_numpy_mirror(A, N, stepped, monkeypatch):
-    """RIAB_THIN_SPIKES=1 and dt * max_fr <= 1/8 (here 0.01 * 1 Hz): PlaceCells / GridCells without OU noise use the thinned
-    spike stream (candidate octets at rate 1-(1-dt*max_fr)^8, accepted with rate/max_fr; riab_b200.cu: thin_rows).  Bit-equal
-    to the NumPy mirror for odd agent counts, ragged cell counts, several cell chunks (N > 2048), riab_run and the stepped
-    API; still Bernoulli(dt * rate) (Neurons.py:682-684).  (Off by default: measured slower than the dense stream.)"""
+def test_thinned_spikes_match_numpy_mirror(A, N, stepped):
+    """dt * max_fr <= 1/16 (here 0.01 * 1 Hz and 0.01 * 3 Hz): PlaceCells / GridCells without OU noise use the thinned spike
+    stream (Binomial(128, dt*max_fr) candidates per (agent, 128-cell block) at uniformly drawn distinct cells, accepted with
+    rate/max_fr; riab_b200.cu: thin_block).  Bit-equal to the NumPy mirror for odd agent counts, ragged cell counts, several
+    cell chunks (N > 2048), riab_run and the stepped API; still Bernoulli(dt * rate) (Neurons.py:682-684)."""
     import ratinabox_b200 as rb
-    monkeypatch.setenv("RIAB_THIN_SPIKES", "1")
     E, Ag = make(rb, A)
     PCs = rb.PlaceCells(Ag, {"n": N, "wall_geometry": "line_of_sight"})
     GCs = rb.GridCells(Ag, {"n": 64, "max_fr": 3.0})
@@ -144,6 +143,21 @@ def test_thinned_spikes_match_numpy_mirror(A, N, stepped, monkeypatch):
         p = 0.01 * h["firingrate"].astype(np.float64)
         n_sp, mu, var = h["spikes"].sum(), p.sum(), (p * (1 - p)).sum()
         assert abs(n_sp - mu) < 6 * np.sqrt(var) + 1, (n_sp, mu)
+
+
+def test_dense_spike_stream_on_request(monkeypatch):
+    """RIAB_DENSE_SPIKES=1 keeps the dense stream (one threshold test per rate in the pair loop) for bounded populations
+    too: bit-equal to its NumPy mirror through the lean consumers and riab_run."""
+    import ratinabox_b200 as rb
+    monkeypatch.setenv("RIAB_DENSE_SPIKES", "1")
+    A = 96
+    E, Ag = make(rb, A)
+    PCs = rb.PlaceCells(Ag, {"n": 512, "wall_geometry": "line_of_sight"})
+    Ag.run(2)
+    h = PCs.get_history_arrays()
+    for s in range(2):
+        want = expected_spikes(11, s, np.arange(A), h["firingrate"][s], 0.01, pop=0, fr_bound=1.0)
+        assert np.array_equal(h["spikes"][s], want), s
 
 
 def test_multistep_tracking_config1():
