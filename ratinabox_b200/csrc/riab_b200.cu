@@ -329,7 +329,11 @@ struct PlacePolicy {
   static constexpr int REC = place_rec(WI);
   static constexpr bool LIGHT = (WI == 0) && (DESC >= 0);   // few instructions per rate: HBM-bound consumers
   static constexpr bool XU_BOUND = false;
-  static constexpr bool THIN = true;                        // rates lie in [min_fr, max_fr]: thinned spikes apply
+  // rates lie in [min_fr, max_fr], so the thinned spike stream applies, but it measured slower for place cells: the
+  // Euclidean Gaussian loop is HBM-bound and hides the dense stream's instructions under its stores (c2e 56-60 us dense,
+  // 75 us thinned), the line-of-sight loop with the post-pass needs 8 producer warps and loses next to them (c2 105 us
+  // dense, 109-120 us thinned; gpurun_out/r02[b-f]_*).  The dense stream stays.
+  static constexpr bool THIN = false;
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
   static __device__ __forceinline__ void prepare(double* aux, const double* s_walls, const Const& c) {
     place_wall_invariants(aux, s_walls + 4 * c.wall0, WI > 0 ? c.n_inner : 0);
@@ -356,7 +360,7 @@ struct GridPolicy {
   static constexpr int CPT = CPT_;
   static constexpr int REC = 4;
   static constexpr bool LIGHT = false;    // 36 cell registers per thread do not fit StepCfg<8>'s 56-register consumers
-  static constexpr bool THIN = true;
+  static constexpr bool THIN = true;      // bounded rates, consumer-bound loop: thinned spikes (c3 93.5 -> 80 us)
   static constexpr bool XU_BOUND = false; // 3 MUFU.COS per rate, yet issue-bound: PRMT+FADD instead of I2F measured slower (95.6 vs 91.3 us, c3)
   static __device__ __forceinline__ const double* head_dir(const Const&) { return nullptr; }
   static __device__ __forceinline__ void prepare(double*, const double*, const Const&) {}
@@ -411,44 +415,49 @@ struct OvcPolicy {
 //                        (mbarrier empty[slot]).
 // The float64 motion latency (a ~2.5k-instruction dependent chain) is thereby hidden behind the
 // HBM-bound rate writes of earlier tiles instead of idling the CTA.
-// Warp-role configuration.  The register file is re-balanced between the roles with setmaxnreg
-// (producers run ~130-register float64 code, consumers need 56..88):
-//   StepCfg<4>: 4 producer + 16 consumer warps (640 threads x 96 regs): heavy consumers
-//               (line-of-sight / spikes / noise) set the pace, so they get 104 registers and the 4
-//               producers run (spilling) in 64 -- their latency stays hidden (measured: r104 > r96 > r88).
-//               112 / 56 does not fit the CTA's own allocation (see step_cfg_fits below) and hangs.
-//   StepCfg<8>: 8 producer + 16 consumer warps (768 threads x 80 regs): light consumers (Euclidean
-//               Gaussian / grid cells without spikes) run at the HBM write rate, so the float64
-//               motion chain (~14 us per 32-agent tile) needs twice the producer warps to keep up.
+// Warp-role configuration.  The register file is re-balanced between the roles with setmaxnreg (the float64 motion code wants
+// ~130 registers, the consumers 56..104).  Three splits, all 16 consumer warps (measurements: DESIGN.md section 4):
+//   StepCfg<4>:  4 producers x 64 registers (spilling), consumers x 104 (640 threads x 96 at launch).  Pair loops with
+//                spikes or OU noise: the consumers set the pace (c2 105 us, c3 with thinned spikes 80 us) and want the
+//                registers.  (8 producers next to them measured worse for the thinned grid cells, 91 us, and within the
+//                build-to-build spread for the dense stream: 105-111 us.)
+//   StepCfg<8>:  8 producers x 128, consumers x 56 (768 threads x 80): light consumers without spikes (Euclidean Gaussian
+//                place cells) run at the HBM write rate, so the float64 motion chain (~14 us per 32-agent tile) needs the
+//                producer warps and the registers to keep up.
+//   StepCfg<12>: 8 producers x 48 (spilling), consumers x 96 (768 threads x 80): heavier loops WITHOUT spikes (line of sight,
+//                grid cells).  With 4 producers these sat on the edge -- 3.5 tiles x 21-25 us per producer and step: the
+//                no-spike c2 whole run measured 73-86 us from one build to the next (the placement of the consumers' loop
+//                relative to the 64 KB of motion code the producers stream through the instruction cache seems to decide),
+//                72-76 us with 8 producers; consumers at 96 instead of 104 registers lose < 2 %.
+// A split that exceeds a sub-partition's launch allocation hangs (step_cfg_fits below).
 constexpr int RW = 16;    // consumer warps
-template <int MW_>
+template <int ID>
 struct StepCfg {
-  static constexpr int MW = MW_;
+  static_assert(ID == 4 || ID == 8 || ID == 12, "unknown warp-role configuration");
+  static constexpr int MW = (ID == 4) ? 4 : 8;                     // producer warps
   static constexpr int CTAS = 1;                                  // CTAs per SM
-  static constexpr int NS = (MW_ >= 8) ? MW_ : 2 * MW_;      // ring slots (multiple of MW; static smem <= 48 KB)
-  static constexpr int THREADS = (MW_ + RW) * 32;
-  static constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8;   // what __launch_bounds__(THREADS, 1) allocates
-#ifndef RIAB_RP4
-#define RIAB_RP4 64
-#endif
-#ifndef RIAB_RC4
-#define RIAB_RC4 104
-#endif
-  static constexpr int REGS_PRODUCER = (MW_ >= 8) ? 128 : RIAB_RP4;
-  static constexpr int REGS_CONSUMER = (MW_ >= 8) ? 56 : RIAB_RC4;
+  static constexpr int NS = (ID == 8) ? MW : 2 * MW;              // ring slots (multiple of MW; static smem <= 48 KB)
+  static constexpr int THREADS = (MW + RW) * 32;
+  // what __launch_bounds__(THREADS, 1) allocates: the register file is per SM sub-partition (16384 registers, warp w on
+  // sub-partition w % 4), so ptxas sizes for the fullest one -- 704 threads (22 warps, 6 on one sub-partition) get 80, not 88
+  static constexpr int WARPS_SP = (MW + RW + 3) / 4;
+  static constexpr int REGS_LAUNCH = (16384 / (WARPS_SP * 32)) / 8 * 8;
+  static constexpr int REGS_PRODUCER = (ID == 4) ? 64 : (ID == 8) ? 128 : 48;
+  static constexpr int REGS_CONSUMER = (ID == 4) ? 104 : (ID == 8) ? 56 : 96;
 };
 // (Round 2 also tried TWO CTAs per SM of 2 producer + 16 consumer warps with 2 cells per consumer thread -- 56 registers,
 // twice the resident consumer warps.  Same step time within 3 %: the consumers are bound by the math dispatch port -- ALU-pipe
 // and packed FP32 instructions hold it two cycles each -- not by latency, so more warps bought nothing.  The cell-count
 // template parameter CPT of the policies is what remains of it.)
-// setmaxnreg only moves registers WITHIN the CTA's launch allocation (THREADS x REGS_LAUNCH): an .inc blocks until enough
-// warps of the same CTA have released theirs with .dec.  A split whose total exceeds the allocation therefore never
-// completes -- the hang of round 1's 112 / 56 experiment: 16*32*112 + 4*32*56 = 64512 > 640*96 = 61440.
+// setmaxnreg only moves registers WITHIN the launch allocation of a sub-partition (its warps x REGS_LAUNCH): an .inc blocks
+// until enough warps have released theirs with .dec.  A split whose total exceeds the allocation therefore never
+// completes -- the hang of round 1's 112 / 56 experiment (4 x 32 x 112 + 32 x 56 = 16128 > 5 x 32 x 96 = 15360) and of a
+// 6-producer variant with 96-register consumers in round 2 (4 x 32 x 96 + 2 x 32 x 64 = 16384 > 6 x 32 x 80).
 template <class C>
 constexpr bool step_cfg_fits() {
-  return RW * 32 * C::REGS_CONSUMER + C::MW * 32 * C::REGS_PRODUCER <= C::THREADS * C::REGS_LAUNCH;
+  return (RW / 4) * 32 * C::REGS_CONSUMER + ((C::MW + 3) / 4) * 32 * C::REGS_PRODUCER <= C::WARPS_SP * 32 * C::REGS_LAUNCH;
 }
-static_assert(step_cfg_fits<StepCfg<4>>() && step_cfg_fits<StepCfg<8>>(),
+static_assert(step_cfg_fits<StepCfg<4>>() && step_cfg_fits<StepCfg<8>>() && step_cfg_fits<StepCfg<12>>(),
               "setmaxnreg split exceeds the CTA's register allocation: the kernel would hang");
 // setmaxnreg towards N registers from the launch allocation L (inc when N > L, dec when N < L)
 template <int N, int L> __device__ __forceinline__ void reg_set() {
@@ -457,9 +466,13 @@ template <int N, int L> __device__ __forceinline__ void reg_set() {
 }
 
 // ring slots of a (policy, configuration): the configuration's count, halved for the fat records (8 inner walls, object
-// vector cells: 160 B per agent) so that the static shared memory stays under 48 KB next to the thinned-spike queues
+// vector cells: 160 B per agent) while the ring would not fit in 40 KB of the 48 KB static shared memory
 template <class P, class C>
-constexpr int ring_slots() { return (P::REC > 24 && C::NS >= 2 * C::MW) ? C::NS / 2 : C::NS; }
+constexpr int ring_slots() {
+  int ns = C::NS;
+  while (ns >= 2 * C::MW && ns * (TA * P::REC * 4 + 16) > 40 * 1024) ns /= 2;
+  return ns;
+}
 
 // Consumer groups of the lean slot loop: each ring slot is consumed by ONE group, slot q by group q % G.  A group must see
 // every phase of the slots it waits on (an mbarrier parity wait cannot skip a phase), so G has to divide the ring size.
@@ -541,59 +554,65 @@ __device__ __forceinline__ void consume_pairs(int& a, const int a_end, const typ
 // The pair loop does nothing for spikes.  After a slot's rates are stored the warp runs this once: ~1.3 candidates per
 // lane at p' = 0.01, one Philox call per lane serves four of them; the rates are read back from L2 (this warp stored them),
 // accepted bits go into the spike rows the producer cleared with RED.OR.  NumPy mirror: tests/philox_np.py (expected_spikes_thin).
-template <int CPT>
-__device__ __forceinline__ void thin_block(const OutK& out, const TailCtx& tc, const float* __restrict__ rates,
-                                           uint32_t* __restrict__ spikes, const long long row_lo, const int rows) {
-  static_assert(CPT == 4, "a warp covers one 128-cell block");
+// An out-of-line call (like slot_fixups): inlined, its ~40 live registers made ptxas park cell registers of the pair loop in
+// local memory (8 LDL per pair iteration: the pass then cost more than the dense stream it replaces).  `out` is the kernel's
+// __grid_constant__ parameter, so its address can be passed without a local copy.
+__device__ __noinline__ void thin_block(const OutK* __restrict__ outp, const int cell0, const int n_cells, const uint32_t c2,
+                                        const uint32_t c3_spk, const float* __restrict__ rates, uint32_t* __restrict__ spikes,
+                                        const long long row_lo, const int rows) {
+  const OutK& out = *outp;
   const int lane = threadIdx.x & 31;
-  const int blk0 = tc.cell0 - CPT * lane;                 // first cell of the warp's block (warp-uniform)
-  const int cells_left = tc.n_cells - blk0;
-  if (cells_left <= 0 || spikes == nullptr) return;      // padding block
+  const int blk0 = cell0 - 4 * lane;                      // first cell of the warp's block (warp-uniform)
+  const int cells_left = n_cells - blk0;
+  if (lane >= rows || cells_left <= 0 || spikes == nullptr) return;   // (lanes leave independently: no warp-wide operation in here)
   const uint32_t B = (uint32_t)(blk0 >> 7);
   const long long row = row_lo + lane;
   const unsigned long long gid = (unsigned long long)(out.id_offset + row);
   const uint32_t c1w = B ^ ((uint32_t)(gid >> 32) << 24);
-  const uint32_t c3w = (tc.c3_spk & 0x00ffffffu) | (RIAB_STREAM_THIN << 24);
-  uint32_t R[4];
+  const uint32_t c3w = (c3_spk & 0x00ffffffu) | (RIAB_STREAM_THIN << 24);
+  uint32_t rk[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) rk[i] = out.rk7[i];
+  uint32_t R[4] = {(uint32_t)gid, c1w, c2, c3w};
+  philox_keyed<7>(R, rk);
   int K = 0;
-  if (lane < rows) {
-    R[0] = (uint32_t)gid; R[1] = c1w; R[2] = tc.c2; R[3] = c3w;
-    philox_keyed<7>(R, out.rk7);
-    while (K < 32 && R[0] >= out.thin_cdf[K]) ++K;
-  }
-  if (K == 0) return;                                      // (lanes leave independently: no warp-wide operation in here)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) K += (R[0] >= out.thin_cdf[k]) ? 1 : 0;        // independent compares
+  if (K == 8) while (K < 32 && R[0] >= out.thin_cdf[K]) ++K;
+  if (K == 0) return;
+  const float c1 = out.thin_c1, c0 = out.thin_c0;
   const float* rrow = rates + row * out.ld + blk0;
   uint32_t* srow = spikes + row * out.spike_ld + 4u * B;
   unsigned long long occ_lo = 0ull, occ_hi = 0ull;
   int cnt = 0;
   for (uint32_t n = 0u;;) {
-    bool take[4];
+    uint32_t take = 0u;
     int pos[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       pos[j] = (int)((R[1] >> (7 * j)) & 127u);
       const unsigned long long oh_lo = (pos[j] < 64) ? (1ull << pos[j]) : 0ull;
       const unsigned long long oh_hi = (pos[j] < 64) ? 0ull : (1ull << (pos[j] - 64));
-      take[j] = (cnt < K) && (((occ_lo & oh_lo) | (occ_hi & oh_hi)) == 0ull);
-      if (take[j]) { occ_lo |= oh_lo; occ_hi |= oh_hi; ++cnt; }
-      take[j] = take[j] && (pos[j] < cells_left);       // candidates on padding cells count, but have no rate
+      const bool fresh = (cnt < K) && (((occ_lo & oh_lo) | (occ_hi & oh_hi)) == 0ull);
+      if (fresh) { occ_lo |= oh_lo; occ_hi |= oh_hi; ++cnt; }
+      if (fresh && pos[j] < cells_left) take |= 1u << j;   // candidates on padding cells count, but have no rate
     }
     float rate[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       rate[j] = 0.f;
-      if (take[j]) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate[j]) : "l"(rrow + pos[j]));
+      if ((take >> j) & 1u) asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(rate[j]) : "l"(rrow + pos[j]));
     }
     const uint32_t dith = R[1] >> 28;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t m = ((j < 2 ? R[2] : R[3]) >> (16 * (j & 1))) & 0xffffu;
       const float x = (float)((m << 4) | dith);
-      if (take[j] && fmaf(x, out.thin_c1, out.thin_c0) < rate[j]) atomicOr(srow + (pos[j] & 3), 1u << (pos[j] >> 2));
+      if (((take >> j) & 1u) && fmaf(x, c1, c0) < rate[j]) atomicOr(srow + (pos[j] & 3), 1u << (pos[j] >> 2));
     }
     if (cnt >= K || ++n >= 256u) break;
-    R[0] = (uint32_t)gid; R[1] = c1w ^ (n << 16); R[2] = tc.c2; R[3] = c3w;
-    philox_keyed<7>(R, out.rk7);
+    R[0] = (uint32_t)gid; R[1] = c1w ^ (n << 16); R[2] = c2; R[3] = c3w;
+    philox_keyed<7>(R, rk);
   }
 }
 
@@ -728,7 +747,7 @@ __device__ __forceinline__ void consumer_slots(const typename P::Const& pc, cons
         }
         if (SPK == 2) {
           __syncwarp();      // orders this warp's rate stores before the read-back
-          if constexpr (CPT == 4) thin_block<CPT>(out, tc, out.rates, out.spikes, a0 + a_lo, a_hi - a_lo);
+          if constexpr (CPT == 4) thin_block(&out, tc.cell0, tc.n_cells, tc.c2, tc.c3_spk, out.rates, out.spikes, a0 + a_lo, a_hi - a_lo);
         }
       }
     }
@@ -874,7 +893,7 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
         }
         if constexpr (SPK == 2) {
           __syncwarp();                                  // this warp's rate stores before the read-back
-          thin_block<CPT>(out, tc, rates, spikes, a0 + a_lo, a_hi - a_lo);
+          thin_block(&out, tc.cell0, tc.n_cells, tc.c2, tc.c3_spk, rates, spikes, a0 + a_lo, a_hi - a_lo);
         }
       }
       __syncwarp();
@@ -887,7 +906,7 @@ __device__ __forceinline__ void consumer_fast(const typename P::Const& pc, const
 template <class P, int MODE, int SPK, bool NOISE, class C>
 __global__ void __launch_bounds__(C::THREADS, C::CTAS) k_step(const EnvK env, const riab_agents ag,
                                                           const riab_motion_params mp, const MotionDerived md,
-                                                          const riab_step_io io, const typename P::Const pc, const OutK out,
+                                                          const riab_step_io io, const typename P::Const pc, const __grid_constant__ OutK out,
                                                           const double* __restrict__ pos_in, const long long n_rows,
                                                           const RunK run) {
   __shared__ __align__(16) double s_walls[MAXW * 4];
@@ -1686,12 +1705,17 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
     if (sms_of[dev] == 0) RIAB_CUDA_OK(cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev));
     g_num_sms = sms_of[dev];
   }
+  const bool spikes = out_in.spikes != nullptr, noise = out_in.noise != nullptr;
+  // thinned stream: bounded rates AND a policy for which it measured faster (P::THIN); see the policies
+  const bool thin = spikes && !noise && out_in.thin && P::THIN;
+  // warp-role configuration (see StepCfg)
+  const int cfg = (noise || spikes) ? 4 : ((P::LIGHT && MODE != 0) ? 8 : 12);
   // agents per ring slot: 32 for large batches; small ones get equal shares per (CTA, consumer group)
   OutK outk = out_in;
   {
     const int ct = pc.n_pad / P::CPT;                                 // cell-threads of one consumer group
-    const long long groups = (ct > 0 && ct <= RW * 32) ? (long long)g_num_sms * lean_groups(ct, ring_slots<P, StepCfg<4>>())
-                                                         : (long long)g_num_sms;
+    const int ring = (cfg == 4) ? ring_slots<P, StepCfg<4>>() : (cfg == 8) ? ring_slots<P, StepCfg<8>>() : ring_slots<P, StepCfg<12>>();
+    const long long groups = (ct > 0 && ct <= RW * 32) ? (long long)g_num_sms * lean_groups(ct, ring) : (long long)g_num_sms;
     int ta = TA;
     if (n_rows < 4ll * TA * groups) {
       const long long per = (n_rows + groups - 1) / groups;          // agents per group if every group gets one slot
@@ -1709,20 +1733,18 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   if (run_in != nullptr) run = *run_in;
   const long long n_tiles = (n_rows + out.tile_agents - 1) / out.tile_agents;
   const unsigned grid = (unsigned)(n_tiles < g_num_sms ? n_tiles : g_num_sms);
-  const bool spikes = out.spikes != nullptr, noise = out.noise != nullptr;
   MotionDerived md;
   memset(&md, 0, sizeof(md));
   if (MODE != 0) derive_motion(mp, md);
   if (noise) k_step<P, MODE, 1, true, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
-  else if (spikes && out.thin) {
+  else if (thin) {
     if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
-    else return fail(RIAB_ERR_INVALID, "thinned spikes requested for a population without a rate bound");
   }
   else if (spikes) k_step<P, MODE, 1, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
   else {
-    // light consumers without spikes run at the HBM write rate: twice the producer warps (only instantiated for them)
+    // light consumers without spikes run at the HBM write rate: fat producers (only instantiated for them)
     if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, 0, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
-    else k_step<P, MODE, 0, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
+    else k_step<P, MODE, 0, false, StepCfg<12>><<<grid, StepCfg<12>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
   }
   g_launches++;
   RIAB_CUDA_OK(cudaGetLastError());

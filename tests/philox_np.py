@@ -58,9 +58,9 @@ def agent_normals(seed, step, agents):
 
 def expected_spikes(seed, step, agents, fr, dt, pop=0, fr_bound=None):
     """(A, n_cells) bool spikes of one step given the float32 rates `fr` (A, n_cells).
-    fr_bound = max(min_fr, max_fr) of a PlaceCells / GridCells population without OU noise: the library uses the thinned
+    fr_bound = max(min_fr, max_fr) of a GridCells population without OU noise: the library uses the thinned
     stream when dt * fr_bound * (1 + 2^-10) <= 1/16 (expected_spikes_thin; RIAB_DENSE_SPIKES=1 in the environment turns it
-    off); otherwise -- and always for every other population -- the dense one:
+    off); otherwise -- and always for every other population (expected_spikes_of) -- the dense one:
         spike <=> m < fma(rate, dt*65536, -v)      (riab_b200.cu: spike_ballots)
     One Philox4x32-7 call per (agent pair gid>>1, 4-cell group); agent half gid&1 takes words 2h, 2h+1 as four
     16-bit integers m; all eight share the dither v = ((r0^r2)>>8) * 2^-24.  The float32 fma is mirrored
@@ -85,6 +85,14 @@ def expected_spikes(seed, step, agents, fr, dt, pop=0, fr_bound=None):
     q = np.float64(np.float32(np.float32(dt) * np.float32(65536.0)))
     thr = (fr.astype(np.float64) * q - vv).astype(np.float32)
     return m < thr
+
+
+def expected_spikes_of(ns, seed, step, agents, fr, dt, pop=0, fr_bound=None):
+    """expected_spikes for a ratinabox_b200 population: the library uses the thinned stream for GridCells only (bounded
+    rates and a pair loop for which it measured faster; riab_b200.cu: GridPolicy::THIN, launch_tile) -- PlaceCells keep the
+    dense stream whatever their rate bound."""
+    thin_ok = type(ns).__name__ == "GridCells"
+    return expected_spikes(seed, step, agents, fr, dt, pop=pop, fr_bound=fr_bound if thin_ok else None)
 
 
 STREAM_THIN = 4

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import riab_oracle as O
-from philox_np import expected_spikes
+from philox_np import expected_spikes, expected_spikes_of
 
 pytestmark = pytest.mark.gpu
 
@@ -54,7 +54,7 @@ def test_ragged_sizes_all_wall_templates(A, N, k):
     assert h["firingrate"].shape == want and h["spikes"].shape == want
     # spikes of the last step against the NumPy mirror of the Philox stream (population 0)
     sp = h["spikes"][-1].reshape(A, N)
-    assert np.array_equal(sp, expected_spikes(9, steps - 1, np.arange(A), fr, 0.01, pop=0, fr_bound=4.0))
+    assert np.array_equal(sp, expected_spikes_of(PCs, 9, steps - 1, np.arange(A), fr, 0.01, pop=0, fr_bound=4.0))
     assert np.isfinite(pos).all() and not np.array_equal(pos, pos0)
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 import riab_oracle as O
-from philox_np import agent_normals, expected_spikes
+from philox_np import agent_normals, expected_spikes, expected_spikes_of
 
 pytestmark = pytest.mark.gpu
 
@@ -114,21 +114,22 @@ def test_spikes_match_numpy_philox():
     h = PCs.get_history_arrays()
     assert h["firingrate"].shape == (3, A, N) and h["spikes"].shape == (3, A, N) and h["spikes"].dtype == bool
     for s in range(3):
-        want = expected_spikes(11, s, np.arange(A), h["firingrate"][s], 0.05, pop=0, fr_bound=15.0)
+        want = expected_spikes_of(PCs, 11, s, np.arange(A), h["firingrate"][s], 0.05, pop=0, fr_bound=15.0)
         assert np.array_equal(h["spikes"][s], want), s
     assert 0.02 < h["spikes"].mean() < 0.6
 
 
 @pytest.mark.parametrize("A,N,stepped", [(131, 300, False), (64, 1024, False), (70, 128, True), (33, 2304, False)])
 def test_thinned_spikes_match_numpy_mirror(A, N, stepped):
-    """dt * max_fr <= 1/16 (here 0.01 * 1 Hz and 0.01 * 3 Hz): PlaceCells / GridCells without OU noise use the thinned spike
-    stream (Binomial(128, dt*max_fr) candidates per (agent, 128-cell block) at uniformly drawn distinct cells, accepted with
-    rate/max_fr; riab_b200.cu: thin_block).  Bit-equal to the NumPy mirror for odd agent counts, ragged cell counts, several
-    cell chunks (N > 2048), riab_run and the stepped API; still Bernoulli(dt * rate) (Neurons.py:682-684)."""
+    """GridCells without OU noise and dt * max_fr <= 1/16 (here 0.01 * 3 Hz) use the thinned spike stream
+    (Binomial(128, dt*max_fr) candidates per (agent, 128-cell block) at uniformly drawn distinct cells, accepted with
+    rate/max_fr; riab_b200.cu: thin_block); the PlaceCells next to them keep the dense stream.  Both bit-equal to their NumPy
+    mirrors for odd agent counts, ragged cell counts, several cell chunks (N > 2048), riab_run and the stepped API; both
+    Bernoulli(dt * rate) (Neurons.py:682-684)."""
     import ratinabox_b200 as rb
     E, Ag = make(rb, A)
     PCs = rb.PlaceCells(Ag, {"n": N, "wall_geometry": "line_of_sight"})
-    GCs = rb.GridCells(Ag, {"n": 64, "max_fr": 3.0})
+    GCs = rb.GridCells(Ag, {"n": N, "max_fr": 3.0})
     steps = 3
     if stepped:
         for _ in range(steps):
@@ -138,7 +139,7 @@ def test_thinned_spikes_match_numpy_mirror(A, N, stepped):
     for pop, (Ns, bound) in enumerate(((PCs, 1.0), (GCs, 3.0))):
         h = Ns.get_history_arrays()
         for s in range(steps):
-            want = expected_spikes(11, s, np.arange(A), h["firingrate"][s].reshape(A, Ns.n), 0.01, pop=pop, fr_bound=bound)
+            want = expected_spikes_of(Ns, 11, s, np.arange(A), h["firingrate"][s].reshape(A, Ns.n), 0.01, pop=pop, fr_bound=bound)
             assert np.array_equal(h["spikes"][s].reshape(A, Ns.n), want), (pop, s)
         p = 0.01 * h["firingrate"].astype(np.float64)
         n_sp, mu, var = h["spikes"].sum(), p.sum(), (p * (1 - p)).sum()
@@ -146,17 +147,17 @@ def test_thinned_spikes_match_numpy_mirror(A, N, stepped):
 
 
 def test_dense_spike_stream_on_request(monkeypatch):
-    """RIAB_DENSE_SPIKES=1 keeps the dense stream (one threshold test per rate in the pair loop) for bounded populations
-    too: bit-equal to its NumPy mirror through the lean consumers and riab_run."""
+    """RIAB_DENSE_SPIKES=1 keeps the dense stream (one threshold test per rate in the pair loop) for GridCells too:
+    bit-equal to its NumPy mirror through the lean consumers and riab_run."""
     import ratinabox_b200 as rb
     monkeypatch.setenv("RIAB_DENSE_SPIKES", "1")
     A = 96
     E, Ag = make(rb, A)
-    PCs = rb.PlaceCells(Ag, {"n": 512, "wall_geometry": "line_of_sight"})
+    GCs = rb.GridCells(Ag, {"n": 512})
     Ag.run(2)
-    h = PCs.get_history_arrays()
+    h = GCs.get_history_arrays()
     for s in range(2):
-        want = expected_spikes(11, s, np.arange(A), h["firingrate"][s], 0.01, pop=0, fr_bound=1.0)
+        want = expected_spikes_of(GCs, 11, s, np.arange(A), h["firingrate"][s], 0.01, pop=0, fr_bound=1.0)
         assert np.array_equal(h["spikes"][s], want), s
 
 
