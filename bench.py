@@ -456,7 +456,11 @@ def main():
     scaling = "strong" if wl.get("strong") else "weak"
     config = {"workload": f"{args.workload}: {wl['desc']}", "agents_per_gpu": A_rank, "n_cells": n_cells,
               "cells": kind, "wall_geometry": geom, "n_walls": 4 + len(wl["walls"]), "dt": 0.01,
-              "spikes": not args.no_spikes, "history": "device rings (rates: last rows within 8 GiB; agent rows: all)",
+              "spikes": not args.no_spikes,
+              "spike_stream": (None if args.no_spikes else
+                               {"place": "dense Philox4x32-7 stream in the pair loop", "grid": "thinned (Binomial candidates per 128-cell block)",
+                                "bvc": "dense, in the integration kernel's epilogue"}.get(kind, "per population: place dense / grid thinned / bvc dense")),
+              "history": "device rings (rates: last rows within 8 GiB; agent rows: all)",
               "l2": "each step writes >= 2x L2 of fresh rate rows (inputs larger than L2)",
               "parallelism": f"agents sharded x{world}, no step-path collective"}
 
