@@ -425,7 +425,7 @@ struct OvcPolicy {
 //                place cells) run at the HBM write rate, so the float64 motion chain (~14 us per 32-agent tile) needs the
 //                producer warps and the registers to keep up.
 //   StepCfg<12>: 8 producers x 48 (spilling), consumers x 96 (768 threads x 80): heavier loops WITHOUT spikes (line of sight,
-//                grid cells).  With 4 producers these sat on the edge -- 3.5 tiles x 21-25 us per producer and step: the
+//                grid cells) and the light loop WITH the dense spike stream (c2e 59 -> 56 us).  With 4 producers these sat on the edge -- 3.5 tiles x 21-25 us per producer and step: the
 //                no-spike c2 whole run measured 73-86 us from one build to the next (the placement of the consumers' loop
 //                relative to the 64 KB of motion code the producers stream through the instruction cache seems to decide),
 //                72-76 us with 8 producers; consumers at 96 instead of 104 registers lose < 2 %.
@@ -1709,7 +1709,7 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   // thinned stream: bounded rates AND a policy for which it measured faster (P::THIN); see the policies
   const bool thin = spikes && !noise && out_in.thin && P::THIN;
   // warp-role configuration (see StepCfg)
-  const int cfg = (noise || spikes) ? 4 : ((P::LIGHT && MODE != 0) ? 8 : 12);
+  const int cfg = (noise || thin || (spikes && !P::LIGHT)) ? 4 : (spikes ? 12 : ((P::LIGHT && MODE != 0) ? 8 : 12));
   // agents per ring slot: 32 for large batches; small ones get equal shares per (CTA, consumer group)
   OutK outk = out_in;
   {
@@ -1740,7 +1740,12 @@ int launch_tile(const EnvK& env, const riab_agents& ag, const riab_motion_params
   else if (thin) {
     if constexpr (P::THIN) k_step<P, MODE, 2, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
   }
-  else if (spikes) k_step<P, MODE, 1, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
+  else if (spikes) {
+    // dense stream: light consumers (Euclidean Gaussian place cells) are producer-bound next to 4 producer warps (c2e 59 us),
+    // with 8 they run at 56 us; the heavier loops keep the 104-register consumers
+    if constexpr (P::LIGHT) k_step<P, MODE, 1, false, StepCfg<12>><<<grid, StepCfg<12>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
+    else k_step<P, MODE, 1, false, StepCfg<4>><<<grid, StepCfg<4>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
+  }
   else {
     // light consumers without spikes run at the HBM write rate: fat producers (only instantiated for them)
     if constexpr (P::LIGHT && MODE != 0) k_step<P, MODE, 0, false, StepCfg<8>><<<grid, StepCfg<8>::THREADS, 0, s>>>(env, ag, mp, md, io, pc, out, pos_in, n_rows, run);
