@@ -384,3 +384,28 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["steps"] * d["ms_per_step"] * 1e-3 <= d["wall_s"]          # the timed region fits inside the run
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "c2" in d["config"]["workload"]
+
+
+def test_step_kernels_got_the_launch_registers_the_setmaxnreg_split_assumes():
+    """k_step re-balances registers between its producer and consumer warps with setmaxnreg, which can only move registers
+    inside what the launch allocated per SM sub-partition (riab_b200.cu: StepCfg::REGS_LAUNCH, step_cfg_fits): if ptxas gave a
+    kernel FEWER registers than the model assumes, the consumers' setmaxnreg.inc never completes and the kernel hangs (a
+    6-producer variant did exactly that in round 2: 704 threads get 80 registers, not 88).  Every instantiation in the built
+    library must therefore carry its configuration's launch count: 96 for StepCfg<4> (20 warps, 5 per sub-partition), 80 for
+    StepCfg<8> and StepCfg<12> (24 warps, 6 per sub-partition), and fit the 48 KB of static shared memory."""
+    import shutil
+    import subprocess
+    from ratinabox_b200 import _lib
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    txt = subprocess.run([tool, "--dump-resource-usage", _lib.lib_path()], capture_output=True, text=True, check=True).stdout
+    found = re.findall(r"Function (\S*6k_stepI\S*?7StepCfgILi(\d+)E\S*):\s*\n\s*REG:(\d+) STACK:\d+ SHARED:(\d+)", txt)
+    assert len(found) > 50, len(found)
+    want = {"4": 96, "8": 80, "12": 80}
+    seen = set()
+    for name, cfg, reg, shared in found:
+        assert int(reg) == want[cfg], (name[:120], cfg, reg)
+        assert int(shared) <= 48 * 1024, (name[:120], shared)
+        seen.add(cfg)
+    assert seen == {"4", "8", "12"}
